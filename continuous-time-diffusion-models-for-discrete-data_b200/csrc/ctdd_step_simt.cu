@@ -1,0 +1,453 @@
+// CUDA-core reverse-step kernels.
+//   step_small_kernel<S>  S <= 8 (C1: S=2, C2: S=3): one thread owns 8 consecutive rows, everything in
+//                         registers, float4 logits loads — HBM-bound by construction.
+//   step_block_kernel     any S: one CTA owns 8 consecutive rows, threads span the state axis. This is the
+//                         general path and the on-GPU cross-check of the tcgen05 path at S=256.
+// Both implement every CTDD_MODE_* / CTDD_BRANCH_* and draw exactly the same Philox uniforms as the tensor
+// path, so the three are interchangeable bit-for-bit up to fp32 rounding of the rates.
+// Reference arithmetic: lib/sampling/sampling.py:31-78 (rates), :127-160 (tau-leap), :278-293 (Euler),
+// :423-453 / :459-503 (midpoint), :170-221 (corrector); lib/models/model_utils.py:30-60.
+#include "ctdd_common.cuh"
+
+namespace ctdd {
+
+struct StepArgs {
+  int mode, branch, D, S, reject_multi;
+  long long rows;        // N*D
+  long long row_offset;  // multiple of 8
+  const float* logits;
+  long long ld, batch_stride;
+  const int* x_eval;
+  const int* x_base;
+  const float* Q;
+  const float* QT;
+  const float* Rb;
+  const float* RbT;
+  float beta, h, eps;
+  unsigned long long seed, offset;
+  int* x_out;
+  float* rr_out;
+  float* ratio_out;
+  unsigned long long* stats;
+};
+
+__device__ __forceinline__ const float* logits_row(const StepArgs& a, long long r) {
+  const long long n = r / a.D, d = r - n * a.D;
+  return a.logits + n * a.batch_stride + d * a.ld;
+}
+
+struct RowStats { int changed_base, nonzero, changed_eval, jumped, multi; };
+
+__device__ __forceinline__ int finalize_jump(int xb, int xe, int jump, int cnt, int reject_multi, int S,
+                                             RowStats& st) {
+  st.jumped += (cnt > 0);
+  st.multi += (cnt > 1);
+  if (reject_multi && cnt > 1) jump = 0;
+  st.nonzero += (jump != 0);
+  int xn = xb + jump;
+  xn = xn < 0 ? 0 : (xn > S - 1 ? S - 1 : xn);
+  st.changed_base += (xn != xb);
+  st.changed_eval += (xn != xe);
+  return xn;
+}
+
+__device__ __forceinline__ void flush_stats(const RowStats& st, unsigned long long* stats) {
+  if (!stats) return;
+  int v[5] = {st.changed_base, st.nonzero, st.changed_eval, st.jumped, st.multi};
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    int s = v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(stats + i, (unsigned long long)s);
+  }
+}
+
+// Jump count for one (row, s) given lam and the row's halfword of the two Philox streams.
+__device__ __forceinline__ int jump_count(float lam, uint32_t hi16, uint32_t s, uint64_t group, int half,
+                                          unsigned long long offset, unsigned long long seed) {
+  // exact fast reject: v >= hi16 * 2^-16, and P(K>=1) <= lam
+  if (!(lam > 0.f) || (float)hi16 * 1.52587890625e-05f >= lam) return 0;
+  Philox4 lo = philox_jump(s, group, offset, STREAM_JUMP_LO, seed);
+  const uint32_t w = (hi16 << 16) | philox_half(lo, half);
+  return poisson_from_unit(lam, u32_to_unit(w));
+}
+
+// ------------------------------------------------------------------------------------------------
+// small S: thread per 8 rows
+template <int S>
+__global__ void __launch_bounds__(128) step_small_kernel(StepArgs a) {
+  __shared__ float sQ[S * S], sRb[S * S];
+  for (int i = threadIdx.x; i < S * S; i += blockDim.x) { sQ[i] = a.Q[i]; sRb[i] = a.Rb[i]; }
+  __syncthreads();
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // local row group
+  const long long r0 = g * 8;
+  RowStats st = {0, 0, 0, 0, 0};
+  if (r0 < a.rows) {
+    const int nr = (a.rows - r0) < 8 ? (int)(a.rows - r0) : 8;
+    float lg[8][S];
+    const bool contiguous = (a.ld == S) && (a.batch_stride == (long long)a.D * S) && nr == 8;
+    if (contiguous) {
+      const float4* p = reinterpret_cast<const float4*>(a.logits + r0 * S);
+      float4 buf[2 * S];
+#pragma unroll
+      for (int i = 0; i < 2 * S; ++i) buf[i] = __ldg(p + i);
+      const float* f = reinterpret_cast<const float*>(buf);
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int s = 0; s < S; ++s) lg[r][s] = f[r * S + s];
+    } else {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float* p = logits_row(a, r0 + (r < nr ? r : 0));
+#pragma unroll
+        for (int s = 0; s < S; ++s) lg[r][s] = __ldg(p + s);
+      }
+    }
+    int xe[8], xb[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const long long rr_ = r0 + (r < nr ? r : 0);
+      xe[r] = a.x_eval[rr_];
+      xb[r] = a.x_base ? a.x_base[rr_] : xe[r];
+    }
+    // rates: rate[r][s] holds rr with the s==x entry zeroed (the quantity every mode consumes)
+    float rate[8][S];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int x = xe[r];
+      float m = lg[r][0];
+#pragma unroll
+      for (int s = 1; s < S; ++s) m = fmaxf(m, lg[r][s]);
+      float e[S], sum = 0.f;
+#pragma unroll
+      for (int s = 0; s < S; ++s) { e[s] = expf(lg[r][s] - m); sum += e[s]; }
+      float ratio[S], rfull[S];
+      if (a.branch == CTDD_BRANCH_TAULDR) {
+        float w[S];
+#pragma unroll
+        for (int k = 0; k < S; ++k) w[k] = (e[k] / sum) / (sQ[k * S + x] + a.eps);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          float acc = 0.f;
+#pragma unroll
+          for (int k = 0; k < S; ++k) acc = fmaf(w[k], sQ[k * S + s], acc);
+          ratio[s] = acc;
+          rfull[s] = a.beta * sRb[s * S + x] * acc;
+        }
+      } else {
+        float ll[S];
+        const float lse = m + logf(sum);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          if (a.branch == CTDD_BRANCH_SDDM_DIRECT) {
+            ll[s] = lg[r][s] - lse;
+          } else if (a.branch == CTDD_BRANCH_SDDM_REVERSE_PROB) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < S; ++k) acc = fmaf(e[k] / sum, sQ[k * S + s], acc);
+            ll[s] = logf(acc + 1e-35f);
+          } else {
+            float t[S], tm = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < S; ++k) {
+              const float q = sQ[k * S + s];
+              t[k] = (lg[r][k] - lse) + (q <= 1e-35f ? -1e9f : logf(q));
+              tm = fmaxf(tm, t[k]);
+            }
+            float ts = 0.f;
+#pragma unroll
+            for (int k = 0; k < S; ++k) ts += expf(t[k] - tm);
+            ll[s] = tm + logf(ts);
+          }
+        }
+        float llx = 0.f;
+#pragma unroll
+        for (int s = 0; s < S; ++s) llx = (s == x) ? ll[s] : llx;
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          ratio[s] = expf(ll[s] - llx);
+          rfull[s] = ratio[s] * (a.beta * sRb[x * S + s]);
+        }
+      }
+      if (r < nr) {
+        if (a.rr_out) {
+#pragma unroll
+          for (int s = 0; s < S; ++s) a.rr_out[(r0 + r) * S + s] = rfull[s];
+        }
+        if (a.ratio_out) {
+#pragma unroll
+          for (int s = 0; s < S; ++s) a.ratio_out[(r0 + r) * S + s] = ratio[s];
+        }
+      }
+      const bool corr = (a.mode == CTDD_MODE_TAU_LEAP_CORR || a.mode == CTDD_MODE_EULER_CORR);
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        float v = rfull[s];
+        if (corr) v = v + a.beta * sRb[x * S + s];
+        rate[r][s] = (s == x) ? 0.f : v;
+      }
+    }
+    const uint64_t group = (uint64_t)(a.row_offset + r0) >> 3;
+    if (a.mode == CTDD_MODE_TAU_LEAP || a.mode == CTDD_MODE_TAU_LEAP_CORR || a.mode == CTDD_MODE_MIDPOINT_JUMP) {
+      int jump[8], cnt[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) { jump[r] = 0; cnt[r] = 0; }
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const Philox4 hi = philox_jump(s, group, a.offset, STREAM_JUMP_HI, a.seed);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int k = jump_count(rate[r][s] * a.h, philox_half(hi, r), s, group, r, a.offset, a.seed);
+          if (k) { jump[r] += jump_contrib(k, s, xe[r]); cnt[r] += (k > 4096 ? 4096 : k); }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r < nr) a.x_out[r0 + r] = finalize_jump(xb[r], xe[r], jump[r], cnt[r], a.reject_multi, S, st);
+    } else if (a.mode == CTDD_MODE_MIDPOINT_DRIFT) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        float acc = 0.f;
+#pragma unroll
+        for (int s = 0; s < S; ++s) acc += rate[r][s] * (float)(s - xe[r]);
+        const int ch = (int)rintf(0.5f * a.h * acc);
+        int xn = xe[r] + ch;
+        xn = xn < 0 ? 0 : (xn > S - 1 ? S - 1 : xn);
+        if (r < nr) {
+          a.x_out[r0 + r] = xn;
+          st.changed_base += (xn != xe[r]);
+          st.changed_eval += (xn != xe[r]);
+          st.nonzero += (ch != 0);
+        }
+      }
+    } else if (a.mode == CTDD_MODE_EULER || a.mode == CTDD_MODE_EULER_CORR) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        float tot = 0.f;
+#pragma unroll
+        for (int s = 0; s < S; ++s) tot += rate[r][s];
+        const float diag = fmaxf(0.f, 1.f - a.h * tot);
+        const int x = xe[r];
+        const float v = u32_to_unit(philox_row_word((uint64_t)(a.row_offset + r0 + r), 0, a.offset, STREAM_ROW, a.seed));
+        float P[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) P[s] = (s == x) ? diag : rate[r][s] * a.h;
+        const int xn = inv_cdf(S, v, [&](int s) {
+          float w = 0.f;
+#pragma unroll
+          for (int q = 0; q < S; ++q) w = (q == s) ? P[q] : w;
+          return w;
+        });
+        if (r < nr) {
+          a.x_out[r0 + r] = xn;
+          st.changed_base += (xn != xb[r]);
+          st.changed_eval += (xn != x);
+        }
+      }
+    }
+  }
+  flush_stats(st, a.stats);
+}
+
+// ------------------------------------------------------------------------------------------------
+// any S: CTA per 8 rows, threads over states.  smem: A[8][S] (operand rows, later reused for per-state
+// terms), small per-row scalars.
+constexpr int BLK_ROWS = 8;
+
+__global__ void __launch_bounds__(256) step_block_kernel(StepArgs a) {
+  extern __shared__ float smem[];
+  const int S = a.S;
+  float* sA = smem;                 // [8][S]
+  float* sT = smem + BLK_ROWS * S;  // [8][S] per-state terms (rates / P)
+  __shared__ int s_xe[BLK_ROWS], s_xb[BLK_ROWS], s_jump[BLK_ROWS], s_cnt[BLK_ROWS];
+  __shared__ float s_llx[BLK_ROWS], s_lse[BLK_ROWS];
+  const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nth >> 5;
+  const long long r0 = (long long)blockIdx.x * BLK_ROWS;
+  const int nr = (a.rows - r0) < BLK_ROWS ? (int)(a.rows - r0) : BLK_ROWS;
+  if (tid < BLK_ROWS) {
+    const long long r = r0 + (tid < nr ? tid : 0);
+    s_xe[tid] = a.x_eval[r];
+    s_xb[tid] = a.x_base ? a.x_base[r] : s_xe[tid];
+    s_jump[tid] = 0; s_cnt[tid] = 0; s_llx[tid] = 0.f;
+  }
+  __syncthreads();
+  // 1. softmax statistics and operand rows: warp w handles rows w, w+nwarp, ...
+  for (int r = warp; r < BLK_ROWS; r += nwarp) {
+    const float* lp = logits_row(a, r0 + (r < nr ? r : 0));
+    const int x = s_xe[r];
+    float m = -INFINITY;
+    for (int k = lane; k < S; k += 32) m = fmaxf(m, __ldg(lp + k));
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int k = lane; k < S; k += 32) sum += expf(__ldg(lp + k) - m);
+    sum = warp_sum(sum);
+    if (lane == 0) s_lse[r] = m + logf(sum);
+    for (int k = lane; k < S; k += 32) {
+      const float p = expf(__ldg(lp + k) - m) / sum;
+      float v;
+      if (a.branch == CTDD_BRANCH_TAULDR) v = p / (a.QT[(size_t)x * S + k] + a.eps);
+      else if (a.branch == CTDD_BRANCH_SDDM_REVERSE_LOGSCALE) v = __ldg(lp + k) - (m + logf(sum));  // log p
+      else v = p;
+      sA[r * S + k] = v;
+    }
+  }
+  __syncthreads();
+  // 2. contraction over k for this thread's states; 3. rates
+  for (int s = tid; s < S; s += nth) {
+    float acc[BLK_ROWS];
+#pragma unroll
+    for (int r = 0; r < BLK_ROWS; ++r) acc[r] = 0.f;
+    if (a.branch == CTDD_BRANCH_TAULDR || a.branch == CTDD_BRANCH_SDDM_REVERSE_PROB) {
+      for (int k = 0; k < S; ++k) {
+        const float q = __ldg(a.Q + (size_t)k * S + s);
+#pragma unroll
+        for (int r = 0; r < BLK_ROWS; ++r) acc[r] = fmaf(sA[r * S + k], q, acc[r]);
+      }
+    } else if (a.branch == CTDD_BRANCH_SDDM_REVERSE_LOGSCALE) {
+      float mx[BLK_ROWS];
+#pragma unroll
+      for (int r = 0; r < BLK_ROWS; ++r) mx[r] = -INFINITY;
+      for (int k = 0; k < S; ++k) {
+        const float q = __ldg(a.Q + (size_t)k * S + s);
+        const float lq = q <= 1e-35f ? -1e9f : logf(q);
+#pragma unroll
+        for (int r = 0; r < BLK_ROWS; ++r) mx[r] = fmaxf(mx[r], sA[r * S + k] + lq);
+      }
+      for (int k = 0; k < S; ++k) {
+        const float q = __ldg(a.Q + (size_t)k * S + s);
+        const float lq = q <= 1e-35f ? -1e9f : logf(q);
+#pragma unroll
+        for (int r = 0; r < BLK_ROWS; ++r) acc[r] += expf(sA[r * S + k] + lq - mx[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < BLK_ROWS; ++r) acc[r] = mx[r] + logf(acc[r]);  // ll[s]
+    }
+#pragma unroll
+    for (int r = 0; r < BLK_ROWS; ++r) {
+      float v = acc[r];
+      if (a.branch == CTDD_BRANCH_SDDM_REVERSE_PROB) v = logf(v + 1e-35f);
+      else if (a.branch == CTDD_BRANCH_SDDM_DIRECT) v = __ldg(logits_row(a, r0 + (r < nr ? r : 0)) + s) - s_lse[r];
+      sT[r * S + s] = v;  // tauLDR: ratio; SDDM: ll
+      if (a.branch != CTDD_BRANCH_TAULDR && s == s_xe[r]) s_llx[r] = v;
+    }
+  }
+  __syncthreads();
+  const bool corr = (a.mode == CTDD_MODE_TAU_LEAP_CORR || a.mode == CTDD_MODE_EULER_CORR);
+  for (int s = tid; s < S; s += nth) {
+#pragma unroll
+    for (int r = 0; r < BLK_ROWS; ++r) {
+      const int x = s_xe[r];
+      float ratio, rfull;
+      if (a.branch == CTDD_BRANCH_TAULDR) {
+        ratio = sT[r * S + s];
+        rfull = a.beta * __ldg(a.RbT + (size_t)x * S + s) * ratio;
+      } else {
+        ratio = expf(sT[r * S + s] - s_llx[r]);
+        rfull = ratio * (a.beta * __ldg(a.Rb + (size_t)x * S + s));
+      }
+      if (r < nr) {
+        if (a.rr_out) a.rr_out[(r0 + r) * S + s] = rfull;
+        if (a.ratio_out) a.ratio_out[(r0 + r) * S + s] = ratio;
+      }
+      float v = rfull;
+      if (corr) v = v + a.beta * __ldg(a.Rb + (size_t)x * S + s);
+      sA[r * S + s] = (s == x) ? 0.f : v;  // zeroed rates (sA is free again)
+    }
+  }
+  __syncthreads();
+  RowStats st = {0, 0, 0, 0, 0};
+  const uint64_t group = (uint64_t)(a.row_offset + r0) >> 3;
+  if (a.mode == CTDD_MODE_TAU_LEAP || a.mode == CTDD_MODE_TAU_LEAP_CORR || a.mode == CTDD_MODE_MIDPOINT_JUMP) {
+    for (int s = tid; s < S; s += nth) {
+      const Philox4 hi = philox_jump(s, group, a.offset, STREAM_JUMP_HI, a.seed);
+#pragma unroll
+      for (int r = 0; r < BLK_ROWS; ++r) {
+        const int k = jump_count(sA[r * S + s] * a.h, philox_half(hi, r), s, group, r, a.offset, a.seed);
+        if (k) {
+          atomicAdd(&s_jump[r], jump_contrib(k, s, s_xe[r]));
+          atomicAdd(&s_cnt[r], k > 4096 ? 4096 : k);
+        }
+      }
+    }
+    __syncthreads();
+    if (tid < nr)
+      a.x_out[r0 + tid] = finalize_jump(s_xb[tid], s_xe[tid], s_jump[tid], s_cnt[tid], a.reject_multi, S, st);
+  } else if (a.mode == CTDD_MODE_MIDPOINT_DRIFT) {
+    // deterministic: warp r reduces row r in a fixed order
+    for (int r = warp; r < BLK_ROWS; r += nwarp) {
+      float acc = 0.f;
+      for (int s = lane; s < S; s += 32) acc += sA[r * S + s] * (float)(s - s_xe[r]);
+      acc = warp_sum(acc);
+      if (lane == 0 && r < nr) {
+        const int ch = (int)rintf(0.5f * a.h * acc);
+        int xn = s_xe[r] + ch;
+        xn = xn < 0 ? 0 : (xn > S - 1 ? S - 1 : xn);
+        a.x_out[r0 + r] = xn;
+        st.changed_base += (xn != s_xe[r]);
+        st.changed_eval += (xn != s_xe[r]);
+        st.nonzero += (ch != 0);
+      }
+    }
+  } else if (a.mode == CTDD_MODE_EULER || a.mode == CTDD_MODE_EULER_CORR) {
+    if (tid < nr) {
+      const int r = tid, x = s_xe[r];
+      float tot = 0.f;
+      for (int s = 0; s < S; ++s) tot += sA[r * S + s];
+      const float diag = fmaxf(0.f, 1.f - a.h * tot);
+      const float v = u32_to_unit(philox_row_word((uint64_t)(a.row_offset + r0 + r), 0, a.offset, STREAM_ROW, a.seed));
+      const float h = a.h;
+      const float* rowp = sA + r * S;
+      const int xn = inv_cdf(S, v, [&](int s) { return s == x ? diag : rowp[s] * h; });
+      a.x_out[r0 + r] = xn;
+      st.changed_base += (xn != s_xb[r]);
+      st.changed_eval += (xn != x);
+    }
+  }
+  flush_stats(st, a.stats);
+}
+
+int launch_step_simt(const ctdd_step_params* p, cudaStream_t st) {
+  StepArgs a;
+  a.mode = p->mode; a.branch = p->branch; a.D = p->D; a.S = p->S; a.reject_multi = p->reject_multi;
+  a.rows = (long long)p->N * p->D; a.row_offset = p->row_offset;
+  a.logits = p->logits; a.ld = p->ld_logits; a.batch_stride = p->batch_stride_logits;
+  a.x_eval = p->x_eval; a.x_base = p->x_base; a.Q = p->Q; a.QT = p->QT; a.Rb = p->Rb; a.RbT = p->RbT;
+  a.beta = p->beta; a.h = p->h; a.eps = p->eps; a.seed = p->seed; a.offset = p->offset;
+  a.x_out = p->x_out; a.rr_out = p->rr_out; a.ratio_out = p->ratio_out;
+  a.stats = reinterpret_cast<unsigned long long*>(p->stats_out);
+  const int S = p->S;
+  if (S <= 8 && S >= 2) {
+    const long long groups = (a.rows + 7) / 8;
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((groups + threads - 1) / threads);
+    switch (S) {
+      case 2: step_small_kernel<2><<<blocks, threads, 0, st>>>(a); break;
+      case 3: step_small_kernel<3><<<blocks, threads, 0, st>>>(a); break;
+      case 4: step_small_kernel<4><<<blocks, threads, 0, st>>>(a); break;
+      case 5: step_small_kernel<5><<<blocks, threads, 0, st>>>(a); break;
+      case 6: step_small_kernel<6><<<blocks, threads, 0, st>>>(a); break;
+      case 7: step_small_kernel<7><<<blocks, threads, 0, st>>>(a); break;
+      default: step_small_kernel<8><<<blocks, threads, 0, st>>>(a); break;
+    }
+    CTDD_CHECK_LAUNCH("step_small_kernel");
+    return 0;
+  }
+  const size_t smem = (size_t)2 * BLK_ROWS * S * sizeof(float);
+  if (smem > 200 * 1024) { set_error("ctdd_reverse_step: S=%d too large for the block path", S); return 2; }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(step_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  int threads = ((S + 31) / 32) * 32;
+  if (threads > 256) threads = 256;
+  if (threads < 64) threads = 64;
+  const unsigned blocks = (unsigned)((a.rows + BLK_ROWS - 1) / BLK_ROWS);
+  step_block_kernel<<<blocks, threads, smem, st>>>(a);
+  CTDD_CHECK_LAUNCH("step_block_kernel");
+  return 0;
+}
+
+}  // namespace ctdd

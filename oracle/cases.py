@@ -1,0 +1,84 @@
+"""TEST INFRASTRUCTURE ONLY — the named parity cases shared by oracle/make_golden.py and tests/.
+
+Each case fixes a forward process, a stub score network (StubNet: bitwise identical on CPU and CUDA), the sampler
+config and a Philox seed, at sizes the CPU oracle finishes in seconds.
+"""
+from __future__ import annotations
+
+FORWARD = {
+    "gauss256": dict(mixin="GaussianTargetRate", kind="gaussian", S=256,
+                     model=dict(rate_sigma=6.0, Q_sigma=512.0, time_exp=100.0, time_base=3.0)),
+    "gauss32": dict(mixin="GaussianTargetRate", kind="gaussian", S=32,
+                    model=dict(rate_sigma=3.0, Q_sigma=20.0, time_exp=50.0, time_base=1.0)),
+    "uni2": dict(mixin="UniformRate", kind="uniform", S=2, model=dict(rate_const=1.0)),
+    "univar3_logsqr": dict(mixin="UniformVariantRate", kind="uniform_variant", S=3, model=dict(rate_const=2.0, t_func="log_sqr")),
+    "univar2_sqrtcos": dict(mixin="UniformVariantRate", kind="uniform_variant", S=2, model=dict(rate_const=2.0, t_func="sqrt_cos")),
+    "univar5_log": dict(mixin="UniformVariantRate", kind="uniform_variant", S=5,
+                        model=dict(rate_const=0.5, t_func="log", time_base=1.0, time_exp=10.0)),
+    "bd16": dict(mixin="BirthDeathForwardBase", kind="birth_death", S=16, model=dict(sigma_min=1.0, sigma_max=10.0)),
+}
+FORWARD_TIMES = {"gauss256": [0.05, 1.0], "gauss32": [0.01, 0.2, 0.6, 1.0], "uni2": [0.01, 0.5, 1.0],
+                 "univar3_logsqr": [0.001, 0.3, 1.0], "univar2_sqrtcos": [0.007, 0.5, 0.99999],
+                 "univar5_log": [0.01, 0.5, 1.0], "bd16": [0.01, 0.5, 1.0]}
+
+# (name, forward, N, D, loss.name, logit_type, stub(scale, width), t)
+RATES = [
+    ("rr_gauss256_tauldr", "gauss256", 2, 5, "CTElbo", None, (0.5, 10.0), 0.3),
+    ("rr_gauss256_revprob", "gauss256", 2, 5, "CatRM", "reverse_prob", (0.5, 10.0), 0.3),
+    ("rr_gauss32_tauldr", "gauss32", 3, 7, "NLL", None, (1.0, 3.0), 0.05),
+    ("rr_gauss32_direct", "gauss32", 3, 7, "CatRM", "direct", (1.0, 3.0), 0.5),
+    ("rr_gauss32_logscale", "gauss32", 3, 7, "ScoreElbo", "reverse_logscale", (1.0, 3.0), 0.5),
+    ("rr_univar3_tauldr", "univar3_logsqr", 4, 9, "CTElboLambda", None, (1.0, None), 0.4),
+    ("rr_univar3_revprob", "univar3_logsqr", 4, 9, "CatRMNLL", "reverse_prob", (1.0, None), 0.4),
+    ("rr_uni2_direct", "uni2", 4, 8, "SDDMElbo", "direct", (1.0, None), 0.7),
+]
+
+_S = dict(eps_ratio=1e-9, corrector_step_size_multiplier=1.5, corrector_entry_time=0.0, num_corrector_steps=0,
+          is_ordinal=True, initial_dist="gaussian")
+
+# (name, sampler class, forward, N, D, loss.name, logit_type, stub(scale,width), sampler overrides, max_t, seed)
+SAMPLERS = [
+    ("taul_gauss256_ord", "TauL", "gauss256", 8, 12, "CTElbo", None, (0.3, 12.0),
+     dict(num_steps=8, min_t=0.01), 1.0, 101),
+    ("taul_gauss256_corr_crm", "TauL", "gauss256", 8, 12, "CatRM", "reverse_prob", (0.3, 12.0),
+     dict(num_steps=6, min_t=0.01, corrector_entry_time=0.3, num_corrector_steps=2), 1.0, 102),
+    ("taul_uni2_nonord", "TauL", "univar2_sqrtcos", 64, 32, "CTElboLambda", None, (1.0, None),
+     dict(num_steps=20, min_t=0.007, is_ordinal=False, initial_dist="uniform"), 0.99999, 103),
+    ("taul_gauss32_direct", "TauL", "gauss32", 16, 10, "CatRM", "direct", (1.0, 3.0),
+     dict(num_steps=10, min_t=0.01), 1.0, 104),
+    ("lbjf_univar3_pc", "LBJF", "univar3_logsqr", 32, 225, "NLL", None, (1.0, None),
+     dict(num_steps=12, min_t=0.001, corrector_entry_time=0.1, num_corrector_steps=2, initial_dist="uniform"), 1.0, 105),
+    ("lbjf_gauss32_crm", "LBJF", "gauss32", 16, 10, "CatRMNLL", "reverse_prob", (1.0, 3.0),
+     dict(num_steps=10, min_t=0.01), 1.0, 106),
+    ("midpoint_univar3", "MidPointTauL", "univar3_logsqr", 32, 40, "CTElbo", None, (0.3, 0.7),
+     dict(num_steps=10, min_t=0.001, is_ordinal=False, initial_dist="uniform"), 1.0, 107),
+    ("midpoint_uni2_ord", "MidPointTauL", "univar2_sqrtcos", 32, 32, "ScoreElbo", "reverse_prob", (1.0, None),
+     dict(num_steps=10, min_t=0.007, is_ordinal=True, initial_dist="uniform"), 0.99999, 108),
+    ("pctaul_univar3", "PCTauL", "univar3_logsqr", 16, 30, "CatRM", "direct", (0.3, 0.7),
+     dict(num_steps=10, min_t=0.001, corrector_entry_time=0.3, num_corrector_steps=1, initial_dist="uniform"), 1.0, 109),
+    ("pctaul_gauss32", "PCTauL", "gauss32", 8, 10, "CTElbo", None, (1.0, 3.0),
+     dict(num_steps=8, min_t=0.01, corrector_entry_time=0.2, num_corrector_steps=1), 1.0, 110),
+    ("condtaul_gauss32", "ConditionalTauLeaping", "gauss32", 8, 10, "CTElbo", None, (1.0, 3.0),
+     dict(num_steps=8, min_t=0.01, condition_dim=4, reject_multiple_jumps=True), 1.0, 111),
+    ("condpctaul_gauss32", "ConditionalPCTauLeaping", "gauss32", 8, 10, "CTElbo", None, (1.0, 3.0),
+     dict(num_steps=8, min_t=0.01, condition_dim=4, reject_multiple_jumps=True, corrector_entry_time=0.3,
+          num_corrector_steps=1), 1.0, 112),
+]
+
+
+def sampler_cfg(make_cfg, case):
+    """Build the config object (same keys as the reference's ml_collections configs) for a SAMPLERS case."""
+    name, cls, fwd, N, D, loss_name, logit_type, stub, over, max_t, seed = case
+    f = FORWARD[fwd]
+    S = f["S"]
+    s = dict(_S)
+    s.update(over)
+    s["name"] = cls
+    data_name = {2: "SyntheticData", 3: "Maze3S"}.get(S, "DiscreteCIFAR10")
+    loss = dict(name=loss_name, eps_ratio=1e-9, nll_weight=0.001, min_time=0.01, one_forward_pass=True,
+                logit_type=logit_type if logit_type else "reverse_prob", loss_type="rm", ce_coeff=0.0)
+    model = dict(f["model"])
+    model["concat_dim"] = D
+    model.setdefault("Q_sigma", 20.0)
+    return make_cfg(data=dict(S=S, shape=[D], name=data_name), model=model, training=dict(max_t=max_t, n_iters=1000),
+                    sampler=s, loss=loss, device="cpu")

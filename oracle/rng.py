@@ -1,0 +1,178 @@
+"""TEST INFRASTRUCTURE ONLY — CPU restatement of the device RNG maps (csrc/ctdd_common.cuh).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
+package; the product path (ctdd_b200) never does.
+
+The reference (TAUnSDDM) draws with torch.poisson / Categorical.sample / torch.rand and sets no seeds, so
+"identical inputs and injected uniforms" (BASELINE.json north_star) needs a shared uniform -> sample map.
+This module defines that map bit-for-bit the way the CUDA kernels evaluate it:
+
+  * Philox4x32-10 (Salmon et al., SC'11; Random123 constants) keyed on (seed), counter =
+    (state s | sub-index, global-row group, call offset, stream id);
+  * jump uniforms: one Philox call serves 8 consecutive global rows at one state s; the row takes halfword
+    (row & 7); the 32-bit uniform is (hi16 << 16 | lo16) from streams JUMP_HI / JUMP_LO;
+  * per-row uniforms: one call serves 4 consecutive rows (word row & 3);
+  * v = (word + 0.5) * 2^-32 in fp32; Poisson by upper-tail inverse CDF; categorical by sequential fp32 cumsum.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+STREAM_JUMP_HI = 0
+STREAM_JUMP_LO = 1
+STREAM_ROW = 2
+STREAM_INIT = 3
+STREAM_NOISE_XT = 4
+STREAM_TILDE_DIM = 5
+STREAM_TILDE_VAL = 6
+
+_M0 = np.uint64(0xD2511F53)
+_M1 = np.uint64(0xCD9E8D57)
+_W0 = 0x9E3779B9
+_W1 = 0xBB67AE85
+_MASK = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(c0, c1, c2, c3, k0: int, k1: int):
+    """Vectorised Philox4x32-10. c* are broadcastable uint32 arrays; returns 4 uint32 arrays."""
+    c0, c1, c2, c3 = np.broadcast_arrays(
+        np.asarray(c0, dtype=np.uint64), np.asarray(c1, dtype=np.uint64),
+        np.asarray(c2, dtype=np.uint64), np.asarray(c3, dtype=np.uint64))
+    c0, c1, c2, c3 = c0 & _MASK, c1 & _MASK, c2 & _MASK, c3 & _MASK
+    k0 &= 0xFFFFFFFF
+    k1 &= 0xFFFFFFFF
+    for _ in range(10):
+        p0 = _M0 * c0
+        p1 = _M1 * c2
+        hi0, lo0 = p0 >> np.uint64(32), p0 & _MASK
+        hi1, lo1 = p1 >> np.uint64(32), p1 & _MASK
+        n0 = hi1 ^ c1 ^ np.uint64(k0)
+        n2 = hi0 ^ c3 ^ np.uint64(k1)
+        c0, c1, c2, c3 = n0, lo1, n2, lo0
+        k0 = (k0 + _W0) & 0xFFFFFFFF
+        k1 = (k1 + _W1) & 0xFFFFFFFF
+    return (c0.astype(np.uint32), c1.astype(np.uint32), c2.astype(np.uint32), c3.astype(np.uint32))
+
+
+def _c3(stream: int, offset: int, hi_bits):
+    return (np.uint64(stream) | (np.uint64((offset >> 32) & 0xFFFF) << np.uint64(8))
+            | ((np.asarray(hi_bits, dtype=np.uint64) & np.uint64(0xFF)) << np.uint64(24)))
+
+
+def jump_halfwords(rows: int, S: int, row_offset: int, offset: int, stream: int, seed: int) -> np.ndarray:
+    """uint32 array (rows, S) of 16-bit halfwords for global rows row_offset .. row_offset+rows."""
+    grow = np.arange(rows, dtype=np.uint64) + np.uint64(row_offset)
+    groups = np.unique(grow >> np.uint64(3))
+    s = np.arange(S, dtype=np.uint64)
+    w = philox4x32_10(s[None, :], (groups & _MASK)[:, None], np.uint64(offset & 0xFFFFFFFF),
+                      _c3(stream, offset, groups >> np.uint64(32))[:, None],
+                      seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    words = np.stack(w, axis=-1)  # (G, S, 4)
+    gidx = ((grow >> np.uint64(3)) - groups[0]).astype(np.int64)
+    half = (grow & np.uint64(7)).astype(np.int64)
+    sel = words[gidx, :, half >> 1]  # (rows, S)
+    return (sel >> (16 * (half & 1)).astype(np.uint32)[:, None]) & np.uint32(0xFFFF)
+
+
+def u32_to_unit(word: np.ndarray) -> np.ndarray:
+    """(word + 0.5) * 2^-32 in fp32 with a single rounding (device: I2F.RN then FFMA)."""
+    f = word.astype(np.uint32).astype(np.float32)  # round-to-nearest-even, like cvt.rn.f32.u32
+    return (f.astype(np.float64) * 2.0 ** -32 + 2.0 ** -33).astype(np.float32)
+
+
+def jump_units(rows: int, S: int, row_offset: int, offset: int, seed: int) -> np.ndarray:
+    """fp32 (rows, S) jump uniforms v in (0, 1]."""
+    hi = jump_halfwords(rows, S, row_offset, offset, STREAM_JUMP_HI, seed)
+    lo = jump_halfwords(rows, S, row_offset, offset, STREAM_JUMP_LO, seed)
+    return u32_to_unit((hi << np.uint32(16)) | lo)
+
+
+def row_units(rows: int, row_offset: int, offset: int, stream: int, seed: int, sub: int = 0) -> np.ndarray:
+    """fp32 (rows,) per-row uniforms v in (0, 1]."""
+    grow = np.arange(rows, dtype=np.uint64) + np.uint64(row_offset)
+    w = philox4x32_10(np.uint64(sub), (grow >> np.uint64(2)) & _MASK, np.uint64(offset & 0xFFFFFFFF),
+                      _c3(stream, offset, grow >> np.uint64(34)), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    words = np.stack(w, axis=-1)
+    return u32_to_unit(words[np.arange(rows), (grow & np.uint64(3)).astype(np.int64)])
+
+
+def _fma32(a, b, c):
+    return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(np.float32)
+
+
+def poisson_sf0(lam: np.ndarray) -> np.ndarray:
+    """P(K >= 1), fp32: 3-term series below 2^-6, else 1 - exp(-lam)."""
+    lam = lam.astype(np.float32)
+    t = _fma32(lam, np.float32(-0.16666667), np.float32(0.5))
+    u = _fma32(-lam, t, np.float32(1.0))
+    small = (lam * u).astype(np.float32)
+    with np.errstate(over="ignore", under="ignore"):
+        big = (np.float32(1.0) - np.exp(-lam).astype(np.float32)).astype(np.float32)
+    return np.where(lam < np.float32(0.015625), small, big)
+
+
+def poisson_from_unit(lam: np.ndarray, v: np.ndarray) -> np.ndarray:
+    """Upper-tail inverse CDF  k = #{j >= 0 : v < P(K > j)}  (int64), same op order as the device code."""
+    lam = np.asarray(lam, dtype=np.float32)
+    v = np.asarray(v, dtype=np.float32)
+    k = np.zeros(lam.shape, dtype=np.int64)
+    pos = lam > 0
+    sf = poisson_sf0(np.where(pos, lam, np.float32(1.0)))
+    act = pos & (v < sf)
+    idx = np.flatnonzero(act)
+    if idx.size == 0:
+        return k
+    l = lam.ravel()[idx]
+    vv = v.ravel()[idx]
+    s = sf.ravel()[idx].copy()
+    out = np.ones(idx.size, dtype=np.int64)
+    small = l <= np.float32(64.0)
+    # exact recurrence
+    si = np.flatnonzero(small)
+    if si.size:
+        ls, vs, ss = l[si], vv[si], s[si]
+        with np.errstate(under="ignore"):
+            p = np.exp(-ls).astype(np.float32)
+        kmax = (ls + np.float32(10.0) * np.sqrt(ls).astype(np.float32) + np.float32(12.0)).astype(np.float32).astype(np.int64)
+        kk = np.ones(si.size, dtype=np.int64)
+        live = kk < kmax
+        while live.any():
+            p = np.where(live, ((p * ls).astype(np.float32) / kk.astype(np.float32)).astype(np.float32), p)
+            ss = np.where(live, (ss - p).astype(np.float32), ss)
+            stop = live & (vs >= ss)
+            live = live & ~stop
+            kk = np.where(live, kk + 1, kk)
+            live = live & (kk < kmax)
+        out[si] = kk
+    bi = np.flatnonzero(~small)
+    if bi.size:
+        from scipy.special import ndtri
+        lb = np.minimum(l[bi], np.float32(1.0e9))
+        z = (-ndtri(vv[bi].astype(np.float64))).astype(np.float32)
+        kf = (lb + np.sqrt(lb).astype(np.float32) * z).astype(np.float32)
+        kf = (kf + ((z * z - np.float32(1.0)) * np.float32(0.16666667)).astype(np.float32)).astype(np.float32)
+        kf = np.rint(kf)
+        kf = np.where(kf > 1.0, kf, 1.0)
+        kf = np.minimum(kf, 2.0e9)
+        out[bi] = kf.astype(np.int64)
+    k.ravel()[idx] = out
+    return k
+
+
+def inv_cdf(weights: np.ndarray, v: np.ndarray) -> np.ndarray:
+    """Row-wise categorical draw: first index with sequential-fp32 cumsum > v * total.
+
+    weights (rows, n) fp32 unnormalised; v (rows,) in (0,1]. Falls back to the last positive weight.
+    """
+    w = np.asarray(weights, dtype=np.float32)
+    cum = np.cumsum(w, axis=1, dtype=np.float32)  # sequential accumulation in fp32
+    tot = cum[:, -1]
+    target = (np.minimum(np.asarray(v, np.float32), np.float32(0.99999994)) * tot).astype(np.float32)
+    gt = cum > target[:, None]
+    first = gt.argmax(axis=1)
+    none = ~gt.any(axis=1)
+    if none.any():
+        posw = w > 0
+        last = np.where(posw.any(axis=1), w.shape[1] - 1 - posw[:, ::-1].argmax(axis=1), 0)
+        first = np.where(none, last, first)
+    return first.astype(np.int64)
