@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — reverse-CTMC hot-path benchmark (driver contract: see the task statement / DESIGN.md §Measurement).
+
+A "step" is ONE reverse-rate evaluation fused with the tau-leaping state update (TauL predictor step,
+reference lib/sampling/sampling.py:119-160) over the per-GPU batch of the named workload, on synthetic logits.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C4|C3|C2|C1] [--impl ours|reference]
+
+Workloads (BASELINE.json configs / SURVEY.md §8d):
+  C4  CIFAR10-shape  S=256 D=3072 B=1024/GPU GaussianTargetRate, TauL   <- default (the metric's config)
+  C3  MNIST-shape    S=256 D=784  B=1024/GPU
+  C2  maze           S=3   D=225  B=16384/GPU UniformVariantRate(log_sqr), Euler (LBJF) step
+  C1  synthetic      S=2   D=32   B=65536/GPU UniformVariantRate(sqrt_cos), TauL non-ordinal
+
+Metric: reverse-step TFLOP/s with algorithmic work 2*B*D*S^2 per step (for S<=8 workloads the line also carries
+GB/s, which is what bounds them).  Weak scaling: every rank owns B rows; no data-path collective.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "C4": dict(S=256, D=3072, B=1024, fwd="gaussian", mode="tau_leap", ordinal=True, loss="CTElbo", num_steps=1000, cpu_N=8,
+               model=dict(rate_sigma=6.0, Q_sigma=512.0, time_exp=100.0, time_base=3.0), max_t=1.0, min_t=0.01),
+    "C3": dict(S=256, D=784, B=1024, fwd="gaussian", mode="tau_leap", ordinal=True, loss="CTElbo", num_steps=1000, cpu_N=32,
+               model=dict(rate_sigma=6.0, Q_sigma=512.0, time_exp=100.0, time_base=3.0), max_t=1.0, min_t=0.01),
+    "C2": dict(S=3, D=225, B=16384, fwd="uniform_variant", mode="euler", ordinal=True, loss="CTElbo", num_steps=500, cpu_N=1024,
+               model=dict(rate_const=2.0, t_func="log_sqr"), max_t=1.0, min_t=0.001),
+    "C1": dict(S=2, D=32, B=65536, fwd="uniform_variant", mode="tau_leap", ordinal=False, loss="CTElbo", num_steps=500, cpu_N=4096,
+               model=dict(rate_const=2.0, t_func="sqrt_cos"), max_t=0.99999, min_t=0.007),
+}
+MIXIN = {"gaussian": "GaussianTargetRate", "uniform_variant": "UniformVariantRate"}
+
+
+def synth_logits(B, D, S, seed, device, x0=None):
+    """Denoiser-like synthetic logits (SURVEY §8d family L2): -(s - x0)^2 / (2*8^2) + randn."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    if x0 is None:
+        x0 = torch.randint(0, S, (B, D), generator=g, device=device)
+    s = torch.arange(S, device=device, dtype=torch.float32)
+    out = torch.randn((B, D, S), generator=g, device=device)
+    if S > 8:
+        out -= (s.view(1, 1, S) - x0.unsqueeze(-1).float()) ** 2 / (2.0 * 8.0 ** 2)
+    return out, x0
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of this rank's GPU during the timed region."""
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.proc = None
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tc_burst=d["bf16_tflops"], tc_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, src="fallback")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port (torch-CPU restatement of the reference step) on the host cores
+
+def cpu_reference_step_time(w, n_cpu, steps, warmup):
+    """Times get_reverse_rates + Poisson/Euler update exactly as the reference composes them (oracle port), N=n_cpu."""
+    from oracle import ctmc_oracle as oc
+    torch.set_num_threads(os.cpu_count() or 1)
+    S, D = w["S"], w["D"]
+    fp = oc.ForwardProcess(w["fwd"], S, **w["model"])
+    logits, x0 = synth_logits(n_cpu, D, S, 1234, "cpu")
+    x = x0.clone()
+    ts = np.linspace(w["max_t"], w["min_t"], steps + warmup)
+    h = (w["max_t"] - w["min_t"]) / w["num_steps"]
+    times = []
+    with torch.no_grad():
+        for i, t in enumerate(ts):
+            t0 = time.perf_counter()
+            t_ones = float(t) * torch.ones((n_cpu,))
+            Q, R = fp.transition(t_ones), fp.rate(t_ones)            # N identical copies, as the reference builds them
+            rr, _ = oc.reverse_rates(logits, x, Q, R, w["loss"], "reverse_prob", 1e-9)
+            rz = oc._zero_at(rr, x)
+            if w["mode"] == "euler":
+                tot = rz.sum(-1, keepdim=True)
+                oh = torch.nn.functional.one_hot(x.long(), S)
+                P = rz * h + torch.clip(1.0 - h * tot, min=0) * oh
+                P = P / P.sum(-1, keepdim=True)
+                x = torch.distributions.categorical.Categorical(logits=torch.log(P + 1e-35).view(-1, S)).sample().view(n_cpu, D)
+            else:
+                k = torch.poisson(rz * h)
+                if not w["ordinal"]:
+                    k = k * (k.sum(-1, keepdim=True) <= 1)
+                diff = torch.arange(S).view(1, 1, S) - x.unsqueeze(-1)
+                x = torch.clamp(x + (k * diff).sum(-1), 0, S - 1).long()
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return float(np.mean(times))
+
+
+def flops_per_step(B, D, S):
+    return 2.0 * B * D * S * S
+
+
+def run_reference(args, w, rank, world):
+    if rank != 0:
+        return
+    n_cpu = w["cpu_N"]
+    t = cpu_reference_step_time(w, n_cpu, args.steps, args.warmup)
+    val = flops_per_step(n_cpu, w["D"], w["S"]) / t / 1e12
+    line = {
+        "impl": "reference", "metric": "reverse_step_tflops", "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: S={w['S']} D={w['D']} {w['mode']} step, CPU sample N={n_cpu} rows of the B={w['B']} batch"},
+        "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"N={n_cpu} samples x D={w['D']} per step, {args.steps} steps (oracle port of the reference's "
+                                   f"get_reverse_rates + update; /root/reference is Python and cannot travel to the GPU box)",
+                         "sample_steps_per_s": n_cpu / t},
+        "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_ours(args, w, rank, world, local_rank):
+    import torch.distributed as dist
+    from ctdd_b200 import _native as nat, make_config, ops
+    from ctdd_b200.lib.models import forward_model as fm
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    S, D, B = w["S"], w["D"], w["B"]
+    K, W = args.steps, args.warmup
+    cfg = make_config(data=dict(S=S), model=dict(w["model"], Q_sigma=w["model"].get("Q_sigma", 20.0)), device=str(dev))
+    model = getattr(fm, MIXIN[w["fwd"]])(cfg, str(dev))
+    nsteps = K + W
+    ts = np.linspace(w["max_t"], w["min_t"], nsteps)       # timed steps are spread over the whole schedule
+    h = (w["max_t"] - w["min_t"]) / w["num_steps"]
+    Q, QT, beta = model.qt0_tables(list(ts), dev)
+    Rb, RbT = model.base_rate_tables(dev)
+    branch = nat.branch_for(w["loss"], None)
+    mode = nat.MODE_EULER if w["mode"] == "euler" else nat.MODE_TAU_LEAP
+    impl = {"auto": nat.IMPL_AUTO, "simt": nat.IMPL_SIMT, "tc": nat.IMPL_TC}[args.kernels]
+    tc = ops.prep_tc_tables(Q, QT, Rb, 1e-9, branch) if (S == 256 and impl != nat.IMPL_SIMT) else None
+    ws_bytes = int(nat.lib().ctdd_step_workspace_bytes(B * D, S, impl))
+    workspace = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev)
+    # two logits buffers (each >> L2 at the S=256 workloads) alternate between steps
+    nbuf = 2
+    bufs = []
+    x0 = None
+    for i in range(nbuf):
+        lg, x0 = synth_logits(B, D, S, 1234 + 17 * rank + i, dev, None)
+        bufs.append(lg)
+    x = torch.clamp(x0 + torch.randint(-3, 4, x0.shape, device=dev), 0, S - 1).to(torch.int32)
+    row_offset = rank * B * D          # B is a multiple of 8, so every rank's first global row is 8-aligned
+    stats = torch.zeros((nsteps, 8), dtype=torch.int64, device=dev)
+    flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev) if B * D * S * 4 < (512 << 20) else None
+
+    def step(i, xin, logits):
+        return ops.reverse_step(mode, branch, logits, xin, Q[i], QT[i], Rb, RbT, beta[i], h, 1e-9, N=B, D=D, S=S,
+                                reject_multi=not w["ordinal"], seed=0xC7DD, offset=i, row_offset=row_offset, impl=impl,
+                                tc_tables=(tc[i] if tc is not None else None), workspace=workspace, stats=stats[i])["x"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(W):
+        x = step(i, x, bufs[i % nbuf])
+    barrier()
+    launches0 = nat.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        t_start.record()
+        for j in range(K):
+            if flush is not None:
+                flush.fill_(j & 0xFF)          # L2 flush between timed iterations for inputs smaller than L2
+            ev[j][0].record()
+            x = step(W + j, x, bufs[(W + j) % nbuf])
+            ev[j][1].record()
+        t_end.record()
+        barrier()
+    launches = nat.launch_count() - launches0
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))   # step kernels only (flush excluded)
+    total_ms = t_start.elapsed_time(t_end)
+    ms_per_step = kern_ms if flush is not None else total_ms / K
+    t_ms = torch.tensor([ms_per_step], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+
+    # ---- end to end through the C ABI with HOST buffers: H2D logits + state, step, D2H new state, every step ----
+    e2e_steps = max(1, min(K, args.e2e_steps))
+    chunk = max(8, min(B, (192 << 20) // (D * S * 4)) // 8 * 8)   # ~192 MB logits per chunk (multiple of 8 rows), double-buffered
+    nchunks = (B + chunk - 1) // chunk
+    host_logits = torch.empty((B, D, S), dtype=torch.float32, pin_memory=True)
+    host_logits.copy_(bufs[0])
+    host_x = torch.empty((B, D), dtype=torch.int32, pin_memory=True)
+    host_x.copy_(x)
+    host_out = torch.empty((B, D), dtype=torch.int32, pin_memory=True)
+    dl = [torch.empty((chunk, D, S), dtype=torch.float32, device=dev) for _ in range(2)]
+    dx = [torch.empty((chunk, D), dtype=torch.int32, device=dev) for _ in range(2)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    cws = [torch.empty((max(int(nat.lib().ctdd_step_workspace_bytes(chunk * D, S, impl)), 1),), dtype=torch.uint8, device=dev)
+           for _ in range(2)]
+
+    def e2e_step(i):
+        for c in range(nchunks):
+            lo, hi = c * chunk, min(B, (c + 1) * chunk)
+            n = hi - lo
+            s = streams[c & 1]
+            with torch.cuda.stream(s):
+                dl[c & 1][:n].copy_(host_logits[lo:hi], non_blocking=True)
+                dx[c & 1][:n].copy_(host_x[lo:hi], non_blocking=True)
+                ro = row_offset + lo * D
+                out = ops.reverse_step(mode, branch, dl[c & 1][:n], dx[c & 1][:n], Q[i], QT[i], Rb, RbT, beta[i], h, 1e-9,
+                                       N=n, D=D, S=S, reject_multi=not w["ordinal"], seed=0xC7DD, offset=i,
+                                       row_offset=ro, impl=impl, tc_tables=(tc[i] if tc is not None else None),
+                                       workspace=cws[c & 1])["x"]
+                host_out[lo:hi].copy_(out, non_blocking=True)
+        for s in streams:
+            s.synchronize()
+
+    e2e_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    for j in range(e2e_steps):
+        e2e_step(W + j)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    t_e = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t_e.item())
+
+    if rank != 0:
+        return
+    pk = peaks()
+    fl = flops_per_step(B, D, S)
+    tfl = world * fl / (ms * 1e-3) / 1e12
+    bytes_step = 4.0 * B * D * S + 8.0 * B * D          # fp32 logits once + int32 state in/out
+    tensor_bound = S >= 64
+    if tensor_bound:
+        roof = {"bound": "tensor", "achieved": fl / (kern_ms * 1e-3) / 1e12, "peak": pk["tc_burst"], "unit": "TFLOP/s",
+                "traffic": None, "peak_source": pk["src"] + " bf16 dense (burst)",
+                "note": "algorithmic 2*B*D*S^2 per launch; the kernel spends 3 bf16 tensor passes per algorithmic FLOP "
+                        "(split precision), so 1/3 is the ceiling of this fraction",
+                "hbm_gbs": bytes_step / (kern_ms * 1e-3) / 1e9}
+    else:
+        roof = {"bound": "hbm", "achieved": bytes_step / (kern_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                "traffic": None, "peak_source": pk["src"] + " copy bandwidth"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["kernel_ms"] = kern_ms
+    line = {
+        "metric": "reverse_step_tflops", "value": tfl, "unit": "TFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload}: S={S} D={D} B={B}/GPU {w['fwd']} rate, {w['mode']} reverse step "
+                               f"(TauL predictor, lib/sampling/sampling.py:119-160)",
+                   "l2": "inputs larger than L2 (2 alternating logits buffers)" if flush is None else "L2 flushed between timed steps",
+                   "kernels": args.kernels, "times": "steps spread over the schedule max_t..min_t",
+                   "samples_per_s_at_num_steps": world * B / (w["num_steps"] * ms * 1e-3), "num_steps": w["num_steps"]},
+        "roofline": roof,
+        "e2e": {"value": world * fl / (e2e_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(B * D * S * 4 + B * D * 4), "d2h_bytes_per_step": int(B * D * 4),
+                "note": "C-ABI reverse step fed from pinned HOST logits/state, chunked on 2 streams; PCIe-bound"},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+        "gbytes_per_s": world * bytes_step / (ms * 1e-3) / 1e9,
+    }
+    if world == 1 and not args.no_cpu:
+        n_cpu = w["cpu_N"]
+        tc_ = cpu_reference_step_time(w, n_cpu, args.cpu_steps, 1)
+        line["cpu_baseline"] = {"value": flops_per_step(n_cpu, D, S) / tc_ / 1e12, "unit": "TFLOP/s", "cores": os.cpu_count(),
+                                "kind": "port", "sample": f"N={n_cpu} samples x D={D}, {args.cpu_steps} steps of the oracle port",
+                                "ms_per_step": tc_ * 1e3, "sample_steps_per_s": n_cpu / tc_}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C4", choices=list(WORKLOADS))
+    ap.add_argument("--kernels", default="auto", choices=["auto", "simt", "tc"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-steps", type=int, default=5)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, w, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, w, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

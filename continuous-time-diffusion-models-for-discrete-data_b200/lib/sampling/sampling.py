@@ -22,6 +22,7 @@ import torch
 import torch.nn.functional as F
 
 from ... import _native as nat
+from ... import ops
 from . import sampling_utils
 
 
@@ -69,10 +70,7 @@ class StepEngine:
         self.tc_bytes = int(nat.lib().ctdd_tc_tables_bytes(S)) if S == 256 else 0
         self.tc_tables = None
         if self.tc_bytes > 0 and impl != nat.IMPL_SIMT and branch in (nat.BRANCH_TAULDR, nat.BRANCH_SDDM_REVERSE_PROB):
-            T = len(self.times)
-            self.tc_tables = torch.empty((T, self.tc_bytes), dtype=torch.uint8, device=self.device)
-            nat.check(nat.lib().ctdd_prep_tc_tables(nat.ptr(self.Q), nat.ptr(self.QT), nat.ptr(self.Rb), T, S, self.eps,
-                                                    branch, nat.ptr(self.tc_tables), nat.stream()), "ctdd_prep_tc_tables")
+            self.tc_tables = ops.prep_tc_tables(self.Q, self.QT, self.Rb, self.eps, branch)
         ws = int(nat.lib().ctdd_step_workspace_bytes(N * D, S, impl))
         self.workspace = torch.empty((max(ws, 1),), dtype=torch.uint8, device=self.device) if ws > 0 else None
         ncalls = max_calls if max_calls is not None else 4 * len(self.times) + 8
@@ -82,38 +80,27 @@ class StepEngine:
         return self.times[tidx] * torch.ones((self.N,), device=self.device)
 
     def step(self, mode, logits, x_eval, tidx, h, reject_multi=False, x_base=None, draws=True,
-             rr_out=None, ratio_out=None, logits_view=None, stats=None):
+             want_rr=False, want_ratio=False, logits_view=None, stats=None):
         """One fused reverse-rate evaluation + state update. Returns (x_new, stats_row_index).
 
         `draws=False` marks an evaluation that consumes no randomness (midpoint drift, rates only): the Philox
         call counter is not advanced. `stats` overrides the row of self.stats the counters are added to."""
         N, D, S = self.N, self.D, self.S
-        if logits.dtype != torch.float32:
-            logits = logits.float()
-        if logits_view is None:
-            logits = logits.contiguous()
-            base, ld, bstride = logits, S, D * S
-            lptr = nat.ptr(base)
-        else:  # (full logits tensor, first dim index to start from): model output sliced [:, c:, :]
-            full, c = logits_view
-            full = full.contiguous()
-            base, ld, bstride = full, S, full.shape[1] * S
-            lptr = nat.ptr(full) + 4 * c * S
-        x_out = torch.empty((N, D), dtype=torch.int32, device=self.device) if mode != nat.MODE_RATES_ONLY else None
+        off_elems, bstride = 0, None
+        if logits_view is not None:  # (full model output, c): rows live at full[:, c:, :]
+            logits, c = logits_view
+            off_elems, bstride = c * S, logits.shape[1] * S
         row = self.call if self.call < self.stats.shape[0] else self.stats.shape[0] - 1
-        p = nat.StepParams(
-            mode=mode, branch=self.branch, impl=self.impl, N=N, D=D, S=S, row_offset=self.row_offset,
-            logits=lptr, ld_logits=ld, batch_stride_logits=bstride,
-            x_eval=nat.ptr(x_eval), x_base=nat.ptr(x_base),
-            Q=nat.ptr(self.Q[tidx]), QT=nat.ptr(self.QT[tidx]), Rb=nat.ptr(self.Rb), RbT=nat.ptr(self.RbT),
-            tc_tables=(nat.ptr(self.tc_tables[tidx]) if self.tc_tables is not None else None),
-            beta=self.beta[tidx], h=float(h), eps=self.eps, reject_multi=1 if reject_multi else 0,
-            seed=self.seed, offset=self.call,
-            x_out=nat.ptr(x_out), rr_out=nat.ptr(rr_out), ratio_out=nat.ptr(ratio_out),
-            stats_out=(stats.data_ptr() if stats is not None else self.stats[row].data_ptr()),
-            workspace=nat.ptr(self.workspace))
-        nat.check(nat.lib().ctdd_reverse_step(p, nat.stream()), "ctdd_reverse_step")
-        del base
+        out = ops.reverse_step(
+            mode, self.branch, logits, x_eval, self.Q[tidx], self.QT[tidx], self.Rb, self.RbT, self.beta[tidx], h,
+            self.eps, N=N, D=D, S=S, x_base=x_base, reject_multi=reject_multi, seed=self.seed, offset=self.call,
+            row_offset=self.row_offset, impl=self.impl,
+            tc_tables=(self.tc_tables[tidx] if self.tc_tables is not None else None), workspace=self.workspace,
+            stats=(stats if stats is not None else self.stats[row]), want_rr=want_rr, want_ratio=want_ratio,
+            logits_offset_elems=off_elems, batch_stride=bstride)
+        x_out = out["x"]
+        if want_rr or want_ratio:
+            self.last_rates = (out["rr"], out["ratio"])
         if draws:
             self.call += 1
         return x_out, row
@@ -133,10 +120,8 @@ def get_reverse_rates(model, logits, x, t_ones, cfg, N, D, S):
     branch = nat.branch_for(cfg.loss.name, getattr(cfg.loss, "logit_type", None)
                             if cfg.loss.name not in nat.TAULDR_LOSSES else None)
     eng = StepEngine(cfg, model, N, D, S, [t], branch, cfg.sampler.eps_ratio, seed=0, max_calls=1)
-    rr = torch.empty((N, D, S), dtype=torch.float32, device=eng.device)
-    ratio = torch.empty_like(rr)
-    eng.step(nat.MODE_RATES_ONLY, logits, _as_state(x, eng.device), 0, 0.0, draws=False, rr_out=rr, ratio_out=ratio)
-    return rr, ratio
+    eng.step(nat.MODE_RATES_ONLY, logits, _as_state(x, eng.device), 0, 0.0, draws=False, want_rr=True, want_ratio=True)
+    return eng.last_rates
 
 
 def _branch_of(cfg):

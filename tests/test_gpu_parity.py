@@ -1,0 +1,268 @@
+"""GPU: the CUDA path (through the C ABI) against the oracle and the reference-generated fixtures."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases, ctmc_oracle as oc, ref_harness as rh, rng
+from oracle.make_golden import rates_inputs
+from helpers import oracle_forward, product_model, fwd_cfg, mismatch_fraction
+
+pytestmark = pytest.mark.gpu
+
+CLAMP = 1e-8
+
+
+def _nat():
+    from ctdd_b200 import _native as nat
+    return nat
+
+
+def _tables(fp, t, dev="cuda"):
+    tt = torch.tensor([t], dtype=torch.float64).to(torch.float32)
+    Q = fp.transition(tt)[0]
+    return dict(Q=Q.to(dev).contiguous(), QT=Q.t().contiguous().to(dev), Rb=fp.base_rate.to(dev).contiguous(),
+                RbT=fp.base_rate.t().contiguous().to(dev), beta=float(fp.beta(tt)[0]))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(cases.FORWARD))
+def test_qt0_builder_matches_reference(golden, name):
+    """|dQ| <= 5e-7 abs and identical zero pattern outside the clamp band; rows sum to 1 (SURVEY §8c plan (1))."""
+    from ctdd_b200 import make_config
+    g = golden["forward"]
+    cfg = fwd_cfg(name, make_config)
+    from ctdd_b200.lib.models import forward_model as fm
+    m = getattr(fm, cases.FORWARD[name]["mixin"])(cfg, "cuda")
+    t = torch.tensor(cases.FORWARD_TIMES[name], dtype=torch.float32, device="cuda")
+    Q = m.transition(t).cpu().numpy()
+    ref = g[f"{name}/transition"]
+    assert np.abs(Q - ref).max() <= 5e-7
+    band = np.abs(ref - CLAMP) < 5e-7
+    assert np.array_equal((Q == 0) | band, (ref == 0) | band)
+    if name != "uni2":
+        np.testing.assert_allclose(Q.sum(-1), 1.0, atol=1e-5)
+    np.testing.assert_allclose(m.rate(t).cpu().numpy(), g[f"{name}/rate"], rtol=2e-6, atol=0)
+    if f"{name}/transit_between" in g:
+        tb = m.transit_between(0.5 * t, t).cpu().numpy()
+        assert np.abs(tb - g[f"{name}/transit_between"]).max() <= 2e-6
+    if f"{name}/rate_mat" in g:
+        y = torch.from_numpy(g[f"{name}/rate_mat_y"]).cuda()
+        np.testing.assert_allclose(m.rate_mat(y, t).cpu().numpy(), g[f"{name}/rate_mat"], rtol=2e-6, atol=0)
+
+
+def test_qt0_tables_transpose_and_cache():
+    from ctdd_b200 import make_config
+    from ctdd_b200.lib.models import forward_model as fm
+    m = fm.GaussianTargetRate(fwd_cfg("gauss32", make_config), "cuda")
+    Q, QT, beta = m.qt0_tables([1.0, 0.5, 0.01], "cuda")
+    assert torch.equal(Q.transpose(1, 2).contiguous(), QT)
+    assert m.qt0_tables([1.0, 0.5, 0.01], "cuda")[0] is Q
+    fp = oracle_forward("gauss32")
+    np.testing.assert_allclose(beta, fp.beta(torch.tensor([1.0, 0.5, 0.01])).numpy(), rtol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _impls():
+    nat = _nat()
+    return [nat.IMPL_SIMT, nat.IMPL_AUTO]
+
+
+@pytest.mark.parametrize("impl_i", [0, 1])
+@pytest.mark.parametrize("case", cases.RATES, ids=[c[0] for c in cases.RATES])
+def test_reverse_rates_match_reference(golden, case, impl_i):
+    """Reverse rates with the reference's q/R injected: 1e-4 relative, exact zeros preserved (§8c plan (2))."""
+    from ctdd_b200 import ops
+    nat = _nat()
+    name, fwd, N, D, loss_name, logit_type, stub, t = case
+    logits, x, S = rates_inputs(case)
+    fp = oracle_forward(fwd)
+    tb = _tables(fp, t)
+    branch = nat.branch_for(loss_name, logit_type)
+    impl = _impls()[impl_i]
+    tc = ops.prep_tc_tables(tb["Q"][None], tb["QT"][None], tb["Rb"], 1e-9, branch) if (S == 256 and impl != nat.IMPL_SIMT) else None
+    out = ops.reverse_step(nat.MODE_RATES_ONLY, branch, logits.cuda(), x.to(torch.int32).cuda(), tb["Q"], tb["QT"], tb["Rb"],
+                           tb["RbT"], tb["beta"], 0.0, 1e-9, N=N, D=D, S=S, impl=impl,
+                           tc_tables=(tc[0] if tc is not None else None), want_rr=True, want_ratio=True)
+    g = golden["rates"]
+    for key, got in (("rr", out["rr"]), ("ratio", out["ratio"])):
+        ref = g[f"{name}/{key}"]
+        got = got.cpu().numpy()
+        big = np.abs(ref) > 1e-30
+        rel = np.abs(got - ref)[big] / np.abs(ref)[big]
+        assert rel.max() <= 1e-4, (key, rel.max())
+        assert np.all(np.abs(got[~big]) <= 1e-30)
+
+
+def _random_problem(fwd, N, D, t, seed, width, scale=0.5):
+    fp = oracle_forward(fwd)
+    S = fp.S
+    g = np.random.Generator(np.random.PCG64(seed))
+    x0 = g.integers(0, S, (N, D))
+    s = np.arange(S)
+    logits = scale * 4.0 * g.standard_normal((N, D, S))
+    if width is not None:
+        logits = logits - (s[None, None, :] - x0[:, :, None]) ** 2 / (2.0 * width ** 2)
+    x = np.clip(x0 + g.integers(-2, 3, (N, D)), 0, S - 1)
+    return fp, torch.from_numpy(logits.astype(np.float32)), torch.from_numpy(x), S
+
+
+STEP_CASES = [
+    # fwd, N, D, t, h, loss, logit_type, width
+    ("gauss256", 6, 40, 0.9, 0.004, "CTElbo", None, 12.0),
+    ("gauss256", 6, 40, 0.2, 0.01, "CatRM", "reverse_prob", 12.0),
+    ("gauss32", 16, 33, 0.5, 0.02, "NLL", None, 3.0),
+    ("gauss32", 16, 33, 0.5, 0.02, "CatRM", "direct", 3.0),
+    ("gauss32", 16, 33, 0.5, 0.02, "ScoreElbo", "reverse_logscale", 3.0),
+    ("univar3_logsqr", 32, 225, 0.4, 0.05, "CTElbo", None, None),
+    ("univar2_sqrtcos", 64, 32, 0.6, 0.05, "CatRMNLL", "reverse_prob", None),
+    ("univar5_log", 24, 19, 0.6, 0.05, "CTElbo", None, None),
+]
+
+
+@pytest.mark.parametrize("impl_i", [0, 1])
+@pytest.mark.parametrize("sc", STEP_CASES, ids=[f"{c[0]}-{c[5]}-{c[6]}" for c in STEP_CASES])
+def test_step_modes_match_oracle(sc, impl_i):
+    """Every update mode on identical inputs and injected uniforms: integer states bit-exact modulo threshold ties."""
+    from ctdd_b200 import ops
+    nat = _nat()
+    fwd, N, D, t, h, loss_name, logit_type, width = sc
+    fp, logits, x, S = _random_problem(fwd, N, D, t, 11, width)
+    tb = _tables(fp, t)
+    branch = nat.branch_for(loss_name, logit_type)
+    impl = _impls()[impl_i]
+    lt = logit_type or "reverse_prob"
+    tt = torch.tensor([t], dtype=torch.float64).to(torch.float32)
+    Qo, Ro = fp.transition(tt), fp.rate(tt)
+    rr, _ = oc.reverse_rates(logits, x, Qo, Ro, loss_name, lt, 1e-9)
+    rz = oc._zero_at(rr, x)
+    rz_corr = oc._zero_at(Ro.expand(N, -1, -1)[torch.arange(N).view(N, 1), x.long()] + rz, x)
+    tc = ops.prep_tc_tables(tb["Q"][None], tb["QT"][None], tb["Rb"], 1e-9, branch) if (
+        S == 256 and impl != nat.IMPL_SIMT and branch in (nat.BRANCH_TAULDR, nat.BRANCH_SDDM_REVERSE_PROB)) else None
+    xe = x.to(torch.int32).cuda()
+    lg = logits.cuda()
+    seed = 4242
+
+    def run(mode, offset, reject=False, x_base=None):
+        stats = torch.zeros(8, dtype=torch.int64, device="cuda")
+        out = ops.reverse_step(mode, branch, lg, xe, tb["Q"], tb["QT"], tb["Rb"], tb["RbT"], tb["beta"], h, 1e-9,
+                               N=N, D=D, S=S, impl=impl, tc_tables=(tc[0] if tc is not None else None),
+                               reject_multi=reject, seed=seed, offset=offset, x_base=x_base, stats=stats)
+        return out["x"].cpu().numpy().astype(np.int64), stats.cpu().numpy()
+
+    tol = 2e-3
+    for reject in (False, True):
+        got, st = run(nat.MODE_TAU_LEAP, 3, reject)
+        want, ost = oc.tau_leap_update(rz, x, x, h, S, reject, 3, seed)
+        assert mismatch_fraction(got, want.numpy()) <= tol
+        assert abs(st[nat.STAT_CHANGED_BASE] - ost["changed_base"]) <= max(2, tol * N * D)
+        assert abs(st[nat.STAT_ROWS_MULTI] - ost["rows_multi"]) <= max(2, tol * N * D)
+    got, _ = run(nat.MODE_TAU_LEAP_CORR, 5)
+    want, _ = oc.tau_leap_update(rz_corr, x, x, h, S, False, 5, seed)
+    assert mismatch_fraction(got, want.numpy()) <= tol
+    got, _ = run(nat.MODE_MIDPOINT_DRIFT, 0)
+    want = oc.midpoint_drift(rz, x, 20 * h if False else h, S)
+    assert mismatch_fraction(got, want.numpy()) <= tol
+    g = np.random.Generator(np.random.PCG64(5))
+    xb = torch.from_numpy(np.clip(x.numpy() + g.integers(-1, 2, x.shape), 0, S - 1))
+    got, st = run(nat.MODE_MIDPOINT_JUMP, 7, True, xb.to(torch.int32).cuda())
+    want, ost = oc.tau_leap_update(rz, x, xb, h, S, True, 7, seed)
+    assert mismatch_fraction(got, want.numpy()) <= tol
+    assert abs(st[nat.STAT_NONZERO_JUMP] - ost["nonzero_jump"]) <= max(2, tol * N * D)
+    got, _ = run(nat.MODE_EULER, 9)
+    want, _ = oc.euler_update(rz, x, h, S, 9, seed)
+    assert mismatch_fraction(got, want.numpy()) <= tol
+    got, _ = run(nat.MODE_EULER_CORR, 10)
+    want, _ = oc.euler_update(rz_corr, x, h, S, 10, seed)
+    assert mismatch_fraction(got, want.numpy()) <= tol
+
+
+def test_row_offset_sharding_is_invariant():
+    """Philox is keyed on the GLOBAL row: two half-batches with row offsets == one full batch (multi-GPU invariance)."""
+    from ctdd_b200 import ops
+    nat = _nat()
+    fp, logits, x, S = _random_problem("gauss32", 16, 24, 0.5, 3, 3.0)
+    tb = _tables(fp, 0.5)
+    kw = dict(Q=tb["Q"], QT=tb["QT"], Rb=tb["Rb"], RbT=tb["RbT"], beta=tb["beta"], h=0.05, eps=1e-9, S=S, D=24, seed=9, offset=2)
+    full = ops.reverse_step(nat.MODE_TAU_LEAP, nat.BRANCH_TAULDR, logits.cuda(), x.to(torch.int32).cuda(), N=16, **kw)["x"]
+    lo = ops.reverse_step(nat.MODE_TAU_LEAP, nat.BRANCH_TAULDR, logits[:8].cuda(), x[:8].to(torch.int32).cuda(), N=8, **kw)["x"]
+    hi = ops.reverse_step(nat.MODE_TAU_LEAP, nat.BRANCH_TAULDR, logits[8:].cuda(), x[8:].to(torch.int32).cuda(), N=8,
+                          row_offset=8 * 24, **kw)["x"]
+    assert torch.equal(full, torch.cat([lo, hi]))
+    with pytest.raises(RuntimeError):
+        ops.reverse_step(nat.MODE_TAU_LEAP, nat.BRANCH_TAULDR, logits[8:].cuda(), x[8:].to(torch.int32).cuda(), N=8,
+                         row_offset=3, **kw)
+
+
+def test_initial_samples_and_noising_match_oracle():
+    from ctdd_b200 import ops
+    from ctdd_b200.lib.sampling import sampling
+    for S, dist, std in ((256, "gaussian", 512.0), (3, "uniform", None), (32, "gaussian", 4.0)):
+        x = sampling.get_initial_samples(50, 37, "cuda", S, dist, std, seed=77).cpu().numpy()
+        want = oc.initial_samples(50, 37, S, dist, std, 77).numpy()
+        assert mismatch_fraction(x, want) <= 1e-3
+    fp = oracle_forward("gauss32")
+    B, D, S = 12, 50, 32
+    g = np.random.Generator(np.random.PCG64(1))
+    x0 = torch.from_numpy(g.integers(0, S, (B, D)))
+    ts = torch.from_numpy(g.uniform(0.01, 1.0, B).astype(np.float32))
+    Q = fp.transition(ts)
+    beta = fp.beta(ts)
+    xt, xtil = ops.noise_xt(Q.cuda(), fp.base_rate.cuda(), beta.cuda(), x0.to(torch.int32).cuda(), seed=5, offset=3)
+    from oracle import loss_oracle as lo
+    wxt, wtil = lo.noise_xt(Q, fp.rate(ts), x0, seed=5, offset=3)
+    assert mismatch_fraction(xt.cpu().numpy(), wxt.numpy()) <= 1e-3
+    assert mismatch_fraction(xtil.cpu().numpy(), wtil.numpy()) <= 5e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _run_product_sampler(case, inject_oracle_q, impl=None):
+    from ctdd_b200 import make_config
+    from ctdd_b200.lib.sampling import sampling_utils
+    import ctdd_b200.lib.sampling.sampling  # noqa: F401
+    name, cls, fwd, N, D, loss_name, logit_type, stub, over, max_t, seed = case
+    cfg = cases.sampler_cfg(make_config, case)
+    cfg.device = "cuda"
+    S = cfg.data.S
+    m = product_model(fwd, cfg, D, seed, stub[0], stub[1])
+    if inject_oracle_q:
+        fp = oracle_forward(fwd)
+
+        def tables(ts, device):
+            t32 = torch.tensor([float(t) for t in ts], dtype=torch.float64).to(torch.float32)
+            Q = fp.transition(t32)
+            return Q.to(device).contiguous(), Q.transpose(1, 2).contiguous().to(device), [float(b) for b in fp.beta(t32)]
+
+        m.qt0_tables = tables
+    cfg.sampler.name = cls
+    sampler = sampling_utils.get_sampler(cfg)
+    sampler.seed = seed
+    if impl is not None:
+        sampler.impl = impl
+    args = ()
+    if "condition_dim" in over:
+        g = np.random.Generator(np.random.PCG64(seed))
+        args = (torch.from_numpy(g.integers(0, S, (N, over["condition_dim"]))),)
+    res = sampler.sample(m, N, *args)
+    return res if isinstance(res, tuple) else (res,)
+
+
+@pytest.mark.parametrize("case", cases.SAMPLERS, ids=[c[0] for c in cases.SAMPLERS])
+def test_samplers_match_reference_fixtures(golden, case):
+    """Whole reverse process vs the reference's own sampler output (injected uniforms, reference q injected):
+    final integer states bit-exact except threshold ties (§8c plan (3)); diagnostics agree."""
+    name = case[0]
+    res = _run_product_sampler(case, inject_oracle_q=True)
+    g = golden["samplers"]
+    assert res[0].dtype.kind == "i" and res[0].shape == g[f"{name}/x"].shape
+    assert mismatch_fraction(res[0], g[f"{name}/x"]) <= 5e-3
+    for i, extra in enumerate(res[1:]):
+        np.testing.assert_allclose(np.asarray(extra, dtype=np.float64), g[f"{name}/diag{i}"], atol=0.02, rtol=0.05,
+                                   equal_nan=True)
+
+
+@pytest.mark.parametrize("case", [cases.SAMPLERS[0], cases.SAMPLERS[4], cases.SAMPLERS[6]], ids=lambda c: c[0])
+def test_samplers_native_q_close_to_reference(golden, case):
+    """Same, with q_{t|0} from the CUDA builder: clamp-band flips may move a few states (SURVEY §7 hard part 3)."""
+    name = case[0]
+    res = _run_product_sampler(case, inject_oracle_q=False)
+    assert mismatch_fraction(res[0], golden["samplers"][f"{name}/x"]) <= 0.03
