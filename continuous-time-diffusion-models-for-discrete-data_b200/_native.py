@@ -41,7 +41,7 @@ class StepParams(ctypes.Structure):
         ("logits", c_void_p), ("ld_logits", c_int64), ("batch_stride_logits", c_int64),
         ("x_eval", c_void_p), ("x_base", c_void_p),
         ("Q", c_void_p), ("QT", c_void_p), ("Rb", c_void_p), ("RbT", c_void_p),
-        ("tc_tables", c_void_p),
+        ("tc_tables", c_void_p), ("tc_static", c_void_p),
         ("beta", c_float), ("h", c_float), ("eps", c_float),
         ("reject_multi", c_int32),
         ("seed", c_uint64), ("offset", c_uint64),
@@ -86,6 +86,10 @@ def lib() -> ctypes.CDLL:
     L.ctdd_reverse_step.argtypes = [ctypes.POINTER(StepParams), c_void_p]
     L.ctdd_tc_tables_bytes.argtypes = [c_int]
     L.ctdd_tc_tables_bytes.restype = c_int64
+    L.ctdd_tc_static_bytes.argtypes = [c_int]
+    L.ctdd_tc_static_bytes.restype = c_int64
+    L.ctdd_prep_tc_static.argtypes = [c_void_p, c_int, c_void_p, c_void_p]
+    L.ctdd_prep_tc_static.restype = c_int
     L.ctdd_prep_tc_tables.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_void_p]
     L.ctdd_sample_categorical_shared.argtypes = [c_void_p, c_int, c_int64, c_int64, c_uint64, c_uint64, c_void_p, c_void_p]
     L.ctdd_noise_xt.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p]

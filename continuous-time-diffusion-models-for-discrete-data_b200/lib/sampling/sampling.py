@@ -68,9 +68,10 @@ class StepEngine:
         self.Q, self.QT, self.beta = model.qt0_tables(self.times, self.device)
         self.Rb, self.RbT = model.base_rate_tables(self.device)
         self.tc_bytes = int(nat.lib().ctdd_tc_tables_bytes(S)) if S == 256 else 0
-        self.tc_tables = None
+        self.tc_tables = self.tc_static = None
         if self.tc_bytes > 0 and impl != nat.IMPL_SIMT and branch in (nat.BRANCH_TAULDR, nat.BRANCH_SDDM_REVERSE_PROB):
             self.tc_tables = ops.prep_tc_tables(self.Q, self.QT, self.Rb, self.eps, branch)
+            self.tc_static = ops.prep_tc_static(self.Rb)
         ws = int(nat.lib().ctdd_step_workspace_bytes(N * D, S, impl))
         self.workspace = torch.empty((max(ws, 1),), dtype=torch.uint8, device=self.device) if ws > 0 else None
         ncalls = max_calls if max_calls is not None else 4 * len(self.times) + 8
@@ -95,7 +96,8 @@ class StepEngine:
             mode, self.branch, logits, x_eval, self.Q[tidx], self.QT[tidx], self.Rb, self.RbT, self.beta[tidx], h,
             self.eps, N=N, D=D, S=S, x_base=x_base, reject_multi=reject_multi, seed=self.seed, offset=self.call,
             row_offset=self.row_offset, impl=self.impl,
-            tc_tables=(self.tc_tables[tidx] if self.tc_tables is not None else None), workspace=self.workspace,
+            tc_tables=(self.tc_tables[tidx] if self.tc_tables is not None else None), tc_static=self.tc_static,
+            workspace=self.workspace,
             stats=(stats if stats is not None else self.stats[row]), want_rr=want_rr, want_ratio=want_ratio,
             logits_offset_elems=off_elems, batch_stride=bstride)
         x_out = out["x"]

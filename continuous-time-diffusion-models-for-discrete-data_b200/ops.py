@@ -32,8 +32,19 @@ def prep_tc_tables(Q, QT, Rb, eps, branch):
     return out
 
 
+def prep_tc_static(Rb):
+    """Time-independent tables of the tcgen05 path (uint8 blob) or None when the path is unavailable for this S."""
+    S = Rb.shape[-1]
+    nbytes = int(nat.lib().ctdd_tc_static_bytes(S))
+    if nbytes <= 0:
+        return None
+    out = torch.empty((nbytes,), dtype=torch.uint8, device=Rb.device)
+    nat.check(nat.lib().ctdd_prep_tc_static(nat.ptr(Rb), S, nat.ptr(out), nat.stream()), "ctdd_prep_tc_static")
+    return out
+
+
 def reverse_step(mode, branch, logits, x_eval, Q, QT, Rb, RbT, beta, h, eps, *, N, D, S, x_base=None,
-                 reject_multi=False, seed=0, offset=0, row_offset=0, impl=nat.IMPL_AUTO, tc_tables=None,
+                 reject_multi=False, seed=0, offset=0, row_offset=0, impl=nat.IMPL_AUTO, tc_tables=None, tc_static=None,
                  workspace=None, stats=None, want_rr=False, want_ratio=False, logits_offset_elems=0,
                  batch_stride=None):
     """One fused reverse-rate evaluation (+ state update). Returns dict(x=..., rr=..., ratio=...)."""
@@ -52,7 +63,7 @@ def reverse_step(mode, branch, logits, x_eval, Q, QT, Rb, RbT, beta, h, eps, *, 
         logits=nat.ptr(logits) + 4 * int(logits_offset_elems), ld_logits=S,
         batch_stride_logits=(int(batch_stride) if batch_stride is not None else D * S),
         x_eval=nat.ptr(x_eval), x_base=nat.ptr(x_base),
-        Q=nat.ptr(Q), QT=nat.ptr(QT), Rb=nat.ptr(Rb), RbT=nat.ptr(RbT), tc_tables=nat.ptr(tc_tables),
+        Q=nat.ptr(Q), QT=nat.ptr(QT), Rb=nat.ptr(Rb), RbT=nat.ptr(RbT), tc_tables=nat.ptr(tc_tables), tc_static=nat.ptr(tc_static),
         beta=float(beta), h=float(h), eps=float(eps), reject_multi=1 if reject_multi else 0,
         seed=int(seed), offset=int(offset),
         x_out=nat.ptr(x_out), rr_out=nat.ptr(rr), ratio_out=nat.ptr(ratio),

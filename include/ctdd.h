@@ -113,6 +113,7 @@ typedef struct ctdd_step_params {
   const float* Rb;       /* [S,S] base rate */
   const float* RbT;      /* [S,S] transpose of Rb */
   const void* tc_tables; /* blob from ctdd_prep_tc_tables for this time point, or NULL (SIMT only) */
+  const void* tc_static; /* blob from ctdd_prep_tc_static (time-independent tables), or NULL (SIMT only) */
   float beta;            /* rate scalar beta(t) */
   float h;               /* step length (corrector multiplier already applied) */
   float eps;             /* sampler.eps_ratio */
@@ -133,6 +134,9 @@ int ctdd_reverse_step(const ctdd_step_params* p, void* stream);
  * order the kernel loads them into tensor memory, the gathered-denominator table
  * 1/(Q[k,x]+eps) (tauLDR) and the midpoint drift table.  T time points at once. */
 int64_t ctdd_tc_tables_bytes(int S);
+/* time-independent tables of the tcgen05 path: Rb^T and Rb with zeroed diagonals (epilogue gathers) */
+int64_t ctdd_tc_static_bytes(int S);
+int ctdd_prep_tc_static(const float* Rb, int S, void* static_out, void* stream);
 int ctdd_prep_tc_tables(const float* Q, const float* QT, const float* Rb, int T, int S, float eps,
                         int branch, void* tables_out, void* stream);
 

@@ -67,6 +67,16 @@ def _impls():
     return [nat.IMPL_SIMT, nat.IMPL_AUTO]
 
 
+def _tc(tb, branch, S, impl):
+    """tcgen05-path tables for S == 256; IMPL_AUTO is upgraded to IMPL_TC there so a silent SIMT fallback cannot pass."""
+    from ctdd_b200 import ops
+    nat = _nat()
+    if S != 256 or impl == nat.IMPL_SIMT or branch not in (nat.BRANCH_TAULDR, nat.BRANCH_SDDM_REVERSE_PROB):
+        return impl, None, None
+    tabs = ops.prep_tc_tables(tb["Q"][None], tb["QT"][None], tb["Rb"], 1e-9, branch)
+    return nat.IMPL_TC, tabs[0], ops.prep_tc_static(tb["Rb"])
+
+
 @pytest.mark.parametrize("impl_i", [0, 1])
 @pytest.mark.parametrize("case", cases.RATES, ids=[c[0] for c in cases.RATES])
 def test_reverse_rates_match_reference(golden, case, impl_i):
@@ -78,11 +88,10 @@ def test_reverse_rates_match_reference(golden, case, impl_i):
     fp = oracle_forward(fwd)
     tb = _tables(fp, t)
     branch = nat.branch_for(loss_name, logit_type)
-    impl = _impls()[impl_i]
-    tc = ops.prep_tc_tables(tb["Q"][None], tb["QT"][None], tb["Rb"], 1e-9, branch) if (S == 256 and impl != nat.IMPL_SIMT) else None
+    impl, tct, tcs = _tc(tb, branch, S, _impls()[impl_i])
     out = ops.reverse_step(nat.MODE_RATES_ONLY, branch, logits.cuda(), x.to(torch.int32).cuda(), tb["Q"], tb["QT"], tb["Rb"],
                            tb["RbT"], tb["beta"], 0.0, 1e-9, N=N, D=D, S=S, impl=impl,
-                           tc_tables=(tc[0] if tc is not None else None), want_rr=True, want_ratio=True)
+                           tc_tables=tct, tc_static=tcs, want_rr=True, want_ratio=True)
     g = golden["rates"]
     for key, got in (("rr", out["rr"]), ("ratio", out["ratio"])):
         ref = g[f"{name}/{key}"]
@@ -129,23 +138,24 @@ def test_step_modes_match_oracle(sc, impl_i):
     fp, logits, x, S = _random_problem(fwd, N, D, t, 11, width)
     tb = _tables(fp, t)
     branch = nat.branch_for(loss_name, logit_type)
-    impl = _impls()[impl_i]
+    impl, tct, tcs = _tc(tb, branch, S, _impls()[impl_i])
     lt = logit_type or "reverse_prob"
     tt = torch.tensor([t], dtype=torch.float64).to(torch.float32)
     Qo, Ro = fp.transition(tt), fp.rate(tt)
     rr, _ = oc.reverse_rates(logits, x, Qo, Ro, loss_name, lt, 1e-9)
     rz = oc._zero_at(rr, x)
     rz_corr = oc._zero_at(Ro.expand(N, -1, -1)[torch.arange(N).view(N, 1), x.long()] + rz, x)
-    tc = ops.prep_tc_tables(tb["Q"][None], tb["QT"][None], tb["Rb"], 1e-9, branch) if (
-        S == 256 and impl != nat.IMPL_SIMT and branch in (nat.BRANCH_TAULDR, nat.BRANCH_SDDM_REVERSE_PROB)) else None
     xe = x.to(torch.int32).cuda()
     lg = logits.cuda()
     seed = 4242
 
     def run(mode, offset, reject=False, x_base=None):
         stats = torch.zeros(8, dtype=torch.int64, device="cuda")
+        use = impl
+        if impl == nat.IMPL_TC and mode in (nat.MODE_MIDPOINT_DRIFT, nat.MODE_EULER, nat.MODE_EULER_CORR):
+            use = nat.IMPL_AUTO   # these modes run on the CUDA-core path at S=256
         out = ops.reverse_step(mode, branch, lg, xe, tb["Q"], tb["QT"], tb["Rb"], tb["RbT"], tb["beta"], h, 1e-9,
-                               N=N, D=D, S=S, impl=impl, tc_tables=(tc[0] if tc is not None else None),
+                               N=N, D=D, S=S, impl=use, tc_tables=tct, tc_static=tcs,
                                reject_multi=reject, seed=seed, offset=offset, x_base=x_base, stats=stats)
         return out["x"].cpu().numpy().astype(np.int64), stats.cpu().numpy()
 
@@ -160,7 +170,7 @@ def test_step_modes_match_oracle(sc, impl_i):
     want, _ = oc.tau_leap_update(rz_corr, x, x, h, S, False, 5, seed)
     assert mismatch_fraction(got, want.numpy()) <= tol
     got, _ = run(nat.MODE_MIDPOINT_DRIFT, 0)
-    want = oc.midpoint_drift(rz, x, 20 * h if False else h, S)
+    want = oc.midpoint_drift(rz, x, h, S)
     assert mismatch_fraction(got, want.numpy()) <= tol
     g = np.random.Generator(np.random.PCG64(5))
     xb = torch.from_numpy(np.clip(x.numpy() + g.integers(-1, 2, x.shape), 0, S - 1))
@@ -266,3 +276,32 @@ def test_samplers_native_q_close_to_reference(golden, case):
     name = case[0]
     res = _run_product_sampler(case, inject_oracle_q=False)
     assert mismatch_fraction(res[0], golden["samplers"][f"{name}/x"]) <= 0.03
+
+
+def test_tc_path_full_tiles_and_tail_match_simt():
+    """tcgen05 path vs the CUDA-core path on the same inputs (both through the C ABI): ragged row counts (tile tails),
+    several tiles per CTA, both branches; rates within 1e-4, states identical up to threshold ties."""
+    from ctdd_b200 import ops
+    nat = _nat()
+    for (N, D) in ((1, 1), (3, 21), (7, 640), (64, 300)):
+        for loss_name, lt in (("CTElbo", None), ("CatRM", "reverse_prob")):
+            fp, logits, x, S = _random_problem("gauss256", N, D, 0.35, 17 + N, 12.0)
+            tb = _tables(fp, 0.35)
+            branch = nat.branch_for(loss_name, lt)
+            _, tct, tcs = _tc(tb, branch, S, nat.IMPL_AUTO)
+            kw = dict(N=N, D=D, S=S, tc_tables=tct, tc_static=tcs)
+            args = (branch, logits.cuda(), x.to(torch.int32).cuda(), tb["Q"], tb["QT"], tb["Rb"], tb["RbT"], tb["beta"])
+            r_tc = ops.reverse_step(nat.MODE_RATES_ONLY, *args, 0.0, 1e-9, impl=nat.IMPL_TC, want_rr=True, want_ratio=True, **kw)
+            r_si = ops.reverse_step(nat.MODE_RATES_ONLY, *args, 0.0, 1e-9, impl=nat.IMPL_SIMT, want_rr=True, want_ratio=True, **kw)
+            for key in ("rr", "ratio"):
+                a, b = r_tc[key].cpu().numpy(), r_si[key].cpu().numpy()
+                big = np.abs(b) > 1e-30
+                assert (np.abs(a - b)[big] / np.abs(b)[big]).max() <= 1e-4
+                assert np.all(np.abs(a[~big]) <= 1e-30)
+            for mode, reject in ((nat.MODE_TAU_LEAP, False), (nat.MODE_TAU_LEAP, True), (nat.MODE_TAU_LEAP_CORR, False)):
+                st1 = torch.zeros(8, dtype=torch.int64, device="cuda")
+                st2 = torch.zeros(8, dtype=torch.int64, device="cuda")
+                x_tc = ops.reverse_step(mode, *args, 0.01, 1e-9, impl=nat.IMPL_TC, reject_multi=reject, seed=5, offset=1, stats=st1, **kw)["x"]
+                x_si = ops.reverse_step(mode, *args, 0.01, 1e-9, impl=nat.IMPL_SIMT, reject_multi=reject, seed=5, offset=1, stats=st2, **kw)["x"]
+                assert mismatch_fraction(x_tc.cpu().numpy(), x_si.cpu().numpy()) <= 2e-3
+                assert np.abs(st1.cpu().numpy() - st2.cpu().numpy()).max() <= max(2, 2e-3 * N * D)
