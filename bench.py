@@ -196,6 +196,7 @@ def run_ours(args, w, rank, world, local_rank):
     mode = nat.MODE_EULER if w["mode"] == "euler" else nat.MODE_TAU_LEAP
     impl = {"auto": nat.IMPL_AUTO, "simt": nat.IMPL_SIMT, "tc": nat.IMPL_TC}[args.kernels]
     tc = ops.prep_tc_tables(Q, QT, Rb, 1e-9, branch) if (S == 256 and impl != nat.IMPL_SIMT) else None
+    tcs = ops.prep_tc_static(Rb) if tc is not None else None
     ws_bytes = int(nat.lib().ctdd_step_workspace_bytes(B * D, S, impl))
     workspace = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev)
     # two logits buffers (each >> L2 at the S=256 workloads) alternate between steps
@@ -213,7 +214,8 @@ def run_ours(args, w, rank, world, local_rank):
     def step(i, xin, logits):
         return ops.reverse_step(mode, branch, logits, xin, Q[i], QT[i], Rb, RbT, beta[i], h, 1e-9, N=B, D=D, S=S,
                                 reject_multi=not w["ordinal"], seed=0xC7DD, offset=i, row_offset=row_offset, impl=impl,
-                                tc_tables=(tc[i] if tc is not None else None), workspace=workspace, stats=stats[i])["x"]
+                                tc_tables=(tc[i] if tc is not None else None), tc_static=tcs, workspace=workspace,
+                                stats=stats[i])["x"]
 
     def barrier():
         if world > 1:
@@ -272,7 +274,7 @@ def run_ours(args, w, rank, world, local_rank):
                 out = ops.reverse_step(mode, branch, dl[c & 1][:n], dx[c & 1][:n], Q[i], QT[i], Rb, RbT, beta[i], h, 1e-9,
                                        N=n, D=D, S=S, reject_multi=not w["ordinal"], seed=0xC7DD, offset=i,
                                        row_offset=ro, impl=impl, tc_tables=(tc[i] if tc is not None else None),
-                                       workspace=cws[c & 1])["x"]
+                                       tc_static=tcs, workspace=cws[c & 1])["x"]
                 host_out[lo:hi].copy_(out, non_blocking=True)
         for s in streams:
             s.synchronize()

@@ -45,6 +45,10 @@ extern "C" int ctdd_reverse_step(const ctdd_step_params* p, void* stream) {
   if (p->mode == CTDD_MODE_RATES_ONLY && !p->rr_out && !p->ratio_out) { set_error("ctdd_reverse_step: RATES_ONLY needs rr_out or ratio_out"); return 2; }
   if (p->ld_logits < p->S) { set_error("ctdd_reverse_step: ld_logits < S"); return 2; }
   if (p->row_offset & 7) { set_error("ctdd_reverse_step: row_offset must be a multiple of 8 (got %lld)", (long long)p->row_offset); return 2; }
+  if ((p->tc_tables != nullptr) != (p->tc_static != nullptr)) {
+    set_error("ctdd_reverse_step: tc_tables and tc_static must be given together (got only one); refusing to fall back silently");
+    return 2;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   const bool want_tc = (p->impl == CTDD_IMPL_TC) || (p->impl == CTDD_IMPL_AUTO && tc_supports(p));
   if (want_tc) {

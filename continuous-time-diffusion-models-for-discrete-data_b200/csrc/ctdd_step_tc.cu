@@ -12,7 +12,7 @@
 //     in fp32 TMEM; epilogue warps read the accumulator with tcgen05.ld (lane = state s, column = row), scale by
 //     the gathered forward rate R_b[s,x] and draw the per-(row,s) Poisson jump counts.
 // Each CTA owns one half of the state axis (128 TMEM lanes); the two halves of a row are combined by a small
-// finalize kernel.  Warp roles: 4 epilogue warps (TMEM quadrants), 1 MMA-issue warp, 8 producer warps.
+// finalize kernel.  Warp roles: 8 epilogue warps (2 per TMEM quadrant), 1 MMA-issue warp, 8 producer warps.
 #include "ctdd_common.cuh"
 #include <cuda_bf16.h>
 
@@ -24,11 +24,11 @@ constexpr int NT = 64;                 // data rows per tile (= UMMA N)
 constexpr int STAGES = 3;              // smem operand stages
 constexpr int ACC = 2;                 // TMEM accumulator buffers
 constexpr int RING = 8;                // per-tile side-info ring (>= STAGES + ACC + 1)
-constexpr int NUM_EPI_WARPS = 4;
-constexpr int MMA_WARP = 4;
-constexpr int FIRST_PROD_WARP = 5;
+constexpr int NUM_EPI_WARPS = 8;       // warps e and e+4 share TMEM quadrant e&3 and split the tile's columns
+constexpr int MMA_WARP = 8;
+constexpr int FIRST_PROD_WARP = 9;
 constexpr int NUM_PROD_WARPS = 8;
-constexpr int NUM_THREADS = (FIRST_PROD_WARP + NUM_PROD_WARPS) * 32;  // 416
+constexpr int NUM_THREADS = (FIRST_PROD_WARP + NUM_PROD_WARPS) * 32;  // 544
 constexpr int ROWS_PER_PROD = NT / NUM_PROD_WARPS;                   // 8
 constexpr int KBLOCK_BYTES = NT * 128;         // one 64-wide K block of one split: NT rows x 128 B
 constexpr int SPLIT_BYTES = 4 * KBLOCK_BYTES;  // K = 256 -> 4 blocks
@@ -96,11 +96,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra DONE_%=;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware, do not spin
       : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -172,7 +172,20 @@ __device__ __forceinline__ float4 ld_stream(const float* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // bf16 hi/mid split of two floats, packed (element 0 in the low half)
 __device__ __forceinline__ void split2(float a0, float a1, uint32_t& hi, uint32_t& mid) {
@@ -184,12 +197,9 @@ __device__ __forceinline__ void split2(float a0, float a1, uint32_t& hi, uint32_
   mid = *reinterpret_cast<uint32_t*>(&m);
 }
 
-// rare path: the 16-bit pre-filter did not exclude a jump -> full 32-bit uniform, exact inverse CDF
-__device__ __noinline__ void slow_jump(float lam, uint32_t hw, int s, uint64_t group, int jj, unsigned long long offset,
-                                       unsigned long long seed, int x, int* jump, int* cnt) {
-  const Philox4 lo = philox_jump((uint32_t)s, group, offset, STREAM_JUMP_LO, seed);
-  const uint32_t w = (hw << 16) | philox_half(lo, jj);
-  const int k = poisson_from_unit(lam, u32_to_unit(w));
+// rare path: the full 32-bit uniform is below lambda, so a jump is possible -> exact inverse CDF + accumulation
+__device__ __noinline__ void jump_tail(float lam, float v, int s, int x, int* jump, int* cnt) {
+  const int k = poisson_from_unit(lam, v);
   if (k) {
     atomicAdd(jump, jump_contrib(k, s, x));
     atomicAdd(cnt, k > 4096 ? 4096 : k);
@@ -197,6 +207,11 @@ __device__ __noinline__ void slow_jump(float lam, uint32_t hw, int s, uint64_t g
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
+constexpr int PROD_BATCH = 4;          // rows whose loads are issued together by a producer warp
+constexpr int PREFETCH_TILES = 3;      // L2 bulk-prefetch distance (tiles of this CTA's sequence)
+
+// TAULDR: tauLDR rates (else SDDM reverse_prob); CORR: corrector adds R_t[x,:]; RATES: RATES_ONLY mode
+template <bool TAULDR, bool CORR, bool RATES>
 __global__ void __launch_bounds__(NUM_THREADS, 1) step_tc_kernel(const Args a) {
   extern __shared__ uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -218,8 +233,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) step_tc_kernel(const Args a) {
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
 
-  // Q^T halves -> tensor memory (A operand). Epilogue warp q owns TMEM lanes [32q, 32q+32).
-  if (warp < NUM_EPI_WARPS) {
+  // Q^T halves -> tensor memory (A operand). Warp q < 4 owns TMEM lanes [32q, 32q+32).
+  if (warp < 4) {
     const int srow = hs * 128 + warp * 32 + lane;
 #pragma unroll 1
     for (int split = 0; split < 2; ++split) {
@@ -244,66 +259,107 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) step_tc_kernel(const Args a) {
   if (warp >= FIRST_PROD_WARP) {
     // ======================================================================== producers: one warp per row
     const int pw = warp - FIRST_PROD_WARP;
-    const float* tabA = reinterpret_cast<const float*>(a.tab + TAB_A_OFF);
-    const bool tauldr = (a.branch == CTDD_BRANCH_TAULDR);
-    const float hb = (a.mode == CTDD_MODE_RATES_ONLY) ? 1.0f : a.h * a.beta;   // rates-only ignores the step length
+    // lane owns k = 4*lane .. 4*lane+3 and 128 + 4*lane .. +3: two fully coalesced 512-byte warp loads per row
+    const float* tabA = reinterpret_cast<const float*>(a.tab + TAB_A_OFF) + 4 * lane;
+    const float hb = RATES ? 1.0f : a.h * a.beta;   // rates-only ignores the step length
+    const bool contiguous = (a.ld == S) && (a.batch_stride == (long long)a.D * S);
+    const bool can_prefetch = contiguous && hs == 0 && pw == 0 && lane == 0;
+    const uint32_t rows32 = (uint32_t)(a.rows < 0x7fffffffLL ? a.rows : 0x7fffffffLL);
     for (int i = 0; i < my_tiles; ++i) {
       const int tile = tile0 + i * tile_step;
       const int st = i % STAGES, slot = i % RING;
+      if (can_prefetch) {   // pull a later tile of this CTA pair's sequence into L2 while this one is processed
+        const long long pt = (long long)tile + (long long)PREFETCH_TILES * tile_step;
+        if (pt < a.num_tiles) {
+          const long long r0 = pt * NT;
+          const long long nrow = (a.rows - r0) < NT ? (a.rows - r0) : NT;
+          l2_prefetch_bulk(a.logits + r0 * S, (uint32_t)(nrow * S * 4));
+        }
+      }
       mbar_wait(&sm.empty[st], ((i / STAGES) & 1) ^ 1);
       uint8_t* stage = sm.stage[st];
-#pragma unroll 2
-      for (int rr = 0; rr < ROWS_PER_PROD; ++rr) {
-        const int r = pw + NUM_PROD_WARPS * rr;
-        const long long g = (long long)tile * NT + r;
-        uint32_t hi[4] = {0, 0, 0, 0}, mid[4] = {0, 0, 0, 0};
-        Side si = {0.f, 0.f, 0, 0.f};
-        if (g < a.rows) {
-          const long long n = g / a.D, d = g - n * a.D;
-          const float* lp = a.logits + n * a.batch_stride + d * a.ld + 8 * lane;
-          const float4 v0 = ld_stream(lp), v1 = ld_stream(lp + 4);
-          const int x = __ldg(a.x_eval + g);
-          const float4 t0 = __ldg(reinterpret_cast<const float4*>(tabA + (size_t)x * S + 8 * lane));
-          const float4 t1 = __ldg(reinterpret_cast<const float4*>(tabA + (size_t)x * S + 8 * lane + 4));
-          float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-          const float t[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-          float m = v[0];
+#pragma unroll 1
+      for (int b0 = 0; b0 < ROWS_PER_PROD; b0 += PROD_BATCH) {
+        float4 v0[PROD_BATCH], v1[PROD_BATCH], t0[PROD_BATCH], t1[PROD_BATCH];
+        int xr[PROD_BATCH];
+        bool ok[PROD_BATCH];
+        // issue every load of the batch before touching the data
 #pragma unroll
-          for (int j = 1; j < 8; ++j) m = fmaxf(m, v[j]);
+        for (int j = 0; j < PROD_BATCH; ++j) {
+          const int r = pw + NUM_PROD_WARPS * (b0 + j);
+          const long long g = (long long)tile * NT + r;
+          ok[j] = g < a.rows;
+          const long long gc = ok[j] ? g : 0;
+          const float* lp;
+          if (contiguous) {
+            lp = a.logits + gc * S + 4 * lane;
+          } else {
+            const uint32_t n = (uint32_t)gc / (uint32_t)a.D, d = (uint32_t)gc - n * (uint32_t)a.D;
+            lp = a.logits + (long long)n * a.batch_stride + (long long)d * a.ld + 4 * lane;
+          }
+          v0[j] = ld_stream(lp);
+          v1[j] = ld_stream(lp + 128);
+          xr[j] = __ldg(a.x_eval + gc);
+        }
+#pragma unroll
+        for (int j = 0; j < PROD_BATCH; ++j) {
+          const float* tp = tabA + ((size_t)xr[j] << 8);
+          t0[j] = __ldg(reinterpret_cast<const float4*>(tp));
+          t1[j] = __ldg(reinterpret_cast<const float4*>(tp + 128));
+        }
+#pragma unroll
+        for (int j = 0; j < PROD_BATCH; ++j) {
+          const int r = pw + NUM_PROD_WARPS * (b0 + j);
+          float v[8] = {v0[j].x, v0[j].y, v0[j].z, v0[j].w, v1[j].x, v1[j].y, v1[j].z, v1[j].w};
+          const float t[8] = {t0[j].x, t0[j].y, t0[j].z, t0[j].w, t1[j].x, t1[j].y, t1[j].z, t1[j].w};
+          float m = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
           m = warp_max(m);
+          const float ml = -m * 1.4426950408889634f;
           float sum = 0.f, dot = 0.f;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            v[j] = exp2f((v[j] - m) * 1.4426950408889634f);
-            sum += v[j];
-            dot = fmaf(v[j], t[j], dot);
+          for (int q = 0; q < 8; ++q) {
+            v[q] = ex2_approx(fmaf(v[q], 1.4426950408889634f, ml));     // exp(v - max)
+            sum += v[q];
+            if (!TAULDR) dot = fmaf(v[q], t[q], dot);
           }
           sum = warp_sum(sum);
-          const float rs = 1.0f / sum;
-          if (tauldr) {
+          const float rs = __frcp_rn(sum);
+          Side si;
+          if (TAULDR) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] *= t[j];           // e_k / (Q[k,x] + eps); 1/sum applied in the epilogue
+            for (int q = 0; q < 8; ++q) v[q] *= t[q];             // e_k / (Q[k,x] + eps); 1/sum applied in the epilogue
             si.c1 = hb * rs * 0.0078125f;                          // lambda * 2^-7 = D * c1 * R_b[s,x]
             si.c0 = 0.f;
           } else {
             dot = warp_sum(dot);
-            const float inv = 1.0f / (dot * rs + 1e-35f);          // 1 / (pQ[x] + 1e-35)
+            const float inv = __frcp_rn(fmaf(dot, rs, 1e-35f));    // 1 / (pQ[x] + 1e-35)
             si.c1 = hb * rs * inv * 0.0078125f;
             si.c0 = hb * 1e-35f * inv * 0.0078125f;
           }
-          si.x = x;
+          si.x = xr[j];
           si.rs = rs;
+          uint32_t hi[4], mid[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) split2(v[2 * j], v[2 * j + 1], hi[j], mid[j]);
-        }
-        // lane holds k = 8*lane .. 8*lane+7: K block lane/8, 16-byte chunk lane%8, XOR-swizzled by the row
-        const uint32_t off = (uint32_t)(lane >> 3) * KBLOCK_BYTES + (uint32_t)r * 128 + (uint32_t)(((lane & 7) ^ (r & 7)) << 4);
-        *reinterpret_cast<uint4*>(stage + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(stage + SPLIT_BYTES + off) = make_uint4(mid[0], mid[1], mid[2], mid[3]);
-        if (lane == 0) {
-          sm.side[slot][r] = si;
-          sm.jump[slot][r] = 0;
-          sm.cnt[slot][r] = 0;
+          for (int q = 0; q < 4; ++q) split2(v[2 * q], v[2 * q + 1], hi[q], mid[q]);
+          if (!ok[j]) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) hi[q] = mid[q] = 0u;
+            si.c1 = si.c0 = si.rs = 0.f;
+            si.x = 0;
+          }
+          // k = 4*lane..+3 lives in K block lane/16, 16-byte chunk (lane%16)/2 (XOR-swizzled by the row), half lane&1;
+          // k = 128 + 4*lane..+3 two K blocks further on
+          const uint32_t off = (uint32_t)(lane >> 4) * KBLOCK_BYTES + (uint32_t)r * 128 +
+                               (uint32_t)(((((lane & 15) >> 1) ^ (r & 7)) << 4) | ((lane & 1) << 3));
+          *reinterpret_cast<uint2*>(stage + off) = make_uint2(hi[0], hi[1]);
+          *reinterpret_cast<uint2*>(stage + off + 2 * KBLOCK_BYTES) = make_uint2(hi[2], hi[3]);
+          *reinterpret_cast<uint2*>(stage + SPLIT_BYTES + off) = make_uint2(mid[0], mid[1]);
+          *reinterpret_cast<uint2*>(stage + SPLIT_BYTES + off + 2 * KBLOCK_BYTES) = make_uint2(mid[2], mid[3]);
+          if (lane == 0) {
+            sm.side[slot][r] = si;
+            sm.jump[slot][r] = 0;
+            sm.cnt[slot][r] = 0;
+          }
         }
       }
       fence_proxy_async();
@@ -342,85 +398,104 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) step_tc_kernel(const Args a) {
     __syncwarp();
   } else {
     // ======================================================================== epilogue: lane = state s
-    const int q = warp;
+    const int q = warp & 3;                // TMEM quadrant
+    const int ch = warp >> 2;              // which 32 columns of the tile
     const int s = hs * 128 + q * 32 + lane;
-    const bool tauldr = (a.branch == CTDD_BRANCH_TAULDR);
-    const float* tabE = reinterpret_cast<const float*>(a.stat + (tauldr ? ST_RBZT_OFF : ST_RBZ_OFF));
-    const float* tabC = reinterpret_cast<const float*>(a.stat + ST_RBZ_OFF);   // corrector add: Rb[x][s], zero diag
-    const float* tabFull = tauldr ? a.RbT : a.Rb;                                // diagonal kept, for rr_out
-    const bool corr = (a.mode == CTDD_MODE_TAU_LEAP_CORR);
-    const bool rates_only = (a.mode == CTDD_MODE_RATES_ONLY);
-    const float hb7 = (rates_only ? 1.0f : a.h * a.beta) * 0.0078125f;
+    const float* tabE = reinterpret_cast<const float*>(a.stat + (TAULDR ? ST_RBZT_OFF : ST_RBZ_OFF)) + s;
+    const float* tabC = reinterpret_cast<const float*>(a.stat + ST_RBZ_OFF) + s;   // corrector add: Rb[x][s], zero diag
+    const float* tabFull = (TAULDR ? a.RbT : a.Rb) + s;                             // diagonal kept, for rr_out
+    const float hb7 = (RATES ? 1.0f : a.h * a.beta) * 0.0078125f;
+    const uint32_t side_base = smem_u32(&sm.side[0][0]);
+    const int c0 = 32 * ch;
     for (int i = 0; i < my_tiles; ++i) {
       const int tile = tile0 + i * tile_step;
       const int b = i % ACC, slot = i % RING;
       mbar_wait(&sm.side_full[slot], (i / RING) & 1);
       mbar_wait(&sm.tmem_full[b], (i / ACC) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + TM_ACC + b * NT;
       const long long g0 = (long long)tile * NT;
-#pragma unroll 1
-      for (int c0 = 0; c0 < NT; c0 += 32) {
-        uint32_t acc[32];
-        tmem_ld32(taddr + c0, acc);
-        tmem_ld_wait();
-        if (c0 + 32 == NT) {  // accumulator fully in registers: hand the buffer back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sm.tmem_empty[b]);
-        }
-        if (rates_only) {
+      const uint32_t side_slot = side_base + (uint32_t)(slot * NT + c0) * (uint32_t)sizeof(Side);
+      uint32_t acc[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + TM_ACC + b * NT + c0, acc);
+      tmem_ld_wait();
+      tc_fence_before();   // accumulator is in registers: hand the buffer back to the MMA warp
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.tmem_empty[b]);
+      if (RATES) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const long long g = g0 + c0 + j;
-            if (g >= a.rows) continue;
-            const Side si = sm.side[slot][c0 + j];
-            const float d = __uint_as_float(acc[j]);
-            float ratio, rfull;
-            if (tauldr) {
-              ratio = d * si.rs;
-              rfull = a.beta * __ldg(tabFull + (size_t)si.x * S + s) * ratio;
-            } else {
-              // ratio = (pQ[s] + 1e-35) / (pQ[x] + 1e-35);  c1/c0 carry h*beta*2^-7, undo it
-              ratio = fmaf(d, si.c1, si.c0) / hb7;
-              rfull = ratio * (a.beta * __ldg(tabFull + (size_t)si.x * S + s));
+        for (int j = 0; j < 32; ++j) {
+          const long long g = g0 + c0 + j;
+          if (g >= a.rows) continue;
+          const float4 si = lds128(side_slot + (uint32_t)j * 16);
+          const int x = __float_as_int(si.z);
+          const float d = __uint_as_float(acc[j]);
+          float ratio, rfull;
+          if (TAULDR) {
+            ratio = d * si.w;
+            rfull = a.beta * __ldg(tabFull + ((size_t)x << 8)) * ratio;
+          } else {
+            // ratio = (pQ[s] + 1e-35) / (pQ[x] + 1e-35);  c1/c0 carry 2^-7
+            ratio = fmaf(d, si.x, si.y) * 128.0f;
+            rfull = ratio * (a.beta * __ldg(tabFull + ((size_t)x << 8)));
+          }
+          if (a.rr_out) a.rr_out[g * S + s] = rfull;
+          if (a.ratio_out) a.ratio_out[g * S + s] = ratio;
+        }
+        continue;
+      }
+      // two passes of 16 columns keep the live register set small (544 threads -> 96 registers per thread)
+#pragma unroll
+      for (int h0 = 0; h0 < 32; h0 += 16) {
+        // ---- phase 1 (branch-free, full ILP): lambda and the 16-bit pre-filter
+        float lam7[16];
+        Philox4 ph[2];
+        uint32_t need = 0;
+#pragma unroll
+        for (int j8 = 0; j8 < 16; j8 += 8) {
+          const uint64_t group = (uint64_t)(a.row_offset + g0 + c0 + h0 + j8) >> 3;
+          ph[j8 >> 3] = philox_jump((uint32_t)s, group, a.offset, STREAM_JUMP_HI, a.seed);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const float4 si = lds128(side_slot + (uint32_t)(h0 + j8 + jj) * 16);
+            const size_t xo = (size_t)__float_as_int(si.z) << 8;
+            float l7 = fmaf(__uint_as_float(acc[h0 + j8 + jj]), si.x, si.y) * __ldg(tabE + xo);
+            if (CORR) l7 = fmaf(hb7, __ldg(tabC + xo), l7);
+            lam7[j8 + jj] = l7;
+            // halfword jj of the Philox output OR'ed into the mantissa of 1.0f: 1 + hi16 * 2^-23 (one PRMT)
+            const uint32_t fb = __byte_perm(ph[j8 >> 3].w[jj >> 1], 0x3F800000u, (jj & 1) ? 0x7632 : 0x7610);
+            // v >= hi16 * 2^-16 and P(K >= 1) <= lambda: when hi16 * 2^-16 >= lambda the count is certainly 0
+            need |= ((__uint_as_float(fb) - 1.0f) < l7 ? 1u : 0u) << (j8 + jj);
+          }
+        }
+        // ---- phase 2 (rare, grows with the jump rate): low 16 bits of the uniform, exact inverse CDF
+        if (__any_sync(0xffffffffu, need != 0)) {
+#pragma unroll
+          for (int j8 = 0; j8 < 16; j8 += 8) {
+            const uint32_t gm = (need >> j8) & 0xFFu;
+            if (__any_sync(0xffffffffu, gm != 0)) {
+              const uint64_t group = (uint64_t)(a.row_offset + g0 + c0 + h0 + j8) >> 3;
+              const Philox4 lo = philox_jump((uint32_t)s, group, a.offset, STREAM_JUMP_LO, a.seed);
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                if ((gm >> jj) & 1u) {
+                  const uint32_t w = (philox_half(ph[j8 >> 3], jj) << 16) | philox_half(lo, jj);
+                  const float v = u32_to_unit(w);
+                  const float lam = lam7[j8 + jj] * 128.0f;
+                  if (v < lam) {
+                    const int col = c0 + h0 + j8 + jj;
+                    const int x = __float_as_int(lds128(side_slot + (uint32_t)(h0 + j8 + jj) * 16).z);
+                    jump_tail(lam, v, s, x, &sm.jump[slot][col], &sm.cnt[slot][col]);
+                  }
+                }
+              }
             }
-            if (a.rr_out) a.rr_out[g * S + s] = rfull;
-            if (a.ratio_out) a.ratio_out[g * S + s] = ratio;
-          }
-          continue;
-        }
-#pragma unroll
-        for (int j8 = 0; j8 < 32; j8 += 8) {
-          const uint64_t group = (uint64_t)(a.row_offset + g0 + c0 + j8) >> 3;
-          const Philox4 ph = philox_jump((uint32_t)s, group, a.offset, STREAM_JUMP_HI, a.seed);
-          float lam7[8];
-          int xs[8];
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const Side si = sm.side[slot][c0 + j8 + jj];
-            xs[jj] = si.x;
-            const float tab = __ldg(tabE + (size_t)si.x * S + s);
-            float l7 = fmaf(__uint_as_float(acc[j8 + jj]), si.c1, si.c0) * tab;
-            if (corr) l7 = fmaf(hb7, __ldg(tabC + (size_t)si.x * S + s), l7);
-            lam7[jj] = l7;
-          }
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const uint32_t hw = philox_half(ph, jj);
-            const float gthr = __uint_as_float(0x3F800000u | hw) - 1.0f;   // hi16 * 2^-23, exact
-            if (gthr < lam7[jj])                                            // else v >= lambda >= P(K>=1): k = 0
-              slow_jump(lam7[jj] * 128.0f, hw, s, group, jj, a.offset, a.seed, xs[jj], &sm.jump[slot][c0 + j8 + jj],
-                        &sm.cnt[slot][c0 + j8 + jj]);
           }
         }
       }
-      if (!rates_only) {
-        epi_bar_sync();
-        const int t = threadIdx.x;
-        // the producers cannot reach this ring slot again before RING - (STAGES + ACC) more tiles have been drained
-        if (t < NT && g0 + t < a.rows) a.partial[(size_t)hs * a.rows + g0 + t] = make_int2(sm.jump[slot][t], sm.cnt[slot][t]);
-      }
+      epi_bar_sync();
+      const int t = threadIdx.x;
+      // the producers cannot reach this ring slot again before RING - (STAGES + ACC) more tiles have been drained
+      if (t < NT && g0 + t < a.rows) a.partial[(size_t)hs * a.rows + g0 + t] = make_int2(sm.jump[slot][t], sm.cnt[slot][t]);
     }
   }
   tc_fence_before();
@@ -518,15 +593,21 @@ int launch_step_tc(const ctdd_step_params* p, cudaStream_t st) {
   static int num_sms = 0;
   static bool attr_set = false;
   const size_t smem_bytes = sizeof(Smem) + 1024;
+  typedef void (*kern_t)(const Args);
+  static const kern_t kerns[2][3] = {
+      {step_tc_kernel<false, false, false>, step_tc_kernel<false, true, false>, step_tc_kernel<false, false, true>},
+      {step_tc_kernel<true, false, false>, step_tc_kernel<true, true, false>, step_tc_kernel<true, false, true>}};
   if (!attr_set) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaFuncSetAttribute(step_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
-      set_error("ctdd_reverse_step: cannot reserve %zu bytes of shared memory for the tcgen05 kernel", smem_bytes);
-      cudaGetLastError();
-      return 1;
-    }
+    for (int i = 0; i < 2; ++i)
+      for (int j = 0; j < 3; ++j)
+        if (cudaFuncSetAttribute(kerns[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
+          set_error("ctdd_reverse_step: cannot reserve %zu bytes of shared memory for the tcgen05 kernel", smem_bytes);
+          cudaGetLastError();
+          return 1;
+        }
     attr_set = true;
   }
   Args a;
@@ -544,7 +625,9 @@ int launch_step_tc(const ctdd_step_params* p, cudaStream_t st) {
   int grid = num_sms & ~1;                         // CTA pairs (state halves) share a tile sequence
   if (grid > 2 * a.num_tiles) grid = 2 * a.num_tiles;
   if (grid < 2) grid = 2;
-  step_tc_kernel<<<grid, NUM_THREADS, smem_bytes, st>>>(a);
+  const int ki = (p->branch == CTDD_BRANCH_TAULDR) ? 1 : 0;
+  const int kj = (p->mode == CTDD_MODE_RATES_ONLY) ? 2 : (p->mode == CTDD_MODE_TAU_LEAP_CORR ? 1 : 0);
+  kerns[ki][kj]<<<grid, NUM_THREADS, smem_bytes, st>>>(a);
   CTDD_CHECK_LAUNCH("step_tc_kernel");
   if (p->mode != CTDD_MODE_RATES_ONLY) {
     const int threads = 256;
