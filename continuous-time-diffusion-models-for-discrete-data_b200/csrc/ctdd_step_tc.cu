@@ -525,14 +525,19 @@ __global__ void step_tc_finalize_kernel(const int2* __restrict__ partial, const 
     v[0] = xn != xb; v[2] = xn != xe;
     x_out[r] = xn;
   }
-  if (stats) {
+  if (stats) {   // block-level reduction: one atomic per counter per CTA
+    __shared__ int red[5];
+    if (threadIdx.x < 5) red[threadIdx.x] = 0;
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
       int s = v[i];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if ((threadIdx.x & 31) == 0 && s) atomicAdd(stats + i, (unsigned long long)s);
+      if ((threadIdx.x & 31) == 0 && s) atomicAdd(&red[i], s);
     }
+    __syncthreads();
+    if (threadIdx.x < 5 && red[threadIdx.x]) atomicAdd(stats + threadIdx.x, (unsigned long long)red[threadIdx.x]);
   }
 }
 
@@ -630,7 +635,7 @@ int launch_step_tc(const ctdd_step_params* p, cudaStream_t st) {
   kerns[ki][kj]<<<grid, NUM_THREADS, smem_bytes, st>>>(a);
   CTDD_CHECK_LAUNCH("step_tc_kernel");
   if (p->mode != CTDD_MODE_RATES_ONLY) {
-    const int threads = 256;
+    const int threads = 1024;
     step_tc_finalize_kernel<<<(unsigned)((a.rows + threads - 1) / threads), threads, 0, st>>>(
         a.partial, a.x_eval, a.x_base, a.rows, a.reject_multi, a.x_out, a.stats);
     CTDD_CHECK_LAUNCH("step_tc_finalize_kernel");
