@@ -57,9 +57,9 @@ class LossParams(ctypes.Structure):
         ("logits", c_void_p), ("Q", c_void_p), ("QT", c_void_p), ("Rb", c_void_p), ("beta", c_void_p),
         ("x0", c_void_p), ("xt", c_void_p), ("x_tilde", c_void_p),
         ("eps", c_float),
-        ("out_a", c_void_p), ("out_b", c_void_p), ("out_c", c_void_p), ("out_nll", c_void_p),
-        ("ga", c_void_p), ("gb", c_void_p), ("gc", c_void_p), ("gn", c_void_p),
-        ("grad_logits", c_void_p),
+        ("out_a", c_void_p), ("out_b", c_void_p), ("out_c", c_void_p), ("out_d", c_void_p), ("out_nll", c_void_p),
+        ("ga", c_void_p), ("gb", c_void_p), ("gd", c_void_p), ("gn", c_void_p),
+        ("grad_logits", c_void_p), ("workspace", c_void_p),
     ]
 
 
@@ -93,6 +93,8 @@ def lib() -> ctypes.CDLL:
     L.ctdd_prep_tc_tables.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_void_p]
     L.ctdd_sample_categorical_shared.argtypes = [c_void_p, c_int, c_int64, c_int64, c_uint64, c_uint64, c_void_p, c_void_p]
     L.ctdd_noise_xt.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p]
+    L.ctdd_loss_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    L.ctdd_loss_workspace_bytes.restype = c_int64
     L.ctdd_loss_forward.argtypes = [ctypes.POINTER(LossParams), c_void_p]
     L.ctdd_loss_backward.argtypes = [ctypes.POINTER(LossParams), c_void_p]
     for name in ("ctdd_build_qt0", "ctdd_build_rate", "ctdd_reverse_step", "ctdd_prep_tc_tables",

@@ -1,4 +1,356 @@
-// loss kernels — placeholder
+// Fused loss terms (forward + backward w.r.t. the logits) for the three loss families of lib/losses/losses.py:
+//   CTDD_LOSS_CTELBO  tauLDR CT-ELBO   losses.py:108-286  (CTElbo, NLL, CTElboLambda, CondCTElbo)
+//   CTDD_LOSS_SDDM    SDDM ELBO        losses.py:1345-1500 (ScoreElbo), :389-544 (SDDMElbo)
+//   CTDD_LOSS_CRM     ratio matching   losses.py:794-890 (CatRM), :1146-1242 (CatRMNLL)
+// One CTA owns 8 rows (b, d..d+7) of ONE sample, so the per-sample q_{t|0} is shared by the CTA; threads span the
+// state axis. The (rows x S)(S x S) contractions against the per-sample Q run on CUDA cores in this round
+// (2*B*D*S^2 FLOP forward, 4*B*D*S^2 backward: the backward recomputes u instead of saving a (B,D,S) tensor).
+// Per-sample reductions are returned as [B] vectors; the final means / weights are combined by the Python classes.
 #include "ctdd_common.cuh"
-extern "C" int ctdd_loss_forward(const ctdd_loss_params*, void*) { ctdd::set_error("ctdd_loss_forward: not built"); return 3; }
-extern "C" int ctdd_loss_backward(const ctdd_loss_params*, void*) { ctdd::set_error("ctdd_loss_backward: not built"); return 3; }
+
+namespace ctdd {
+namespace loss {
+
+constexpr int ROWS = 8;
+
+struct Args {
+  int kind, logit_type, crm_type, B, D, S;
+  const float* logits;
+  const float* Q;
+  const float* QT;
+  const float* Rb;
+  const float* beta;
+  const int* x0;
+  const int* xt;       // state the ratio/reg terms are evaluated at (CTELBO: reg_x; SDDM/CRM: state of the logits)
+  const int* x_tilde;  // CTELBO: signal-term state; SDDM: == xt
+  const float* G;      // CTELBO: [B][x][k] = beta * sum_s Rb[s,x][s!=x] Q[k,s] / (Q[k,x]+eps)
+  const float* baseZ;  // [B] sum_d z_b[x_tilde_d]
+  float eps;
+  float* out_a; float* out_b; float* out_c; float* out_d; float* out_nll;
+  const float* ga; const float* gb; const float* gd; const float* gn;
+  float* grad;
+};
+
+__device__ __forceinline__ float log1mexp_ref(float v) {  // lib/utils/utils.py:86-91
+  const float x = -fabsf(v);
+  return x > -0.693f ? logf(-expm1f(x)) : log1pf(-expf(x));
+}
+
+// G[b][x][k] = beta_b * (sum_s RzT[x][s] * QT_b[s][k]) / (QT_b[x][k] + eps), RzT[x][s] = Rb[s][x] (s != x)
+__global__ void __launch_bounds__(256) ctelbo_table_kernel(const float* __restrict__ QT, const float* __restrict__ Rb,
+                                                          const float* __restrict__ beta, int S, float eps,
+                                                          float* __restrict__ G) {
+  __shared__ float sA[16][17], sB[16][17];
+  const int b = blockIdx.z, tx = threadIdx.x, ty = threadIdx.y;
+  const int x = blockIdx.y * 16 + ty, k = blockIdx.x * 16 + tx;
+  const float* qt = QT + (size_t)b * S * S;
+  float acc = 0.f;
+  for (int s0 = 0; s0 < S; s0 += 16) {
+    const int sa = s0 + tx, sb = s0 + ty;
+    sA[ty][tx] = (x < S && sa < S && sa != x) ? Rb[(size_t)sa * S + x] : 0.f;
+    sB[ty][tx] = (sb < S && k < S) ? qt[(size_t)sb * S + k] : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < 16; ++m) acc = fmaf(sA[ty][m], sB[m][tx], acc);
+    __syncthreads();
+  }
+  if (x < S && k < S) G[((size_t)b * S + x) * S + k] = beta[b] * acc / (qt[(size_t)x * S + k] + eps);
+}
+
+__global__ void basez_kernel(const float* __restrict__ Rb, const float* __restrict__ beta, const int* __restrict__ x_tilde,
+                             int D, int S, float* __restrict__ baseZ) {
+  const int b = blockIdx.x;
+  float acc = 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const int x = x_tilde[(size_t)b * D + d];
+    acc += -beta[b] * Rb[(size_t)x * S + x];
+  }
+  acc = warp_sum(acc);
+  __shared__ float red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) baseZ[b] = v;
+  }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(256) loss_kernel(const Args a) {
+  extern __shared__ float smem[];
+  const int S = a.S;
+  float* sP = smem;                 // [8][S] softmax p
+  float* sA = smem + ROWS * S;      // [8][S] GEMM operand (p * a, or p), later dp
+  float* sU = smem + 2 * ROWS * S;  // [8][S] u, later the s-space cotangent
+  __shared__ int s_x0[ROWS], s_xr[ROWS], s_xt[ROWS];
+  __shared__ float s_llx[ROWS], s_lse[ROWS], s_row_a[ROWS], s_row_b[ROWS], s_row_c[ROWS], s_row_d[ROWS], s_row_n[ROWS];
+  const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nth >> 5;
+  const int b = blockIdx.y;
+  const int d0 = blockIdx.x * ROWS;
+  const int nr = (a.D - d0) < ROWS ? (a.D - d0) : ROWS;
+  const float* Q = a.Q + (size_t)b * S * S;
+  const float* QT = a.QT + (size_t)b * S * S;
+  const float beta = a.beta[b];
+  const bool ctelbo = a.kind == CTDD_LOSS_CTELBO;
+  const bool direct = !ctelbo && a.logit_type == CTDD_BRANCH_SDDM_DIRECT;
+  if (tid < ROWS) {
+    const size_t r = (size_t)b * a.D + d0 + (tid < nr ? tid : 0);
+    s_x0[tid] = a.x0[r];
+    s_xr[tid] = a.xt[r];
+    s_xt[tid] = a.x_tilde ? a.x_tilde[r] : a.xt[r];
+    s_row_a[tid] = s_row_b[tid] = s_row_c[tid] = s_row_d[tid] = s_row_n[tid] = 0.f;
+  }
+  __syncthreads();
+  // 1. softmax, GEMM operand
+  for (int r = warp; r < ROWS; r += nwarp) {
+    const float* lp = a.logits + ((size_t)b * a.D + d0 + (r < nr ? r : 0)) * S;
+    float m = -INFINITY;
+    for (int k = lane; k < S; k += 32) m = fmaxf(m, lp[k]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int k = lane; k < S; k += 32) sum += expf(lp[k] - m);
+    sum = warp_sum(sum);
+    const float lse = m + logf(sum);
+    if (lane == 0) { s_lse[r] = lse; s_row_n[r] = lse - lp[s_x0[r]]; }
+    const int xt = s_xt[r];
+    for (int k = lane; k < S; k += 32) {
+      const float p = expf(lp[k] - m) / sum;
+      sP[r * S + k] = p;
+      sA[r * S + k] = ctelbo ? p / (QT[(size_t)xt * S + k] + a.eps) : p;
+    }
+  }
+  __syncthreads();
+  // 2. u[r][s] = sum_k A[r][k] Q[k][s]
+  if (!direct) {
+    for (int s = tid; s < S; s += nth) {
+      float acc[ROWS];
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
+      for (int k = 0; k < S; ++k) {
+        const float q = __ldg(Q + (size_t)k * S + s);
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) acc[r] = fmaf(sA[r * S + k], q, acc[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) sU[r * S + s] = acc[r];
+    }
+  } else {
+    for (int s = tid; s < S; s += nth)
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r)
+        sU[r * S + s] = a.logits[((size_t)b * a.D + d0 + (r < nr ? r : 0)) * S + s] - s_lse[r];  // ll directly
+  }
+  __syncthreads();
+  // SDDM / CRM: ll[s] and ll at the evaluation state
+  if (!ctelbo) {
+    for (int s = tid; s < S; s += nth)
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        float ll = sU[r * S + s];
+        if (!direct) ll = logf(ll + 1e-35f);
+        if (s == s_xr[r]) s_llx[r] = ll;
+      }
+    __syncthreads();
+  }
+  // 3. per-(row, s) terms; row reductions by warp r
+  const float baseZ = (a.kind != CTDD_LOSS_CRM) ? a.baseZ[b] : 0.f;
+  for (int r = warp; r < ROWS; r += nwarp) {
+    const int x0 = s_x0[r], xr = s_xr[r], xt = s_xt[r];
+    const float ga = BWD ? a.ga[b] : 0.f, gb = BWD ? a.gb[b] : 0.f, gd = BWD ? a.gd[b] : 0.f;
+    float ra = 0.f, rb = 0.f, rc = 0.f, wsum = 0.f;
+    if (ctelbo) {
+      const float den = Q[(size_t)x0 * S + xt] + a.eps;
+      const float zt = -beta * a.Rb[(size_t)xt * S + xt];
+      const float* Gr = a.G + ((size_t)b * S + xr) * S;
+      for (int s = lane; s < S; s += 32) {
+        const float u = sU[r * S + s];
+        const float w = (s == xt) ? 0.f : beta * a.Rb[(size_t)s * S + xt] * Q[(size_t)x0 * S + s] / den;
+        const float Z = baseZ - zt + (-beta * a.Rb[(size_t)s * S + s]);
+        rb += w * logf(u + a.eps);
+        rc += w / Z;
+        ra += sP[r * S + s] * Gr[s];                 // reg: sum_k p_k G[x_reg][k]   (index s doubles as k)
+        if (BWD) sU[r * S + s] = gb * w / (u + a.eps);  // cotangent of u
+      }
+    } else {
+      const float llx = s_llx[r];
+      const float den = Q[(size_t)x0 * S + xr] + a.eps;
+      const float zt = -beta * a.Rb[(size_t)xr * S + xr];
+      for (int s = lane; s < S; s += 32) {
+        const float uraw = sU[r * S + s];
+        const float ll = direct ? uraw : logf(uraw + 1e-35f);
+        float dll = 0.f;
+        if (a.kind == CTDD_LOSS_SDDM) {
+          const float rs = (s == xr) ? 0.f : beta * a.Rb[(size_t)s * S + xr];
+          const float e = expf(ll - llx);
+          const float w = (s == xr) ? 0.f : rs * Q[(size_t)x0 * S + s] / den;
+          const float Z = baseZ - zt + (-beta * a.Rb[(size_t)s * S + s]);
+          ra += e * rs;
+          rb += w * (ll - llx);
+          rc += w / Z;
+          wsum += w;
+          dll = ga * e * rs + gb * w;
+        } else {  // CRM
+          if (a.crm_type == 1) {          // mle
+            ra += -log1mexp_ref(ll);
+            const float el = expf(ll);
+            dll = (s == xr) ? 0.f : ga * el / (1.f - el);
+          } else if (a.crm_type == 2) {   // elbo
+            if (s != xr) {
+              const float e = expf(ll - llx);
+              const float qsx = Q[(size_t)s * S + xr], qxs = Q[(size_t)xr * S + s];
+              ra += e * qsx - (llx - ll) * qxs;
+              wsum += e * qsx + qxs;
+              dll = ga * (e * qsx + qxs);
+            }
+          }
+        }
+        if (BWD) sU[r * S + s] = direct ? dll : dll / (uraw + 1e-35f);   // cotangent of u (or of ll for direct)
+      }
+    }
+    ra = warp_sum(ra); rb = warp_sum(rb); rc = warp_sum(rc); wsum = warp_sum(wsum);
+    float rd = 0.f;
+    if (!ctelbo) {
+      const float llx = s_llx[r];
+      float dllx;
+      if (a.kind == CTDD_LOSS_SDDM) {
+        dllx = -ga * ra - gb * wsum;
+      } else {
+        if (a.crm_type == 0) { ra = -llx; dllx = -ga; }
+        else if (a.crm_type == 1) { ra = -((float)(S - 1) * llx) + ra + log1mexp_ref(llx); dllx = -ga * (float)(S - 1); }
+        else { dllx = -ga * wsum; }
+      }
+      rd = -llx;
+      dllx -= gd;
+      if (BWD) {
+        __syncwarp();
+        // the cotangent at the evaluation state also receives d/d ll_x; for reverse_prob u_x + 1e-35 = exp(ll_x)
+        if (lane == 0) sU[r * S + xr] += dllx / (direct ? 1.f : expf(llx));
+      }
+    }
+    if (lane == 0) { s_row_a[r] = ra; s_row_b[r] = rb; s_row_c[r] = rc; s_row_d[r] = rd; }
+  }
+  __syncthreads();
+  if (!BWD) {
+    if (tid == 0) {
+      float A = 0.f, Bv = 0.f, C = 0.f, Dd = 0.f, Nn = 0.f;
+      for (int r = 0; r < nr; ++r) { A += s_row_a[r]; Bv += s_row_b[r]; C += s_row_c[r]; Dd += s_row_d[r]; Nn += s_row_n[r]; }
+      atomicAdd(a.out_a + b, A);
+      atomicAdd(a.out_b + b, Bv);
+      atomicAdd(a.out_c + b, C);
+      atomicAdd(a.out_d + b, Dd);
+      atomicAdd(a.out_nll + b, Nn);
+    }
+    return;
+  }
+  // 4. dp[r][k] = a[k] * sum_s V[r][s] Q[k][s]  (+ reg part)  — threads over k, QT[s][k] coalesced
+  const float gn = a.gn[b];
+  for (int k = tid; k < S; k += nth) {
+    float acc[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
+    if (!direct) {
+      for (int s = 0; s < S; ++s) {
+        const float q = __ldg(QT + (size_t)s * S + k);
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) acc[r] = fmaf(sU[r * S + s], q, acc[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      float dp = acc[r];
+      if (ctelbo) {
+        dp = dp / (QT[(size_t)s_xt[r] * S + k] + a.eps) + a.ga[b] * a.G[((size_t)b * S + s_xr[r]) * S + k];
+      }
+      sA[r * S + k] = dp;
+    }
+  }
+  __syncthreads();
+  // 5. softmax Jacobian + cross-entropy gradient
+  for (int r = warp; r < ROWS; r += nwarp) {
+    if (r >= nr) continue;
+    float dot = 0.f;
+    if (direct) {
+      for (int k = lane; k < S; k += 32) dot += sU[r * S + k];          // sum_s dll_s
+    } else {
+      for (int k = lane; k < S; k += 32) dot += sP[r * S + k] * sA[r * S + k];
+    }
+    dot = warp_sum(dot);
+    float* gp = a.grad + ((size_t)b * a.D + d0 + r) * S;
+    const int x0 = s_x0[r];
+    for (int k = lane; k < S; k += 32) {
+      const float p = sP[r * S + k];
+      float g = direct ? (sU[r * S + k] - p * dot) : p * (sA[r * S + k] - dot);
+      g += gn * (p - (k == x0 ? 1.f : 0.f));
+      gp[k] = g;
+    }
+  }
+}
+
+}  // namespace loss
+}  // namespace ctdd
+
+namespace {
+int run_loss(const ctdd_loss_params* p, void* stream, bool bwd) {
+  using namespace ctdd;
+  using namespace ctdd::loss;
+  if (!p) { set_error("ctdd_loss: null params"); return 2; }
+  if (p->B <= 0 || p->D <= 0 || p->S < 2) { set_error("ctdd_loss: bad sizes"); return 2; }
+  if (p->kind < CTDD_LOSS_CTELBO || p->kind > CTDD_LOSS_SDDM) { set_error("ctdd_loss: unknown kind %d", p->kind); return 2; }
+  if (!p->logits || !p->Q || !p->QT || !p->Rb || !p->beta || !p->x0 || !p->xt) { set_error("ctdd_loss: null input"); return 2; }
+  if (p->kind != CTDD_LOSS_CTELBO && !(p->logit_type == CTDD_BRANCH_SDDM_DIRECT || p->logit_type == CTDD_BRANCH_SDDM_REVERSE_PROB)) {
+    set_error("ctdd_loss: logit_type %d not supported by the fused kernels (direct / reverse_prob)", p->logit_type);
+    return 3;
+  }
+  if (p->kind == CTDD_LOSS_CTELBO && !p->x_tilde) { set_error("ctdd_loss: x_tilde required"); return 2; }
+  if (bwd && (!p->ga || !p->gb || !p->gd || !p->gn || !p->grad_logits)) { set_error("ctdd_loss_backward: null gradient pointer"); return 2; }
+  if (!bwd && (!p->out_a || !p->out_b || !p->out_c || !p->out_d || !p->out_nll)) { set_error("ctdd_loss_forward: null output pointer"); return 2; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int S = p->S;
+  const size_t smem = (size_t)3 * ROWS * S * sizeof(float);
+  if (smem > 200 * 1024) { set_error("ctdd_loss: S=%d too large", S); return 2; }
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(loss_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(loss_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  Args a;
+  a.kind = p->kind; a.logit_type = p->logit_type; a.crm_type = p->crm_type; a.B = p->B; a.D = p->D; a.S = S;
+  a.logits = p->logits; a.Q = p->Q; a.QT = p->QT; a.Rb = p->Rb; a.beta = p->beta;
+  a.x0 = p->x0; a.xt = p->xt; a.x_tilde = p->x_tilde; a.eps = p->eps;
+  a.G = reinterpret_cast<const float*>(p->workspace);
+  a.baseZ = p->workspace ? reinterpret_cast<const float*>(p->workspace) + (p->kind == CTDD_LOSS_CTELBO ? (size_t)p->B * S * S : 0) : nullptr;
+  a.out_a = p->out_a; a.out_b = p->out_b; a.out_c = p->out_c; a.out_d = p->out_d; a.out_nll = p->out_nll;
+  a.ga = p->ga; a.gb = p->gb; a.gd = p->gd; a.gn = p->gn; a.grad = p->grad_logits;
+  if (p->kind != CTDD_LOSS_CRM) {
+    if (!p->workspace) { set_error("ctdd_loss: workspace required (ctdd_loss_workspace_bytes)"); return 2; }
+    if (!bwd) {  // tables are built by the forward call and reused by the backward call (same workspace)
+      if (p->kind == CTDD_LOSS_CTELBO) {
+        const int tiles = (S + 15) / 16;
+        dim3 grid(tiles, tiles, p->B), block(16, 16);
+        ctelbo_table_kernel<<<grid, block, 0, st>>>(p->QT, p->Rb, p->beta, S, p->eps, const_cast<float*>(a.G));
+        CTDD_CHECK_LAUNCH("ctelbo_table_kernel");
+      }
+      basez_kernel<<<p->B, 256, 0, st>>>(p->Rb, p->beta, p->x_tilde ? p->x_tilde : p->xt, p->D, S, const_cast<float*>(a.baseZ));
+      CTDD_CHECK_LAUNCH("basez_kernel");
+    }
+  }
+  int threads = ((S + 31) / 32) * 32;
+  if (threads > 256) threads = 256;
+  if (threads < 64) threads = 64;
+  dim3 grid((p->D + ROWS - 1) / ROWS, p->B);
+  if (bwd) loss_kernel<true><<<grid, threads, smem, st>>>(a);
+  else loss_kernel<false><<<grid, threads, smem, st>>>(a);
+  CTDD_CHECK_LAUNCH("loss_kernel");
+  return 0;
+}
+}  // namespace
+
+extern "C" int64_t ctdd_loss_workspace_bytes(int kind, int B, int S) {
+  if (kind == CTDD_LOSS_CTELBO) return ((int64_t)B * S * S + B) * 4;
+  if (kind == CTDD_LOSS_SDDM) return (int64_t)B * 4;
+  return 0;
+}
+extern "C" int ctdd_loss_forward(const ctdd_loss_params* p, void* stream) { return run_loss(p, stream, false); }
+extern "C" int ctdd_loss_backward(const ctdd_loss_params* p, void* stream) { return run_loss(p, stream, true); }

@@ -90,3 +90,49 @@ def noise_xt(Q, Rb, beta, x0, seed, offset=0, batch_offset=0, want_tilde=True):
                                       nat.ptr(x0.contiguous()), B, D, S, int(batch_offset), int(seed), int(offset),
                                       nat.ptr(xt), nat.ptr(xtilde), nat.stream()), "ctdd_noise_xt")
     return xt, xtilde
+
+
+class _LossTerms(torch.autograd.Function):
+    """Per-sample loss terms (out_a, out_b, out_c, out_d, out_nll), each (B,), differentiable w.r.t. `logits`
+    through the fused backward kernel (include/ctdd.h: ctdd_loss_forward / ctdd_loss_backward)."""
+
+    @staticmethod
+    def forward(ctx, logits, kind, logit_branch, crm_type, Q, QT, Rb, beta, x0, xt, x_tilde, eps):
+        B, D, S = logits.shape
+        dev = logits.device
+        logits = logits.contiguous().float()
+        outs = torch.zeros((5, B), dtype=torch.float32, device=dev)
+        nbytes = int(nat.lib().ctdd_loss_workspace_bytes(kind, B, S))
+        ws = torch.empty((max(nbytes, 4),), dtype=torch.uint8, device=dev)
+        p = nat.LossParams(kind=kind, logit_type=logit_branch, crm_type=crm_type, B=B, D=D, S=S,
+                           logits=nat.ptr(logits), Q=nat.ptr(Q), QT=nat.ptr(QT), Rb=nat.ptr(Rb), beta=nat.ptr(beta),
+                           x0=nat.ptr(x0), xt=nat.ptr(xt), x_tilde=nat.ptr(x_tilde), eps=float(eps),
+                           out_a=outs[0].data_ptr(), out_b=outs[1].data_ptr(), out_c=outs[2].data_ptr(),
+                           out_d=outs[3].data_ptr(), out_nll=outs[4].data_ptr(), workspace=nat.ptr(ws))
+        nat.check(nat.lib().ctdd_loss_forward(p, nat.stream()), "ctdd_loss_forward")
+        ctx.save_for_backward(logits, Q, QT, Rb, beta, x0, xt, x_tilde if x_tilde is not None else xt, ws)
+        ctx.meta = (kind, logit_branch, crm_type, float(eps), x_tilde is not None)
+        return outs[0], outs[1], outs[2], outs[3], outs[4]
+
+    @staticmethod
+    def backward(ctx, ga, gb, gc, gd, gn):
+        logits, Q, QT, Rb, beta, x0, xt, x_tilde, ws = ctx.saved_tensors
+        kind, logit_branch, crm_type, eps, has_tilde = ctx.meta
+        B, D, S = logits.shape
+        z = lambda g: (g if g is not None else torch.zeros((B,), device=logits.device)).contiguous().float()
+        ga, gb, gd, gn = z(ga), z(gb), z(gd), z(gn)
+        grad = torch.empty_like(logits)
+        p = nat.LossParams(kind=kind, logit_type=logit_branch, crm_type=crm_type, B=B, D=D, S=S,
+                           logits=nat.ptr(logits), Q=nat.ptr(Q), QT=nat.ptr(QT), Rb=nat.ptr(Rb), beta=nat.ptr(beta),
+                           x0=nat.ptr(x0), xt=nat.ptr(xt), x_tilde=(nat.ptr(x_tilde) if has_tilde else None), eps=eps,
+                           ga=nat.ptr(ga), gb=nat.ptr(gb), gd=nat.ptr(gd), gn=nat.ptr(gn), grad_logits=nat.ptr(grad),
+                           workspace=nat.ptr(ws))
+        nat.check(nat.lib().ctdd_loss_backward(p, nat.stream()), "ctdd_loss_backward")
+        return (grad,) + (None,) * 11
+
+
+def loss_terms(logits, kind, Q, QT, Rb, beta, x0, xt, x_tilde=None, eps=1e-9, logit_branch=nat.BRANCH_SDDM_REVERSE_PROB,
+               crm_type=0):
+    """(out_a, out_b, out_c, out_d, out_nll) per sample — see ctdd_loss_params in include/ctdd.h."""
+    return _LossTerms.apply(logits, kind, logit_branch, crm_type, Q.contiguous(), QT.contiguous(), Rb, beta.contiguous().float(),
+                            x0.contiguous(), xt.contiguous(), x_tilde.contiguous() if x_tilde is not None else None, eps)

@@ -170,17 +170,19 @@ typedef struct ctdd_loss_params {
   const float* Rb;       /* [S,S] */
   const float* beta;     /* [B] */
   const int32_t* x0;     /* [B,D] minibatch */
-  const int32_t* xt;     /* [B,D] state the logits were evaluated at */
-  const int32_t* x_tilde;/* [B,D] */
+  const int32_t* xt;     /* [B,D] state the reg / ratio terms are evaluated at (CTELBO: reg_x; SDDM, CRM: state of the logits) */
+  const int32_t* x_tilde;/* [B,D] CTELBO: state of the signal term; SDDM: NULL (== xt); CRM: unused */
   float eps;
-  /* forward outputs */
-  float* out_a;          /* [B]  CTELBO: reg term      CRM: sum_d loss   SDDM: reg term */
-  float* out_b;          /* [B]  CTELBO/SDDM: outer_sum                                  */
-  float* out_c;          /* [B]  CTELBO/SDDM: sig_norm CRM: sum_d (-ll_x)                 */
-  float* out_nll;        /* [B]  sum_d CrossEntropy(logits[b,d,:], x0[b,d])               */
-  /* backward: grad_logits[b,d,:] = ga[b]*d out_a + gb[b]*d out_b + gn[b]*d out_nll (+ gc for CRM out_c) */
-  const float* ga; const float* gb; const float* gc; const float* gn;
+  /* forward outputs, per sample [B]; the caller zeroes them (the kernel accumulates with atomics) */
+  float* out_a;          /* CTELBO / SDDM: reg term                       CRM: sum_d loss_type term */
+  float* out_b;          /* CTELBO / SDDM: outer_sum (signal)                                      */
+  float* out_c;          /* CTELBO / SDDM: sig_norm (does not depend on the logits)                */
+  float* out_d;          /* SDDM / CRM: sum_d (-ll_x)   (ScoreElbo's ratio-matching term)          */
+  float* out_nll;        /* sum_d CrossEntropy(logits[b,d,:], x0[b,d])                            */
+  /* backward: grad_logits[b] = ga[b]*d out_a + gb[b]*d out_b + gd[b]*d out_d + gn[b]*d out_nll */
+  const float* ga; const float* gb; const float* gd; const float* gn;
   float* grad_logits;    /* [B,D,S] */
+  void* workspace;       /* >= ctdd_loss_workspace_bytes(kind, B, S); written by forward, read by backward */
 } ctdd_loss_params;
 
 enum {
@@ -189,6 +191,7 @@ enum {
   CTDD_LOSS_SDDM = 2     /* losses.py:1345-1500 (ScoreElbo), :389-544 (SDDMElbo) */
 };
 
+int64_t ctdd_loss_workspace_bytes(int kind, int B, int S);
 int ctdd_loss_forward(const ctdd_loss_params* p, void* stream);
 int ctdd_loss_backward(const ctdd_loss_params* p, void* stream);
 

@@ -82,3 +82,43 @@ def sampler_cfg(make_cfg, case):
     model.setdefault("Q_sigma", 20.0)
     return make_cfg(data=dict(S=S, shape=[D], name=data_name), model=model, training=dict(max_t=max_t, n_iters=1000),
                     sampler=s, loss=loss, device="cpu")
+
+
+# (name, loss class, forward, B, D, loss overrides, t_hi, seed, n_iter)
+# t_hi is the upper end of the reference's time draw for that class (losses.py: max_t / 1.0).
+LOSSES = [
+    ("ctelbo_gauss32", "CTElbo", "gauss32", 6, 10, dict(), 1.0, 201, 0),
+    ("ctelbo_gauss32_2pass", "CTElbo", "gauss32", 6, 10, dict(one_forward_pass=False), 1.0, 202, 0),
+    ("ctelbo_gauss256", "CTElbo", "gauss256", 3, 6, dict(nll_weight=0.01), 1.0, 203, 0),
+    ("nll_univar3", "NLL", "univar3_logsqr", 8, 9, dict(), 1.0, 204, 0),
+    ("ctelbolambda_uni2", "CTElboLambda", "univar2_sqrtcos", 8, 16, dict(), 0.99999, 205, 300),
+    ("condctelbo_gauss32", "CondCTElbo", "gauss32", 6, 10, dict(condition_dim=4), 1.0, 206, 0),
+    ("catrm_gauss32_rm", "CatRM", "gauss32", 6, 10, dict(logit_type="reverse_prob", loss_type="rm"), 1.0, 207, 0),
+    ("catrm_gauss32_mle_direct", "CatRM", "gauss32", 6, 10, dict(logit_type="direct", loss_type="mle"), 1.0, 208, 0),
+    ("catrm_univar3_elbo", "CatRM", "univar3_logsqr", 8, 9, dict(logit_type="reverse_prob", loss_type="elbo", ce_coeff=0.25), 1.0, 209, 0),
+    ("catrm_gauss32_logscale", "CatRM", "gauss32", 4, 6, dict(logit_type="reverse_logscale", loss_type="rm"), 1.0, 210, 0),
+    ("catrmnll_gauss256", "CatRMNLL", "gauss256", 3, 6, dict(logit_type="reverse_prob", loss_type="rm", nll_weight=0.01), 1.0, 211, 0),
+    ("scoreelbo_gauss32", "ScoreElbo", "gauss32", 6, 10, dict(logit_type="reverse_prob"), 1.0, 212, 0),
+    ("sddmelbo_gauss256", "SDDMElbo", "gauss256", 3, 6, dict(logit_type="reverse_prob", nll_weight=0.01), 1.0, 213, 0),
+    ("sddmelbo_uni2_direct", "SDDMElbo", "uni2", 8, 16, dict(logit_type="direct"), 1.0, 214, 0),
+    ("scoreelbo_gauss32_logscale", "ScoreElbo", "gauss32", 4, 6, dict(logit_type="reverse_logscale"), 1.0, 215, 0),
+    ("nlloriginal_gauss32", "NLLOriginal", "gauss32", 6, 10, dict(), 1.0, 216, 0),
+]
+
+# losses whose calc_loss takes (minibatch, state) rather than (state, minibatch)  
+LOSS_MINIBATCH_FIRST = ("SDDMElbo", "CondCTElbo", "CatRMNLL", "ScoreElbo")
+
+
+def loss_cfg(make_cfg, case, device="cpu"):
+    name, cls, fwd, B, D, over, t_hi, seed, n_iter = case
+    f = FORWARD[fwd]
+    S = f["S"]
+    loss = dict(name=cls, eps_ratio=1e-9, nll_weight=0.001, min_time=0.01, one_forward_pass=True,
+                logit_type="reverse_prob", loss_type="rm", ce_coeff=0.0, condition_dim=0)
+    loss.update(over)
+    model = dict(f["model"])
+    model["concat_dim"] = D
+    model.setdefault("Q_sigma", 20.0)
+    return make_cfg(data=dict(S=S, shape=[D], name="DiscreteCIFAR10"), model=model,
+                    training=dict(max_t=t_hi if cls in ("CTElbo", "NLL", "CTElboLambda", "CatRMNLL") else 1.0, n_iters=1000),
+                    loss=loss, device=device)

@@ -106,12 +106,13 @@ class Injector:
     """Patches the reference's random draws; `schedule` lists the stream of each Categorical.sample call."""
 
     def __init__(self, ref, seed: int, init_x: torch.Tensor = None, ts: torch.Tensor = None,
-                 cat_schedule=None, cat_offset: int = 0):
+                 cat_schedule=None, cat_offset: int = 0, cat_log: list = None):
         self.ref, self.seed, self.init_x, self.ts = ref, seed, init_x, ts
         self.call = 0                 # jump / Euler call counter (the kernels' `offset`)
         self.cat_schedule = list(cat_schedule) if cat_schedule else None
         self.cat_offset = cat_offset
         self.cat_i = 0
+        self.cat_log = cat_log        # optional list collecting every Categorical draw (loss fixtures)
 
     def __enter__(self):
         P = torch.distributions.poisson.Poisson
@@ -139,7 +140,10 @@ class Injector:
                 stream, off = rng.STREAM_ROW, inj.call
                 inj.call += 1
             v = rng.row_units(p2.shape[0], 0, off, stream, inj.seed)
-            return torch.from_numpy(rng.inv_cdf(p2, v).reshape(shp))
+            draw = torch.from_numpy(rng.inv_cdf(p2, v).reshape(shp))
+            if inj.cat_log is not None:
+                inj.cat_log.append(draw.clone())
+            return draw
 
         def init_samples(N, D, device, S, initial_dist, initial_dist_std=None):
             if inj.init_x is not None:
