@@ -25,8 +25,8 @@ void count_launch(int n = 1);
 // ------------------------------------------------------------------------------------------------
 // RNG streams (Philox counter word c3)
 enum : uint32_t {
-  STREAM_JUMP_HI = 0,   // top 16 bits of the per-(row, s) jump uniform
-  STREAM_JUMP_LO = 1,   // low 16 bits, only evaluated on the slow path
+  STREAM_JUMP = 0,      // per-row tau-leap draws: call 0 word 0 = total count, further words = picks
+  STREAM_RESERVED = 1,
   STREAM_ROW = 2,       // one 32-bit uniform per row (Euler categorical draw)
   STREAM_INIT = 3,      // initial samples
   STREAM_NOISE_XT = 4,  // forward noising x_t
@@ -65,23 +65,26 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
   return o;
 }
 
-// Jump-uniform layout: one Philox call serves 8 consecutive GLOBAL rows at one state s:
-//   counter = (s, grow >> 3, offset_lo, stream | offset_hi << 8), halfword (grow & 7) of the 128-bit output.
-__host__ __device__ __forceinline__ Philox4 philox_jump(uint32_t s, uint64_t grow_group, uint64_t offset,
-                                                       uint32_t stream, uint64_t seed) {
-  return philox4x32_10(s, (uint32_t)grow_group, (uint32_t)offset,
-                       stream | ((uint32_t)(offset >> 32) << 8) | ((uint32_t)(grow_group >> 32) << 24),
+// Tau-leap draws of one GLOBAL row: Philox call c of the row's stream, counter = (c, grow, offset_lo, stream | ...).
+//   call 0 word 0     -> uniform of the row's TOTAL jump count K ~ Poisson(sum_s lam_s)
+//   call 0 words 1..3 -> uniforms of picks 0..2;  call 1 + (j-3)/4 word (j-3)%4 -> pick j >= 3
+// Each pick chooses its target state ~ Categorical(lam_s / sum) by inverse CDF: S independent Poisson counts through
+// the superposition identity (oracle/rng.py poisson_rows is the op-for-op restatement).
+constexpr int JUMP_PICK_CAP = 4096;
+__host__ __device__ __forceinline__ Philox4 philox_rowjump(uint64_t grow, uint32_t call, uint64_t offset, uint64_t seed) {
+  return philox4x32_10(call, (uint32_t)grow, (uint32_t)offset,
+                       STREAM_JUMP | (((uint32_t)(offset >> 32) & 0xFFFFu) << 8) | (((uint32_t)(grow >> 32) & 0xFFu) << 24),
                        (uint32_t)seed, (uint32_t)(seed >> 32));
 }
-__host__ __device__ __forceinline__ uint32_t philox_half(const Philox4& p, int i) {
-  return (p.w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+__host__ __device__ __forceinline__ uint32_t philox_word(const Philox4& p, int i) {   // register-only select
+  return i == 0 ? p.w[0] : (i == 1 ? p.w[1] : (i == 2 ? p.w[2] : p.w[3]));
 }
 
 // Per-row 32-bit draw: one Philox call serves 4 consecutive global rows: counter = (sub, grow >> 2, ...).
 __host__ __device__ __forceinline__ uint32_t philox_row_word(uint64_t grow, uint32_t sub, uint64_t offset,
                                                             uint32_t stream, uint64_t seed) {
   Philox4 p = philox4x32_10(sub, (uint32_t)(grow >> 2), (uint32_t)offset,
-                            stream | ((uint32_t)(offset >> 32) << 8) | ((uint32_t)(grow >> 34) << 24),
+                            stream | (((uint32_t)(offset >> 32) & 0xFFFFu) << 8) | (((uint32_t)(grow >> 34) & 0xFFu) << 24),
                             (uint32_t)seed, (uint32_t)(seed >> 32));
   return p.w[grow & 3];
 }
@@ -138,12 +141,6 @@ __host__ __device__ __forceinline__ int poisson_from_unit(float lam, float v) {
   return (int)k;
 }
 
-// Jump contribution k*(s-x) with k saturated so row sums cannot overflow int32.
-__host__ __device__ __forceinline__ int jump_contrib(int k, int s, int x) {
-  int kk = k > 4096 ? 4096 : k;
-  return kk * (s - x);
-}
-
 // Inverse-CDF categorical draw from unnormalised weights: first index whose sequential fp32 cumulative
 // sum exceeds v * total; falls back to the last positive weight. v in (0,1].
 template <class F>
@@ -160,6 +157,58 @@ __device__ __forceinline__ int inv_cdf(int n, float v, F weight) {
     if (cum > target) return s;
   }
   return last;
+}
+
+// Tau-leap of one row in the oracle's op order (sequential fp32 sums): lam(s) must return the row's rate * h with
+// the entry s == x zeroed, rounded the same way on every call. Returns (sum_j (s_j - x), min(K, cap)).
+template <class F>
+__device__ __forceinline__ int2 tau_leap_row_seq(int S, int x, uint64_t grow, uint64_t offset, uint64_t seed, F lam) {
+  float tot = 0.f;
+  for (int s = 0; s < S; ++s) tot = __fadd_rn(tot, lam(s));
+  const Philox4 p0 = philox_rowjump(grow, 0, offset, seed);
+  int K = poisson_from_unit(tot, u32_to_unit(p0.w[0]));
+  if (K <= 0) return make_int2(0, 0);
+  if (K > JUMP_PICK_CAP) K = JUMP_PICK_CAP;
+  int jump = 0;
+  Philox4 pc = p0;
+  for (int j = 0; j < K; ++j) {
+    uint32_t w;
+    if (j < 3) {
+      w = philox_word(p0, 1 + j);
+    } else {
+      const int i = j - 3;
+      if ((i & 3) == 0) pc = philox_rowjump(grow, 1u + (uint32_t)(i >> 2), offset, seed);
+      w = philox_word(pc, i & 3);
+    }
+    const float target = __fmul_rn(fminf(u32_to_unit(w), 0.99999994f), tot);
+    float cum = 0.f;
+    int last = 0, pick = -1;
+    for (int s = 0; s < S; ++s) {
+      const float v = lam(s);
+      cum = __fadd_rn(cum, v);
+      if (v > 0.f) last = s;
+      if (cum > target) { pick = s; break; }
+    }
+    if (pick < 0) pick = last;
+    jump += pick - x;
+  }
+  return make_int2(jump, K);
+}
+
+// per-thread statistics counters (CTDD_STAT_* order) and the common end of every jump update
+struct RowStats { int changed_base, nonzero, changed_eval, jumped, multi; };
+
+__device__ __forceinline__ int finalize_jump(int xb, int xe, int jump, int cnt, int reject_multi, int S,
+                                             RowStats& st) {
+  st.jumped += (cnt > 0);
+  st.multi += (cnt > 1);
+  if (reject_multi && cnt > 1) jump = 0;
+  st.nonzero += (jump != 0);
+  int xn = xb + jump;
+  xn = xn < 0 ? 0 : (xn > S - 1 ? S - 1 : xn);
+  st.changed_base += (xn != xb);
+  st.changed_eval += (xn != xe);
+  return xn;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

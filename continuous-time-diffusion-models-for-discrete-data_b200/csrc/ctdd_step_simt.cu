@@ -3,8 +3,8 @@
 //                         registers, float4 logits loads — HBM-bound by construction.
 //   step_block_kernel     any S: one CTA owns 8 consecutive rows, threads span the state axis. This is the
 //                         general path and the on-GPU cross-check of the tcgen05 path at S=256.
-// Both implement every CTDD_MODE_* / CTDD_BRANCH_* and draw exactly the same Philox uniforms as the tensor
-// path, so the three are interchangeable bit-for-bit up to fp32 rounding of the rates.
+// Both implement every CTDD_MODE_* / CTDD_BRANCH_* and draw exactly the same per-row Philox uniforms as the tensor
+// path (superposition map, ctdd_common.cuh), so the three are interchangeable up to fp32 rounding of the rates.
 // Reference arithmetic: lib/sampling/sampling.py:31-78 (rates), :127-160 (tau-leap), :278-293 (Euler),
 // :423-453 / :459-503 (midpoint), :170-221 (corrector); lib/models/model_utils.py:30-60.
 #include "ctdd_common.cuh"
@@ -36,21 +36,6 @@ __device__ __forceinline__ const float* logits_row(const StepArgs& a, long long 
   return a.logits + n * a.batch_stride + d * a.ld;
 }
 
-struct RowStats { int changed_base, nonzero, changed_eval, jumped, multi; };
-
-__device__ __forceinline__ int finalize_jump(int xb, int xe, int jump, int cnt, int reject_multi, int S,
-                                             RowStats& st) {
-  st.jumped += (cnt > 0);
-  st.multi += (cnt > 1);
-  if (reject_multi && cnt > 1) jump = 0;
-  st.nonzero += (jump != 0);
-  int xn = xb + jump;
-  xn = xn < 0 ? 0 : (xn > S - 1 ? S - 1 : xn);
-  st.changed_base += (xn != xb);
-  st.changed_eval += (xn != xe);
-  return xn;
-}
-
 __device__ __forceinline__ void flush_stats(const RowStats& st, unsigned long long* stats) {
   if (!stats) return;
   int v[5] = {st.changed_base, st.nonzero, st.changed_eval, st.jumped, st.multi};
@@ -61,16 +46,6 @@ __device__ __forceinline__ void flush_stats(const RowStats& st, unsigned long lo
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0 && s) atomicAdd(stats + i, (unsigned long long)s);
   }
-}
-
-// Jump count for one (row, s) given lam and the row's halfword of the two Philox streams.
-__device__ __forceinline__ int jump_count(float lam, uint32_t hi16, uint32_t s, uint64_t group, int half,
-                                          unsigned long long offset, unsigned long long seed) {
-  // exact fast reject: v >= hi16 * 2^-16, and P(K>=1) <= lam
-  if (!(lam > 0.f) || (float)hi16 * 1.52587890625e-05f >= lam) return 0;
-  Philox4 lo = philox_jump(s, group, offset, STREAM_JUMP_LO, seed);
-  const uint32_t w = (hi16 << 16) | philox_half(lo, half);
-  return poisson_from_unit(lam, u32_to_unit(w));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -189,23 +164,19 @@ __global__ void __launch_bounds__(128) step_small_kernel(StepArgs a) {
         rate[r][s] = (s == x) ? 0.f : v;
       }
     }
-    const uint64_t group = (uint64_t)(a.row_offset + r0) >> 3;
     if (a.mode == CTDD_MODE_TAU_LEAP || a.mode == CTDD_MODE_TAU_LEAP_CORR || a.mode == CTDD_MODE_MIDPOINT_JUMP) {
-      int jump[8], cnt[8];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) { jump[r] = 0; cnt[r] = 0; }
+      for (int r = 0; r < 8; ++r) {
+        if (r >= nr) continue;
+        const float h = a.h;
+        const int2 jc = tau_leap_row_seq(S, xe[r], (uint64_t)(a.row_offset + r0 + r), a.offset, a.seed, [&](int s) {
+          float w = 0.f;
 #pragma unroll
-      for (int s = 0; s < S; ++s) {
-        const Philox4 hi = philox_jump(s, group, a.offset, STREAM_JUMP_HI, a.seed);
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const int k = jump_count(rate[r][s] * a.h, philox_half(hi, r), s, group, r, a.offset, a.seed);
-          if (k) { jump[r] += jump_contrib(k, s, xe[r]); cnt[r] += (k > 4096 ? 4096 : k); }
-        }
+          for (int q = 0; q < S; ++q) w = (q == s) ? rate[r][q] : w;
+          return __fmul_rn(w, h);
+        });
+        a.x_out[r0 + r] = finalize_jump(xb[r], xe[r], jc.x, jc.y, a.reject_multi, S, st);
       }
-#pragma unroll
-      for (int r = 0; r < 8; ++r)
-        if (r < nr) a.x_out[r0 + r] = finalize_jump(xb[r], xe[r], jump[r], cnt[r], a.reject_multi, S, st);
     } else if (a.mode == CTDD_MODE_MIDPOINT_DRIFT) {
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
@@ -261,7 +232,7 @@ __global__ void __launch_bounds__(256) step_block_kernel(StepArgs a) {
   const int S = a.S;
   float* sA = smem;                 // [8][S]
   float* sT = smem + BLK_ROWS * S;  // [8][S] per-state terms (rates / P)
-  __shared__ int s_xe[BLK_ROWS], s_xb[BLK_ROWS], s_jump[BLK_ROWS], s_cnt[BLK_ROWS];
+  __shared__ int s_xe[BLK_ROWS], s_xb[BLK_ROWS];
   __shared__ float s_llx[BLK_ROWS], s_lse[BLK_ROWS];
   const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nth >> 5;
   const long long r0 = (long long)blockIdx.x * BLK_ROWS;
@@ -270,7 +241,7 @@ __global__ void __launch_bounds__(256) step_block_kernel(StepArgs a) {
     const long long r = r0 + (tid < nr ? tid : 0);
     s_xe[tid] = a.x_eval[r];
     s_xb[tid] = a.x_base ? a.x_base[r] : s_xe[tid];
-    s_jump[tid] = 0; s_cnt[tid] = 0; s_llx[tid] = 0.f;
+    s_llx[tid] = 0.f;
   }
   __syncthreads();
   // 1. softmax statistics and operand rows: warp w handles rows w, w+nwarp, ...
@@ -358,22 +329,16 @@ __global__ void __launch_bounds__(256) step_block_kernel(StepArgs a) {
   }
   __syncthreads();
   RowStats st = {0, 0, 0, 0, 0};
-  const uint64_t group = (uint64_t)(a.row_offset + r0) >> 3;
   if (a.mode == CTDD_MODE_TAU_LEAP || a.mode == CTDD_MODE_TAU_LEAP_CORR || a.mode == CTDD_MODE_MIDPOINT_JUMP) {
-    for (int s = tid; s < S; s += nth) {
-      const Philox4 hi = philox_jump(s, group, a.offset, STREAM_JUMP_HI, a.seed);
-#pragma unroll
-      for (int r = 0; r < BLK_ROWS; ++r) {
-        const int k = jump_count(sA[r * S + s] * a.h, philox_half(hi, r), s, group, r, a.offset, a.seed);
-        if (k) {
-          atomicAdd(&s_jump[r], jump_contrib(k, s, s_xe[r]));
-          atomicAdd(&s_cnt[r], k > 4096 ? 4096 : k);
-        }
-      }
+    // one thread per row, oracle op order (this path doubles as the on-GPU cross-check of the tensor path)
+    if (tid < nr) {
+      const int r = tid;
+      const float h = a.h;
+      const float* rowp = sA + r * S;
+      const int2 jc = tau_leap_row_seq(S, s_xe[r], (uint64_t)(a.row_offset + r0 + r), a.offset, a.seed,
+                                       [&](int s) { return __fmul_rn(rowp[s], h); });
+      a.x_out[r0 + r] = finalize_jump(s_xb[r], s_xe[r], jc.x, jc.y, a.reject_multi, S, st);
     }
-    __syncthreads();
-    if (tid < nr)
-      a.x_out[r0 + tid] = finalize_jump(s_xb[tid], s_xe[tid], s_jump[tid], s_cnt[tid], a.reject_multi, S, st);
   } else if (a.mode == CTDD_MODE_MIDPOINT_DRIFT) {
     // deterministic: warp r reduces row r in a fixed order
     for (int r = warp; r < BLK_ROWS; r += nwarp) {

@@ -1,18 +1,23 @@
 // tcgen05 reverse-step kernel for S == 256 (configs C3/C4/C5): the (N*D x S)(S x S) contraction of
 // lib/sampling/sampling.py:57 on 5th-generation tensor cores, fused with softmax, the q_{t|0} denominators, the
-// forward-rate multiply and the Philox Poisson tau-leap (sampling.py:127-160).
+// forward-rate multiply and the Philox tau-leap / midpoint-drift state update (sampling.py:127-160, :423-503).
 //
-// Formulation (transposed, "Z" in DESIGN.md):  D[s, row] = sum_k Q^T[s, k] * a[row, k]
-//   * M side  = state s.  Q^T (bf16 hi + mid split, 2 x 128 TMEM columns) is loaded ONCE per CTA into tensor
-//     memory and used as the A operand of tcgen05.mma (TS form) — it is never re-read from shared memory.
-//   * N side  = data rows. Producer warps (one warp per row) read fp32 logits straight from HBM with coalesced
-//     128-bit loads, do the row softmax with shuffles, multiply by the gathered reciprocal denominators
-//     1/(Q[k,x]+eps), split to bf16 hi/mid and store the row K-major into a 128B-swizzled smem stage.
-//   * 3 tensor passes  Qh*ah + Qh*am + Qm*ah  (dropped terms ~2^-16 relative, all terms non-negative) accumulate
-//     in fp32 TMEM; epilogue warps read the accumulator with tcgen05.ld (lane = state s, column = row), scale by
-//     the gathered forward rate R_b[s,x] and draw the per-(row,s) Poisson jump counts.
-// Each CTA owns one half of the state axis (128 TMEM lanes); the two halves of a row are combined by a small
-// finalize kernel.  Warp roles: 8 epilogue warps (2 per TMEM quadrant), 1 MMA-issue warp, 8 producer warps.
+// One CTA PAIR (thread-block cluster of 2, tcgen05 cta_group::2) owns a sequence of 128-row tiles:
+//   D[s, row] = sum_k Q^T[s, k] * a[row, k]        M = 256 states (128 per CTA), N = 128 rows, K = 256
+//   * M side = state s. Each CTA keeps ITS 128-state half of Q^T (bf16 hi + mid split, 2 x 128 TMEM columns)
+//     resident in tensor memory as the A operand (TS form) for the whole kernel.
+//   * N side = data rows. Each CTA's producer warps (one warp per row) build 64 of the tile's 128 rows: fp32 logits
+//     straight from HBM with coalesced 128-bit loads, row softmax by shuffles, gathered reciprocal denominators
+//     1/(Q[k,x]+eps), bf16 hi/mid split, K-major 128B-swizzled smem stage.  Every row is produced exactly once.
+//     The producer also computes the row's TOTAL jump rate from a precomputed table dot product
+//     (Lambda = c * sum_k e_k G[x][k], G = (Q Rbz)[k,x] / (Q[k,x]+eps)) and draws the row's jump count K.
+//   * 3 tensor passes  Qh*ah + Qh*am + Qm*ah  accumulate in fp32 TMEM (2 accumulators x 128 columns per CTA).
+//   * Epilogue: each CTA reads its 128 states x 128 rows with tcgen05.ld and scatters them (local st.shared /
+//     remote st.shared::cluster) into the [row][state] gather buffer of the CTA that OWNS the row, so that each
+//     owner sees all 256 states of its 64 rows.  The same warps then run the row sampler (one warp per row):
+//     lam_s = D_s * c * Rbz[s,x], warp prefix sum, K inverse-CDF picks (superposition map of ctdd_common.cuh),
+//     clamp, rejection, statistics, x_out.  Rows with K == 0 cost one store.
+// Warp roles per CTA: 8 epilogue/sampler warps, 1 MMA-issue warp (leader CTA only issues), 8 producer warps.
 #include "ctdd_common.cuh"
 #include <cuda_bf16.h>
 
@@ -20,49 +25,57 @@ namespace ctdd {
 namespace tc {
 
 constexpr int S = 256;
-constexpr int NT = 64;                 // data rows per tile (= UMMA N)
-constexpr int STAGES = 3;              // smem operand stages
+constexpr int NH = 64;                 // rows produced and sampled by one CTA per tile
+constexpr int NT = 2 * NH;             // rows per pair tile (= UMMA N)
+constexpr int STAGES = 2;              // smem operand stages
 constexpr int ACC = 2;                 // TMEM accumulator buffers
-constexpr int RING = 8;                // per-tile side-info ring (>= STAGES + ACC + 1)
-constexpr int NUM_EPI_WARPS = 8;       // warps e and e+4 share TMEM quadrant e&3 and split the tile's columns
+constexpr int RING = 8;                // per-tile side-info ring
+constexpr int NUM_EPI_WARPS = 8;       // warp w: TMEM quadrant w&3, column half w>>2 (= owner CTA of those rows)
 constexpr int MMA_WARP = 8;
 constexpr int FIRST_PROD_WARP = 9;
 constexpr int NUM_PROD_WARPS = 8;
 constexpr int NUM_THREADS = (FIRST_PROD_WARP + NUM_PROD_WARPS) * 32;  // 544
-constexpr int ROWS_PER_PROD = NT / NUM_PROD_WARPS;                   // 8
-constexpr int KBLOCK_BYTES = NT * 128;         // one 64-wide K block of one split: NT rows x 128 B
+constexpr int ROWS_PER_PROD = NH / NUM_PROD_WARPS;                   // 8
+constexpr int ROWS_PER_SAMPLER = NH / NUM_EPI_WARPS;                 // 8
+constexpr int KBLOCK_BYTES = NH * 128;         // one 64-wide K block of one split: NH rows x 128 B
 constexpr int SPLIT_BYTES = 4 * KBLOCK_BYTES;  // K = 256 -> 4 blocks
 constexpr int STAGE_BYTES = 2 * SPLIT_BYTES;   // hi + mid
 constexpr int TMEM_COLS = 512;
-constexpr int TM_QH = 0, TM_QM = 128, TM_ACC = 256;  // TMEM column map
+constexpr int TM_QH = 0, TM_QM = 128, TM_ACC = 256;  // TMEM column map (accumulator b at TM_ACC + b * NT)
 
 // per-time-point table blob (ctdd_prep_tc_tables)
 constexpr size_t TAB_QH_OFF = 0;                                 // uint32 [256][128]  bf16 pairs of Q^T hi
 constexpr size_t TAB_QM_OFF = TAB_QH_OFF + (size_t)S * 128 * 4;  // uint32 [256][128]  bf16 pairs of Q^T mid
-constexpr size_t TAB_A_OFF = TAB_QM_OFF + (size_t)S * 128 * 4;   // float  [256][256]  tauLDR: 1/(Q[k,x]+eps); SDDM: Q[k,x]
-constexpr size_t TAB_BYTES = TAB_A_OFF + (size_t)S * S * 4;
+constexpr size_t TAB_A_OFF = TAB_QM_OFF + (size_t)S * 128 * 4;   // float [x][k]  tauLDR: 1/(Q[k,x]+eps); SDDM: Q[k,x]
+constexpr size_t TAB_G_OFF = TAB_A_OFF + (size_t)S * S * 4;      // float [x][k]  total-rate table (see prep_g_kernel)
+constexpr size_t TAB_BYTES = TAB_G_OFF + (size_t)S * S * 4;
 // static blob (ctdd_prep_tc_static)
 constexpr size_t ST_RBZT_OFF = 0;                                // float [x][s] = Rb[s][x], zero at s == x
 constexpr size_t ST_RBZ_OFF = (size_t)S * S * 4;                 // float [x][s] = Rb[x][s], zero at s == x
-constexpr size_t ST_BYTES = 2 * (size_t)S * S * 4;
+constexpr size_t ST_ROWSUM_OFF = 2 * (size_t)S * S * 4;          // float [x] = sum_s Rbz[x][s]
+constexpr size_t ST_BYTES = ST_ROWSUM_OFF + (size_t)S * 4;
 
-struct __align__(16) Side { float c1, c0; int x; float rs; };
+enum { KM_JUMP = 0, KM_CORR = 1, KM_RATES = 2, KM_DRIFT = 3 };
+
+struct __align__(16) Side { float c1, c0; int x; int K; uint32_t w1, w2, w3; int valid; };
 
 struct Smem {
   alignas(1024) uint8_t stage[STAGES][STAGE_BYTES];
-  Side side[RING][NT];
-  int jump[RING][NT];
-  int cnt[RING][NT];
-  alignas(8) uint64_t full[STAGES];
-  uint64_t empty[STAGES];
-  uint64_t side_full[RING];
-  uint64_t tmem_full[ACC];
-  uint64_t tmem_empty[ACC];
+  alignas(16) float gather[NH][S];   // [row owned by this CTA][state]: accumulator values, then prefix sums
+  Side side[RING][NH];
+  alignas(8) uint64_t full[STAGES];  // used in the leader CTA: 8 local + 8 remote producer warps
+  uint64_t empty[STAGES];            // multicast tcgen05.commit
+  uint64_t side_full[RING];          // local producers -> local samplers
+  uint64_t tmem_full[ACC];           // multicast tcgen05.commit
+  uint64_t tmem_empty[ACC];          // used in the leader CTA: 8 local + 8 remote epilogue warps
+  uint64_t gather_full;              // 4 local + 4 remote epilogue warps have written this CTA's gather buffer
+  uint64_t gather_free_local;        // the 8 local sampler warps are done with this CTA's gather buffer
+  uint64_t gather_free_remote;       // the 8 sampler warps of the PARTNER are done with the partner's buffer
   uint32_t tmem_base;
 };
 
 struct Args {
-  int mode, branch, D, reject_multi;
+  int branch, D, reject_multi;
   long long rows, row_offset;
   const float* logits;
   long long ld, batch_stride;
@@ -78,25 +91,42 @@ struct Args {
   float* rr_out;
   float* ratio_out;
   unsigned long long* stats;
-  int2* partial;          // [2][rows] (jump, count) per state half
   int num_tiles;
 };
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory object in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// arrive on a barrier addressed in the cluster window (own or partner CTA), release at cluster scope
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra DONE_%=;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
@@ -104,28 +134,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"((uint32_t)TMEM_COLS)
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"((uint32_t)TMEM_COLS)
                : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"((uint32_t)TMEM_COLS) : "memory");
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"((uint32_t)TMEM_COLS) : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+// signal the barrier at this smem offset in BOTH CTAs of the pair when all prior MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
 }
-// D[tmem] (+)= A[tmem] * B[smem desc]   (kind::f16, bf16 inputs, fp32 accumulate)
-__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem desc] over the CTA pair (kind::f16, bf16 inputs, fp32 accumulate)
+__device__ __forceinline__ void umma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n"
       "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -139,7 +172,8 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// fp32 accumulate, bf16 A and B, K-major both, N = 128, M = 256 (pair)
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -177,15 +211,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
+__device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
 }
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // bf16 hi/mid split of two floats, packed (element 0 in the low half)
 __device__ __forceinline__ void split2(float a0, float a1, uint32_t& hi, uint32_t& mid) {
@@ -197,34 +228,34 @@ __device__ __forceinline__ void split2(float a0, float a1, uint32_t& hi, uint32_
   mid = *reinterpret_cast<uint32_t*>(&m);
 }
 
-// rare path: the full 32-bit uniform is below lambda, so a jump is possible -> exact inverse CDF + accumulation
-__device__ __noinline__ void jump_tail(float lam, float v, int s, int x, int* jump, int* cnt) {
-  const int k = poisson_from_unit(lam, v);
-  if (k) {
-    atomicAdd(jump, jump_contrib(k, s, x));
-    atomicAdd(cnt, k > 4096 ? 4096 : k);
-  }
+__device__ __forceinline__ int warp_sum_int(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
-constexpr int PROD_BATCH = 4;          // rows whose loads are issued together by a producer warp
-constexpr int PREFETCH_TILES = 3;      // L2 bulk-prefetch distance (tiles of this CTA's sequence)
+constexpr int PROD_BATCH = 2;          // rows whose loads are issued together by a producer warp
+constexpr int PREFETCH_TILES = 3;      // L2 bulk-prefetch distance (tiles of this pair's sequence)
 
-// TAULDR: tauLDR rates (else SDDM reverse_prob); CORR: corrector adds R_t[x,:]; RATES: RATES_ONLY mode
-template <bool TAULDR, bool CORR, bool RATES>
-__global__ void __launch_bounds__(NUM_THREADS, 1) step_tc_kernel(const Args a) {
+// TAULDR: tauLDR rates (else SDDM reverse_prob); KM: KM_JUMP / KM_CORR (corrector adds R_t[x,:]) / KM_RATES / KM_DRIFT
+template <bool TAULDR, int KM>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step_tc_kernel(const Args a) {
   extern __shared__ uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int hs = blockIdx.x & 1;                 // state half owned by this CTA
-  const int tile0 = blockIdx.x >> 1;
-  const int tile_step = gridDim.x >> 1;
-  const int my_tiles = (a.num_tiles > tile0) ? (a.num_tiles - tile0 + tile_step - 1) / tile_step : 0;
+  const uint32_t rank = cluster_ctarank();       // state half owned by this CTA; rank 0 issues the MMAs
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+  const int my_tiles = (a.num_tiles > pair) ? (a.num_tiles - pair + npairs - 1) / npairs : 0;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&sm.full[i], NUM_PROD_WARPS); mbar_init(&sm.empty[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&sm.full[i], 2 * NUM_PROD_WARPS); mbar_init(&sm.empty[i], 1); }
     for (int i = 0; i < RING; ++i) mbar_init(&sm.side_full[i], NUM_PROD_WARPS);
-    for (int i = 0; i < ACC; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], NUM_EPI_WARPS); }
+    for (int i = 0; i < ACC; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], 2 * NUM_EPI_WARPS); }
+    mbar_init(&sm.gather_full, NUM_EPI_WARPS);
+    mbar_init(&sm.gather_free_local, NUM_EPI_WARPS);
+    mbar_init(&sm.gather_free_remote, NUM_EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == MMA_WARP) tmem_alloc(&sm.tmem_base);
@@ -233,9 +264,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) step_tc_kernel(const Args a) {
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
 
-  // Q^T halves -> tensor memory (A operand). Warp q < 4 owns TMEM lanes [32q, 32q+32).
+  // Q^T half of this CTA -> tensor memory (A operand). Warp q < 4 owns TMEM lanes [32q, 32q+32).
   if (warp < 4) {
-    const int srow = hs * 128 + warp * 32 + lane;
+    const int srow = (int)rank * 128 + warp * 32 + lane;
 #pragma unroll 1
     for (int split = 0; split < 2; ++split) {
       const uint4* src = reinterpret_cast<const uint4*>(a.tab + (split ? TAB_QM_OFF : TAB_QH_OFF)) + (size_t)srow * 32;
@@ -253,7 +284,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) step_tc_kernel(const Args a) {
     tmem_st_wait();
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();    // barriers initialised and both A halves resident before any cross-CTA traffic
   tc_fence_after();
 
   if (warp >= FIRST_PROD_WARP) {
@@ -261,18 +292,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) step_tc_kernel(const Args a) {
     const int pw = warp - FIRST_PROD_WARP;
     // lane owns k = 4*lane .. 4*lane+3 and 128 + 4*lane .. +3: two fully coalesced 512-byte warp loads per row
     const float* tabA = reinterpret_cast<const float*>(a.tab + TAB_A_OFF) + 4 * lane;
-    const float hb = RATES ? 1.0f : a.h * a.beta;   // rates-only ignores the step length
+    const float* tabG = reinterpret_cast<const float*>(a.tab + TAB_G_OFF) + 4 * lane;
+    const float* rowsumZ = reinterpret_cast<const float*>(a.stat + ST_ROWSUM_OFF);
+    const float hb = (KM == KM_RATES) ? 1.0f : a.h * a.beta;   // rates-only ignores the step length
     const bool contiguous = (a.ld == S) && (a.batch_stride == (long long)a.D * S);
-    const bool can_prefetch = contiguous && hs == 0 && pw == 0 && lane == 0;
-    const uint32_t rows32 = (uint32_t)(a.rows < 0x7fffffffLL ? a.rows : 0x7fffffffLL);
+    const bool can_prefetch = contiguous && pw == 0 && lane == 0;
+    const uint32_t full_addr = mapa(smem_u32(&sm.full[0]), 0);   // the leader's full[] barriers
     for (int i = 0; i < my_tiles; ++i) {
-      const int tile = tile0 + i * tile_step;
+      const int tile = pair + i * npairs;
       const int st = i % STAGES, slot = i % RING;
-      if (can_prefetch) {   // pull a later tile of this CTA pair's sequence into L2 while this one is processed
-        const long long pt = (long long)tile + (long long)PREFETCH_TILES * tile_step;
-        if (pt < a.num_tiles) {
-          const long long r0 = pt * NT;
-          const long long nrow = (a.rows - r0) < NT ? (a.rows - r0) : NT;
+      const long long g0 = (long long)tile * NT + (long long)rank * NH;   // first row built by this CTA
+      if (can_prefetch) {   // pull this CTA's rows of a later tile into L2 while this one is processed
+        const long long r0 = g0 + (long long)PREFETCH_TILES * npairs * NT;
+        if (r0 < a.rows) {
+          const long long nrow = (a.rows - r0) < NH ? (a.rows - r0) : NH;
           l2_prefetch_bulk(a.logits + r0 * S, (uint32_t)(nrow * S * 4));
         }
       }
@@ -280,14 +313,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) step_tc_kernel(const Args a) {
       uint8_t* stage = sm.stage[st];
 #pragma unroll 1
       for (int b0 = 0; b0 < ROWS_PER_PROD; b0 += PROD_BATCH) {
-        float4 v0[PROD_BATCH], v1[PROD_BATCH], t0[PROD_BATCH], t1[PROD_BATCH];
+        float4 v0[PROD_BATCH], v1[PROD_BATCH], t0[PROD_BATCH], t1[PROD_BATCH], q0[PROD_BATCH], q1[PROD_BATCH];
         int xr[PROD_BATCH];
         bool ok[PROD_BATCH];
         // issue every load of the batch before touching the data
 #pragma unroll
         for (int j = 0; j < PROD_BATCH; ++j) {
           const int r = pw + NUM_PROD_WARPS * (b0 + j);
-          const long long g = (long long)tile * NT + r;
+          const long long g = g0 + r;
           ok[j] = g < a.rows;
           const long long gc = ok[j] ? g : 0;
           const float* lp;
@@ -303,49 +336,53 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) step_tc_kernel(const Args a) {
         }
 #pragma unroll
         for (int j = 0; j < PROD_BATCH; ++j) {
-          const float* tp = tabA + ((size_t)xr[j] << 8);
-          t0[j] = __ldg(reinterpret_cast<const float4*>(tp));
-          t1[j] = __ldg(reinterpret_cast<const float4*>(tp + 128));
+          const size_t xo = (size_t)xr[j] << 8;
+          t0[j] = __ldg(reinterpret_cast<const float4*>(tabA + xo));
+          t1[j] = __ldg(reinterpret_cast<const float4*>(tabA + xo + 128));
+          q0[j] = __ldg(reinterpret_cast<const float4*>(tabG + xo));
+          q1[j] = __ldg(reinterpret_cast<const float4*>(tabG + xo + 128));
         }
+        float lam_tot[PROD_BATCH], c1s[PROD_BATCH], c0s[PROD_BATCH];
 #pragma unroll
         for (int j = 0; j < PROD_BATCH; ++j) {
           const int r = pw + NUM_PROD_WARPS * (b0 + j);
           float v[8] = {v0[j].x, v0[j].y, v0[j].z, v0[j].w, v1[j].x, v1[j].y, v1[j].z, v1[j].w};
           const float t[8] = {t0[j].x, t0[j].y, t0[j].z, t0[j].w, t1[j].x, t1[j].y, t1[j].z, t1[j].w};
+          const float gq[8] = {q0[j].x, q0[j].y, q0[j].z, q0[j].w, q1[j].x, q1[j].y, q1[j].z, q1[j].w};
           float m = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
           m = warp_max(m);
           const float ml = -m * 1.4426950408889634f;
-          float sum = 0.f, dot = 0.f;
+          float sum = 0.f, dot = 0.f, dotg = 0.f;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             v[q] = ex2_approx(fmaf(v[q], 1.4426950408889634f, ml));     // exp(v - max)
             sum += v[q];
+            dotg = fmaf(v[q], gq[q], dotg);
             if (!TAULDR) dot = fmaf(v[q], t[q], dot);
           }
           sum = warp_sum(sum);
+          dotg = warp_sum(dotg);
           const float rs = __frcp_rn(sum);
-          Side si;
+          const float rz = (!TAULDR || KM == KM_CORR) ? __ldg(rowsumZ + xr[j]) : 0.f;
           if (TAULDR) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] *= t[q];             // e_k / (Q[k,x] + eps); 1/sum applied in the epilogue
-            si.c1 = hb * rs * 0.0078125f;                          // lambda * 2^-7 = D * c1 * R_b[s,x]
-            si.c0 = 0.f;
+            for (int q = 0; q < 8; ++q) v[q] *= t[q];             // e_k / (Q[k,x] + eps); 1/sum applied by the sampler
+            c1s[j] = hb * rs;                                      // lam_s = D_s * c1 * Rb[s,x]
+            c0s[j] = 0.f;
           } else {
             dot = warp_sum(dot);
             const float inv = __frcp_rn(fmaf(dot, rs, 1e-35f));    // 1 / (pQ[x] + 1e-35)
-            si.c1 = hb * rs * inv * 0.0078125f;
-            si.c0 = hb * 1e-35f * inv * 0.0078125f;
+            c1s[j] = hb * rs * inv;                                // lam_s = (D_s * c1 + c0) * Rb[x,s]
+            c0s[j] = hb * 1e-35f * inv;
           }
-          si.x = xr[j];
-          si.rs = rs;
+          lam_tot[j] = fmaf(c1s[j], dotg, c0s[j] * rz);
+          if (KM == KM_CORR) lam_tot[j] = fmaf(hb, rz, lam_tot[j]);
           uint32_t hi[4], mid[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) split2(v[2 * q], v[2 * q + 1], hi[q], mid[q]);
           if (!ok[j]) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) hi[q] = mid[q] = 0u;
-            si.c1 = si.c0 = si.rs = 0.f;
-            si.x = 0;
           }
           // k = 4*lane..+3 lives in K block lane/16, 16-byte chunk (lane%16)/2 (XOR-swizzled by the row), half lane&1;
           // k = 128 + 4*lane..+3 two K blocks further on
@@ -355,23 +392,42 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) step_tc_kernel(const Args a) {
           *reinterpret_cast<uint2*>(stage + off + 2 * KBLOCK_BYTES) = make_uint2(hi[2], hi[3]);
           *reinterpret_cast<uint2*>(stage + SPLIT_BYTES + off) = make_uint2(mid[0], mid[1]);
           *reinterpret_cast<uint2*>(stage + SPLIT_BYTES + off + 2 * KBLOCK_BYTES) = make_uint2(mid[2], mid[3]);
-          if (lane == 0) {
-            sm.side[slot][r] = si;
-            sm.jump[slot][r] = 0;
-            sm.cnt[slot][r] = 0;
+        }
+        // lane j of the warp finishes row j of the batch: total jump count and the first pick uniforms
+        if (lane < PROD_BATCH) {
+          float lt = lam_tot[0], c1 = c1s[0], c0 = c0s[0];
+          int x = xr[0];
+          bool valid = ok[0];
+#pragma unroll
+          for (int j = 1; j < PROD_BATCH; ++j)
+            if (lane == j) { lt = lam_tot[j]; c1 = c1s[j]; c0 = c0s[j]; x = xr[j]; valid = ok[j]; }
+          const int r = pw + NUM_PROD_WARPS * (b0 + lane);
+          Side si;
+          si.c1 = c1; si.c0 = c0; si.x = x; si.valid = valid ? 1 : 0;
+          si.K = 0; si.w1 = si.w2 = si.w3 = 0u;
+          if (valid) {
+            if (KM == KM_RATES || KM == KM_DRIFT) {
+              si.K = 1;
+            } else {
+              const Philox4 p0 = philox_rowjump((uint64_t)(a.row_offset + g0 + r), 0, a.offset, a.seed);
+              int K = poisson_from_unit(lt, u32_to_unit(p0.w[0]));
+              si.K = K > JUMP_PICK_CAP ? JUMP_PICK_CAP : K;
+              si.w1 = p0.w[1]; si.w2 = p0.w[2]; si.w3 = p0.w[3];
+            }
           }
+          sm.side[slot][r] = si;
         }
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&sm.full[st]);
+        mbar_arrive_cluster(full_addr + (uint32_t)st * 8u);
         mbar_arrive(&sm.side_full[slot]);
       }
     }
   } else if (warp == MMA_WARP) {
-    // ======================================================================== MMA issue (one thread)
-    if (lane == 0) {
+    // ======================================================================== MMA issue (one thread of the leader CTA)
+    if (rank == 0 && lane == 0) {
       for (int i = 0; i < my_tiles; ++i) {
         const int st = i % STAGES, b = i % ACC;
         mbar_wait(&sm.full[st], (i / STAGES) & 1);
@@ -387,157 +443,192 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) step_tc_kernel(const Args a) {
 #pragma unroll
           for (int k16 = 0; k16 < 16; ++k16) {
             const uint64_t bd = make_b_desc(bsplit + (k16 >> 2) * KBLOCK_BYTES + (k16 & 3) * 32);
-            umma_ts(d_tmem, a_tmem + k16 * 8, bd, IDESC, acc);
+            umma_ts_pair(d_tmem, a_tmem + k16 * 8, bd, IDESC, acc);
             acc = 1;
           }
         }
-        umma_commit(&sm.empty[st]);
-        umma_commit(&sm.tmem_full[b]);
+        umma_commit_pair(&sm.empty[st]);
+        umma_commit_pair(&sm.tmem_full[b]);
       }
     }
     __syncwarp();
   } else {
-    // ======================================================================== epilogue: lane = state s
-    const int q = warp & 3;                // TMEM quadrant
-    const int ch = warp >> 2;              // which 32 columns of the tile
-    const int s = hs * 128 + q * 32 + lane;
-    const float* tabE = reinterpret_cast<const float*>(a.stat + (TAULDR ? ST_RBZT_OFF : ST_RBZ_OFF)) + s;
-    const float* tabC = reinterpret_cast<const float*>(a.stat + ST_RBZ_OFF) + s;   // corrector add: Rb[x][s], zero diag
-    const float* tabFull = (TAULDR ? a.RbT : a.Rb) + s;                             // diagonal kept, for rr_out
-    const float hb7 = (RATES ? 1.0f : a.h * a.beta) * 0.0078125f;
-    const uint32_t side_base = smem_u32(&sm.side[0][0]);
-    const int c0 = 32 * ch;
+    // ======================================================================== epilogue + row sampler
+    const int q = warp & 3;                       // TMEM quadrant -> states rank*128 + 32q + lane
+    const uint32_t owner = (uint32_t)(warp >> 2); // accumulator columns [64*owner, 64*owner+64) belong to CTA `owner`
+    const int s_mine = (int)rank * 128 + q * 32 + lane;
+    const uint32_t gather_dst = mapa(smem_u32(&sm.gather[0][0]), owner) + (uint32_t)s_mine * 4u;
+    const uint32_t gfull_dst = mapa(smem_u32(&sm.gather_full), owner);
+    const uint32_t tempty_dst = mapa(smem_u32(&sm.tmem_empty[0]), 0);
+    const uint32_t gfree_remote_dst = mapa(smem_u32(&sm.gather_free_remote), rank ^ 1u);
+    uint64_t* const gfree_wait = (owner == rank) ? &sm.gather_free_local : &sm.gather_free_remote;
+    const float* tabE = reinterpret_cast<const float*>(a.stat + (TAULDR ? ST_RBZT_OFF : ST_RBZ_OFF)) + 8 * lane;
+    const float* tabC = reinterpret_cast<const float*>(a.stat + ST_RBZ_OFF) + 8 * lane;   // corrector add: Rb[x][s], zero diag
+    const float* tabFull = (TAULDR ? a.RbT : a.Rb) + 8 * lane;                             // diagonal kept, for rr_out
+    const float hb = a.h * a.beta;
+    RowStats stt = {0, 0, 0, 0, 0};
     for (int i = 0; i < my_tiles; ++i) {
-      const int tile = tile0 + i * tile_step;
+      const int tile = pair + i * npairs;
       const int b = i % ACC, slot = i % RING;
-      mbar_wait(&sm.side_full[slot], (i / RING) & 1);
+      // ---- phase A: accumulator (this CTA's 128 states x this warp's 64 rows) -> gather buffer of the rows' owner
       mbar_wait(&sm.tmem_full[b], (i / ACC) & 1);
+      mbar_wait(gfree_wait, (i & 1) ^ 1);
       tc_fence_after();
-      const long long g0 = (long long)tile * NT;
-      const uint32_t side_slot = side_base + (uint32_t)(slot * NT + c0) * (uint32_t)sizeof(Side);
-      uint32_t acc[32];
-      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + TM_ACC + b * NT + c0, acc);
-      tmem_ld_wait();
-      tc_fence_before();   // accumulator is in registers: hand the buffer back to the MMA warp
+#pragma unroll
+      for (int c0 = 0; c0 < NH; c0 += 32) {
+        uint32_t acc[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + TM_ACC + b * NT + owner * NH + c0, acc);
+        tmem_ld_wait();
+        if (owner == rank) {
+          float* dst = &sm.gather[c0][s_mine];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dst[j * S] = __uint_as_float(acc[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) st_cluster_f32(gather_dst + (uint32_t)(c0 + j) * (S * 4), __uint_as_float(acc[j]));
+        }
+      }
+      tc_fence_before();   // accumulator has been read: hand the buffer back to the MMA warp
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.tmem_empty[b]);
-      if (RATES) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const long long g = g0 + c0 + j;
-          if (g >= a.rows) continue;
-          const float4 si = lds128(side_slot + (uint32_t)j * 16);
-          const int x = __float_as_int(si.z);
-          const float d = __uint_as_float(acc[j]);
-          float ratio, rfull;
-          if (TAULDR) {
-            ratio = d * si.w;
-            rfull = a.beta * __ldg(tabFull + ((size_t)x << 8)) * ratio;
-          } else {
-            // ratio = (pQ[s] + 1e-35) / (pQ[x] + 1e-35);  c1/c0 carry 2^-7
-            ratio = fmaf(d, si.x, si.y) * 128.0f;
-            rfull = ratio * (a.beta * __ldg(tabFull + ((size_t)x << 8)));
-          }
-          if (a.rr_out) a.rr_out[g * S + s] = rfull;
-          if (a.ratio_out) a.ratio_out[g * S + s] = ratio;
-        }
-        continue;
+      if (lane == 0) {
+        mbar_arrive_cluster(tempty_dst + (uint32_t)b * 8u);
+        mbar_arrive_cluster(gfull_dst);
       }
-      // two passes of 16 columns keep the live register set small (544 threads -> 96 registers per thread)
-#pragma unroll
-      for (int h0 = 0; h0 < 32; h0 += 16) {
-        // ---- phase 1 (branch-free, full ILP): lambda and the 16-bit pre-filter
-        float lam7[16];
-        Philox4 ph[2];
-        uint32_t need = 0;
-#pragma unroll
-        for (int j8 = 0; j8 < 16; j8 += 8) {
-          const uint64_t group = (uint64_t)(a.row_offset + g0 + c0 + h0 + j8) >> 3;
-          ph[j8 >> 3] = philox_jump((uint32_t)s, group, a.offset, STREAM_JUMP_HI, a.seed);
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const float4 si = lds128(side_slot + (uint32_t)(h0 + j8 + jj) * 16);
-            const size_t xo = (size_t)__float_as_int(si.z) << 8;
-            float l7 = fmaf(__uint_as_float(acc[h0 + j8 + jj]), si.x, si.y) * __ldg(tabE + xo);
-            if (CORR) l7 = fmaf(hb7, __ldg(tabC + xo), l7);
-            lam7[j8 + jj] = l7;
-            // halfword jj of the Philox output OR'ed into the mantissa of 1.0f: 1 + hi16 * 2^-23 (one PRMT)
-            const uint32_t fb = __byte_perm(ph[j8 >> 3].w[jj >> 1], 0x3F800000u, (jj & 1) ? 0x7632 : 0x7610);
-            // v >= hi16 * 2^-16 and P(K >= 1) <= lambda: when hi16 * 2^-16 >= lambda the count is certainly 0
-            need |= ((__uint_as_float(fb) - 1.0f) < l7 ? 1u : 0u) << (j8 + jj);
+      // ---- phase B: sample the rows this CTA owns (warp w: rows 8w .. 8w+7 of the CTA's 64)
+      mbar_wait(&sm.side_full[slot], (i / RING) & 1);
+      mbar_wait(&sm.gather_full, i & 1);
+      const long long g0 = (long long)tile * NT + (long long)rank * NH;
+#pragma unroll 1
+      for (int rr = 0; rr < ROWS_PER_SAMPLER; ++rr) {
+        const int r = warp * ROWS_PER_SAMPLER + rr;
+        const Side si = sm.side[slot][r];
+        if (!si.valid) continue;
+        const long long g = g0 + r;
+        const int x = si.x;
+        if (KM != KM_RATES && KM != KM_DRIFT && si.K == 0) {
+          if (lane == 0) {
+            const int xb = a.x_base ? a.x_base[g] : x;
+            a.x_out[g] = finalize_jump(xb, x, 0, 0, a.reject_multi, S, stt);
           }
+          continue;
         }
-        // ---- phase 2 (rare, grows with the jump rate): low 16 bits of the uniform, exact inverse CDF
-        if (__any_sync(0xffffffffu, need != 0)) {
+        float* grow_p = &sm.gather[r][0];
+        const float4 d0 = *reinterpret_cast<const float4*>(grow_p + 8 * lane);
+        const float4 d1 = *reinterpret_cast<const float4*>(grow_p + 8 * lane + 4);
+        float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        const size_t xo = (size_t)x << 8;
+        if (KM == KM_RATES) {
+          const float4 f0 = __ldg(reinterpret_cast<const float4*>(tabFull + xo));
+          const float4 f1 = __ldg(reinterpret_cast<const float4*>(tabFull + xo + 4));
+          const float f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+          float ratio[8], rfull[8];
 #pragma unroll
-          for (int j8 = 0; j8 < 16; j8 += 8) {
-            const uint32_t gm = (need >> j8) & 0xFFu;
-            if (__any_sync(0xffffffffu, gm != 0)) {
-              const uint64_t group = (uint64_t)(a.row_offset + g0 + c0 + h0 + j8) >> 3;
-              const Philox4 lo = philox_jump((uint32_t)s, group, a.offset, STREAM_JUMP_LO, a.seed);
-#pragma unroll
-              for (int jj = 0; jj < 8; ++jj) {
-                if ((gm >> jj) & 1u) {
-                  const uint32_t w = (philox_half(ph[j8 >> 3], jj) << 16) | philox_half(lo, jj);
-                  const float v = u32_to_unit(w);
-                  const float lam = lam7[j8 + jj] * 128.0f;
-                  if (v < lam) {
-                    const int col = c0 + h0 + j8 + jj;
-                    const int x = __float_as_int(lds128(side_slot + (uint32_t)(h0 + j8 + jj) * 16).z);
-                    jump_tail(lam, v, s, x, &sm.jump[slot][col], &sm.cnt[slot][col]);
-                  }
-                }
-              }
-            }
+          for (int e = 0; e < 8; ++e) {
+            ratio[e] = fmaf(d[e], si.c1, si.c0);
+            rfull[e] = TAULDR ? a.beta * f[e] * ratio[e] : ratio[e] * (a.beta * f[e]);
           }
+          if (a.rr_out) {
+            float4* o = reinterpret_cast<float4*>(a.rr_out + g * S + 8 * lane);
+            o[0] = make_float4(rfull[0], rfull[1], rfull[2], rfull[3]);
+            o[1] = make_float4(rfull[4], rfull[5], rfull[6], rfull[7]);
+          }
+          if (a.ratio_out) {
+            float4* o = reinterpret_cast<float4*>(a.ratio_out + g * S + 8 * lane);
+            o[0] = make_float4(ratio[0], ratio[1], ratio[2], ratio[3]);
+            o[1] = make_float4(ratio[4], ratio[5], ratio[6], ratio[7]);
+          }
+          continue;
+        }
+        // lam_s for s = 8*lane .. 8*lane+7 (zero at s == x through the zero-diagonal tables)
+        const float4 e0 = __ldg(reinterpret_cast<const float4*>(tabE + xo));
+        const float4 e1 = __ldg(reinterpret_cast<const float4*>(tabE + xo + 4));
+        const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[e] = fmaf(d[e], si.c1, si.c0) * ev[e];
+        if (KM == KM_CORR) {
+          const float4 c0v = __ldg(reinterpret_cast<const float4*>(tabC + xo));
+          const float4 c1v = __ldg(reinterpret_cast<const float4*>(tabC + xo + 4));
+          const float cv[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d[e] = fmaf(hb, cv[e], d[e]);
+        }
+        if (KM == KM_DRIFT) {
+          // sampling.py:433-453: x' = clip(x + round_half_even(h/2 * sum_s rr_s (s - x)))
+          float acc = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc = fmaf(d[e], (float)(8 * lane + e - x), acc);
+          acc = warp_sum(acc);
+          if (lane == 0) {
+            const int ch = (int)rintf(0.5f * acc);
+            int xn = x + ch;
+            xn = xn < 0 ? 0 : (xn > S - 1 ? S - 1 : xn);
+            a.x_out[g] = xn;
+            stt.changed_base += (xn != x);
+            stt.changed_eval += (xn != x);
+            stt.nonzero += (ch != 0);
+          }
+          continue;
+        }
+        // inclusive prefix sums over the 256 states: in-lane, then across lanes
+#pragma unroll
+        for (int e = 1; e < 8; ++e) d[e] += d[e - 1];
+        float incl = d[7];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float n = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += n;
+        }
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 0.f;
+        const float total = __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[e] += excl;
+        __syncwarp();
+        *reinterpret_cast<float4*>(grow_p + 8 * lane) = make_float4(d[0], d[1], d[2], d[3]);
+        *reinterpret_cast<float4*>(grow_p + 8 * lane + 4) = make_float4(d[4], d[5], d[6], d[7]);
+        __syncwarp();
+        // K picks, one per lane: first state whose prefix sum exceeds v * total
+        const int K = si.K;
+        int jump = 0;
+        for (int base = 0; base < K; base += 32) {
+          const int j = base + lane;
+          uint32_t w = (j == 0) ? si.w1 : (j == 1 ? si.w2 : si.w3);
+          if (K > 3) {   // warp-uniform
+            const int jj = j >= 3 ? j - 3 : 0;
+            const Philox4 pc = philox_rowjump((uint64_t)(a.row_offset + g), 1u + (uint32_t)(jj >> 2), a.offset, a.seed);
+            if (j >= 3) w = philox_word(pc, jj & 3);
+          }
+          const float target = fminf(u32_to_unit(w), 0.99999994f) * total;
+          int lo = 0;
+#pragma unroll
+          for (int step = 128; step >= 1; step >>= 1)
+            if (!(grow_p[lo + step - 1] > target)) lo += step;
+          jump += (j < K) ? (lo - x) : 0;
+        }
+        jump = warp_sum_int(jump);
+        if (lane == 0) {
+          const int xb = a.x_base ? a.x_base[g] : x;
+          a.x_out[g] = finalize_jump(xb, x, jump, K, a.reject_multi, S, stt);
         }
       }
-      epi_bar_sync();
-      const int t = threadIdx.x;
-      // the producers cannot reach this ring slot again before RING - (STAGES + ACC) more tiles have been drained
-      if (t < NT && g0 + t < a.rows) a.partial[(size_t)hs * a.rows + g0 + t] = make_int2(sm.jump[slot][t], sm.cnt[slot][t]);
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&sm.gather_free_local);
+        mbar_arrive_cluster(gfree_remote_dst);
+      }
+    }
+    if (lane == 0 && a.stats) {
+      const int v[5] = {stt.changed_base, stt.nonzero, stt.changed_eval, stt.jumped, stt.multi};
+#pragma unroll
+      for (int k = 0; k < 5; ++k)
+        if (v[k]) atomicAdd(a.stats + k, (unsigned long long)v[k]);
     }
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();     // no CTA of the pair may exit (or free tensor memory) while the other can still reach it
   if (warp == MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem);
-  }
-}
-
-// combine the two state halves of every row: x_new = clamp(x_base + jump), rejection, statistics
-__global__ void step_tc_finalize_kernel(const int2* __restrict__ partial, const int* __restrict__ x_eval,
-                                        const int* __restrict__ x_base, long long rows, int reject_multi,
-                                        int* __restrict__ x_out, unsigned long long* stats) {
-  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  int v[5] = {0, 0, 0, 0, 0};
-  if (r < rows) {
-    const int2 p0 = partial[r], p1 = partial[rows + r];
-    int jump = p0.x + p1.x;
-    const int cnt = p0.y + p1.y;
-    const int xe = x_eval[r], xb = x_base ? x_base[r] : xe;
-    v[3] = cnt > 0; v[4] = cnt > 1;
-    if (reject_multi && cnt > 1) jump = 0;
-    v[1] = jump != 0;
-    int xn = xb + jump;
-    xn = xn < 0 ? 0 : (xn > S - 1 ? S - 1 : xn);
-    v[0] = xn != xb; v[2] = xn != xe;
-    x_out[r] = xn;
-  }
-  if (stats) {   // block-level reduction: one atomic per counter per CTA
-    __shared__ int red[5];
-    if (threadIdx.x < 5) red[threadIdx.x] = 0;
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      int s = v[i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if ((threadIdx.x & 31) == 0 && s) atomicAdd(&red[i], s);
-    }
-    __syncthreads();
-    if (threadIdx.x < 5 && red[threadIdx.x]) atomicAdd(stats + threadIdx.x, (unsigned long long)red[threadIdx.x]);
   }
 }
 
@@ -564,13 +655,42 @@ __global__ void prep_tables_kernel(const float* __restrict__ QT, int T, float ep
   }
 }
 
+// Total-rate table: sum_s lam_s of a row is one dot product of the row's exponentials with G[x][.]
+//   tauLDR: G[x][k] = (sum_s Rb[s][x] [s != x] Q[k][s]) / (Q[k][x] + eps)     (lam_s = c * Rb[s,x] * sum_k e_k Q[k,s] / (Q[k,x]+eps))
+//   SDDM  : G[x][k] =  sum_s Rb[x][s] [s != x] Q[k][s]                        (lam_s = (c1 * sum_k e_k Q[k,s] + c0) * Rb[x,s])
+__global__ void __launch_bounds__(256) prep_g_kernel(const float* __restrict__ QT, const float* __restrict__ Rb, float eps,
+                                                    int branch, uint8_t* __restrict__ out) {
+  __shared__ float sA[16][17], sB[16][17];
+  const int t = blockIdx.z, tx = threadIdx.x, ty = threadIdx.y;
+  const int x = blockIdx.y * 16 + ty, k = blockIdx.x * 16 + tx;
+  const float* qt = QT + (size_t)t * S * S;
+  float* G = reinterpret_cast<float*>(out + (size_t)t * TAB_BYTES + TAB_G_OFF);
+  float acc = 0.f;
+  for (int s0 = 0; s0 < S; s0 += 16) {
+    const int sa = s0 + tx, sb = s0 + ty;
+    sA[ty][tx] = (sa == x) ? 0.f : (branch == CTDD_BRANCH_TAULDR ? Rb[(size_t)sa * S + x] : Rb[(size_t)x * S + sa]);
+    sB[ty][tx] = qt[(size_t)sb * S + k];
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < 16; ++m) acc = fmaf(sA[ty][m], sB[m][tx], acc);
+    __syncthreads();
+  }
+  G[(size_t)x * S + k] = (branch == CTDD_BRANCH_TAULDR) ? acc / (qt[(size_t)x * S + k] + eps) : acc;
+}
+
 __global__ void prep_static_kernel(const float* __restrict__ Rb, uint8_t* __restrict__ out) {
   float* rbzt = reinterpret_cast<float*>(out + ST_RBZT_OFF);
   float* rbz = reinterpret_cast<float*>(out + ST_RBZ_OFF);
+  float* rowsum = reinterpret_cast<float*>(out + ST_ROWSUM_OFF);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S * S; i += gridDim.x * blockDim.x) {
     const int x = i / S, s = i % S;
     rbzt[i] = (s == x) ? 0.f : Rb[(size_t)s * S + x];
     rbz[i] = (s == x) ? 0.f : Rb[i];
+  }
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < S; x += gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < S; ++s) acc += (s == x) ? 0.f : Rb[(size_t)x * S + s];
+    rowsum[x] = acc;
   }
 }
 
@@ -580,17 +700,19 @@ bool tc_supports(const ctdd_step_params* p) {
   if (p->S != tc::S) return false;
   if (!(p->branch == CTDD_BRANCH_TAULDR || p->branch == CTDD_BRANCH_SDDM_REVERSE_PROB)) return false;
   if (!(p->mode == CTDD_MODE_TAU_LEAP || p->mode == CTDD_MODE_TAU_LEAP_CORR || p->mode == CTDD_MODE_MIDPOINT_JUMP ||
-        p->mode == CTDD_MODE_RATES_ONLY))
+        p->mode == CTDD_MODE_MIDPOINT_DRIFT || p->mode == CTDD_MODE_RATES_ONLY))
     return false;
   if (!p->tc_tables || !p->tc_static) return false;
-  if (p->mode != CTDD_MODE_RATES_ONLY && !p->workspace) return false;
   if ((p->ld_logits & 3) || (p->batch_stride_logits & 3) || (reinterpret_cast<uintptr_t>(p->logits) & 15)) return false;
+  if (p->mode == CTDD_MODE_RATES_ONLY &&
+      ((reinterpret_cast<uintptr_t>(p->rr_out) & 15) || (reinterpret_cast<uintptr_t>(p->ratio_out) & 15)))
+    return false;
   return true;
 }
 
 long long tc_workspace_bytes(long long rows, int S) {
-  if (S != tc::S) return 0;
-  return 2 * rows * (long long)sizeof(int2);
+  (void)rows; (void)S;
+  return 0;   // every row is finished inside the kernel (no cross-kernel partials)
 }
 
 int launch_step_tc(const ctdd_step_params* p, cudaStream_t st) {
@@ -599,15 +721,15 @@ int launch_step_tc(const ctdd_step_params* p, cudaStream_t st) {
   static bool attr_set = false;
   const size_t smem_bytes = sizeof(Smem) + 1024;
   typedef void (*kern_t)(const Args);
-  static const kern_t kerns[2][3] = {
-      {step_tc_kernel<false, false, false>, step_tc_kernel<false, true, false>, step_tc_kernel<false, false, true>},
-      {step_tc_kernel<true, false, false>, step_tc_kernel<true, true, false>, step_tc_kernel<true, false, true>}};
+  static const kern_t kerns[2][4] = {
+      {step_tc_kernel<false, KM_JUMP>, step_tc_kernel<false, KM_CORR>, step_tc_kernel<false, KM_RATES>, step_tc_kernel<false, KM_DRIFT>},
+      {step_tc_kernel<true, KM_JUMP>, step_tc_kernel<true, KM_CORR>, step_tc_kernel<true, KM_RATES>, step_tc_kernel<true, KM_DRIFT>}};
   if (!attr_set) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     for (int i = 0; i < 2; ++i)
-      for (int j = 0; j < 3; ++j)
+      for (int j = 0; j < 4; ++j)
         if (cudaFuncSetAttribute(kerns[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
           set_error("ctdd_reverse_step: cannot reserve %zu bytes of shared memory for the tcgen05 kernel", smem_bytes);
           cudaGetLastError();
@@ -616,7 +738,7 @@ int launch_step_tc(const ctdd_step_params* p, cudaStream_t st) {
     attr_set = true;
   }
   Args a;
-  a.mode = p->mode; a.branch = p->branch; a.D = p->D; a.reject_multi = p->reject_multi;
+  a.branch = p->branch; a.D = p->D; a.reject_multi = p->reject_multi;
   a.rows = (long long)p->N * p->D; a.row_offset = p->row_offset;
   a.logits = p->logits; a.ld = p->ld_logits; a.batch_stride = p->batch_stride_logits;
   a.x_eval = p->x_eval; a.x_base = p->x_base;
@@ -625,21 +747,17 @@ int launch_step_tc(const ctdd_step_params* p, cudaStream_t st) {
   a.RbT = p->RbT; a.Rb = p->Rb; a.beta = p->beta; a.h = p->h; a.seed = p->seed; a.offset = p->offset;
   a.x_out = p->x_out; a.rr_out = p->rr_out; a.ratio_out = p->ratio_out;
   a.stats = reinterpret_cast<unsigned long long*>(p->stats_out);
-  a.partial = reinterpret_cast<int2*>(p->workspace);
   a.num_tiles = (int)((a.rows + NT - 1) / NT);
-  int grid = num_sms & ~1;                         // CTA pairs (state halves) share a tile sequence
-  if (grid > 2 * a.num_tiles) grid = 2 * a.num_tiles;
-  if (grid < 2) grid = 2;
+  int pairs = num_sms / 2;                           // one CTA pair (cluster of 2) per TPC
+  if (pairs > a.num_tiles) pairs = a.num_tiles;
+  if (pairs < 1) pairs = 1;
   const int ki = (p->branch == CTDD_BRANCH_TAULDR) ? 1 : 0;
-  const int kj = (p->mode == CTDD_MODE_RATES_ONLY) ? 2 : (p->mode == CTDD_MODE_TAU_LEAP_CORR ? 1 : 0);
-  kerns[ki][kj]<<<grid, NUM_THREADS, smem_bytes, st>>>(a);
+  int kj = KM_JUMP;
+  if (p->mode == CTDD_MODE_RATES_ONLY) kj = KM_RATES;
+  else if (p->mode == CTDD_MODE_TAU_LEAP_CORR) kj = KM_CORR;
+  else if (p->mode == CTDD_MODE_MIDPOINT_DRIFT) kj = KM_DRIFT;
+  kerns[ki][kj]<<<2 * pairs, NUM_THREADS, smem_bytes, st>>>(a);
   CTDD_CHECK_LAUNCH("step_tc_kernel");
-  if (p->mode != CTDD_MODE_RATES_ONLY) {
-    const int threads = 1024;
-    step_tc_finalize_kernel<<<(unsigned)((a.rows + threads - 1) / threads), threads, 0, st>>>(
-        a.partial, a.x_eval, a.x_base, a.rows, a.reject_multi, a.x_out, a.stats);
-    CTDD_CHECK_LAUNCH("step_tc_finalize_kernel");
-  }
   return 0;
 }
 
@@ -651,15 +769,18 @@ extern "C" int64_t ctdd_tc_static_bytes(int S) { return S == ctdd::tc::S ? (int6
 extern "C" int ctdd_prep_tc_tables(const float* Q, const float* QT, const float* Rb, int T, int S, float eps,
                                    int branch, void* tables_out, void* stream) {
   using namespace ctdd;
-  (void)Q; (void)Rb;
+  (void)Q;
   if (S != tc::S) { set_error("ctdd_prep_tc_tables: the tcgen05 path needs S == 256 (got %d)", S); return 2; }
-  if (!QT || !tables_out || T <= 0) { set_error("ctdd_prep_tc_tables: bad arguments"); return 2; }
-  for (int t0 = 0; t0 < T; t0 += 65535) {
-    const int nt = (T - t0) < 65535 ? (T - t0) : 65535;
+  if (!QT || !Rb || !tables_out || T <= 0) { set_error("ctdd_prep_tc_tables: bad arguments"); return 2; }
+  for (int t0 = 0; t0 < T; t0 += 32768) {
+    const int nt = (T - t0) < 32768 ? (T - t0) : 32768;
+    uint8_t* out = reinterpret_cast<uint8_t*>(tables_out) + (size_t)t0 * tc::TAB_BYTES;
     dim3 grid(32, nt);
-    tc::prep_tables_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(QT + (size_t)t0 * S * S, nt, eps, branch,
-                                                                  reinterpret_cast<uint8_t*>(tables_out) + (size_t)t0 * tc::TAB_BYTES);
+    tc::prep_tables_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(QT + (size_t)t0 * S * S, nt, eps, branch, out);
     CTDD_CHECK_LAUNCH("prep_tables_kernel");
+    dim3 ggrid(S / 16, S / 16, nt), gblock(16, 16);
+    tc::prep_g_kernel<<<ggrid, gblock, 0, (cudaStream_t)stream>>>(QT + (size_t)t0 * S * S, Rb, eps, branch, out);
+    CTDD_CHECK_LAUNCH("prep_g_kernel");
   }
   return 0;
 }

@@ -207,9 +207,7 @@ def tau_leap_update(rates_z: torch.Tensor, x_eval: torch.Tensor, x_base: torch.T
     """sampling.py:127-160 (and :481-503 for midpoint stage 2). rates_z: (N,D,S) with s==x_eval zeroed."""
     N, D, _ = rates_z.shape
     lam = (rates_z.detach() * h).numpy().reshape(N * D, S)
-    V = rng.jump_units(N * D, S, row_offset, offset, seed)
-    k = rng.poisson_from_unit(lam, V)
-    kc = np.minimum(k, 4096)
+    kc, _ = rng.poisson_rows(lam, row_offset, offset, seed)
     diff = np.arange(S, dtype=np.int64)[None, :] - x_eval.numpy().reshape(-1, 1).astype(np.int64)
     jump = (kc * diff).sum(axis=1)
     cnt = kc.sum(axis=1)

@@ -6,7 +6,7 @@ pin oracle/ctmc_oracle.py and to generate tests/golden/*.npz.  Nothing here is i
 The reference needs `torchtyping` (absent) -> 5-line shim.  lib.models.models is NOT imported (pulls timm /
 matplotlib); stub models compose nn.Module with the reference's own rate mixins instead.
 Randomness is injected by patching, inside the imported reference only:
-  torch.distributions.poisson.Poisson.sample       -> rng.poisson_from_unit(rate, jump uniforms)
+  torch.distributions.poisson.Poisson.sample       -> rng.poisson_rows(rate) (superposition map on per-row uniforms)
   torch.distributions.categorical.Categorical.sample -> rng.inv_cdf(probs, per-row uniforms of a scheduled stream)
   lib.sampling.sampling.get_initial_samples        -> oracle initial samples
   torch.rand (loss time draw)                      -> injected ts
@@ -124,9 +124,9 @@ class Injector:
             rate = self_.rate
             S = rate.shape[-1]
             lam = rate.detach().numpy().astype(np.float32).reshape(-1, S)
-            V = rng.jump_units(lam.shape[0], S, 0, inj.call, inj.seed)
+            counts, _ = rng.poisson_rows(lam, 0, inj.call, inj.seed)
             inj.call += 1
-            return torch.from_numpy(rng.poisson_from_unit(lam, V).reshape(rate.shape)).to(rate.dtype)
+            return torch.from_numpy(counts.reshape(rate.shape)).to(rate.dtype)
 
         def c_sample(self_, sample_shape=torch.Size()):
             probs = self_.probs.detach().numpy().astype(np.float32)

@@ -9,17 +9,22 @@ This module defines that map bit-for-bit the way the CUDA kernels evaluate it:
 
   * Philox4x32-10 (Salmon et al., SC'11; Random123 constants) keyed on (seed), counter =
     (state s | sub-index, global-row group, call offset, stream id);
-  * jump uniforms: one Philox call serves 8 consecutive global rows at one state s; the row takes halfword
-    (row & 7); the 32-bit uniform is (hi16 << 16 | lo16) from streams JUMP_HI / JUMP_LO;
-  * per-row uniforms: one call serves 4 consecutive rows (word row & 3);
+  * tau-leap jump counts of one row (poisson_rows): the S independent Poisson(lam_s) counts are drawn through the
+    superposition identity — total K ~ Poisson(sum_s lam_s) by upper-tail inverse CDF on the row's first uniform,
+    then K categorical picks over lam_s / sum by inverse CDF on further uniforms of the same row — which is the
+    same joint law as S independent draws (tests/test_rng_maps.py checks marginals and independence);
+    Philox call c of row g: counter (c, g, offset, STREAM_JUMP); word 0 of call 0 is the total's uniform, words
+    1..3 picks 0..2, call 1 + (j-3)//4 word (j-3)%4 pick j >= 3;
+  * per-row uniforms (Euler, initial state, noising): one call serves 4 consecutive rows (word row & 3);
   * v = (word + 0.5) * 2^-32 in fp32; Poisson by upper-tail inverse CDF; categorical by sequential fp32 cumsum.
 """
 from __future__ import annotations
 
 import numpy as np
 
-STREAM_JUMP_HI = 0
-STREAM_JUMP_LO = 1
+STREAM_JUMP = 0       # per-row tau-leap draws (total count + picks)
+STREAM_RESERVED = 1
+JUMP_PICK_CAP = 4096  # picks evaluated per row (rows whose total exceeds it are clamp-saturated anyway)
 STREAM_ROW = 2
 STREAM_INIT = 3
 STREAM_NOISE_XT = 4
@@ -59,32 +64,40 @@ def _c3(stream: int, offset: int, hi_bits):
             | ((np.asarray(hi_bits, dtype=np.uint64) & np.uint64(0xFF)) << np.uint64(24)))
 
 
-def jump_halfwords(rows: int, S: int, row_offset: int, offset: int, stream: int, seed: int) -> np.ndarray:
-    """uint32 array (rows, S) of 16-bit halfwords for global rows row_offset .. row_offset+rows."""
-    grow = np.arange(rows, dtype=np.uint64) + np.uint64(row_offset)
-    groups = np.unique(grow >> np.uint64(3))
-    s = np.arange(S, dtype=np.uint64)
-    w = philox4x32_10(s[None, :], (groups & _MASK)[:, None], np.uint64(offset & 0xFFFFFFFF),
-                      _c3(stream, offset, groups >> np.uint64(32))[:, None],
-                      seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    words = np.stack(w, axis=-1)  # (G, S, 4)
-    gidx = ((grow >> np.uint64(3)) - groups[0]).astype(np.int64)
-    half = (grow & np.uint64(7)).astype(np.int64)
-    sel = words[gidx, :, half >> 1]  # (rows, S)
-    return (sel >> (16 * (half & 1)).astype(np.uint32)[:, None]) & np.uint32(0xFFFF)
-
-
 def u32_to_unit(word: np.ndarray) -> np.ndarray:
     """(word + 0.5) * 2^-32 in fp32 with a single rounding (device: I2F.RN then FFMA)."""
     f = word.astype(np.uint32).astype(np.float32)  # round-to-nearest-even, like cvt.rn.f32.u32
     return (f.astype(np.float64) * 2.0 ** -32 + 2.0 ** -33).astype(np.float32)
 
 
-def jump_units(rows: int, S: int, row_offset: int, offset: int, seed: int) -> np.ndarray:
-    """fp32 (rows, S) jump uniforms v in (0, 1]."""
-    hi = jump_halfwords(rows, S, row_offset, offset, STREAM_JUMP_HI, seed)
-    lo = jump_halfwords(rows, S, row_offset, offset, STREAM_JUMP_LO, seed)
-    return u32_to_unit((hi << np.uint32(16)) | lo)
+def rowjump_words(grow: np.ndarray, offset: int, seed: int, call) -> np.ndarray:
+    """uint32 (len(grow), 4): Philox call `call` (scalar or per-row array) of the tau-leap stream of global rows grow."""
+    grow = np.asarray(grow, dtype=np.uint64)
+    w = philox4x32_10(np.asarray(call, dtype=np.uint64), grow & _MASK, np.uint64(offset & 0xFFFFFFFF),
+                      _c3(STREAM_JUMP, offset, grow >> np.uint64(32)), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    return np.stack(w, axis=-1)
+
+
+def rowjump_total_unit(rows: int, row_offset: int, offset: int, seed: int) -> np.ndarray:
+    """fp32 (rows,): the uniform that decides the row's total jump count."""
+    grow = np.arange(rows, dtype=np.uint64) + np.uint64(row_offset)
+    return u32_to_unit(rowjump_words(grow, offset, seed, 0)[:, 0])
+
+
+def rowjump_pick_units(grow: np.ndarray, offset: int, seed: int, npicks: int) -> np.ndarray:
+    """fp32 (len(grow), npicks): pick uniforms j = 0..npicks-1 of the given global rows."""
+    grow = np.asarray(grow, dtype=np.uint64)
+    out = np.empty((grow.shape[0], npicks), dtype=np.float32)
+    first = rowjump_words(grow, offset, seed, 0)
+    for j in range(min(3, npicks)):
+        out[:, j] = u32_to_unit(first[:, 1 + j])
+    for c in range(1, 1 + (max(npicks - 3, 0) + 3) // 4):
+        w = rowjump_words(grow, offset, seed, c)
+        for i in range(4):
+            j = 3 + 4 * (c - 1) + i
+            if j < npicks:
+                out[:, j] = u32_to_unit(w[:, i])
+    return out
 
 
 def row_units(rows: int, row_offset: int, offset: int, stream: int, seed: int, sub: int = 0) -> np.ndarray:
@@ -176,3 +189,40 @@ def inv_cdf(weights: np.ndarray, v: np.ndarray) -> np.ndarray:
         last = np.where(posw.any(axis=1), w.shape[1] - 1 - posw[:, ::-1].argmax(axis=1), 0)
         first = np.where(none, last, first)
     return first.astype(np.int64)
+
+
+def poisson_rows(lam: np.ndarray, row_offset: int, offset: int, seed: int):
+    """Jump counts k[r, s] ~ independent Poisson(lam[r, s]) through the superposition map (module docstring).
+
+    lam (rows, S) fp32 >= 0. Returns (counts (rows, S) int64, total (rows,) int64); counts.sum(1) == min(total, cap).
+    Op order = device order of the CUDA-core kernels: sequential fp32 cumsum over s, total = last cumsum entry,
+    K = poisson_from_unit(total, v0), pick j = first s with cum[s] > min(v_j, 1 - 2^-24) * total.
+    """
+    lam = np.ascontiguousarray(lam, dtype=np.float32)
+    rows, S = lam.shape
+    cum = np.cumsum(lam, axis=1, dtype=np.float32)
+    tot = cum[:, -1]
+    v0 = rowjump_total_unit(rows, row_offset, offset, seed)
+    K = poisson_from_unit(tot, v0)
+    counts = np.zeros((rows, S), dtype=np.int64)
+    idx = np.flatnonzero(K > 0)
+    if idx.size == 0:
+        return counts, K
+    Kc = np.minimum(K[idx], JUMP_PICK_CAP)
+    kmax = int(Kc.max())
+    picks = rowjump_pick_units(idx.astype(np.uint64) + np.uint64(row_offset), offset, seed, kmax)
+    w = lam[idx]
+    c = cum[idx]
+    t = tot[idx]
+    posw = w > 0
+    last = np.where(posw.any(axis=1), S - 1 - posw[:, ::-1].argmax(axis=1), 0)
+    for j in range(kmax):
+        live = Kc > j
+        if not live.any():
+            break
+        target = (np.minimum(picks[:, j], np.float32(0.99999994)) * t).astype(np.float32)
+        gt = c > target[:, None]
+        s_j = np.where(gt.any(axis=1), gt.argmax(axis=1), last)
+        li = np.flatnonzero(live)
+        np.add.at(counts, (idx[li], s_j[li]), 1)
+    return counts, K

@@ -152,7 +152,7 @@ def test_step_modes_match_oracle(sc, impl_i):
     def run(mode, offset, reject=False, x_base=None):
         stats = torch.zeros(8, dtype=torch.int64, device="cuda")
         use = impl
-        if impl == nat.IMPL_TC and mode in (nat.MODE_MIDPOINT_DRIFT, nat.MODE_EULER, nat.MODE_EULER_CORR):
+        if impl == nat.IMPL_TC and mode in (nat.MODE_EULER, nat.MODE_EULER_CORR):
             use = nat.IMPL_AUTO   # these modes run on the CUDA-core path at S=256
         out = ops.reverse_step(mode, branch, lg, xe, tb["Q"], tb["QT"], tb["Rb"], tb["RbT"], tb["beta"], h, 1e-9,
                                N=N, D=D, S=S, impl=use, tc_tables=tct, tc_static=tcs,
@@ -283,7 +283,7 @@ def test_tc_path_full_tiles_and_tail_match_simt():
     several tiles per CTA, both branches; rates within 1e-4, states identical up to threshold ties."""
     from ctdd_b200 import ops
     nat = _nat()
-    for (N, D) in ((1, 1), (3, 21), (7, 640), (64, 300)):
+    for (N, D) in ((1, 1), (3, 21), (7, 640), (64, 300), (48, 2048)):   # the last: > RING tiles per CTA pair
         for loss_name, lt in (("CTElbo", None), ("CatRM", "reverse_prob")):
             fp, logits, x, S = _random_problem("gauss256", N, D, 0.35, 17 + N, 12.0)
             tb = _tables(fp, 0.35)

@@ -1,0 +1,46 @@
+"""CPU: the uniform -> jump-count map used by every tau-leap kernel and by the injected reference (oracle/rng.py
+poisson_rows) draws S INDEPENDENT Poisson(lam_s) counts per row (superposition: total ~ Poisson(sum lam), picks ~
+Categorical(lam / sum)).  Checked here: marginal pmfs, means, pairwise independence, determinism, sharding."""
+import numpy as np
+from scipy.stats import poisson
+
+from oracle import rng
+
+
+def test_poisson_rows_marginals_and_independence():
+    lam_row = np.array([0.0, 0.02, 0.7, 0.0, 1.9, 0.3, 0.004, 2.5], dtype=np.float32)
+    n = 400_000
+    lam = np.tile(lam_row, (n, 1))
+    k, K = rng.poisson_rows(lam, 0, 7, 0xC7DD)
+    assert k.shape == lam.shape and np.array_equal(k.sum(1), K)
+    assert np.all(k[:, lam_row == 0] == 0)
+    se = np.sqrt(lam_row / n) + 1e-9
+    assert np.all(np.abs(k.mean(0) - lam_row) < 5 * se)
+    for s, l in enumerate(lam_row):
+        if l == 0:
+            continue
+        for kk in range(0, 8):
+            p = poisson.pmf(kk, l)
+            assert abs((k[:, s] == kk).mean() - p) < 5 * np.sqrt(p * (1 - p) / n) + 2e-5
+    # independence: covariances vanish (a multinomial split WITHOUT the Poisson total would give -n p_i p_j)
+    c = np.cov(k[:, lam_row > 0].T.astype(np.float64))
+    off = c - np.diag(np.diag(c))
+    assert np.abs(off).max() < 0.012
+    np.testing.assert_allclose(np.diag(c), lam_row[lam_row > 0], rtol=0.03, atol=2e-4)
+    # joint check on one pair: P(k_2 = 0, k_4 = 0) = exp(-(lam_2 + lam_4))
+    both0 = ((k[:, 2] == 0) & (k[:, 4] == 0)).mean()
+    assert abs(both0 - np.exp(-(0.7 + 1.9))) < 3e-3
+
+
+def test_poisson_rows_is_a_function_of_global_row_and_offset():
+    g = np.random.Generator(np.random.PCG64(5))
+    lam = (g.random((64, 16)) * 0.4).astype(np.float32)
+    a, _ = rng.poisson_rows(lam, 0, 3, 11)
+    b0, _ = rng.poisson_rows(lam[:24], 0, 3, 11)
+    b1, _ = rng.poisson_rows(lam[24:], 24, 3, 11)
+    assert np.array_equal(a, np.concatenate([b0, b1]))          # batch sharding does not change the draws
+    c, _ = rng.poisson_rows(lam, 0, 4, 11)
+    assert not np.array_equal(a, c)                             # a new call offset gives new draws
+    big = np.full((4, 8), 200.0, dtype=np.float32)              # total 1600 per row: picks are capped, counts bounded
+    kb, Kb = rng.poisson_rows(big, 0, 0, 1)
+    assert np.all(Kb > 1000) and np.all(kb.sum(1) <= rng.JUMP_PICK_CAP)
