@@ -24,6 +24,10 @@ NVCC_FLAGS = [
 ]
 
 
+if os.environ.get("CTDD_TRACE"):   # diagnostic build: per-tile clock stamps in the tcgen05 kernel (tools/tc_trace.py)
+    NVCC_FLAGS.append("-DCTDD_TC_TRACE")
+
+
 def _sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 

@@ -25,18 +25,19 @@ namespace ctdd {
 namespace tc {
 
 constexpr int S = 256;
-constexpr int NH = 64;                 // rows produced and sampled by one CTA per tile
+constexpr int NH = 32;                 // rows produced and sampled by one CTA per tile
 constexpr int NT = 2 * NH;             // rows per pair tile (= UMMA N)
-constexpr int STAGES = 2;              // smem operand stages
-constexpr int ACC = 2;                 // TMEM accumulator buffers
-constexpr int RING = 8;                // per-tile side-info ring
+constexpr int STAGES = 3;              // smem operand stages
+constexpr int ACC = 4;                 // TMEM accumulator buffers (NT columns each)
+constexpr int GBUF = 2;                // gather buffers: phase A of tile i+1 overlaps the sampling of tile i
+constexpr int RING = 16;               // per-tile side-info ring (> STAGES + ACC + GBUF + 2)
 constexpr int NUM_EPI_WARPS = 8;       // warp w: TMEM quadrant w&3, column half w>>2 (= owner CTA of those rows)
 constexpr int MMA_WARP = 8;
 constexpr int FIRST_PROD_WARP = 9;
 constexpr int NUM_PROD_WARPS = 8;
 constexpr int NUM_THREADS = (FIRST_PROD_WARP + NUM_PROD_WARPS) * 32;  // 544
-constexpr int ROWS_PER_PROD = NH / NUM_PROD_WARPS;                   // 8
-constexpr int ROWS_PER_SAMPLER = NH / NUM_EPI_WARPS;                 // 8
+constexpr int ROWS_PER_PROD = NH / NUM_PROD_WARPS;                   // 4
+constexpr int ROWS_PER_SAMPLER = NH / NUM_EPI_WARPS;                 // 4
 constexpr int KBLOCK_BYTES = NH * 128;         // one 64-wide K block of one split: NH rows x 128 B
 constexpr int SPLIT_BYTES = 4 * KBLOCK_BYTES;  // K = 256 -> 4 blocks
 constexpr int STAGE_BYTES = 2 * SPLIT_BYTES;   // hi + mid
@@ -61,16 +62,16 @@ struct __align__(16) Side { float c1, c0; int x; int K; uint32_t w1, w2, w3; int
 
 struct Smem {
   alignas(1024) uint8_t stage[STAGES][STAGE_BYTES];
-  alignas(16) float gather[NH][S];   // [row owned by this CTA][state]: accumulator values, then prefix sums
+  alignas(16) float gather[GBUF][NH][S];   // [row owned by this CTA][state]: accumulator values, then prefix sums
   Side side[RING][NH];
   alignas(8) uint64_t full[STAGES];  // used in the leader CTA: 8 local + 8 remote producer warps
   uint64_t empty[STAGES];            // multicast tcgen05.commit
   uint64_t side_full[RING];          // local producers -> local samplers
   uint64_t tmem_full[ACC];           // multicast tcgen05.commit
   uint64_t tmem_empty[ACC];          // used in the leader CTA: 8 local + 8 remote epilogue warps
-  uint64_t gather_full;              // 4 local + 4 remote epilogue warps have written this CTA's gather buffer
-  uint64_t gather_free_local;        // the 8 local sampler warps are done with this CTA's gather buffer
-  uint64_t gather_free_remote;       // the 8 sampler warps of the PARTNER are done with the partner's buffer
+  uint64_t gather_full[GBUF];        // 4 local + 4 remote epilogue warps have written this CTA's gather buffer
+  uint64_t gather_free_local[GBUF];  // the 8 local sampler warps are done with this CTA's gather buffer
+  uint64_t gather_free_remote[GBUF]; // the 8 sampler warps of the PARTNER are done with the partner's buffer
   uint32_t tmem_base;
 };
 
@@ -117,24 +118,35 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// arrive on a barrier addressed in the cluster window (own or partner CTA), release at cluster scope
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+// arrive on a barrier addressed in the cluster window (own or partner CTA). RELEASE: the arriving thread's earlier
+// writes (and, through __syncwarp, its warp's) are visible to whoever acquires the phase; RELAXED: pure signalling
+// (tensor-memory reads already fenced with tcgen05.fence, or buffers whose values were consumed before the arrive).
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait for a phase; the try_wait suspends in hardware up to the time hint instead of spinning
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1, %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra DONE_%=;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware, do not spin
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
       : "memory");
 }
+// same, for phases completed by arrivals from the partner CTA: acquire at cluster scope once the phase has flipped
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  mbar_wait(bar, parity);
+  asm volatile("fence.acq_rel.cluster;" ::: "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -235,8 +247,23 @@ __device__ __forceinline__ int warp_sum_int(int v) {
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
-constexpr int PROD_BATCH = 2;          // rows whose loads are issued together by a producer warp
-constexpr int PREFETCH_TILES = 3;      // L2 bulk-prefetch distance (tiles of this pair's sequence)
+#ifdef CTDD_TC_TRACE
+// diagnostic build only (CTDD_TRACE=1 python build.py): per-tile clock stamps of one CTA's roles, read back with
+// ctdd_debug_trace_read; never compiled into the product library
+constexpr int TRACE_TILES = 1024, TRACE_EVENTS = 8, TRACE_ROLES = 4;
+__device__ long long g_trace[2][TRACE_ROLES][TRACE_TILES][TRACE_EVENTS];
+#define TRACE(role, tile, ev)                                                                       \
+  do {                                                                                              \
+    if (blockIdx.x < 2 && (tile) < TRACE_TILES) g_trace[blockIdx.x][role][tile][ev] = clock64();    \
+  } while (0)
+#else
+#define TRACE(role, tile, ev) do { } while (0)
+#endif
+
+constexpr int PROD_BATCH = 2;          // rows processed together by a producer warp (two batches per tile)
+constexpr int PREFETCH_TILES = 6;      // L2 bulk-prefetch distance (tiles of this pair's sequence)
+
+struct RowLoad { float4 v0, v1; int x; bool ok; };
 
 // TAULDR: tauLDR rates (else SDDM reverse_prob); KM: KM_JUMP / KM_CORR (corrector adds R_t[x,:]) / KM_RATES / KM_DRIFT
 template <bool TAULDR, int KM>
@@ -253,9 +280,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     for (int i = 0; i < STAGES; ++i) { mbar_init(&sm.full[i], 2 * NUM_PROD_WARPS); mbar_init(&sm.empty[i], 1); }
     for (int i = 0; i < RING; ++i) mbar_init(&sm.side_full[i], NUM_PROD_WARPS);
     for (int i = 0; i < ACC; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], 2 * NUM_EPI_WARPS); }
-    mbar_init(&sm.gather_full, NUM_EPI_WARPS);
-    mbar_init(&sm.gather_free_local, NUM_EPI_WARPS);
-    mbar_init(&sm.gather_free_remote, NUM_EPI_WARPS);
+    for (int i = 0; i < GBUF; ++i) {
+      mbar_init(&sm.gather_full[i], NUM_EPI_WARPS);
+      mbar_init(&sm.gather_free_local[i], NUM_EPI_WARPS);
+      mbar_init(&sm.gather_free_remote[i], NUM_EPI_WARPS);
+    }
     fence_barrier_init();
   }
   if (warp == MMA_WARP) tmem_alloc(&sm.tmem_base);
@@ -298,131 +327,149 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     const bool contiguous = (a.ld == S) && (a.batch_stride == (long long)a.D * S);
     const bool can_prefetch = contiguous && pw == 0 && lane == 0;
     const uint32_t full_addr = mapa(smem_u32(&sm.full[0]), 0);   // the leader's full[] barriers
-    for (int i = 0; i < my_tiles; ++i) {
+    const int nbatch = my_tiles * (ROWS_PER_PROD / PROD_BATCH);
+
+    // logits + state of batch `bi` (tile bi / 2, rows pw + 8 * (2 * (bi & 1) + j)): issued one batch ahead of their use
+    auto issue = [&](int bi, RowLoad (&L)[PROD_BATCH]) {
+      const int tile = pair + (bi / (ROWS_PER_PROD / PROD_BATCH)) * npairs;
+      const long long g0 = (long long)tile * NT + (long long)rank * NH;
+      const int b0 = (bi % (ROWS_PER_PROD / PROD_BATCH)) * PROD_BATCH;
+#pragma unroll
+      for (int j = 0; j < PROD_BATCH; ++j) {
+        const long long g = g0 + pw + NUM_PROD_WARPS * (b0 + j);
+        L[j].ok = (bi < nbatch) && (g < a.rows);
+        const long long gc = L[j].ok ? g : 0;
+        const float* lp;
+        if (contiguous) {
+          lp = a.logits + gc * S + 4 * lane;
+        } else {
+          const uint32_t n = (uint32_t)gc / (uint32_t)a.D, d = (uint32_t)gc - n * (uint32_t)a.D;
+          lp = a.logits + (long long)n * a.batch_stride + (long long)d * a.ld + 4 * lane;
+        }
+        L[j].v0 = ld_stream(lp);
+        L[j].v1 = ld_stream(lp + 128);
+        L[j].x = __ldg(a.x_eval + gc);
+      }
+    };
+
+    RowLoad cur[PROD_BATCH], nxt[PROD_BATCH];
+    issue(0, cur);
+    // lane i (< 4) collects the scalars of this warp's i-th row of the tile and finishes it after the batches
+    float my_lam = 0.f, my_c1 = 0.f, my_c0 = 0.f;
+    int my_x = 0;
+    bool my_ok = false;
+#pragma unroll 1
+    for (int bi = 0; bi < nbatch; ++bi) {
+      const int i = bi / (ROWS_PER_PROD / PROD_BATCH);
+      const int b0 = (bi % (ROWS_PER_PROD / PROD_BATCH)) * PROD_BATCH;
       const int tile = pair + i * npairs;
       const int st = i % STAGES, slot = i % RING;
       const long long g0 = (long long)tile * NT + (long long)rank * NH;   // first row built by this CTA
-      if (can_prefetch) {   // pull this CTA's rows of a later tile into L2 while this one is processed
-        const long long r0 = g0 + (long long)PREFETCH_TILES * npairs * NT;
-        if (r0 < a.rows) {
-          const long long nrow = (a.rows - r0) < NH ? (a.rows - r0) : NH;
-          l2_prefetch_bulk(a.logits + r0 * S, (uint32_t)(nrow * S * 4));
-        }
+      // table rows of the current batch (x arrived with the previous batch's prefetch), then the next batch's logits
+      float4 t0[PROD_BATCH], t1[PROD_BATCH], q0[PROD_BATCH], q1[PROD_BATCH];
+#pragma unroll
+      for (int j = 0; j < PROD_BATCH; ++j) {
+        const size_t xo = (size_t)cur[j].x << 8;
+        t0[j] = __ldg(reinterpret_cast<const float4*>(tabA + xo));
+        t1[j] = __ldg(reinterpret_cast<const float4*>(tabA + xo + 128));
+        q0[j] = __ldg(reinterpret_cast<const float4*>(tabG + xo));
+        q1[j] = __ldg(reinterpret_cast<const float4*>(tabG + xo + 128));
       }
-      mbar_wait(&sm.empty[st], ((i / STAGES) & 1) ^ 1);
+      issue(bi + 1, nxt);
+      if (b0 == 0) {
+        if (can_prefetch) {   // pull this CTA's rows of a later tile into L2 while this one is processed
+          const long long r0 = g0 + (long long)PREFETCH_TILES * npairs * NT;
+          if (r0 < a.rows) {
+            const long long nrow = (a.rows - r0) < NH ? (a.rows - r0) : NH;
+            l2_prefetch_bulk(a.logits + r0 * S, (uint32_t)(nrow * S * 4));
+          }
+        }
+        if (pw == 0 && lane == 0) TRACE(0, i, 0);
+        mbar_wait(&sm.empty[st], ((i / STAGES) & 1) ^ 1);
+        if (pw == 0 && lane == 0) TRACE(0, i, 1);
+      }
       uint8_t* stage = sm.stage[st];
-#pragma unroll 1
-      for (int b0 = 0; b0 < ROWS_PER_PROD; b0 += PROD_BATCH) {
-        float4 v0[PROD_BATCH], v1[PROD_BATCH], t0[PROD_BATCH], t1[PROD_BATCH], q0[PROD_BATCH], q1[PROD_BATCH];
-        int xr[PROD_BATCH];
-        bool ok[PROD_BATCH];
-        // issue every load of the batch before touching the data
 #pragma unroll
-        for (int j = 0; j < PROD_BATCH; ++j) {
-          const int r = pw + NUM_PROD_WARPS * (b0 + j);
-          const long long g = g0 + r;
-          ok[j] = g < a.rows;
-          const long long gc = ok[j] ? g : 0;
-          const float* lp;
-          if (contiguous) {
-            lp = a.logits + gc * S + 4 * lane;
-          } else {
-            const uint32_t n = (uint32_t)gc / (uint32_t)a.D, d = (uint32_t)gc - n * (uint32_t)a.D;
-            lp = a.logits + (long long)n * a.batch_stride + (long long)d * a.ld + 4 * lane;
-          }
-          v0[j] = ld_stream(lp);
-          v1[j] = ld_stream(lp + 128);
-          xr[j] = __ldg(a.x_eval + gc);
+      for (int j = 0; j < PROD_BATCH; ++j) {
+        const int r = pw + NUM_PROD_WARPS * (b0 + j);
+        float c1, c0;
+        float v[8] = {cur[j].v0.x, cur[j].v0.y, cur[j].v0.z, cur[j].v0.w, cur[j].v1.x, cur[j].v1.y, cur[j].v1.z, cur[j].v1.w};
+        const float t[8] = {t0[j].x, t0[j].y, t0[j].z, t0[j].w, t1[j].x, t1[j].y, t1[j].z, t1[j].w};
+        const float gq[8] = {q0[j].x, q0[j].y, q0[j].z, q0[j].w, q1[j].x, q1[j].y, q1[j].z, q1[j].w};
+        float m = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+        m = warp_max(m);
+        const float ml = -m * 1.4426950408889634f;
+        float sum = 0.f, dot = 0.f, dotg = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          v[q] = ex2_approx(fmaf(v[q], 1.4426950408889634f, ml));     // exp(v - max)
+          sum += v[q];
+          dotg = fmaf(v[q], gq[q], dotg);
+          if (!TAULDR) dot = fmaf(v[q], t[q], dot);
         }
+        sum = warp_sum(sum);
+        dotg = warp_sum(dotg);
+        const float rs = __frcp_rn(sum);
+        const float rz = (!TAULDR || KM == KM_CORR) ? __ldg(rowsumZ + cur[j].x) : 0.f;
+        if (TAULDR) {
 #pragma unroll
-        for (int j = 0; j < PROD_BATCH; ++j) {
-          const size_t xo = (size_t)xr[j] << 8;
-          t0[j] = __ldg(reinterpret_cast<const float4*>(tabA + xo));
-          t1[j] = __ldg(reinterpret_cast<const float4*>(tabA + xo + 128));
-          q0[j] = __ldg(reinterpret_cast<const float4*>(tabG + xo));
-          q1[j] = __ldg(reinterpret_cast<const float4*>(tabG + xo + 128));
+          for (int q = 0; q < 8; ++q) v[q] *= t[q];             // e_k / (Q[k,x] + eps); 1/sum applied by the sampler
+          c1 = hb * rs;                                          // lam_s = D_s * c1 * Rb[s,x]
+          c0 = 0.f;
+        } else {
+          dot = warp_sum(dot);
+          const float inv = __frcp_rn(fmaf(dot, rs, 1e-35f));    // 1 / (pQ[x] + 1e-35)
+          c1 = hb * rs * inv;                                    // lam_s = (D_s * c1 + c0) * Rb[x,s]
+          c0 = hb * 1e-35f * inv;
         }
-        float lam_tot[PROD_BATCH], c1s[PROD_BATCH], c0s[PROD_BATCH];
+        float lam_tot = fmaf(c1, dotg, c0 * rz);
+        if (KM == KM_CORR) lam_tot = fmaf(hb, rz, lam_tot);
+        if (lane == b0 + j) { my_lam = lam_tot; my_c1 = c1; my_c0 = c0; my_x = cur[j].x; my_ok = cur[j].ok; }
+        uint32_t hi[4], mid[4];
 #pragma unroll
-        for (int j = 0; j < PROD_BATCH; ++j) {
-          const int r = pw + NUM_PROD_WARPS * (b0 + j);
-          float v[8] = {v0[j].x, v0[j].y, v0[j].z, v0[j].w, v1[j].x, v1[j].y, v1[j].z, v1[j].w};
-          const float t[8] = {t0[j].x, t0[j].y, t0[j].z, t0[j].w, t1[j].x, t1[j].y, t1[j].z, t1[j].w};
-          const float gq[8] = {q0[j].x, q0[j].y, q0[j].z, q0[j].w, q1[j].x, q1[j].y, q1[j].z, q1[j].w};
-          float m = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
-          m = warp_max(m);
-          const float ml = -m * 1.4426950408889634f;
-          float sum = 0.f, dot = 0.f, dotg = 0.f;
+        for (int q = 0; q < 4; ++q) split2(v[2 * q], v[2 * q + 1], hi[q], mid[q]);
+        if (!cur[j].ok) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            v[q] = ex2_approx(fmaf(v[q], 1.4426950408889634f, ml));     // exp(v - max)
-            sum += v[q];
-            dotg = fmaf(v[q], gq[q], dotg);
-            if (!TAULDR) dot = fmaf(v[q], t[q], dot);
-          }
-          sum = warp_sum(sum);
-          dotg = warp_sum(dotg);
-          const float rs = __frcp_rn(sum);
-          const float rz = (!TAULDR || KM == KM_CORR) ? __ldg(rowsumZ + xr[j]) : 0.f;
-          if (TAULDR) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] *= t[q];             // e_k / (Q[k,x] + eps); 1/sum applied by the sampler
-            c1s[j] = hb * rs;                                      // lam_s = D_s * c1 * Rb[s,x]
-            c0s[j] = 0.f;
-          } else {
-            dot = warp_sum(dot);
-            const float inv = __frcp_rn(fmaf(dot, rs, 1e-35f));    // 1 / (pQ[x] + 1e-35)
-            c1s[j] = hb * rs * inv;                                // lam_s = (D_s * c1 + c0) * Rb[x,s]
-            c0s[j] = hb * 1e-35f * inv;
-          }
-          lam_tot[j] = fmaf(c1s[j], dotg, c0s[j] * rz);
-          if (KM == KM_CORR) lam_tot[j] = fmaf(hb, rz, lam_tot[j]);
-          uint32_t hi[4], mid[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) split2(v[2 * q], v[2 * q + 1], hi[q], mid[q]);
-          if (!ok[j]) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) hi[q] = mid[q] = 0u;
-          }
-          // k = 4*lane..+3 lives in K block lane/16, 16-byte chunk (lane%16)/2 (XOR-swizzled by the row), half lane&1;
-          // k = 128 + 4*lane..+3 two K blocks further on
-          const uint32_t off = (uint32_t)(lane >> 4) * KBLOCK_BYTES + (uint32_t)r * 128 +
-                               (uint32_t)(((((lane & 15) >> 1) ^ (r & 7)) << 4) | ((lane & 1) << 3));
-          *reinterpret_cast<uint2*>(stage + off) = make_uint2(hi[0], hi[1]);
-          *reinterpret_cast<uint2*>(stage + off + 2 * KBLOCK_BYTES) = make_uint2(hi[2], hi[3]);
-          *reinterpret_cast<uint2*>(stage + SPLIT_BYTES + off) = make_uint2(mid[0], mid[1]);
-          *reinterpret_cast<uint2*>(stage + SPLIT_BYTES + off + 2 * KBLOCK_BYTES) = make_uint2(mid[2], mid[3]);
+          for (int q = 0; q < 4; ++q) hi[q] = mid[q] = 0u;
         }
-        // lane j of the warp finishes row j of the batch: total jump count and the first pick uniforms
-        if (lane < PROD_BATCH) {
-          float lt = lam_tot[0], c1 = c1s[0], c0 = c0s[0];
-          int x = xr[0];
-          bool valid = ok[0];
+        // k = 4*lane..+3 lives in K block lane/16, 16-byte chunk (lane%16)/2 (XOR-swizzled by the row), half lane&1;
+        // k = 128 + 4*lane..+3 two K blocks further on
+        const uint32_t off = (uint32_t)(lane >> 4) * KBLOCK_BYTES + (uint32_t)r * 128 +
+                             (uint32_t)(((((lane & 15) >> 1) ^ (r & 7)) << 4) | ((lane & 1) << 3));
+        *reinterpret_cast<uint2*>(stage + off) = make_uint2(hi[0], hi[1]);
+        *reinterpret_cast<uint2*>(stage + off + 2 * KBLOCK_BYTES) = make_uint2(hi[2], hi[3]);
+        *reinterpret_cast<uint2*>(stage + SPLIT_BYTES + off) = make_uint2(mid[0], mid[1]);
+        *reinterpret_cast<uint2*>(stage + SPLIT_BYTES + off + 2 * KBLOCK_BYTES) = make_uint2(mid[2], mid[3]);
+      }
 #pragma unroll
-          for (int j = 1; j < PROD_BATCH; ++j)
-            if (lane == j) { lt = lam_tot[j]; c1 = c1s[j]; c0 = c0s[j]; x = xr[j]; valid = ok[j]; }
-          const int r = pw + NUM_PROD_WARPS * (b0 + lane);
+      for (int j = 0; j < PROD_BATCH; ++j) cur[j] = nxt[j];
+      if (pw == 0 && lane == 0) TRACE(0, i, 2 + (b0 / PROD_BATCH));
+      if (b0 + PROD_BATCH == ROWS_PER_PROD) {   // last batch of the tile
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster_release(full_addr + (uint32_t)st * 8u);   // operand rows are in place
+        if (pw == 0 && lane == 0) TRACE(0, i, 4);
+        // lanes 0..3 finish the warp's rows together: total jump count and the first pick uniforms
+        if (lane < ROWS_PER_PROD) {
+          const int r = pw + NUM_PROD_WARPS * lane;
           Side si;
-          si.c1 = c1; si.c0 = c0; si.x = x; si.valid = valid ? 1 : 0;
+          si.c1 = my_c1; si.c0 = my_c0; si.x = my_x; si.valid = my_ok ? 1 : 0;
           si.K = 0; si.w1 = si.w2 = si.w3 = 0u;
-          if (valid) {
+          if (my_ok) {
             if (KM == KM_RATES || KM == KM_DRIFT) {
               si.K = 1;
             } else {
               const Philox4 p0 = philox_rowjump((uint64_t)(a.row_offset + g0 + r), 0, a.offset, a.seed);
-              int K = poisson_from_unit(lt, u32_to_unit(p0.w[0]));
+              const int K = poisson_from_unit(my_lam, u32_to_unit(p0.w[0]));
               si.K = K > JUMP_PICK_CAP ? JUMP_PICK_CAP : K;
               si.w1 = p0.w[1]; si.w2 = p0.w[2]; si.w3 = p0.w[3];
             }
           }
           sm.side[slot][r] = si;
         }
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive_cluster(full_addr + (uint32_t)st * 8u);
-        mbar_arrive(&sm.side_full[slot]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.side_full[slot]);
+        if (pw == 0 && lane == 0) TRACE(0, i, 5);
       }
     }
   } else if (warp == MMA_WARP) {
@@ -430,8 +477,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     if (rank == 0 && lane == 0) {
       for (int i = 0; i < my_tiles; ++i) {
         const int st = i % STAGES, b = i % ACC;
-        mbar_wait(&sm.full[st], (i / STAGES) & 1);
+        TRACE(1, i, 0);
+        mbar_wait_cluster(&sm.full[st], (i / STAGES) & 1);
+        TRACE(1, i, 1);
         mbar_wait(&sm.tmem_empty[b], ((i / ACC) & 1) ^ 1);
+        TRACE(1, i, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem + TM_ACC + b * NT;
         const uint32_t base = smem_u32(sm.stage[st]);
@@ -449,179 +499,271 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         }
         umma_commit_pair(&sm.empty[st]);
         umma_commit_pair(&sm.tmem_full[b]);
+        TRACE(1, i, 3);
       }
     }
     __syncwarp();
   } else {
     // ======================================================================== epilogue + row sampler
     const int q = warp & 3;                       // TMEM quadrant -> states rank*128 + 32q + lane
-    const uint32_t owner = (uint32_t)(warp >> 2); // accumulator columns [64*owner, 64*owner+64) belong to CTA `owner`
+    const uint32_t owner = (uint32_t)(warp >> 2); // accumulator columns [32*owner, 32*owner+32) belong to CTA `owner`
     const int s_mine = (int)rank * 128 + q * 32 + lane;
-    const uint32_t gather_dst = mapa(smem_u32(&sm.gather[0][0]), owner) + (uint32_t)s_mine * 4u;
-    const uint32_t gfull_dst = mapa(smem_u32(&sm.gather_full), owner);
+    const uint32_t gather_dst = mapa(smem_u32(&sm.gather[0][0][0]), owner) + (uint32_t)s_mine * 4u;
+    const uint32_t gfull_dst = mapa(smem_u32(&sm.gather_full[0]), owner);
     const uint32_t tempty_dst = mapa(smem_u32(&sm.tmem_empty[0]), 0);
-    const uint32_t gfree_remote_dst = mapa(smem_u32(&sm.gather_free_remote), rank ^ 1u);
-    uint64_t* const gfree_wait = (owner == rank) ? &sm.gather_free_local : &sm.gather_free_remote;
+    const uint32_t gfree_remote_dst = mapa(smem_u32(&sm.gather_free_remote[0]), rank ^ 1u);
+    uint64_t* const gfree_wait = (owner == rank) ? &sm.gather_free_local[0] : &sm.gather_free_remote[0];
     const float* tabE = reinterpret_cast<const float*>(a.stat + (TAULDR ? ST_RBZT_OFF : ST_RBZ_OFF)) + 8 * lane;
     const float* tabC = reinterpret_cast<const float*>(a.stat + ST_RBZ_OFF) + 8 * lane;   // corrector add: Rb[x][s], zero diag
     const float* tabFull = (TAULDR ? a.RbT : a.Rb) + 8 * lane;                             // diagonal kept, for rr_out
     const float hb = a.h * a.beta;
     RowStats stt = {0, 0, 0, 0, 0};
-    for (int i = 0; i < my_tiles; ++i) {
-      const int tile = pair + i * npairs;
-      const int b = i % ACC, slot = i % RING;
-      // ---- phase A: accumulator (this CTA's 128 states x this warp's 64 rows) -> gather buffer of the rows' owner
+
+    // phase A of tile i: accumulator (this CTA's 128 states x this warp's 32 rows) -> gather buffer of the rows' owner
+    auto phase_a = [&](int i) {
+      const int b = i % ACC, gb = i % GBUF;
+      const int trole = 2 + (warp >> 2);
+      if ((warp & 3) == 0 && lane == 0) TRACE(trole, i, 0);
       mbar_wait(&sm.tmem_full[b], (i / ACC) & 1);
-      mbar_wait(gfree_wait, (i & 1) ^ 1);
+      if ((warp & 3) == 0 && lane == 0) TRACE(trole, i, 1);
+      mbar_wait(gfree_wait + gb, ((i / GBUF) & 1) ^ 1);
+      if ((warp & 3) == 0 && lane == 0) TRACE(trole, i, 2);
       tc_fence_after();
+      uint32_t acc[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + TM_ACC + b * NT + owner * NH, acc);
+      tmem_ld_wait();
+      if (owner == rank) {
+        float* dst = &sm.gather[gb][0][s_mine];
 #pragma unroll
-      for (int c0 = 0; c0 < NH; c0 += 32) {
-        uint32_t acc[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + TM_ACC + b * NT + owner * NH + c0, acc);
-        tmem_ld_wait();
-        if (owner == rank) {
-          float* dst = &sm.gather[c0][s_mine];
+        for (int j = 0; j < 32; ++j) dst[j * S] = __uint_as_float(acc[j]);
+      } else {
+        const uint32_t dst = gather_dst + (uint32_t)gb * (NH * S * 4);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dst[j * S] = __uint_as_float(acc[j]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) st_cluster_f32(gather_dst + (uint32_t)(c0 + j) * (S * 4), __uint_as_float(acc[j]));
-        }
+        for (int j = 0; j < 32; ++j) st_cluster_f32(dst + (uint32_t)j * (S * 4), __uint_as_float(acc[j]));
       }
       tc_fence_before();   // accumulator has been read: hand the buffer back to the MMA warp
       __syncwarp();
+      if ((warp & 3) == 0 && lane == 0) TRACE(trole, i, 3);
       if (lane == 0) {
-        mbar_arrive_cluster(tempty_dst + (uint32_t)b * 8u);
-        mbar_arrive_cluster(gfull_dst);
+        mbar_arrive_cluster_relaxed(tempty_dst + (uint32_t)b * 8u);
+        mbar_arrive_cluster_release(gfull_dst + (uint32_t)gb * 8u);
       }
-      // ---- phase B: sample the rows this CTA owns (warp w: rows 8w .. 8w+7 of the CTA's 64)
+      if ((warp & 3) == 0 && lane == 0) TRACE(trole, i, 4);
+    };
+
+    if (my_tiles > 0) phase_a(0);
+    for (int i = 0; i < my_tiles; ++i) {
+      // the next tile's accumulator is moved first: the cross-CTA hand-shakes of tile i complete in its shadow
+      if (i + 1 < my_tiles) phase_a(i + 1);
+      // ---- phase B: sample the rows this CTA owns (warp w: rows 4w .. 4w+3 of the CTA's 32)
+      const int tile = pair + i * npairs;
+      const int slot = i % RING, gb = i % GBUF;
+      if ((warp & 3) == 0 && lane == 0) TRACE(2 + (warp >> 2), i, 5);
       mbar_wait(&sm.side_full[slot], (i / RING) & 1);
-      mbar_wait(&sm.gather_full, i & 1);
+      mbar_wait_cluster(&sm.gather_full[gb], (i / GBUF) & 1);
+      if ((warp & 3) == 0 && lane == 0) TRACE(2 + (warp >> 2), i, 6);
       const long long g0 = (long long)tile * NT + (long long)rank * NH;
+      // lanes 0..3 settle the rows without a jump in one go; the rest are processed two rows per iteration
+      uint32_t todo;
+      {
+        bool need = false;
+        if (lane < ROWS_PER_SAMPLER) {
+          const int r = warp * ROWS_PER_SAMPLER + lane;
+          const Side sj = sm.side[slot][r];
+          if (sj.valid) {
+            if (KM != KM_RATES && KM != KM_DRIFT && sj.K == 0) {
+              const long long g = g0 + r;
+              const int xb = a.x_base ? a.x_base[g] : sj.x;
+              a.x_out[g] = finalize_jump(xb, sj.x, 0, 0, a.reject_multi, S, stt);
+            } else {
+              need = true;
+            }
+          }
+        }
+        todo = __ballot_sync(0xffffffffu, need);
+      }
+      if constexpr (KM == KM_RATES || KM == KM_DRIFT) {
 #pragma unroll 1
-      for (int rr = 0; rr < ROWS_PER_SAMPLER; ++rr) {
-        const int r = warp * ROWS_PER_SAMPLER + rr;
-        const Side si = sm.side[slot][r];
-        if (!si.valid) continue;
-        const long long g = g0 + r;
-        const int x = si.x;
-        if (KM != KM_RATES && KM != KM_DRIFT && si.K == 0) {
-          if (lane == 0) {
+        while (todo) {
+          const int rr = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const int r = warp * ROWS_PER_SAMPLER + rr;
+          const Side si = sm.side[slot][r];
+          const long long g = g0 + r;
+          const int x = si.x;
+          const float* grow_p = &sm.gather[gb][r][0];
+          const float4 d0 = *reinterpret_cast<const float4*>(grow_p + 8 * lane);
+          const float4 d1 = *reinterpret_cast<const float4*>(grow_p + 8 * lane + 4);
+          const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+          const size_t xo = (size_t)x << 8;
+          if constexpr (KM == KM_RATES) {
+            const float4 f0 = __ldg(reinterpret_cast<const float4*>(tabFull + xo));
+            const float4 f1 = __ldg(reinterpret_cast<const float4*>(tabFull + xo + 4));
+            const float f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+            float ratio[8], rfull[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              ratio[e] = fmaf(d[e], si.c1, si.c0);
+              rfull[e] = TAULDR ? a.beta * f[e] * ratio[e] : ratio[e] * (a.beta * f[e]);
+            }
+            if (a.rr_out) {
+              float4* o = reinterpret_cast<float4*>(a.rr_out + g * S + 8 * lane);
+              o[0] = make_float4(rfull[0], rfull[1], rfull[2], rfull[3]);
+              o[1] = make_float4(rfull[4], rfull[5], rfull[6], rfull[7]);
+            }
+            if (a.ratio_out) {
+              float4* o = reinterpret_cast<float4*>(a.ratio_out + g * S + 8 * lane);
+              o[0] = make_float4(ratio[0], ratio[1], ratio[2], ratio[3]);
+              o[1] = make_float4(ratio[4], ratio[5], ratio[6], ratio[7]);
+            }
+          } else {
+            // sampling.py:433-453: x' = clip(x + round_half_even(h/2 * sum_s rr_s (s - x)))
+            const float4 e0 = __ldg(reinterpret_cast<const float4*>(tabE + xo));
+            const float4 e1 = __ldg(reinterpret_cast<const float4*>(tabE + xo + 4));
+            const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+            float acc = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc = fmaf(fmaf(d[e], si.c1, si.c0) * ev[e], (float)(8 * lane + e - x), acc);
+            acc = warp_sum(acc);
+            if (lane == 0) {
+              const int ch = (int)rintf(0.5f * acc);
+              int xn = x + ch;
+              xn = xn < 0 ? 0 : (xn > S - 1 ? S - 1 : xn);
+              a.x_out[g] = xn;
+              stt.changed_base += (xn != x);
+              stt.changed_eval += (xn != x);
+              stt.nonzero += (ch != 0);
+            }
+          }
+        }
+      } else {
+        // jump modes: two rows in flight per iteration (independent dependency chains hide the shuffle / smem latency)
+#pragma unroll 1
+        while (todo) {
+          int rrow[2];
+          rrow[0] = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const bool two = todo != 0;
+          rrow[1] = two ? __ffs(todo) - 1 : rrow[0];
+          todo &= todo - 1;   // no-op when todo == 0
+          Side si[2];
+          float* gp[2];
+          float d[2][8];
+          float total[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int r = warp * ROWS_PER_SAMPLER + rrow[u];
+            si[u] = sm.side[slot][r];
+            gp[u] = &sm.gather[gb][r][0];
+          }
+          float4 e0[2], e1[2], c0v[2], c1v[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const size_t xo = (size_t)si[u].x << 8;
+            e0[u] = __ldg(reinterpret_cast<const float4*>(tabE + xo));
+            e1[u] = __ldg(reinterpret_cast<const float4*>(tabE + xo + 4));
+            if (KM == KM_CORR) {
+              c0v[u] = __ldg(reinterpret_cast<const float4*>(tabC + xo));
+              c1v[u] = __ldg(reinterpret_cast<const float4*>(tabC + xo + 4));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float4 d0 = *reinterpret_cast<const float4*>(gp[u] + 8 * lane);
+            const float4 d1 = *reinterpret_cast<const float4*>(gp[u] + 8 * lane + 4);
+            const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+            const float ev[8] = {e0[u].x, e0[u].y, e0[u].z, e0[u].w, e1[u].x, e1[u].y, e1[u].z, e1[u].w};
+            // lam_s for s = 8*lane .. 8*lane+7 (zero at s == x through the zero-diagonal tables)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) d[u][e] = fmaf(dv[e], si[u].c1, si[u].c0) * ev[e];
+            if (KM == KM_CORR) {
+              const float cv[8] = {c0v[u].x, c0v[u].y, c0v[u].z, c0v[u].w, c1v[u].x, c1v[u].y, c1v[u].z, c1v[u].w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) d[u][e] = fmaf(hb, cv[e], d[u][e]);
+            }
+            // inclusive prefix sums over the 256 states: in-lane, then across lanes
+#pragma unroll
+            for (int e = 1; e < 8; ++e) d[u][e] += d[u][e - 1];
+          }
+          float incl[2] = {d[0][7], d[1][7]};
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const float n = __shfl_up_sync(0xffffffffu, incl[u], o);
+              if (lane >= o) incl[u] += n;
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            float excl = __shfl_up_sync(0xffffffffu, incl[u], 1);
+            if (lane == 0) excl = 0.f;
+            total[u] = __shfl_sync(0xffffffffu, incl[u], 31);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) d[u][e] += excl;
+            if (u == 0 || two) {
+              *reinterpret_cast<float4*>(gp[u] + 8 * lane) = make_float4(d[u][0], d[u][1], d[u][2], d[u][3]);
+              *reinterpret_cast<float4*>(gp[u] + 8 * lane + 4) = make_float4(d[u][4], d[u][5], d[u][6], d[u][7]);
+            }
+          }
+          __syncwarp();
+          // K picks, one per lane: first state whose prefix sum exceeds v * total
+          const int K0 = si[0].K, K1 = two ? si[1].K : 0;
+          const int Kmax = K0 > K1 ? K0 : K1;
+          int jump[2] = {0, 0};
+          for (int base = 0; base < Kmax; base += 32) {
+            const int j = base + lane;
+            float target[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              uint32_t w = (j == 0) ? si[u].w1 : (j == 1 ? si[u].w2 : si[u].w3);
+              if (si[u].K > 3 && base < si[u].K) {   // warp-uniform
+                const int jj = j >= 3 ? j - 3 : 0;
+                const long long g = g0 + warp * ROWS_PER_SAMPLER + rrow[u];
+                const Philox4 pc = philox_rowjump((uint64_t)(a.row_offset + g), 1u + (uint32_t)(jj >> 2), a.offset, a.seed);
+                if (j >= 3) w = philox_word(pc, jj & 3);
+              }
+              target[u] = fminf(u32_to_unit(w), 0.99999994f) * total[u];
+            }
+            int lo[2] = {0, 0};
+#pragma unroll
+            for (int step = 128; step >= 1; step >>= 1) {
+#pragma unroll
+              for (int u = 0; u < 2; ++u)
+                if (!(gp[u][lo[u] + step - 1] > target[u])) lo[u] += step;
+            }
+            jump[0] += (j < K0) ? (lo[0] - si[0].x) : 0;
+            jump[1] += (j < K1) ? (lo[1] - si[1].x) : 0;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            jump[0] += __shfl_xor_sync(0xffffffffu, jump[0], o);
+            jump[1] += __shfl_xor_sync(0xffffffffu, jump[1], o);
+          }
+          if (lane < 2 && (lane == 0 || two)) {
+            const int u = lane;
+            const long long g = g0 + warp * ROWS_PER_SAMPLER + rrow[u];
+            const int x = u ? si[1].x : si[0].x;
             const int xb = a.x_base ? a.x_base[g] : x;
-            a.x_out[g] = finalize_jump(xb, x, 0, 0, a.reject_multi, S, stt);
+            a.x_out[g] = finalize_jump(xb, x, u ? jump[1] : jump[0], u ? K1 : K0, a.reject_multi, S, stt);
           }
-          continue;
-        }
-        float* grow_p = &sm.gather[r][0];
-        const float4 d0 = *reinterpret_cast<const float4*>(grow_p + 8 * lane);
-        const float4 d1 = *reinterpret_cast<const float4*>(grow_p + 8 * lane + 4);
-        float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-        const size_t xo = (size_t)x << 8;
-        if (KM == KM_RATES) {
-          const float4 f0 = __ldg(reinterpret_cast<const float4*>(tabFull + xo));
-          const float4 f1 = __ldg(reinterpret_cast<const float4*>(tabFull + xo + 4));
-          const float f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-          float ratio[8], rfull[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            ratio[e] = fmaf(d[e], si.c1, si.c0);
-            rfull[e] = TAULDR ? a.beta * f[e] * ratio[e] : ratio[e] * (a.beta * f[e]);
-          }
-          if (a.rr_out) {
-            float4* o = reinterpret_cast<float4*>(a.rr_out + g * S + 8 * lane);
-            o[0] = make_float4(rfull[0], rfull[1], rfull[2], rfull[3]);
-            o[1] = make_float4(rfull[4], rfull[5], rfull[6], rfull[7]);
-          }
-          if (a.ratio_out) {
-            float4* o = reinterpret_cast<float4*>(a.ratio_out + g * S + 8 * lane);
-            o[0] = make_float4(ratio[0], ratio[1], ratio[2], ratio[3]);
-            o[1] = make_float4(ratio[4], ratio[5], ratio[6], ratio[7]);
-          }
-          continue;
-        }
-        // lam_s for s = 8*lane .. 8*lane+7 (zero at s == x through the zero-diagonal tables)
-        const float4 e0 = __ldg(reinterpret_cast<const float4*>(tabE + xo));
-        const float4 e1 = __ldg(reinterpret_cast<const float4*>(tabE + xo + 4));
-        const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) d[e] = fmaf(d[e], si.c1, si.c0) * ev[e];
-        if (KM == KM_CORR) {
-          const float4 c0v = __ldg(reinterpret_cast<const float4*>(tabC + xo));
-          const float4 c1v = __ldg(reinterpret_cast<const float4*>(tabC + xo + 4));
-          const float cv[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
-#pragma unroll
-          for (int e = 0; e < 8; ++e) d[e] = fmaf(hb, cv[e], d[e]);
-        }
-        if (KM == KM_DRIFT) {
-          // sampling.py:433-453: x' = clip(x + round_half_even(h/2 * sum_s rr_s (s - x)))
-          float acc = 0.f;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc = fmaf(d[e], (float)(8 * lane + e - x), acc);
-          acc = warp_sum(acc);
-          if (lane == 0) {
-            const int ch = (int)rintf(0.5f * acc);
-            int xn = x + ch;
-            xn = xn < 0 ? 0 : (xn > S - 1 ? S - 1 : xn);
-            a.x_out[g] = xn;
-            stt.changed_base += (xn != x);
-            stt.changed_eval += (xn != x);
-            stt.nonzero += (ch != 0);
-          }
-          continue;
-        }
-        // inclusive prefix sums over the 256 states: in-lane, then across lanes
-#pragma unroll
-        for (int e = 1; e < 8; ++e) d[e] += d[e - 1];
-        float incl = d[7];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const float n = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += n;
-        }
-        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-        if (lane == 0) excl = 0.f;
-        const float total = __shfl_sync(0xffffffffu, incl, 31);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) d[e] += excl;
-        __syncwarp();
-        *reinterpret_cast<float4*>(grow_p + 8 * lane) = make_float4(d[0], d[1], d[2], d[3]);
-        *reinterpret_cast<float4*>(grow_p + 8 * lane + 4) = make_float4(d[4], d[5], d[6], d[7]);
-        __syncwarp();
-        // K picks, one per lane: first state whose prefix sum exceeds v * total
-        const int K = si.K;
-        int jump = 0;
-        for (int base = 0; base < K; base += 32) {
-          const int j = base + lane;
-          uint32_t w = (j == 0) ? si.w1 : (j == 1 ? si.w2 : si.w3);
-          if (K > 3) {   // warp-uniform
-            const int jj = j >= 3 ? j - 3 : 0;
-            const Philox4 pc = philox_rowjump((uint64_t)(a.row_offset + g), 1u + (uint32_t)(jj >> 2), a.offset, a.seed);
-            if (j >= 3) w = philox_word(pc, jj & 3);
-          }
-          const float target = fminf(u32_to_unit(w), 0.99999994f) * total;
-          int lo = 0;
-#pragma unroll
-          for (int step = 128; step >= 1; step >>= 1)
-            if (!(grow_p[lo + step - 1] > target)) lo += step;
-          jump += (j < K) ? (lo - x) : 0;
-        }
-        jump = warp_sum_int(jump);
-        if (lane == 0) {
-          const int xb = a.x_base ? a.x_base[g] : x;
-          a.x_out[g] = finalize_jump(xb, x, jump, K, a.reject_multi, S, stt);
         }
       }
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&sm.gather_free_local);
-        mbar_arrive_cluster(gfree_remote_dst);
+        mbar_arrive(&sm.gather_free_local[gb]);
+        mbar_arrive_cluster_relaxed(gfree_remote_dst + (uint32_t)gb * 8u);
       }
+      if ((warp & 3) == 0 && lane == 0) TRACE(2 + (warp >> 2), i, 7);
     }
-    if (lane == 0 && a.stats) {
+    if (a.stats) {
       const int v[5] = {stt.changed_base, stt.nonzero, stt.changed_eval, stt.jumped, stt.multi};
 #pragma unroll
-      for (int k = 0; k < 5; ++k)
-        if (v[k]) atomicAdd(a.stats + k, (unsigned long long)v[k]);
+      for (int k = 0; k < 5; ++k) {
+        const int tot = warp_sum_int(v[k]);
+        if (lane == 0 && tot) atomicAdd(a.stats + k, (unsigned long long)tot);
+      }
     }
   }
   tc_fence_before();
@@ -793,3 +935,9 @@ extern "C" int ctdd_prep_tc_static(const float* Rb, int S, void* static_out, voi
   CTDD_CHECK_LAUNCH("prep_static_kernel");
   return 0;
 }
+
+#ifdef CTDD_TC_TRACE
+extern "C" int ctdd_debug_trace_read(void* host, long long bytes) {
+  return (int)cudaMemcpyFromSymbol(host, ctdd::tc::g_trace, (size_t)bytes);
+}
+#endif
