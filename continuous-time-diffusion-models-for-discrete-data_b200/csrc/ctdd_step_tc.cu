@@ -64,12 +64,13 @@ struct Smem {
   alignas(1024) uint8_t stage[STAGES][STAGE_BYTES];
   alignas(16) float gather[GBUF][NH][S];   // [row owned by this CTA][state]: accumulator values, then prefix sums
   Side side[RING][NH];
-  alignas(8) uint64_t full[STAGES];  // used in the leader CTA: 8 local + 8 remote producer warps
+  alignas(8) uint64_t full[STAGES];  // leader CTA: its 8 producer warps + 1 relayed arrival for the partner's 8
+  uint64_t full_local[STAGES];       // partner CTA: its 8 producer warps; the partner's idle MMA warp relays the phase
   uint64_t empty[STAGES];            // multicast tcgen05.commit
   uint64_t side_full[RING];          // local producers -> local samplers
   uint64_t tmem_full[ACC];           // multicast tcgen05.commit
   uint64_t tmem_empty[ACC];          // used in the leader CTA: 8 local + 8 remote epilogue warps
-  uint64_t gather_full[GBUF];        // 4 local + 4 remote epilogue warps have written this CTA's gather buffer
+  uint64_t gather_full[GBUF];        // 4 local epilogue warps + the bytes of the partner's 4 warps (st.async complete_tx)
   uint64_t gather_free_local[GBUF];  // the 8 local sampler warps are done with this CTA's gather buffer
   uint64_t gather_free_remote[GBUF]; // the 8 sampler warps of the PARTNER are done with the partner's buffer
   uint32_t tmem_base;
@@ -223,8 +224,14 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
-  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+// remote store that reports its bytes to an mbarrier of the destination CTA when it has landed (no fence needed)
+__device__ __forceinline__ void st_async_cluster_f32(uint32_t cluster_addr, float v, uint32_t cluster_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(cluster_addr),
+               "r"(__float_as_uint(v)), "r"(cluster_mbar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
@@ -260,10 +267,9 @@ __device__ long long g_trace[2][TRACE_ROLES][TRACE_TILES][TRACE_EVENTS];
 #define TRACE(role, tile, ev) do { } while (0)
 #endif
 
-constexpr int PROD_BATCH = 2;          // rows processed together by a producer warp (two batches per tile)
 constexpr int PREFETCH_TILES = 6;      // L2 bulk-prefetch distance (tiles of this pair's sequence)
 
-struct RowLoad { float4 v0, v1; int x; bool ok; };
+struct RowLoad { float4 v[4]; int x; bool ok; };
 
 // TAULDR: tauLDR rates (else SDDM reverse_prob); KM: KM_JUMP / KM_CORR (corrector adds R_t[x,:]) / KM_RATES / KM_DRIFT
 template <bool TAULDR, int KM>
@@ -277,11 +283,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
   const int my_tiles = (a.num_tiles > pair) ? (a.num_tiles - pair + npairs - 1) / npairs : 0;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&sm.full[i], 2 * NUM_PROD_WARPS); mbar_init(&sm.empty[i], 1); }
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&sm.full[i], NUM_PROD_WARPS + 1);
+      mbar_init(&sm.full_local[i], NUM_PROD_WARPS);
+      mbar_init(&sm.empty[i], 1);
+    }
     for (int i = 0; i < RING; ++i) mbar_init(&sm.side_full[i], NUM_PROD_WARPS);
     for (int i = 0; i < ACC; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], 2 * NUM_EPI_WARPS); }
     for (int i = 0; i < GBUF; ++i) {
-      mbar_init(&sm.gather_full[i], NUM_EPI_WARPS);
+      mbar_init(&sm.gather_full[i], NUM_EPI_WARPS / 2);
       mbar_init(&sm.gather_free_local[i], NUM_EPI_WARPS);
       mbar_init(&sm.gather_free_remote[i], NUM_EPI_WARPS);
     }
@@ -317,66 +327,63 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
   tc_fence_after();
 
   if (warp >= FIRST_PROD_WARP) {
-    // ======================================================================== producers: one warp per row
+    // ======================================================================== producers: 16 lanes per row, 2 rows per pass
     const int pw = warp - FIRST_PROD_WARP;
-    // lane owns k = 4*lane .. 4*lane+3 and 128 + 4*lane .. +3: two fully coalesced 512-byte warp loads per row
-    const float* tabA = reinterpret_cast<const float*>(a.tab + TAB_A_OFF) + 4 * lane;
-    const float* tabG = reinterpret_cast<const float*>(a.tab + TAB_G_OFF) + 4 * lane;
+    const int half = lane >> 4, l16 = lane & 15;
+    // lane owns k = 64c + 4*l16 .. +3 for c = 0..3: every warp load is two fully coalesced 256-byte row segments, and
+    // each softmax reduction is a 4-step butterfly inside the half-warp (two independent rows keep the pipes busy)
+    const float* tabA = reinterpret_cast<const float*>(a.tab + TAB_A_OFF) + 4 * l16;
+    const float* tabG = reinterpret_cast<const float*>(a.tab + TAB_G_OFF) + 4 * l16;
     const float* rowsumZ = reinterpret_cast<const float*>(a.stat + ST_ROWSUM_OFF);
     const float hb = (KM == KM_RATES) ? 1.0f : a.h * a.beta;   // rates-only ignores the step length
     const bool contiguous = (a.ld == S) && (a.batch_stride == (long long)a.D * S);
     const bool can_prefetch = contiguous && pw == 0 && lane == 0;
-    const uint32_t full_addr = mapa(smem_u32(&sm.full[0]), 0);   // the leader's full[] barriers
-    const int nbatch = my_tiles * (ROWS_PER_PROD / PROD_BATCH);
+    uint64_t* const full_bar = rank == 0 ? &sm.full[0] : &sm.full_local[0];
+    constexpr int PASSES = ROWS_PER_PROD / 2;                    // passes per tile; warp pw builds rows ROWS_PER_PROD*pw ..
+    const int npass = my_tiles * PASSES;
 
-    // logits + state of batch `bi` (tile bi / 2, rows pw + 8 * (2 * (bi & 1) + j)): issued one batch ahead of their use
-    auto issue = [&](int bi, RowLoad (&L)[PROD_BATCH]) {
-      const int tile = pair + (bi / (ROWS_PER_PROD / PROD_BATCH)) * npairs;
-      const long long g0 = (long long)tile * NT + (long long)rank * NH;
-      const int b0 = (bi % (ROWS_PER_PROD / PROD_BATCH)) * PROD_BATCH;
-#pragma unroll
-      for (int j = 0; j < PROD_BATCH; ++j) {
-        const long long g = g0 + pw + NUM_PROD_WARPS * (b0 + j);
-        L[j].ok = (bi < nbatch) && (g < a.rows);
-        const long long gc = L[j].ok ? g : 0;
-        const float* lp;
-        if (contiguous) {
-          lp = a.logits + gc * S + 4 * lane;
-        } else {
-          const uint32_t n = (uint32_t)gc / (uint32_t)a.D, d = (uint32_t)gc - n * (uint32_t)a.D;
-          lp = a.logits + (long long)n * a.batch_stride + (long long)d * a.ld + 4 * lane;
-        }
-        L[j].v0 = ld_stream(lp);
-        L[j].v1 = ld_stream(lp + 128);
-        L[j].x = __ldg(a.x_eval + gc);
+    // logits + state of pass `pi` for this half-warp's row: issued one pass ahead of their use
+    auto issue = [&](int pi, RowLoad& L) {
+      const int tile = pair + (pi / PASSES) * npairs;
+      const long long g = (long long)tile * NT + (long long)rank * NH + ROWS_PER_PROD * pw + 2 * (pi % PASSES) + half;
+      L.ok = (pi < npass) && (g < a.rows);
+      const long long gc = L.ok ? g : 0;
+      const float* lp;
+      if (contiguous) {
+        lp = a.logits + gc * S + 4 * l16;
+      } else {
+        const uint32_t n = (uint32_t)gc / (uint32_t)a.D, d = (uint32_t)gc - n * (uint32_t)a.D;
+        lp = a.logits + (long long)n * a.batch_stride + (long long)d * a.ld + 4 * l16;
       }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) L.v[c] = ld_stream(lp + 64 * c);
+      L.x = __ldg(a.x_eval + gc);
     };
 
-    RowLoad cur[PROD_BATCH], nxt[PROD_BATCH];
+    RowLoad cur, nxt;
     issue(0, cur);
-    // lane i (< 4) collects the scalars of this warp's i-th row of the tile and finishes it after the batches
+    // lane i (< ROWS_PER_PROD) collects the scalars of this warp's i-th row of the tile and finishes it after the passes
     float my_lam = 0.f, my_c1 = 0.f, my_c0 = 0.f;
     int my_x = 0;
     bool my_ok = false;
 #pragma unroll 1
-    for (int bi = 0; bi < nbatch; ++bi) {
-      const int i = bi / (ROWS_PER_PROD / PROD_BATCH);
-      const int b0 = (bi % (ROWS_PER_PROD / PROD_BATCH)) * PROD_BATCH;
+    for (int pi = 0; pi < npass; ++pi) {
+      const int i = pi / PASSES, ps = pi % PASSES;
       const int tile = pair + i * npairs;
       const int st = i % STAGES, slot = i % RING;
       const long long g0 = (long long)tile * NT + (long long)rank * NH;   // first row built by this CTA
-      // table rows of the current batch (x arrived with the previous batch's prefetch), then the next batch's logits
-      float4 t0[PROD_BATCH], t1[PROD_BATCH], q0[PROD_BATCH], q1[PROD_BATCH];
+      // table rows of the current pass (x arrived with the previous pass's prefetch), then the next pass's logits
+      float4 t4[4], g4[4];
+      {
+        const size_t xo = (size_t)cur.x << 8;
 #pragma unroll
-      for (int j = 0; j < PROD_BATCH; ++j) {
-        const size_t xo = (size_t)cur[j].x << 8;
-        t0[j] = __ldg(reinterpret_cast<const float4*>(tabA + xo));
-        t1[j] = __ldg(reinterpret_cast<const float4*>(tabA + xo + 128));
-        q0[j] = __ldg(reinterpret_cast<const float4*>(tabG + xo));
-        q1[j] = __ldg(reinterpret_cast<const float4*>(tabG + xo + 128));
+        for (int c = 0; c < 4; ++c) {
+          t4[c] = __ldg(reinterpret_cast<const float4*>(tabA + xo + 64 * c));
+          g4[c] = __ldg(reinterpret_cast<const float4*>(tabG + xo + 64 * c));
+        }
       }
-      issue(bi + 1, nxt);
-      if (b0 == 0) {
+      issue(pi + 1, nxt);
+      if (ps == 0) {
         if (can_prefetch) {   // pull this CTA's rows of a later tile into L2 while this one is processed
           const long long r0 = g0 + (long long)PREFETCH_TILES * npairs * NT;
           if (r0 < a.rows) {
@@ -389,69 +396,78 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         if (pw == 0 && lane == 0) TRACE(0, i, 1);
       }
       uint8_t* stage = sm.stage[st];
+      {
+        const int r = ROWS_PER_PROD * pw + 2 * ps + half;
+        float v[16], t[16], gq[16];
 #pragma unroll
-      for (int j = 0; j < PROD_BATCH; ++j) {
-        const int r = pw + NUM_PROD_WARPS * (b0 + j);
-        float c1, c0;
-        float v[8] = {cur[j].v0.x, cur[j].v0.y, cur[j].v0.z, cur[j].v0.w, cur[j].v1.x, cur[j].v1.y, cur[j].v1.z, cur[j].v1.w};
-        const float t[8] = {t0[j].x, t0[j].y, t0[j].z, t0[j].w, t1[j].x, t1[j].y, t1[j].z, t1[j].w};
-        const float gq[8] = {q0[j].x, q0[j].y, q0[j].z, q0[j].w, q1[j].x, q1[j].y, q1[j].z, q1[j].w};
-        float m = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
-        m = warp_max(m);
+        for (int c = 0; c < 4; ++c) {
+          v[4 * c] = cur.v[c].x; v[4 * c + 1] = cur.v[c].y; v[4 * c + 2] = cur.v[c].z; v[4 * c + 3] = cur.v[c].w;
+          t[4 * c] = t4[c].x; t[4 * c + 1] = t4[c].y; t[4 * c + 2] = t4[c].z; t[4 * c + 3] = t4[c].w;
+          gq[4 * c] = g4[c].x; gq[4 * c + 1] = g4[c].y; gq[4 * c + 2] = g4[c].z; gq[4 * c + 3] = g4[c].w;
+        }
+        float m = v[0];
+#pragma unroll
+        for (int q = 1; q < 16; ++q) m = fmaxf(m, v[q]);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         const float ml = -m * 1.4426950408889634f;
         float sum = 0.f, dot = 0.f, dotg = 0.f;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 16; ++q) {
           v[q] = ex2_approx(fmaf(v[q], 1.4426950408889634f, ml));     // exp(v - max)
           sum += v[q];
           dotg = fmaf(v[q], gq[q], dotg);
           if (!TAULDR) dot = fmaf(v[q], t[q], dot);
         }
-        sum = warp_sum(sum);
-        dotg = warp_sum(dotg);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+          sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          dotg += __shfl_xor_sync(0xffffffffu, dotg, o);
+          if (!TAULDR) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        }
         const float rs = __frcp_rn(sum);
-        const float rz = (!TAULDR || KM == KM_CORR) ? __ldg(rowsumZ + cur[j].x) : 0.f;
+        const float rz = (!TAULDR || KM == KM_CORR) ? __ldg(rowsumZ + cur.x) : 0.f;
+        float c1, c0;
         if (TAULDR) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) v[q] *= t[q];             // e_k / (Q[k,x] + eps); 1/sum applied by the sampler
-          c1 = hb * rs;                                          // lam_s = D_s * c1 * Rb[s,x]
+          for (int q = 0; q < 16; ++q) v[q] *= t[q];              // e_k / (Q[k,x] + eps); 1/sum applied by the sampler
+          c1 = hb * rs;                                            // lam_s = D_s * c1 * Rb[s,x]
           c0 = 0.f;
         } else {
-          dot = warp_sum(dot);
-          const float inv = __frcp_rn(fmaf(dot, rs, 1e-35f));    // 1 / (pQ[x] + 1e-35)
-          c1 = hb * rs * inv;                                    // lam_s = (D_s * c1 + c0) * Rb[x,s]
+          const float inv = __frcp_rn(fmaf(dot, rs, 1e-35f));      // 1 / (pQ[x] + 1e-35)
+          c1 = hb * rs * inv;                                      // lam_s = (D_s * c1 + c0) * Rb[x,s]
           c0 = hb * 1e-35f * inv;
         }
         float lam_tot = fmaf(c1, dotg, c0 * rz);
         if (KM == KM_CORR) lam_tot = fmaf(hb, rz, lam_tot);
-        if (lane == b0 + j) { my_lam = lam_tot; my_c1 = c1; my_c0 = c0; my_x = cur[j].x; my_ok = cur[j].ok; }
-        uint32_t hi[4], mid[4];
+        // k = 64c + 4*l16 .. +3 lives in K block c, 16-byte chunk l16/2 (XOR-swizzled by the row), half l16&1
+        const uint32_t off = (uint32_t)r * 128 + (uint32_t)((((l16 >> 1) ^ (r & 7)) << 4) | ((l16 & 1) << 3));
 #pragma unroll
-        for (int q = 0; q < 4; ++q) split2(v[2 * q], v[2 * q + 1], hi[q], mid[q]);
-        if (!cur[j].ok) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) hi[q] = mid[q] = 0u;
+        for (int c = 0; c < 4; ++c) {
+          uint32_t h0, m0, h1, m1;
+          split2(v[4 * c], v[4 * c + 1], h0, m0);
+          split2(v[4 * c + 2], v[4 * c + 3], h1, m1);
+          if (!cur.ok) h0 = m0 = h1 = m1 = 0u;
+          *reinterpret_cast<uint2*>(stage + c * KBLOCK_BYTES + off) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2*>(stage + SPLIT_BYTES + c * KBLOCK_BYTES + off) = make_uint2(m0, m1);
         }
-        // k = 4*lane..+3 lives in K block lane/16, 16-byte chunk (lane%16)/2 (XOR-swizzled by the row), half lane&1;
-        // k = 128 + 4*lane..+3 two K blocks further on
-        const uint32_t off = (uint32_t)(lane >> 4) * KBLOCK_BYTES + (uint32_t)r * 128 +
-                             (uint32_t)(((((lane & 15) >> 1) ^ (r & 7)) << 4) | ((lane & 1) << 3));
-        *reinterpret_cast<uint2*>(stage + off) = make_uint2(hi[0], hi[1]);
-        *reinterpret_cast<uint2*>(stage + off + 2 * KBLOCK_BYTES) = make_uint2(hi[2], hi[3]);
-        *reinterpret_cast<uint2*>(stage + SPLIT_BYTES + off) = make_uint2(mid[0], mid[1]);
-        *reinterpret_cast<uint2*>(stage + SPLIT_BYTES + off + 2 * KBLOCK_BYTES) = make_uint2(mid[2], mid[3]);
+        // lanes 2*ps and 2*ps+1 keep the scalars of the two rows of this pass (second row: taken from lane 16)
+        const float o_lam = __shfl_sync(0xffffffffu, lam_tot, 16), o_c1 = __shfl_sync(0xffffffffu, c1, 16);
+        const float o_c0 = __shfl_sync(0xffffffffu, c0, 16);
+        const int o_x = __shfl_sync(0xffffffffu, cur.ok ? cur.x : -1, 16);
+        if (lane == 2 * ps) { my_lam = lam_tot; my_c1 = c1; my_c0 = c0; my_x = cur.x; my_ok = cur.ok; }
+        if (lane == 2 * ps + 1) { my_lam = o_lam; my_c1 = o_c1; my_c0 = o_c0; my_x = o_x < 0 ? 0 : o_x; my_ok = o_x >= 0; }
       }
-#pragma unroll
-      for (int j = 0; j < PROD_BATCH; ++j) cur[j] = nxt[j];
-      if (pw == 0 && lane == 0) TRACE(0, i, 2 + (b0 / PROD_BATCH));
-      if (b0 + PROD_BATCH == ROWS_PER_PROD) {   // last batch of the tile
+      cur = nxt;
+      if (pw == 0 && lane == 0) TRACE(0, i, 2 + (ps & 1));
+      if (ps == PASSES - 1) {   // last pass of the tile
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster_release(full_addr + (uint32_t)st * 8u);   // operand rows are in place
+        if (lane == 0) mbar_arrive(full_bar + st);   // operand rows are in place
         if (pw == 0 && lane == 0) TRACE(0, i, 4);
         // lanes 0..3 finish the warp's rows together: total jump count and the first pick uniforms
         if (lane < ROWS_PER_PROD) {
-          const int r = pw + NUM_PROD_WARPS * lane;
+          const int r = ROWS_PER_PROD * pw + lane;
           Side si;
           si.c1 = my_c1; si.c0 = my_c0; si.x = my_x; si.valid = my_ok ? 1 : 0;
           si.K = 0; si.w1 = si.w2 = si.w3 = 0u;
@@ -484,22 +500,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         TRACE(1, i, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem + TM_ACC + b * NT;
-        const uint32_t base = smem_u32(sm.stage[st]);
-        uint32_t acc = 0;
-#pragma unroll 1
+        // one descriptor per tile; the 48 instructions differ only by compile-time offsets (16-byte units, low word)
+        const uint64_t bd0 = make_b_desc(smem_u32(sm.stage[st]));
+#pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
           const uint32_t a_tmem = tmem + (pass == 2 ? TM_QM : TM_QH);
-          const uint32_t bsplit = base + (pass == 1 ? SPLIT_BYTES : 0);
 #pragma unroll
           for (int k16 = 0; k16 < 16; ++k16) {
-            const uint64_t bd = make_b_desc(bsplit + (k16 >> 2) * KBLOCK_BYTES + (k16 & 3) * 32);
-            umma_ts_pair(d_tmem, a_tmem + k16 * 8, bd, IDESC, acc);
-            acc = 1;
+            const uint32_t boff = (uint32_t)((pass == 1 ? SPLIT_BYTES : 0) + (k16 >> 2) * KBLOCK_BYTES + (k16 & 3) * 32) >> 4;
+            umma_ts_pair(d_tmem, a_tmem + k16 * 8, bd0 + boff, IDESC, (pass | k16) ? 1u : 0u);
           }
         }
         umma_commit_pair(&sm.empty[st]);
         umma_commit_pair(&sm.tmem_full[b]);
         TRACE(1, i, 3);
+      }
+    } else if (rank != 0 && lane == 0) {
+      // partner CTA: relay "my 8 producer warps have filled stage st" to the leader as ONE cluster-scope arrival
+      // (this thread has no memory traffic of its own, so its release costs nothing)
+      const uint32_t full_addr = mapa(smem_u32(&sm.full[0]), 0);
+      for (int i = 0; i < my_tiles; ++i) {
+        const int st = i % STAGES;
+        mbar_wait(&sm.full_local[st], (i / STAGES) & 1);
+        mbar_arrive_cluster_release(full_addr + (uint32_t)st * 8u);
       }
     }
     __syncwarp();
@@ -537,16 +560,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
 #pragma unroll
         for (int j = 0; j < 32; ++j) dst[j * S] = __uint_as_float(acc[j]);
       } else {
+        // the partner's barrier counts these bytes as they land: nothing to fence, nothing to wait for here
         const uint32_t dst = gather_dst + (uint32_t)gb * (NH * S * 4);
+        const uint32_t bar = gfull_dst + (uint32_t)gb * 8u;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) st_cluster_f32(dst + (uint32_t)j * (S * 4), __uint_as_float(acc[j]));
+        for (int j = 0; j < 32; ++j) st_async_cluster_f32(dst + (uint32_t)j * (S * 4), __uint_as_float(acc[j]), bar);
       }
       tc_fence_before();   // accumulator has been read: hand the buffer back to the MMA warp
       __syncwarp();
       if ((warp & 3) == 0 && lane == 0) TRACE(trole, i, 3);
       if (lane == 0) {
         mbar_arrive_cluster_relaxed(tempty_dst + (uint32_t)b * 8u);
-        mbar_arrive_cluster_release(gfull_dst + (uint32_t)gb * 8u);
+        if (owner == rank) {
+          // warp 0 also announces the bytes the partner's four warps will deliver for this phase
+          if (q == 0) mbar_arrive_expect_tx(&sm.gather_full[gb], (NUM_EPI_WARPS / 2) * 32 * NH * 4);
+          else mbar_arrive(&sm.gather_full[gb]);
+        }
       }
       if ((warp & 3) == 0 && lane == 0) TRACE(trole, i, 4);
     };
@@ -560,7 +589,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       const int slot = i % RING, gb = i % GBUF;
       if ((warp & 3) == 0 && lane == 0) TRACE(2 + (warp >> 2), i, 5);
       mbar_wait(&sm.side_full[slot], (i / RING) & 1);
-      mbar_wait_cluster(&sm.gather_full[gb], (i / GBUF) & 1);
+      mbar_wait(&sm.gather_full[gb], (i / GBUF) & 1);
       if ((warp & 3) == 0 && lane == 0) TRACE(2 + (warp >> 2), i, 6);
       const long long g0 = (long long)tile * NT + (long long)rank * NH;
       // lanes 0..3 settle the rows without a jump in one go; the rest are processed two rows per iteration
