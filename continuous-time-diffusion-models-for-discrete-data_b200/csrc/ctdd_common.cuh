@@ -108,6 +108,23 @@ __host__ __device__ __forceinline__ float poisson_sf0(float lam) {
   return 1.0f - expf(-lam);
 }
 
+// lam > 64: Cornish-Fisher normal approximation of the upper-tail quantile (kept out of line: it is rare and its
+// register footprint would otherwise be charged to every caller)
+__host__ __device__ __noinline__ inline int poisson_large_rate(float lam, float v) {
+  if (lam > 1.0e9f) lam = 1.0e9f;
+  // z = upper-tail normal quantile of v
+#ifdef __CUDA_ARCH__
+  float z = -normcdfinvf(v);
+#else
+  float z = 0.0f;  // host build never evaluates this branch (oracle has its own implementation)
+#endif
+  float k = lam + sqrtf(lam) * z + (z * z - 1.0f) * 0.16666667f;
+  k = rintf(k);
+  if (!(k > 1.0f)) k = 1.0f;
+  if (k > 2.0e9f) k = 2.0e9f;
+  return (int)k;
+}
+
 // Upper-tail inverse CDF: k = #{ j >= 0 : v < P(K > j) }, v in (0,1] small <=> many jumps.
 // lam <= 64: exact pmf recurrence in fp32 (capped); lam > 64: Cornish-Fisher normal approximation.
 // Callers may skip the call when v >= lam, because P(K>=1) <= lam.
@@ -127,18 +144,7 @@ __host__ __device__ __forceinline__ int poisson_from_unit(float lam, float v) {
     }
     return k;
   }
-  if (lam > 1.0e9f) lam = 1.0e9f;
-  // z = upper-tail normal quantile of v
-#ifdef __CUDA_ARCH__
-  float z = -normcdfinvf(v);
-#else
-  float z = 0.0f;  // host build never evaluates this branch (oracle has its own implementation)
-#endif
-  float k = lam + sqrtf(lam) * z + (z * z - 1.0f) * 0.16666667f;
-  k = rintf(k);
-  if (!(k > 1.0f)) k = 1.0f;
-  if (k > 2.0e9f) k = 2.0e9f;
-  return (int)k;
+  return poisson_large_rate(lam, v);
 }
 
 // Inverse-CDF categorical draw from unnormalised weights: first index whose sequential fp32 cumulative

@@ -31,11 +31,14 @@ constexpr int STAGES = 3;              // smem operand stages
 constexpr int ACC = 4;                 // TMEM accumulator buffers (NT columns each)
 constexpr int GBUF = 2;                // gather buffers: phase A of tile i+1 overlaps the sampling of tile i
 constexpr int RING = 16;               // per-tile side-info ring (> STAGES + ACC + GBUF + 2)
-constexpr int NUM_EPI_WARPS = 8;       // warp w: TMEM quadrant w&3, column half w>>2 (= owner CTA of those rows)
-constexpr int MMA_WARP = 8;
-constexpr int FIRST_PROD_WARP = 9;
+constexpr int NUM_EPI_WARPS = 8;       // warps 0-7: TMEM quadrant w&3, column half w>>2 (= owner CTA of those rows)
+constexpr int FIRST_PROD_WARP = 8;     // warps 8-15
 constexpr int NUM_PROD_WARPS = 8;
-constexpr int NUM_THREADS = (FIRST_PROD_WARP + NUM_PROD_WARPS) * 32;  // 544
+constexpr int MMA_WARP = 16;           // warps 16-19 form the light warpgroup: MMA issue / relay, count warp, 2 idle
+constexpr int COUNT_WARP = 17;         // draws the jump counts of a tile, lane = row
+constexpr int NUM_THREADS = 20 * 32;   // 640: register allocation is per 4-warp group, so 18 warps cost the same
+constexpr int REGS_HEAVY = 104;        // setmaxnreg targets: samplers + producers / the light warpgroup
+constexpr int REGS_LIGHT = 64;
 constexpr int ROWS_PER_PROD = NH / NUM_PROD_WARPS;                   // 4
 constexpr int ROWS_PER_SAMPLER = NH / NUM_EPI_WARPS;                 // 4
 constexpr int KBLOCK_BYTES = NH * 128;         // one 64-wide K block of one split: NH rows x 128 B
@@ -43,6 +46,8 @@ constexpr int SPLIT_BYTES = 4 * KBLOCK_BYTES;  // K = 256 -> 4 blocks
 constexpr int STAGE_BYTES = 2 * SPLIT_BYTES;   // hi + mid
 constexpr int TMEM_COLS = 512;
 constexpr int TM_QH = 0, TM_QM = 128, TM_ACC = 256;  // TMEM column map (accumulator b at TM_ACC + b * NT)
+constexpr int PREFETCH_TILES = 8;      // HBM -> L2 bulk-prefetch distance (tiles of this pair's sequence)
+constexpr int LRING = 3;               // per-producer-warp ring of raw logits row pairs filled by cp.async.bulk
 
 // per-time-point table blob (ctdd_prep_tc_tables)
 constexpr size_t TAB_QH_OFF = 0;                                 // uint32 [256][128]  bf16 pairs of Q^T hi
@@ -64,10 +69,13 @@ struct Smem {
   alignas(1024) uint8_t stage[STAGES][STAGE_BYTES];
   alignas(16) float gather[GBUF][NH][S];   // [row owned by this CTA][state]: accumulator values, then prefix sums
   Side side[RING][NH];
+  alignas(16) float lring[NUM_PROD_WARPS][LRING][2][S];   // raw fp32 logits rows, two passes ahead of their use
   alignas(8) uint64_t full[STAGES];  // leader CTA: its 8 producer warps + 1 relayed arrival for the partner's 8
   uint64_t full_local[STAGES];       // partner CTA: its 8 producer warps; the partner's idle MMA warp relays the phase
   uint64_t empty[STAGES];            // multicast tcgen05.commit
-  uint64_t side_full[RING];          // local producers -> local samplers
+  uint64_t pre_full[RING];           // local producers -> count warp (row scalars written)
+  uint64_t side_full[RING];          // count warp -> local samplers (jump counts and pick uniforms written)
+  uint64_t lring_full[NUM_PROD_WARPS][LRING];   // cp.async.bulk complete_tx of one row pair
   uint64_t tmem_full[ACC];           // multicast tcgen05.commit
   uint64_t tmem_empty[ACC];          // used in the leader CTA: 8 local + 8 remote epilogue warps
   uint64_t gather_full[GBUF];        // 4 local epilogue warps + the bytes of the partner's 4 warps (st.async complete_tx)
@@ -75,6 +83,8 @@ struct Smem {
   uint64_t gather_free_remote[GBUF]; // the 8 sampler warps of the PARTNER are done with the partner's buffer
   uint32_t tmem_base;
 };
+
+static_assert(sizeof(Smem) + 1024 <= 232448, "shared memory budget of one CTA (227 KB) exceeded");
 
 struct Args {
   int branch, D, reject_multi;
@@ -165,14 +175,18 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
                "h"((uint16_t)3)
                : "memory");
 }
-// D[tmem] (+)= A[tmem] * B[smem desc] over the CTA pair (kind::f16, bf16 inputs, fp32 accumulate)
-__device__ __forceinline__ void umma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem desc] over the CTA pair (kind::f16, bf16 inputs, fp32 accumulate); the descriptor
+// is passed as two 32-bit halves so that the 48 per-tile variants are one 32-bit add each
+__device__ __forceinline__ void umma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint32_t bdesc_lo, uint32_t bdesc_hi, uint32_t idesc,
+                                             uint32_t accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      ".reg .b64 bd;\n"
+      "mov.b64 bd, {%2, %3};\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], bd, %4, p;\n"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // K-major, SWIZZLE_128B operand descriptor: LBO = 1 (unused), SBO = 1024 B (8 rows x 128 B), version 1
@@ -236,6 +250,12 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+// bulk copy global -> this CTA's shared memory; the bytes are reported to `bar` (expect_tx armed by the caller)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 
 // bf16 hi/mid split of two floats, packed (element 0 in the low half)
 __device__ __forceinline__ void split2(float a0, float a1, uint32_t& hi, uint32_t& mid) {
@@ -267,9 +287,6 @@ __device__ long long g_trace[2][TRACE_ROLES][TRACE_TILES][TRACE_EVENTS];
 #define TRACE(role, tile, ev) do { } while (0)
 #endif
 
-constexpr int PREFETCH_TILES = 6;      // L2 bulk-prefetch distance (tiles of this pair's sequence)
-
-struct RowLoad { float4 v[4]; int x; bool ok; };
 
 // TAULDR: tauLDR rates (else SDDM reverse_prob); KM: KM_JUMP / KM_CORR (corrector adds R_t[x,:]) / KM_RATES / KM_DRIFT
 template <bool TAULDR, int KM>
@@ -288,7 +305,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       mbar_init(&sm.full_local[i], NUM_PROD_WARPS);
       mbar_init(&sm.empty[i], 1);
     }
-    for (int i = 0; i < RING; ++i) mbar_init(&sm.side_full[i], NUM_PROD_WARPS);
+    for (int i = 0; i < RING; ++i) { mbar_init(&sm.pre_full[i], NUM_PROD_WARPS); mbar_init(&sm.side_full[i], 1); }
+    for (int w = 0; w < NUM_PROD_WARPS; ++w)
+      for (int i = 0; i < LRING; ++i) mbar_init(&sm.lring_full[w][i], 1);
     for (int i = 0; i < ACC; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], 2 * NUM_EPI_WARPS); }
     for (int i = 0; i < GBUF; ++i) {
       mbar_init(&sm.gather_full[i], NUM_EPI_WARPS / 2);
@@ -326,169 +345,223 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
   cluster_sync_all();    // barriers initialised and both A halves resident before any cross-CTA traffic
   tc_fence_after();
 
-  if (warp >= FIRST_PROD_WARP) {
+  // register budget per role (whole 4-warp groups): the light group hands its registers to samplers and producers
+  if (warp >= FIRST_PROD_WARP && warp < MMA_WARP) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_HEAVY));
     // ======================================================================== producers: 16 lanes per row, 2 rows per pass
     const int pw = warp - FIRST_PROD_WARP;
     const int half = lane >> 4, l16 = lane & 15;
-    // lane owns k = 64c + 4*l16 .. +3 for c = 0..3: every warp load is two fully coalesced 256-byte row segments, and
-    // each softmax reduction is a 4-step butterfly inside the half-warp (two independent rows keep the pipes busy)
+    // lane owns k = 64c + 4*l16 .. +3 for c = 0..3; each softmax reduction is a 4-step butterfly inside the half-warp
+    // (two independent rows per warp keep the pipes busy).  The raw logits rows arrive through a small smem ring that
+    // cp.async.bulk fills two passes ahead, so no global-memory latency sits on the warp's critical path.
     const float* tabA = reinterpret_cast<const float*>(a.tab + TAB_A_OFF) + 4 * l16;
     const float* tabG = reinterpret_cast<const float*>(a.tab + TAB_G_OFF) + 4 * l16;
     const float* rowsumZ = reinterpret_cast<const float*>(a.stat + ST_ROWSUM_OFF);
     const float hb = (KM == KM_RATES) ? 1.0f : a.h * a.beta;   // rates-only ignores the step length
     const bool contiguous = (a.ld == S) && (a.batch_stride == (long long)a.D * S);
-    const bool can_prefetch = contiguous && pw == 0 && lane == 0;
     uint64_t* const full_bar = rank == 0 ? &sm.full[0] : &sm.full_local[0];
     constexpr int PASSES = ROWS_PER_PROD / 2;                    // passes per tile; warp pw builds rows ROWS_PER_PROD*pw ..
     const int npass = my_tiles * PASSES;
 
-    // logits + state of pass `pi` for this half-warp's row: issued one pass ahead of their use
-    auto issue = [&](int pi, RowLoad& L) {
-      const int tile = pair + (pi / PASSES) * npairs;
-      const long long g = (long long)tile * NT + (long long)rank * NH + ROWS_PER_PROD * pw + 2 * (pi % PASSES) + half;
-      L.ok = (pi < npass) && (g < a.rows);
-      const long long gc = L.ok ? g : 0;
-      const float* lp;
-      if (contiguous) {
-        lp = a.logits + gc * S + 4 * l16;
-      } else {
-        const uint32_t n = (uint32_t)gc / (uint32_t)a.D, d = (uint32_t)gc - n * (uint32_t)a.D;
-        lp = a.logits + (long long)n * a.batch_stride + (long long)d * a.ld + 4 * l16;
-      }
+    auto row_ptr = [&](long long g) -> const float* {
+      if (contiguous) return a.logits + g * S;
+      const uint32_t n = (uint32_t)g / (uint32_t)a.D, d = (uint32_t)g - n * (uint32_t)a.D;
+      return a.logits + (long long)n * a.batch_stride + (long long)d * a.ld;
+    };
+    // Running state of the fetch stream (two passes ahead of the compute stream): first row of the pair, pass-in-tile,
+    // ring slot.  Everything advances by additions only - no index arithmetic on the warp's critical path.
+    const long long tile_step = (long long)npairs * NT - 2 * (PASSES - 1);
+    long long gf = (long long)pair * NT + (long long)rank * NH + ROWS_PER_PROD * pw;
+    int f_left = npass, f_ps = 0, f_slot = 0;
+    // lane 0 starts the bulk copy of the next row pair (rows past the end are replaced by row 0: never used; adjacent
+    // rows of a contiguous logits tensor travel as one 2 KB copy); every lane fetches the state of its half's row
+    auto fetch = [&]() -> int {
+      int xv = -1;
+      if (f_left > 0) {
+        if (lane == 0) {
+          uint64_t* bar = &sm.lring_full[pw][f_slot];
+          mbar_arrive_expect_tx(bar, 2 * S * 4);
+          if (contiguous && gf + 1 < a.rows) {
+            bulk_g2s(&sm.lring[pw][f_slot][0][0], a.logits + gf * S, 2 * S * 4, bar);
+          } else {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) L.v[c] = ld_stream(lp + 64 * c);
-      L.x = __ldg(a.x_eval + gc);
+            for (int hf = 0; hf < 2; ++hf) {
+              const long long gg = (gf + hf < a.rows) ? gf + hf : 0;
+              bulk_g2s(&sm.lring[pw][f_slot][hf][0], row_ptr(gg), S * 4, bar);
+            }
+          }
+        }
+        if (gf + half < a.rows) xv = __ldg(a.x_eval + gf + half);
+        if (contiguous && f_ps == 0 && pw == 0 && lane == 0) {   // pull a later tile of this CTA from HBM into L2
+          const long long r0 = gf + (long long)PREFETCH_TILES * npairs * NT;
+          if (r0 < a.rows) {
+            const long long nrow = (a.rows - r0) < NH ? (a.rows - r0) : NH;
+            l2_prefetch_bulk(a.logits + r0 * S, (uint32_t)(nrow * S * 4));
+          }
+        }
+        --f_left;
+        f_slot = (f_slot + 1 == LRING) ? 0 : f_slot + 1;
+        if (++f_ps == PASSES) { f_ps = 0; gf += tile_step; } else { gf += 2; }
+      }
+      return xv;
     };
 
-    RowLoad cur, nxt;
-    issue(0, cur);
-    // lane i (< ROWS_PER_PROD) collects the scalars of this warp's i-th row of the tile and finishes it after the passes
-    float my_lam = 0.f, my_c1 = 0.f, my_c0 = 0.f;
-    int my_x = 0;
-    bool my_ok = false;
+    int x_cur = fetch(), x_n1 = fetch();
+    float4 t4[4], g4[4];
+    {
+      const size_t xo = (size_t)(x_cur < 0 ? 0 : x_cur) << 8;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        t4[c] = __ldg(reinterpret_cast<const float4*>(tabA + xo + 64 * c));
+        g4[c] = __ldg(reinterpret_cast<const float4*>(tabG + xo + 64 * c));
+      }
+    }
+    // running state of the compute stream
+    int i = 0, ps = 0, st = 0, slot = 0, rslot = 0;
+    uint32_t st_par = 1, ring_par = 0;      // parity to wait for on empty[st] / lring_full[rslot]
 #pragma unroll 1
     for (int pi = 0; pi < npass; ++pi) {
-      const int i = pi / PASSES, ps = pi % PASSES;
-      const int tile = pair + i * npairs;
-      const int st = i % STAGES, slot = i % RING;
-      const long long g0 = (long long)tile * NT + (long long)rank * NH;   // first row built by this CTA
-      // table rows of the current pass (x arrived with the previous pass's prefetch), then the next pass's logits
-      float4 t4[4], g4[4];
+      const bool ok = x_cur >= 0;
+      const int x = ok ? x_cur : 0;
+      const int x_n2 = fetch();              // its ring slot was drained by pass pi - 1 (__syncwarp at the loop end)
+      if (ps == 0) {
+        if (pw == 0 && lane == 0) TRACE(0, i, 0);
+        mbar_wait(&sm.empty[st], st_par);
+        if (pw == 0 && lane == 0) TRACE(0, i, 1);
+      }
+      uint8_t* stage = sm.stage[st];
+      mbar_wait(&sm.lring_full[pw][rslot], ring_par);
+      if (pw == 0 && lane == 0) TRACE(0, i, 5 + (ps & 1));
+      const int r = ROWS_PER_PROD * pw + 2 * ps + half;
+      float v[16];
       {
-        const size_t xo = (size_t)cur.x << 8;
+        const float4* src = reinterpret_cast<const float4*>(&sm.lring[pw][rslot][half][4 * l16]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 q4 = src[16 * c];
+          v[4 * c] = q4.x; v[4 * c + 1] = q4.y; v[4 * c + 2] = q4.z; v[4 * c + 3] = q4.w;
+        }
+      }
+      float m4[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) m4[c] = fmaxf(fmaxf(v[4 * c], v[4 * c + 1]), fmaxf(v[4 * c + 2], v[4 * c + 3]));
+      float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      const float ml = -m * 1.4426950408889634f;
+      float sum4[4], dot4[4], dotg4[4];     // four independent accumulation chains
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float tq[4] = {t4[c].x, t4[c].y, t4[c].z, t4[c].w};
+        const float gq[4] = {g4[c].x, g4[c].y, g4[c].z, g4[c].w};
+        sum4[c] = 0.f; dot4[c] = 0.f; dotg4[c] = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float ex = ex2_approx(fmaf(v[4 * c + e], 1.4426950408889634f, ml));     // exp(v - max)
+          sum4[c] += ex;
+          dotg4[c] = fmaf(ex, gq[e], dotg4[c]);
+          if (!TAULDR) dot4[c] = fmaf(ex, tq[e], dot4[c]);
+          v[4 * c + e] = TAULDR ? ex * tq[e] : ex;   // tauLDR operand: e_k / (Q[k,x] + eps); 1/sum applied by the sampler
+        }
+      }
+      float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      float dotg = (dotg4[0] + dotg4[1]) + (dotg4[2] + dotg4[3]);
+      float dot = (dot4[0] + dot4[1]) + (dot4[2] + dot4[3]);
+      // the tables of the NEXT pass are requested as soon as this pass's have been consumed
+      {
+        const size_t xo = (size_t)(x_n1 < 0 ? 0 : x_n1) << 8;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           t4[c] = __ldg(reinterpret_cast<const float4*>(tabA + xo + 64 * c));
           g4[c] = __ldg(reinterpret_cast<const float4*>(tabG + xo + 64 * c));
         }
       }
-      issue(pi + 1, nxt);
-      if (ps == 0) {
-        if (can_prefetch) {   // pull this CTA's rows of a later tile into L2 while this one is processed
-          const long long r0 = g0 + (long long)PREFETCH_TILES * npairs * NT;
-          if (r0 < a.rows) {
-            const long long nrow = (a.rows - r0) < NH ? (a.rows - r0) : NH;
-            l2_prefetch_bulk(a.logits + r0 * S, (uint32_t)(nrow * S * 4));
-          }
-        }
-        if (pw == 0 && lane == 0) TRACE(0, i, 0);
-        mbar_wait(&sm.empty[st], ((i / STAGES) & 1) ^ 1);
-        if (pw == 0 && lane == 0) TRACE(0, i, 1);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        dotg += __shfl_xor_sync(0xffffffffu, dotg, o);
+        if (!TAULDR) dot += __shfl_xor_sync(0xffffffffu, dot, o);
       }
-      uint8_t* stage = sm.stage[st];
-      {
-        const int r = ROWS_PER_PROD * pw + 2 * ps + half;
-        float v[16], t[16], gq[16];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          v[4 * c] = cur.v[c].x; v[4 * c + 1] = cur.v[c].y; v[4 * c + 2] = cur.v[c].z; v[4 * c + 3] = cur.v[c].w;
-          t[4 * c] = t4[c].x; t[4 * c + 1] = t4[c].y; t[4 * c + 2] = t4[c].z; t[4 * c + 3] = t4[c].w;
-          gq[4 * c] = g4[c].x; gq[4 * c + 1] = g4[c].y; gq[4 * c + 2] = g4[c].z; gq[4 * c + 3] = g4[c].w;
-        }
-        float m = v[0];
-#pragma unroll
-        for (int q = 1; q < 16; ++q) m = fmaxf(m, v[q]);
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        const float ml = -m * 1.4426950408889634f;
-        float sum = 0.f, dot = 0.f, dotg = 0.f;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          v[q] = ex2_approx(fmaf(v[q], 1.4426950408889634f, ml));     // exp(v - max)
-          sum += v[q];
-          dotg = fmaf(v[q], gq[q], dotg);
-          if (!TAULDR) dot = fmaf(v[q], t[q], dot);
-        }
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
-          sum += __shfl_xor_sync(0xffffffffu, sum, o);
-          dotg += __shfl_xor_sync(0xffffffffu, dotg, o);
-          if (!TAULDR) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        }
-        const float rs = __frcp_rn(sum);
-        const float rz = (!TAULDR || KM == KM_CORR) ? __ldg(rowsumZ + cur.x) : 0.f;
-        float c1, c0;
-        if (TAULDR) {
-#pragma unroll
-          for (int q = 0; q < 16; ++q) v[q] *= t[q];              // e_k / (Q[k,x] + eps); 1/sum applied by the sampler
-          c1 = hb * rs;                                            // lam_s = D_s * c1 * Rb[s,x]
-          c0 = 0.f;
-        } else {
-          const float inv = __frcp_rn(fmaf(dot, rs, 1e-35f));      // 1 / (pQ[x] + 1e-35)
-          c1 = hb * rs * inv;                                      // lam_s = (D_s * c1 + c0) * Rb[x,s]
-          c0 = hb * 1e-35f * inv;
-        }
-        float lam_tot = fmaf(c1, dotg, c0 * rz);
-        if (KM == KM_CORR) lam_tot = fmaf(hb, rz, lam_tot);
-        // k = 64c + 4*l16 .. +3 lives in K block c, 16-byte chunk l16/2 (XOR-swizzled by the row), half l16&1
-        const uint32_t off = (uint32_t)r * 128 + (uint32_t)((((l16 >> 1) ^ (r & 7)) << 4) | ((l16 & 1) << 3));
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t h0, m0, h1, m1;
-          split2(v[4 * c], v[4 * c + 1], h0, m0);
-          split2(v[4 * c + 2], v[4 * c + 3], h1, m1);
-          if (!cur.ok) h0 = m0 = h1 = m1 = 0u;
-          *reinterpret_cast<uint2*>(stage + c * KBLOCK_BYTES + off) = make_uint2(h0, h1);
-          *reinterpret_cast<uint2*>(stage + SPLIT_BYTES + c * KBLOCK_BYTES + off) = make_uint2(m0, m1);
-        }
-        // lanes 2*ps and 2*ps+1 keep the scalars of the two rows of this pass (second row: taken from lane 16)
-        const float o_lam = __shfl_sync(0xffffffffu, lam_tot, 16), o_c1 = __shfl_sync(0xffffffffu, c1, 16);
-        const float o_c0 = __shfl_sync(0xffffffffu, c0, 16);
-        const int o_x = __shfl_sync(0xffffffffu, cur.ok ? cur.x : -1, 16);
-        if (lane == 2 * ps) { my_lam = lam_tot; my_c1 = c1; my_c0 = c0; my_x = cur.x; my_ok = cur.ok; }
-        if (lane == 2 * ps + 1) { my_lam = o_lam; my_c1 = o_c1; my_c0 = o_c0; my_x = o_x < 0 ? 0 : o_x; my_ok = o_x >= 0; }
+      const float rs = __frcp_rn(sum);
+      if (pw == 0 && lane == 0 && ps == 1) TRACE(0, i, 7);
+      const float rz = (!TAULDR || KM == KM_CORR) ? __ldg(rowsumZ + x) : 0.f;
+      float c1, c0;
+      if (TAULDR) {
+        c1 = hb * rs;                                            // lam_s = D_s * c1 * Rb[s,x]
+        c0 = 0.f;
+      } else {
+        const float inv = __frcp_rn(fmaf(dot, rs, 1e-35f));      // 1 / (pQ[x] + 1e-35)
+        c1 = hb * rs * inv;                                      // lam_s = (D_s * c1 + c0) * Rb[x,s]
+        c0 = hb * 1e-35f * inv;
       }
-      cur = nxt;
+      float lam_tot = fmaf(c1, dotg, c0 * rz);
+      if (KM == KM_CORR) lam_tot = fmaf(hb, rz, lam_tot);
+      // k = 64c + 4*l16 .. +3 lives in K block c, 16-byte chunk l16/2 (XOR-swizzled by the row), half l16&1
+      const uint32_t off = (uint32_t)r * 128 + (uint32_t)((((l16 >> 1) ^ (r & 7)) << 4) | ((l16 & 1) << 3));
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t h0, m0, h1, m1;
+        split2(v[4 * c], v[4 * c + 1], h0, m0);
+        split2(v[4 * c + 2], v[4 * c + 3], h1, m1);
+        if (!ok) h0 = m0 = h1 = m1 = 0u;
+        *reinterpret_cast<uint2*>(stage + c * KBLOCK_BYTES + off) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(stage + SPLIT_BYTES + c * KBLOCK_BYTES + off) = make_uint2(m0, m1);
+      }
+      // row scalars for the count warp and the samplers (one lane per half-warp)
+      if (l16 == 0) {
+        Side si;
+        si.c1 = c1; si.c0 = c0; si.x = x; si.valid = ok ? 1 : 0;
+        si.K = 0; si.w1 = __float_as_uint(lam_tot); si.w2 = si.w3 = 0u;
+        sm.side[slot][r] = si;
+      }
+      x_cur = x_n1;
+      x_n1 = x_n2;
+      if (++rslot == LRING) { rslot = 0; ring_par ^= 1u; }
+      __syncwarp();            // every lane is done with this pass's ring slot
       if (pw == 0 && lane == 0) TRACE(0, i, 2 + (ps & 1));
-      if (ps == PASSES - 1) {   // last pass of the tile
+      if (++ps == PASSES) {     // last pass of the tile
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(full_bar + st);   // operand rows are in place
-        if (pw == 0 && lane == 0) TRACE(0, i, 4);
-        // lanes 0..3 finish the warp's rows together: total jump count and the first pick uniforms
-        if (lane < ROWS_PER_PROD) {
-          const int r = ROWS_PER_PROD * pw + lane;
-          Side si;
-          si.c1 = my_c1; si.c0 = my_c0; si.x = my_x; si.valid = my_ok ? 1 : 0;
-          si.K = 0; si.w1 = si.w2 = si.w3 = 0u;
-          if (my_ok) {
-            if (KM == KM_RATES || KM == KM_DRIFT) {
-              si.K = 1;
-            } else {
-              const Philox4 p0 = philox_rowjump((uint64_t)(a.row_offset + g0 + r), 0, a.offset, a.seed);
-              const int K = poisson_from_unit(my_lam, u32_to_unit(p0.w[0]));
-              si.K = K > JUMP_PICK_CAP ? JUMP_PICK_CAP : K;
-              si.w1 = p0.w[1]; si.w2 = p0.w[2]; si.w3 = p0.w[3];
-            }
-          }
-          sm.side[slot][r] = si;
+        if (lane == 0) {
+          mbar_arrive(full_bar + st);          // operand rows are in place
+          mbar_arrive(&sm.pre_full[slot]);     // row scalars are in place
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.side_full[slot]);
-        if (pw == 0 && lane == 0) TRACE(0, i, 5);
+        if (pw == 0 && lane == 0) TRACE(0, i, 4);
+        ps = 0;
+        ++i;
+        slot = (slot + 1) & (RING - 1);
+        if (++st == STAGES) { st = 0; st_par ^= 1u; }
       }
     }
+  } else if (warp > COUNT_WARP) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_LIGHT));   // idle warps of the light group
+  } else if (warp == COUNT_WARP) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_LIGHT));
+    // ======================================================================== count warp: lane = row of the tile
+    // total jump count K ~ Poisson(Lambda) and the first pick uniforms of every row (superposition map, ctdd_common.cuh)
+    for (int i = 0; i < my_tiles; ++i) {
+      const int tile = pair + i * npairs, slot = i % RING;
+      const long long g0 = (long long)tile * NT + (long long)rank * NH;
+      mbar_wait(&sm.pre_full[slot], (i / RING) & 1);
+      Side si = sm.side[slot][lane];
+      const float lam = __uint_as_float(si.w1);
+      si.w1 = 0u;
+      if (si.valid) {
+        if (KM == KM_RATES || KM == KM_DRIFT) {
+          si.K = 1;
+        } else {
+          const Philox4 p0 = philox_rowjump((uint64_t)(a.row_offset + g0 + lane), 0, a.offset, a.seed);
+          const int K = poisson_from_unit(lam, u32_to_unit(p0.w[0]));
+          si.K = K > JUMP_PICK_CAP ? JUMP_PICK_CAP : K;
+          si.w1 = p0.w[1]; si.w2 = p0.w[2]; si.w3 = p0.w[3];
+        }
+      }
+      sm.side[slot][lane] = si;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.side_full[slot]);
+    }
   } else if (warp == MMA_WARP) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_LIGHT));
     // ======================================================================== MMA issue (one thread of the leader CTA)
     if (rank == 0 && lane == 0) {
       for (int i = 0; i < my_tiles; ++i) {
@@ -502,13 +575,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         const uint32_t d_tmem = tmem + TM_ACC + b * NT;
         // one descriptor per tile; the 48 instructions differ only by compile-time offsets (16-byte units, low word)
         const uint64_t bd0 = make_b_desc(smem_u32(sm.stage[st]));
-#pragma unroll
+        const uint32_t bd_lo = (uint32_t)bd0, bd_hi = (uint32_t)(bd0 >> 32);
+#pragma unroll 1
         for (int pass = 0; pass < 3; ++pass) {
           const uint32_t a_tmem = tmem + (pass == 2 ? TM_QM : TM_QH);
+          const uint32_t lo = bd_lo + (pass == 1 ? (uint32_t)(SPLIT_BYTES >> 4) : 0u);
 #pragma unroll
           for (int k16 = 0; k16 < 16; ++k16) {
-            const uint32_t boff = (uint32_t)((pass == 1 ? SPLIT_BYTES : 0) + (k16 >> 2) * KBLOCK_BYTES + (k16 & 3) * 32) >> 4;
-            umma_ts_pair(d_tmem, a_tmem + k16 * 8, bd0 + boff, IDESC, (pass | k16) ? 1u : 0u);
+            const uint32_t boff = (uint32_t)((k16 >> 2) * KBLOCK_BYTES + (k16 & 3) * 32) >> 4;
+            umma_ts_pair(d_tmem, a_tmem + k16 * 8, lo + boff, bd_hi, IDESC, (pass | k16) ? 1u : 0u);
           }
         }
         umma_commit_pair(&sm.empty[st]);
@@ -527,6 +602,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     }
     __syncwarp();
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_HEAVY));
     // ======================================================================== epilogue + row sampler
     const int q = warp & 3;                       // TMEM quadrant -> states rank*128 + 32q + lane
     const uint32_t owner = (uint32_t)(warp >> 2); // accumulator columns [32*owner, 32*owner+32) belong to CTA `owner`
