@@ -304,6 +304,13 @@ def run_ours(args, w, rank, world, local_rank):
                 "note": "algorithmic 2*B*D*S^2 per launch; the kernel spends 3 bf16 tensor passes per algorithmic FLOP "
                         "(split precision), so 1/3 is the ceiling of this fraction",
                 "hbm_gbs": bytes_step / (kern_ms * 1e-3) / 1e9}
+        # DRAM bytes of one launch from the committed ncu --set full capture of this kernel at this shape
+        # (profiles/r1_step_tc_summary.md: dram__bytes_read.sum + dram__bytes_write.sum); null for other shapes
+        if args.workload == "C4" and impl != nat.IMPL_SIMT:
+            roof["traffic"] = 3.346e9
+        t_floor = max(bytes_step / (pk["hbm"] * 1e9), 3.0 * fl / (pk["tc_burst"] * 1e12))
+        roof["t_floor_ms"] = t_floor * 1e3
+        roof["frac_of_3pass_floor"] = t_floor / (kern_ms * 1e-3)
     else:
         roof = {"bound": "hbm", "achieved": bytes_step / (kern_ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                 "traffic": None, "peak_source": pk["src"] + " copy bandwidth"}

@@ -138,17 +138,20 @@ __device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_add
 __device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// wait for a phase; the try_wait suspends in hardware up to the time hint instead of spinning
+// wait for a phase: one try_wait (which suspends in hardware for a short, implementation-defined time), then a
+// sleep / try_wait loop - a warp that has to wait longer must not eat issue slots of the warps it is waiting for
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "WAIT_%=:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
+      "WAIT_%=:\n"
+      "nanosleep.u32 %3;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@!p bra WAIT_%=;\n"
       "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u), "r"(96u)
       : "memory");
 }
 // same, for phases completed by arrivals from the partner CTA: acquire at cluster scope once the phase has flipped

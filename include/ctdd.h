@@ -15,8 +15,10 @@
  *   - matrices are row-major fp32; Q[k*S + s] = q_{t|0}(x_t = s | x_0 = k); Rb[i*S + j] = base rate
  *     of the forward jump i -> j (rows sum to 0); states are int32 in [0, S);
  *   - "row" means one (n, d) pair; rows are numbered n*D + d (+ row_offset for batch sharding).
- *     All randomness is counter-based Philox4x32-10 keyed on (seed, call offset, GLOBAL row, state),
- *     so results do not depend on the launch geometry or on the number of GPUs.
+ *     All randomness is counter-based Philox4x32-10 keyed on (seed, call offset, GLOBAL row), so results do
+ *     not depend on the launch geometry or on the number of GPUs.  Tau-leap jump counts of a row are drawn
+ *     through the Poisson superposition identity: total K ~ Poisson(sum_s lam_s), then K inverse-CDF picks
+ *     over lam_s / sum (the same joint law as S independent Poisson draws; DESIGN.md §4.2, oracle/rng.py).
  */
 #ifndef CTDD_H_
 #define CTDD_H_
@@ -124,17 +126,18 @@ typedef struct ctdd_step_params {
   float* rr_out;         /* [N*D,S] reverse rates incl. the (non-zeroed) s==x entry, or NULL */
   float* ratio_out;      /* [N*D,S] ratio, or NULL */
   int64_t* stats_out;    /* [CTDD_STAT_COUNT] or NULL */
-  void* workspace;       /* >= ctdd_step_workspace_bytes(N*D, S) bytes, or NULL when that is 0 */
+  void* workspace;       /* >= ctdd_step_workspace_bytes(N*D, S) bytes, or NULL when that is 0 (it is 0 today) */
 } ctdd_step_params;
 
 int64_t ctdd_step_workspace_bytes(int64_t rows, int S, int impl);
 int ctdd_reverse_step(const ctdd_step_params* p, void* stream);
 
 /* Derived per-time-point tables for the tcgen05 path (S == 256): bf16 hi/mid splits of Q^T in the
- * order the kernel loads them into tensor memory, the gathered-denominator table
- * 1/(Q[k,x]+eps) (tauLDR) and the midpoint drift table.  T time points at once. */
+ * order the kernel loads them into tensor memory, the gathered-denominator table 1/(Q[k,x]+eps)
+ * (tauLDR; Q[k,x] for the SDDM branch) and the total-rate table G (sum_s lam_s of a row is one dot
+ * product with G[x][.]).  T time points at once. */
 int64_t ctdd_tc_tables_bytes(int S);
-/* time-independent tables of the tcgen05 path: Rb^T and Rb with zeroed diagonals (epilogue gathers) */
+/* time-independent tables of the tcgen05 path: Rb^T and Rb with zeroed diagonals (sampler gathers), row sums */
 int64_t ctdd_tc_static_bytes(int S);
 int ctdd_prep_tc_static(const float* Rb, int S, void* static_out, void* stream);
 int ctdd_prep_tc_tables(const float* Q, const float* QT, const float* Rb, int T, int S, float eps,
