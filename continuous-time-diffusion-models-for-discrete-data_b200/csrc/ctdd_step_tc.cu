@@ -37,7 +37,10 @@ constexpr int NUM_PROD_WARPS = 8;
 constexpr int MMA_WARP = 16;           // warps 16-19 form the light warpgroup: MMA issue / relay, count warp, 2 idle
 constexpr int COUNT_WARP = 17;         // draws the jump counts of a tile, lane = row
 constexpr int NUM_THREADS = 20 * 32;   // 640: register allocation is per 4-warp group, so 18 warps cost the same
-constexpr int REGS_HEAVY = 104;        // setmaxnreg targets: samplers + producers / the light warpgroup
+// setmaxnreg targets: samplers + producers / the light warpgroup.  The registers handed out by .inc are the ones the
+// CTA's own warps released with .dec: 16 * HEAVY + 4 * LIGHT must not exceed 20 * 96 (the launch allocation), or
+// the .inc never returns.
+constexpr int REGS_HEAVY = 104;
 constexpr int REGS_LIGHT = 64;
 constexpr int ROWS_PER_PROD = NH / NUM_PROD_WARPS;                   // 4
 constexpr int ROWS_PER_SAMPLER = NH / NUM_EPI_WARPS;                 // 4
@@ -395,12 +398,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
           }
         }
         if (gf + half < a.rows) xv = __ldg(a.x_eval + gf + half);
-        if (contiguous && f_ps == 0 && pw == 0 && lane == 0) {   // pull a later tile of this CTA from HBM into L2
+        if (contiguous && f_ps == 0 && lane == 0) {   // pull this warp's 4 rows of a later tile from HBM into L2
           const long long r0 = gf + (long long)PREFETCH_TILES * npairs * NT;
-          if (r0 < a.rows) {
-            const long long nrow = (a.rows - r0) < NH ? (a.rows - r0) : NH;
-            l2_prefetch_bulk(a.logits + r0 * S, (uint32_t)(nrow * S * 4));
-          }
+          if (r0 + ROWS_PER_PROD <= a.rows) l2_prefetch_bulk(a.logits + r0 * S, ROWS_PER_PROD * S * 4);
         }
         --f_left;
         f_slot = (f_slot + 1 == LRING) ? 0 : f_slot + 1;
