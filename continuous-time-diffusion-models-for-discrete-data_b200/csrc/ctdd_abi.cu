@@ -37,10 +37,10 @@ extern "C" int ctdd_reverse_step(const ctdd_step_params* p, void* stream) {
   using namespace ctdd;
   if (!p) { set_error("ctdd_reverse_step: null params"); return 2; }
   if (p->N <= 0 || p->D <= 0 || p->S < 2) { set_error("ctdd_reverse_step: bad sizes N=%d D=%d S=%d", p->N, p->D, p->S); return 2; }
-  if (p->mode < CTDD_MODE_TAU_LEAP || p->mode > CTDD_MODE_RATES_ONLY) { set_error("ctdd_reverse_step: unknown mode %d", p->mode); return 2; }
+  if (p->mode < CTDD_MODE_TAU_LEAP || p->mode > CTDD_MODE_EXACT) { set_error("ctdd_reverse_step: unknown mode %d", p->mode); return 2; }
   if (p->branch < CTDD_BRANCH_TAULDR || p->branch > CTDD_BRANCH_SDDM_REVERSE_LOGSCALE) { set_error("ctdd_reverse_step: unknown branch %d", p->branch); return 2; }
   if (!p->logits || !p->x_eval || !p->Rb || !p->RbT) { set_error("ctdd_reverse_step: null input pointer"); return 2; }
-  if (p->branch != CTDD_BRANCH_SDDM_DIRECT && (!p->Q || !p->QT)) { set_error("ctdd_reverse_step: Q/QT required for this branch"); return 2; }
+  if ((p->branch != CTDD_BRANCH_SDDM_DIRECT || p->mode == CTDD_MODE_EXACT) && (!p->Q || !p->QT)) { set_error("ctdd_reverse_step: Q/QT required for this branch"); return 2; }
   if (p->mode != CTDD_MODE_RATES_ONLY && !p->x_out) { set_error("ctdd_reverse_step: x_out is null"); return 2; }
   if (p->mode == CTDD_MODE_RATES_ONLY && !p->rr_out && !p->ratio_out) { set_error("ctdd_reverse_step: RATES_ONLY needs rr_out or ratio_out"); return 2; }
   if (p->ld_logits < p->S) { set_error("ctdd_reverse_step: ld_logits < S"); return 2; }

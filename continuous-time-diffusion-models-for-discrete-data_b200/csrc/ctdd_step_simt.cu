@@ -98,6 +98,32 @@ __global__ void __launch_bounds__(128) step_small_kernel(StepArgs a) {
       float e[S], sum = 0.f;
 #pragma unroll
       for (int s = 0; s < S; ++s) { e[s] = expf(lg[r][s] - m); sum += e[s]; }
+      if (a.mode == CTDD_MODE_EXACT) {
+        // sampling.py:1008-1052: weight[s'] = (sum_k p_k q_{t-h|0}[k,s']) * q_{t|t-h}[s', x]  (second factor: a.RbT[x][s'])
+        float wgt[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          float acc = 0.f;
+#pragma unroll
+          for (int k = 0; k < S; ++k) acc = fmaf(e[k] / sum, sQ[k * S + s], acc);
+          wgt[s] = acc * __ldg(a.RbT + (size_t)x * S + s);
+        }
+        const float v = u32_to_unit(philox_row_word((uint64_t)(a.row_offset + r0 + r), 0, a.offset, STREAM_ROW, a.seed));
+        const int xn = inv_cdf(S, v, [&](int s) {
+          float w = 0.f;
+#pragma unroll
+          for (int q = 0; q < S; ++q) w = (q == s) ? wgt[q] : w;
+          return w;
+        });
+        if (r < nr) {
+          a.x_out[r0 + r] = xn;
+          st.changed_base += (xn != xb[r]);
+          st.changed_eval += (xn != x);
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) rate[r][s] = 0.f;
+        continue;
+      }
       float ratio[S], rfull[S];
       if (a.branch == CTDD_BRANCH_TAULDR) {
         float w[S];
@@ -258,7 +284,8 @@ __global__ void __launch_bounds__(256) step_block_kernel(StepArgs a) {
     for (int k = lane; k < S; k += 32) {
       const float p = expf(__ldg(lp + k) - m) / sum;
       float v;
-      if (a.branch == CTDD_BRANCH_TAULDR) v = p / (a.QT[(size_t)x * S + k] + a.eps);
+      if (a.mode == CTDD_MODE_EXACT) v = p;
+      else if (a.branch == CTDD_BRANCH_TAULDR) v = p / (a.QT[(size_t)x * S + k] + a.eps);
       else if (a.branch == CTDD_BRANCH_SDDM_REVERSE_LOGSCALE) v = __ldg(lp + k) - (m + logf(sum));  // log p
       else v = p;
       sA[r * S + k] = v;
@@ -270,13 +297,13 @@ __global__ void __launch_bounds__(256) step_block_kernel(StepArgs a) {
     float acc[BLK_ROWS];
 #pragma unroll
     for (int r = 0; r < BLK_ROWS; ++r) acc[r] = 0.f;
-    if (a.branch == CTDD_BRANCH_TAULDR || a.branch == CTDD_BRANCH_SDDM_REVERSE_PROB) {
+    if (a.mode == CTDD_MODE_EXACT || a.branch == CTDD_BRANCH_TAULDR || a.branch == CTDD_BRANCH_SDDM_REVERSE_PROB) {
       for (int k = 0; k < S; ++k) {
         const float q = __ldg(a.Q + (size_t)k * S + s);
 #pragma unroll
         for (int r = 0; r < BLK_ROWS; ++r) acc[r] = fmaf(sA[r * S + k], q, acc[r]);
       }
-    } else if (a.branch == CTDD_BRANCH_SDDM_REVERSE_LOGSCALE) {
+    } else if (a.mode != CTDD_MODE_EXACT && a.branch == CTDD_BRANCH_SDDM_REVERSE_LOGSCALE) {
       float mx[BLK_ROWS];
 #pragma unroll
       for (int r = 0; r < BLK_ROWS; ++r) mx[r] = -INFINITY;
@@ -295,6 +322,11 @@ __global__ void __launch_bounds__(256) step_block_kernel(StepArgs a) {
 #pragma unroll
       for (int r = 0; r < BLK_ROWS; ++r) acc[r] = mx[r] + logf(acc[r]);  // ll[s]
     }
+    if (a.mode == CTDD_MODE_EXACT) {   // weight[s] = (p Q)[s] * q_{t|t-h}[s, x]
+#pragma unroll
+      for (int r = 0; r < BLK_ROWS; ++r) sT[r * S + s] = acc[r] * __ldg(a.RbT + (size_t)s_xe[r] * S + s);
+      continue;
+    }
 #pragma unroll
     for (int r = 0; r < BLK_ROWS; ++r) {
       float v = acc[r];
@@ -305,6 +337,20 @@ __global__ void __launch_bounds__(256) step_block_kernel(StepArgs a) {
     }
   }
   __syncthreads();
+  if (a.mode == CTDD_MODE_EXACT) {
+    RowStats st = {0, 0, 0, 0, 0};
+    if (tid < nr) {
+      const int r = tid, x = s_xe[r];
+      const float v = u32_to_unit(philox_row_word((uint64_t)(a.row_offset + r0 + r), 0, a.offset, STREAM_ROW, a.seed));
+      const float* rowp = sT + r * S;
+      const int xn = inv_cdf(S, v, [&](int s) { return rowp[s]; });
+      a.x_out[r0 + r] = xn;
+      st.changed_base += (xn != s_xb[r]);
+      st.changed_eval += (xn != x);
+    }
+    flush_stats(st, a.stats);
+    return;
+  }
   const bool corr = (a.mode == CTDD_MODE_TAU_LEAP_CORR || a.mode == CTDD_MODE_EULER_CORR);
   for (int s = tid; s < S; s += nth) {
 #pragma unroll

@@ -420,3 +420,55 @@ class ConditionalPCTauLeaping(_SamplerBase):
 for _alias, _cls in (("TauLeaping", TauL), ("ElboTauL", TauL), ("LBJFSampling", LBJF), ("CRMLBJF", LBJF),
                      ("CRMTauL", TauL), ("CRMMidPointTauL", MidPointTauL), ("ElboLBJF", LBJF)):
     sampling_utils.register_alias(_alias, _cls)
+
+
+@sampling_utils.register_sampler
+class ExactSampling(_SamplerBase):
+    """Exact one-step posterior sampling for small state spaces (reference sampling.py:975-1061):
+    x_{t-h} ~ Cat_s'( sum_k p_{0|t}(k | x_t) q_{t-h|0}[k, s'] * q_{t|t-h}[s', x_t] ).
+
+    The reference materialises an (N, D, S, S) tensor and a logsumexp per step; here the contraction, the multiply by the
+    gathered q_{t|t-h} column and the categorical draw are one kernel (CTDD_MODE_EXACT).  Only `model.log_prob == 'cat'`
+    networks are supported (the EBM score functions are out of scope)."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.D = cfg.model.concat_dim
+        self.S = self.cfg.data.S
+        self.num_steps = cfg.sampler.num_steps
+        self.min_t = cfg.sampler.min_t
+        self.initial_dist = cfg.sampler.initial_dist
+        self.max_t = cfg.training.max_t
+        if getattr(cfg.model, "log_prob", "cat") != "cat":
+            raise NotImplementedError("ExactSampling: only model.log_prob == 'cat' is supported")
+
+    def sample(self, model, N):
+        initial_dist_std = self.cfg.model.Q_sigma
+        device = torch.device(model.device)
+        if device.type != "cuda":
+            raise RuntimeError("ctdd_b200 samplers run on CUDA devices only; there is no CPU fallback")
+        S, D = self.S, self.D
+        with torch.no_grad():
+            ts = np.concatenate((np.linspace(self.max_t, self.min_t, self.num_steps), np.array([0])))
+            seed = _seed_from_torch() if self.seed is None else int(self.seed)
+            # q_{t-h|0} and q_{t|t-h} for every step, built once (the reference builds N identical copies per step)
+            t_hi = torch.tensor([float(t) for t in ts[:-1]], dtype=torch.float64).to(torch.float32).to(device)
+            t_lo = torch.tensor([float(t) for t in ts[:-1]], dtype=torch.float64).to(torch.float32)
+            t_lo = (t_lo - torch.tensor([float(ts[i] - ts[i + 1]) for i in range(len(ts) - 1)], dtype=torch.float64)
+                    .to(torch.float32)).to(device)        # t - h in the reference's fp32 arithmetic (sampling.py:1027)
+            Q = model.transition(t_lo).contiguous()
+            QT = Q.transpose(1, 2).contiguous()
+            W = model.transit_between(t_lo, t_hi).contiguous()       # W[i][s', x] = q_{t|t-h}[s', x]
+            WT = W.transpose(1, 2).contiguous()                      # [x][s']
+            Rb, _ = model.base_rate_tables(device)
+            stats = torch.zeros((len(ts) - 1, nat.STAT_COUNT), dtype=torch.int64, device=device)
+            x = get_initial_samples(N, D, device, S, self.initial_dist, initial_dist_std, seed, self.row_offset)
+            for idx, t in enumerate(ts[0:-1]):
+                logits = model(x.long(), float(t) * torch.ones((N,), device=device))
+                x = ops.reverse_step(nat.MODE_EXACT, nat.BRANCH_SDDM_REVERSE_PROB, logits, x, Q[idx], QT[idx], Rb, WT[idx],
+                                     0.0, 0.0, 0.0, N=N, D=D, S=S, seed=seed, offset=idx, row_offset=self.row_offset,
+                                     impl=nat.IMPL_SIMT, stats=stats[idx])["x"]
+            st = stats.cpu().numpy()
+            change_jump = [st[i, nat.STAT_CHANGED_EVAL] / (N * D) for i in range(len(ts) - 1)]
+            return x.detach().cpu().numpy().astype(int), change_jump
+

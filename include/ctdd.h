@@ -49,7 +49,10 @@ enum {
   CTDD_MODE_MIDPOINT_JUMP = 3,   /* sampling.py:459-503: rates at x_eval=x', jumps added to x_base=x      */
   CTDD_MODE_EULER = 4,           /* sampling.py:278-293 (LBJF)                                            */
   CTDD_MODE_EULER_CORR = 5,      /* sampling.py:296-341                                                   */
-  CTDD_MODE_RATES_ONLY = 6       /* get_reverse_rates only: writes rr_out / ratio_out, no state update    */
+  CTDD_MODE_RATES_ONLY = 6,      /* get_reverse_rates only: writes rr_out / ratio_out, no state update    */
+  CTDD_MODE_EXACT = 7            /* sampling.py:1008-1052 (ExactSampling): x' ~ Cat_s'( (softmax(logits) Q)[s'] * W[x][s'] );
+                                    Q = q_{t-h|0}, and the RbT argument carries W[x][s'] = q_{t|t-h}[s', x]; branch, Rb,
+                                    beta, h and eps are ignored; one per-row uniform (Euler stream)        */
 };
 
 /* which kernel family executes a reverse step */

@@ -63,6 +63,12 @@ SAMPLERS = [
     ("condpctaul_gauss32", "ConditionalPCTauLeaping", "gauss32", 8, 10, "CTElbo", None, (1.0, 3.0),
      dict(num_steps=8, min_t=0.01, condition_dim=4, reject_multiple_jumps=True, corrector_entry_time=0.3,
           num_corrector_steps=1), 1.0, 112),
+    ("exact_univar3", "ExactSampling", "univar3_logsqr", 32, 40, "CTElbo", None, (0.3, 0.7),
+     dict(num_steps=10, min_t=0.001, initial_dist="uniform"), 1.0, 113),
+    ("exact_uni2", "ExactSampling", "uni2", 32, 32, "CatRM", "direct", (1.0, None),
+     dict(num_steps=12, min_t=0.01, initial_dist="uniform"), 1.0, 114),
+    ("exact_gauss32", "ExactSampling", "gauss32", 8, 10, "CTElbo", None, (1.0, 3.0),
+     dict(num_steps=8, min_t=0.01), 1.0, 115),
 ]
 
 
@@ -80,6 +86,7 @@ def sampler_cfg(make_cfg, case):
     model = dict(f["model"])
     model["concat_dim"] = D
     model.setdefault("Q_sigma", 20.0)
+    model["log_prob"] = "cat"
     return make_cfg(data=dict(S=S, shape=[D], name=data_name), model=model, training=dict(max_t=max_t, n_iters=1000),
                     sampler=s, loss=loss, device="cpu")
 

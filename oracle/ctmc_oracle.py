@@ -426,3 +426,27 @@ def sample_conditional_pctaul(fp, model, N, total_D, S, conditioner: torch.Tenso
                 call += 1
     x0 = _final_argmax(sliced, x, min_t, N)
     return torch.concat((conditioner.long(), x0), dim=1).numpy().astype(int)
+
+
+def sample_exact(fp, model, N, D, S, *, max_t, min_t, num_steps, initial_dist, init_std, seed):
+    """ExactSampling.sample (sampling.py:994-1061): per step x ~ Cat(logits = logsumexp_k(log p0t[k] +
+    log(q_{t-h|0}[k, s'] * q_{t|t-h}[s', x]))), one categorical per row (per-row stream, call offset = step)."""
+    xt = initial_samples(N, D, S, initial_dist, init_std, seed)
+    ts = np.concatenate((np.linspace(max_t, min_t, num_steps), np.array([0])))
+    change = []
+    n = torch.arange(N).view(N, 1)
+    for idx, t in enumerate(ts[0:-1]):
+        h = ts[idx] - ts[idx + 1]
+        t_ones = t * torch.ones((N,))
+        p0t = F.softmax(model(xt, t_ones), dim=2)
+        t_eps = t - h
+        q_teps_0 = fp.transition(t_eps * torch.ones((1,)))[0]                        # (S,S)
+        q_t_teps = fp.transit_between(t_eps * torch.ones((1,)), t * torch.ones((1,)))[0]  # (S,S): [s', x]
+        col = q_t_teps.t()[xt.long()]                                                 # (N,D,S): q_{t|t-h}[s', x]
+        w = (p0t @ q_teps_0) * col
+        v = rng.row_units(N * D, 0, idx, rng.STREAM_ROW, seed)
+        x_new = torch.from_numpy(rng.inv_cdf(w.detach().numpy().reshape(N * D, S).astype(np.float32), v).reshape(N, D))
+        change.append(float((x_new != xt).sum()) / (N * D))
+        xt = x_new
+    return xt.numpy().astype(int), change
+

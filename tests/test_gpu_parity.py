@@ -243,6 +243,9 @@ def _run_product_sampler(case, inject_oracle_q, impl=None):
             return Q.to(device).contiguous(), Q.transpose(1, 2).contiguous().to(device), [float(b) for b in fp.beta(t32)]
 
         m.qt0_tables = tables
+        # ExactSampling asks the mixin directly (transition / transit_between of two time vectors)
+        m.transition = lambda t: fp.transition(t.detach().cpu().float()).to(t.device)
+        m.transit_between = lambda t1, t2: fp.transit_between(t1.detach().cpu().float(), t2.detach().cpu().float()).to(t1.device)
     cfg.sampler.name = cls
     sampler = sampling_utils.get_sampler(cfg)
     sampler.seed = seed

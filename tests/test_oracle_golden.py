@@ -73,6 +73,9 @@ def _run_oracle_sampler(case):
     if cls == "MidPointTauL":
         return oc.sample_midpoint(fp, model, N, D, S, max_t=max_t, init_std=cfg.model.Q_sigma, is_ordinal=sc.is_ordinal,
                                   loss_name=loss_name, logit_type=lt, **common)
+    if cls == "ExactSampling":
+        return oc.sample_exact(fp, model, N, D, S, max_t=max_t, min_t=sc.min_t, num_steps=sc.num_steps,
+                               initial_dist=sc.initial_dist, init_std=cfg.model.Q_sigma, seed=seed)
     if cls == "PCTauL":
         return (oc.sample_pctaul(fp, model, N, D, S, corrector_entry_time=sc.corrector_entry_time,
                                  num_corrector_steps=sc.num_corrector_steps,
