@@ -50,7 +50,7 @@ constexpr int STAGE_BYTES = 2 * SPLIT_BYTES;   // hi + mid
 constexpr int TMEM_COLS = 512;
 constexpr int TM_QH = 0, TM_QM = 128, TM_ACC = 256;  // TMEM column map (accumulator b at TM_ACC + b * NT)
 constexpr int PREFETCH_TILES = 8;      // HBM -> L2 bulk-prefetch distance (tiles of this pair's sequence)
-constexpr int LRING = 3;               // per-producer-warp ring of raw logits row pairs filled by cp.async.bulk
+constexpr int LRING = 2;               // per-producer-warp ring of raw logits row pairs filled by cp.async.bulk
 
 // per-time-point table blob (ctdd_prep_tc_tables)
 constexpr size_t TAB_QH_OFF = 0;                                 // uint32 [256][128]  bf16 pairs of Q^T hi
@@ -66,13 +66,17 @@ constexpr size_t ST_BYTES = ST_ROWSUM_OFF + (size_t)S * 4;
 
 enum { KM_JUMP = 0, KM_CORR = 1, KM_RATES = 2, KM_DRIFT = 3 };
 
-struct __align__(16) Side { float c1, c0; int x; int K; uint32_t w1, w2, w3; int valid; };
+// per-row hand-over producer -> count warp -> sampler: rate scale, state, jump count K and the uniforms of picks 0..10
+// (pick uniforms beyond that are regenerated by the sampler; rare)
+constexpr int SIDE_PICKS = 11;
+struct __align__(16) Side { float c1, c0; int x; int K; uint32_t w[SIDE_PICKS]; int valid; };
+struct __align__(16) SideHead { float c1, c0; int x; int K; };
 
 struct Smem {
   alignas(1024) uint8_t stage[STAGES][STAGE_BYTES];
   alignas(16) float gather[GBUF][NH][S];   // [row owned by this CTA][state]: accumulator values, then prefix sums
   Side side[RING][NH];
-  alignas(16) float lring[NUM_PROD_WARPS][LRING][2][S];   // raw fp32 logits rows, two passes ahead of their use
+  alignas(16) float lring[NUM_PROD_WARPS][LRING][2][S];   // raw fp32 logits rows, one pass ahead of their use
   alignas(8) uint64_t full[STAGES];  // leader CTA: its 8 producer warps + 1 relayed arrival for the partner's 8
   uint64_t full_local[STAGES];       // partner CTA: its 8 producer warps; the partner's idle MMA warp relays the phase
   uint64_t empty[STAGES];            // multicast tcgen05.commit
@@ -426,7 +430,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     for (int pi = 0; pi < npass; ++pi) {
       const bool ok = x_cur >= 0;
       const int x = ok ? x_cur : 0;
-      const int x_n2 = fetch();              // its ring slot was drained by pass pi - 1 (__syncwarp at the loop end)
       if (ps == 0) {
         if (pw == 0 && lane == 0) TRACE(0, i, 0);
         mbar_wait(&sm.empty[st], st_par);
@@ -514,13 +517,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       if (l16 == 0) {
         Side si;
         si.c1 = c1; si.c0 = c0; si.x = x; si.valid = ok ? 1 : 0;
-        si.K = 0; si.w1 = __float_as_uint(lam_tot); si.w2 = si.w3 = 0u;
+        si.K = 0; si.w[0] = __float_as_uint(lam_tot);
         sm.side[slot][r] = si;
       }
-      x_cur = x_n1;
-      x_n1 = x_n2;
       if (++rslot == LRING) { rslot = 0; ring_par ^= 1u; }
-      __syncwarp();            // every lane is done with this pass's ring slot
+      __syncwarp();            // every lane is done with this pass's ring slot: refill it for the pass after next
+      x_cur = x_n1;
+      x_n1 = fetch();
       if (pw == 0 && lane == 0) TRACE(0, i, 2 + (ps & 1));
       if (++ps == PASSES) {     // last pass of the tile
         fence_proxy_async();
@@ -547,8 +550,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       const long long g0 = (long long)tile * NT + (long long)rank * NH;
       mbar_wait(&sm.pre_full[slot], (i / RING) & 1);
       Side si = sm.side[slot][lane];
-      const float lam = __uint_as_float(si.w1);
-      si.w1 = 0u;
+      const float lam = __uint_as_float(si.w[0]);
+      si.w[0] = 0u;
       if (si.valid) {
         if (KM == KM_RATES || KM == KM_DRIFT) {
           si.K = 1;
@@ -556,7 +559,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
           const Philox4 p0 = philox_rowjump((uint64_t)(a.row_offset + g0 + lane), 0, a.offset, a.seed);
           const int K = poisson_from_unit(lam, u32_to_unit(p0.w[0]));
           si.K = K > JUMP_PICK_CAP ? JUMP_PICK_CAP : K;
-          si.w1 = p0.w[1]; si.w2 = p0.w[2]; si.w3 = p0.w[3];
+          si.w[0] = p0.w[1]; si.w[1] = p0.w[2]; si.w[2] = p0.w[3];
+          // picks 3..10: a call here serves a whole tile of rows (lane = row); in the sampler it would cost a warp per row
+#pragma unroll
+          for (int c = 1; c <= (SIDE_PICKS - 3) / 4; ++c) {
+            if (K > 4 * c - 1) {
+              const Philox4 pc = philox_rowjump((uint64_t)(a.row_offset + g0 + lane), (uint32_t)c, a.offset, a.seed);
+              si.w[4 * c - 1] = pc.w[0]; si.w[4 * c] = pc.w[1]; si.w[4 * c + 1] = pc.w[2]; si.w[4 * c + 2] = pc.w[3];
+            }
+          }
         }
       }
       sm.side[slot][lane] = si;
@@ -696,7 +707,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
           const int rr = __ffs(todo) - 1;
           todo &= todo - 1;
           const int r = warp * ROWS_PER_SAMPLER + rr;
-          const Side si = sm.side[slot][r];
+          const SideHead si = *reinterpret_cast<const SideHead*>(&sm.side[slot][r]);
           const long long g = g0 + r;
           const int x = si.x;
           const float* grow_p = &sm.gather[gb][r][0];
@@ -754,14 +765,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
           const bool two = todo != 0;
           rrow[1] = two ? __ffs(todo) - 1 : rrow[0];
           todo &= todo - 1;   // no-op when todo == 0
-          Side si[2];
+          SideHead si[2];
           float* gp[2];
           float d[2][8];
           float total[2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const int r = warp * ROWS_PER_SAMPLER + rrow[u];
-            si[u] = sm.side[slot][r];
+            si[u] = *reinterpret_cast<const SideHead*>(&sm.side[slot][r]);
             gp[u] = &sm.gather[gb][r][0];
           }
           float4 e0[2], e1[2], c0v[2], c1v[2];
@@ -825,12 +836,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
             float target[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-              uint32_t w = (j == 0) ? si[u].w1 : (j == 1 ? si[u].w2 : si[u].w3);
-              if (si[u].K > 3 && base < si[u].K) {   // warp-uniform
+              uint32_t w = sm.side[slot][warp * ROWS_PER_SAMPLER + rrow[u]].w[j < SIDE_PICKS ? j : 0];
+              if (si[u].K > SIDE_PICKS && base < si[u].K) {   // warp-uniform
                 const int jj = j >= 3 ? j - 3 : 0;
                 const long long g = g0 + warp * ROWS_PER_SAMPLER + rrow[u];
                 const Philox4 pc = philox_rowjump((uint64_t)(a.row_offset + g), 1u + (uint32_t)(jj >> 2), a.offset, a.seed);
-                if (j >= 3) w = philox_word(pc, jj & 3);
+                if (j >= SIDE_PICKS) w = philox_word(pc, jj & 3);
               }
               target[u] = fminf(u32_to_unit(w), 0.99999994f) * total[u];
             }
