@@ -267,13 +267,49 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
                : "memory");
 }
 
+// packed fp32 pairs (Blackwell: one issue slot for two lanes of an FMA / ADD / MUL / SUB)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n.reg .b64 ra, rb, rc, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmov.b64 rc, {%6, %7};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\nmov.b64 {%0, %1}, rd;\n}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nadd.rn.f32x2 rd, ra, rb;\nmov.b64 {%0, %1}, rd;\n}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nsub.rn.f32x2 rd, ra, rb;\nmov.b64 {%0, %1}, rd;\n}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmul.rn.f32x2 rd, ra, rb;\nmov.b64 {%0, %1}, rd;\n}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+
 // bf16 hi/mid split of two floats, packed (element 0 in the low half)
 __device__ __forceinline__ void split2(float a0, float a1, uint32_t& hi, uint32_t& mid) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
   hi = *reinterpret_cast<uint32_t*>(&h);
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+  const float2 r = fsub2(make_float2(a0, a1), make_float2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xFFFF0000u)));
+  __nv_bfloat162 m = __floats2bfloat162_rn(r.x, r.y);
+#else
   const float r0 = a0 - __uint_as_float(hi << 16);
   const float r1 = a1 - __uint_as_float(hi & 0xFFFF0000u);
   __nv_bfloat162 m = __floats2bfloat162_rn(r0, r1);
+#endif
   mid = *reinterpret_cast<uint32_t*>(&m);
 }
 
@@ -455,24 +491,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
       const float ml = -m * 1.4426950408889634f;
-      float sum4[4], dot4[4], dotg4[4];     // four independent accumulation chains
+      // four independent accumulation chains of packed pairs
+      float2 sum2[4], dot2[4], dotg2[4];
+      const float2 l2e2 = make_float2(1.4426950408889634f, 1.4426950408889634f), ml2 = make_float2(ml, ml);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const float tq[4] = {t4[c].x, t4[c].y, t4[c].z, t4[c].w};
-        const float gq[4] = {g4[c].x, g4[c].y, g4[c].z, g4[c].w};
-        sum4[c] = 0.f; dot4[c] = 0.f; dotg4[c] = 0.f;
+        sum2[c] = make_float2(0.f, 0.f); dot2[c] = make_float2(0.f, 0.f); dotg2[c] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float ex = ex2_approx(fmaf(v[4 * c + e], 1.4426950408889634f, ml));     // exp(v - max)
-          sum4[c] += ex;
-          dotg4[c] = fmaf(ex, gq[e], dotg4[c]);
-          if (!TAULDR) dot4[c] = fmaf(ex, tq[e], dot4[c]);
-          v[4 * c + e] = TAULDR ? ex * tq[e] : ex;   // tauLDR operand: e_k / (Q[k,x] + eps); 1/sum applied by the sampler
+        for (int e = 0; e < 4; e += 2) {
+          const float2 tq = e == 0 ? make_float2(t4[c].x, t4[c].y) : make_float2(t4[c].z, t4[c].w);
+          const float2 gq = e == 0 ? make_float2(g4[c].x, g4[c].y) : make_float2(g4[c].z, g4[c].w);
+          const float2 arg = ffma2(make_float2(v[4 * c + e], v[4 * c + e + 1]), l2e2, ml2);
+          const float2 ex = make_float2(ex2_approx(arg.x), ex2_approx(arg.y));     // exp(v - max)
+          sum2[c] = fadd2(sum2[c], ex);
+          dotg2[c] = ffma2(ex, gq, dotg2[c]);
+          if (!TAULDR) dot2[c] = ffma2(ex, tq, dot2[c]);
+          const float2 op = TAULDR ? fmul2(ex, tq) : ex;   // tauLDR operand: e_k / (Q[k,x] + eps); 1/sum applied by the sampler
+          v[4 * c + e] = op.x; v[4 * c + e + 1] = op.y;
         }
       }
-      float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
-      float dotg = (dotg4[0] + dotg4[1]) + (dotg4[2] + dotg4[3]);
-      float dot = (dot4[0] + dot4[1]) + (dot4[2] + dot4[3]);
+      const float2 s01 = fadd2(sum2[0], sum2[1]), s23 = fadd2(sum2[2], sum2[3]), sall = fadd2(s01, s23);
+      const float2 g01 = fadd2(dotg2[0], dotg2[1]), g23 = fadd2(dotg2[2], dotg2[3]), gall = fadd2(g01, g23);
+      float sum = sall.x + sall.y;
+      float dotg = gall.x + gall.y;
+      float dot = 0.f;
+      if (!TAULDR) {
+        const float2 d01 = fadd2(dot2[0], dot2[1]), d23 = fadd2(dot2[2], dot2[3]), dall = fadd2(d01, d23);
+        dot = dall.x + dall.y;
+      }
       // the tables of the NEXT pass are requested as soon as this pass's have been consumed
       {
         const size_t xo = (size_t)(x_n1 < 0 ? 0 : x_n1) << 8;
