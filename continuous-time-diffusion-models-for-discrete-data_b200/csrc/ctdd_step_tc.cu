@@ -889,7 +889,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
                 const Philox4 pc = philox_rowjump((uint64_t)(a.row_offset + g), 1u + (uint32_t)(jj >> 2), a.offset, a.seed);
                 if (j >= SIDE_PICKS) w = philox_word(pc, jj & 3);
               }
-              target[u] = fminf(u32_to_unit(w), 0.99999994f) * total[u];
+              // lanes without a pick get a target below every prefix sum: they all walk the same (broadcast) addresses
+              // instead of scattering 32 random shared-memory reads per step over the banks
+              target[u] = (j < (u ? K1 : K0)) ? fminf(u32_to_unit(w), 0.99999994f) * total[u] : -1.0f;
             }
             int lo[2] = {0, 0};
 #pragma unroll
