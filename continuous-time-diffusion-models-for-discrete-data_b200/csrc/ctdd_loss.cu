@@ -78,8 +78,9 @@ __global__ void basez_kernel(const float* __restrict__ Rb, const float* __restri
 
 template <bool BWD>
 __global__ void __launch_bounds__(256) loss_kernel(const Args a) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const int S = a.S;
+  const bool vec4 = (S & 3) == 0;   // rows of the smem operands are 16-byte aligned only then
   float* sP = smem;                 // [8][S] softmax p
   float* sA = smem + ROWS * S;      // [8][S] GEMM operand (p * a, or p), later dp
   float* sU = smem + 2 * ROWS * S;  // [8][S] u, later the s-space cotangent
@@ -127,7 +128,17 @@ __global__ void __launch_bounds__(256) loss_kernel(const Args a) {
       float acc[ROWS];
 #pragma unroll
       for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
-      for (int k = 0; k < S; ++k) {
+      int k = 0;
+      for (; vec4 && k + 4 <= S; k += 4) {   // 4 contraction steps per 128-bit shared-memory load of every row's operand
+        const float q0 = __ldg(Q + (size_t)k * S + s), q1 = __ldg(Q + (size_t)(k + 1) * S + s);
+        const float q2 = __ldg(Q + (size_t)(k + 2) * S + s), q3 = __ldg(Q + (size_t)(k + 3) * S + s);
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+          const float4 av = *reinterpret_cast<const float4*>(sA + r * S + k);
+          acc[r] = fmaf(av.w, q3, fmaf(av.z, q2, fmaf(av.y, q1, fmaf(av.x, q0, acc[r]))));
+        }
+      }
+      for (; k < S; ++k) {
         const float q = __ldg(Q + (size_t)k * S + s);
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) acc[r] = fmaf(sA[r * S + k], q, acc[r]);
@@ -250,7 +261,17 @@ __global__ void __launch_bounds__(256) loss_kernel(const Args a) {
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
     if (!direct) {
-      for (int s = 0; s < S; ++s) {
+      int s = 0;
+      for (; vec4 && s + 4 <= S; s += 4) {
+        const float q0 = __ldg(QT + (size_t)s * S + k), q1 = __ldg(QT + (size_t)(s + 1) * S + k);
+        const float q2 = __ldg(QT + (size_t)(s + 2) * S + k), q3 = __ldg(QT + (size_t)(s + 3) * S + k);
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+          const float4 uv = *reinterpret_cast<const float4*>(sU + r * S + s);
+          acc[r] = fmaf(uv.w, q3, fmaf(uv.z, q2, fmaf(uv.y, q1, fmaf(uv.x, q0, acc[r]))));
+        }
+      }
+      for (; s < S; ++s) {
         const float q = __ldg(QT + (size_t)s * S + k);
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) acc[r] = fmaf(sU[r * S + s], q, acc[r]);
