@@ -475,6 +475,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       mbar_wait(&sm.lring_full[pw][rslot], ring_par);
       if (pw == 0 && lane == 0) TRACE(0, i, 5 + (ps & 1));
       const int r = ROWS_PER_PROD * pw + 2 * ps + half;
+#ifdef CTDD_EXP_NOPRODUCE   // diagnostic build: producers only run the barrier protocol (isolates MMA + phase A + samplers)
+      const float c1 = 1e-6f, c0 = 0.f, lam_tot = CTDD_EXP_NOPRODUCE;
+      (void)stage; (void)r; (void)ok;
+#else
       float v[16];
       {
         const float4* src = reinterpret_cast<const float4*>(&sm.lring[pw][rslot][half][4 * l16]);
@@ -559,6 +563,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         *reinterpret_cast<uint2*>(stage + c * KBLOCK_BYTES + off) = make_uint2(h0, h1);
         *reinterpret_cast<uint2*>(stage + SPLIT_BYTES + c * KBLOCK_BYTES + off) = make_uint2(m0, m1);
       }
+#endif
       // row scalars for the count warp and the samplers (one lane per half-warp)
       if (l16 == 0) {
         Side si;
@@ -603,7 +608,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
           si.K = 1;
         } else {
           const Philox4 p0 = philox_rowjump((uint64_t)(a.row_offset + g0 + lane), 0, a.offset, a.seed);
+#ifdef CTDD_EXP_NOSAMPLE   // diagnostic build: no row ever jumps (isolates producer + MMA + phase A)
+          const int K = 0;
+          (void)lam;
+#else
           const int K = poisson_from_unit(lam, u32_to_unit(p0.w[0]));
+#endif
           si.K = K > JUMP_PICK_CAP ? JUMP_PICK_CAP : K;
           si.w[0] = p0.w[1]; si.w[1] = p0.w[2]; si.w[2] = p0.w[3];
           // picks 3..10: a call here serves a whole tile of rows (lane = row); in the sampler it would cost a warp per row
@@ -825,8 +835,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const size_t xo = (size_t)si[u].x << 8;
+#ifdef CTDD_EXP_NOTABE      // diagnostic build: no rate-table gather in the sampler
+            e0[u] = make_float4(1.f, 1.f, 1.f, 1.f); e1[u] = e0[u]; (void)xo;
+#else
             e0[u] = __ldg(reinterpret_cast<const float4*>(tabE + xo));
             e1[u] = __ldg(reinterpret_cast<const float4*>(tabE + xo + 4));
+#endif
             if (KM == KM_CORR) {
               c0v[u] = __ldg(reinterpret_cast<const float4*>(tabC + xo));
               c1v[u] = __ldg(reinterpret_cast<const float4*>(tabC + xo + 4));
@@ -898,7 +912,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
             for (int step = 128; step >= 1; step >>= 1) {
 #pragma unroll
               for (int u = 0; u < 2; ++u)
+#ifdef CTDD_EXP_NOSEARCH    // diagnostic build: no binary search
+                lo[u] += (target[u] > 1e30f) ? step : 0;
+#else
                 if (!(gp[u][lo[u] + step - 1] > target[u])) lo[u] += step;
+#endif
             }
             jump[0] += (j < K0) ? (lo[0] - si[0].x) : 0;
             jump[1] += (j < K1) ? (lo[1] - si[1].x) : 0;
