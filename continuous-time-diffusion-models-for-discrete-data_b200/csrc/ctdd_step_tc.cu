@@ -907,15 +907,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
               // instead of scattering 32 random shared-memory reads per step over the banks
               target[u] = (j < (u ? K1 : K0)) ? fminf(u32_to_unit(w), 0.99999994f) * total[u] : -1.0f;
             }
-            int lo[2] = {0, 0};
+            // first prefix sum above the target in three rounds of INDEPENDENT loads (7 splitters of stride 32, 7 of
+            // stride 4, 3 neighbours) instead of eight dependent binary-search steps
+            int lo[2];
 #pragma unroll
-            for (int step = 128; step >= 1; step >>= 1) {
-#pragma unroll
-              for (int u = 0; u < 2; ++u)
-#ifdef CTDD_EXP_NOSEARCH    // diagnostic build: no binary search
-                lo[u] += (target[u] > 1e30f) ? step : 0;
+            for (int u = 0; u < 2; ++u) {
+#ifdef CTDD_EXP_NOSEARCH    // diagnostic build: no search
+              lo[u] = (target[u] > 1e30f) ? 1 : 0;
 #else
-                if (!(gp[u][lo[u] + step - 1] > target[u])) lo[u] += step;
+              const float* P = gp[u];
+              const float T = target[u];
+              int c1 = 0;
+#pragma unroll
+              for (int m = 0; m < 7; ++m) c1 += (P[32 * m + 31] <= T) ? 1 : 0;
+              const float* P1 = P + 32 * c1;
+              int c2 = 0;
+#pragma unroll
+              for (int n = 0; n < 7; ++n) c2 += (P1[4 * n + 3] <= T) ? 1 : 0;
+              const float* P2 = P1 + 4 * c2;
+              const int c3 = ((P2[0] <= T) ? 1 : 0) + ((P2[1] <= T) ? 1 : 0) + ((P2[2] <= T) ? 1 : 0);
+              lo[u] = 32 * c1 + 4 * c2 + c3;
 #endif
             }
             jump[0] += (j < K0) ? (lo[0] - si[0].x) : 0;
