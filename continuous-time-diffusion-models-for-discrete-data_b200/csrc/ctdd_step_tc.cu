@@ -64,7 +64,11 @@ constexpr size_t ST_RBZ_OFF = (size_t)S * S * 4;                 // float [x][s]
 constexpr size_t ST_ROWSUM_OFF = 2 * (size_t)S * S * 4;          // float [x] = sum_s Rbz[x][s]
 constexpr size_t ST_BYTES = ST_ROWSUM_OFF + (size_t)S * 4;
 
-enum { KM_JUMP = 0, KM_CORR = 1, KM_RATES = 2, KM_DRIFT = 3 };
+enum { KM_JUMP = 0, KM_CORR = 1, KM_RATES = 2, KM_DRIFT = 3, KM_EULER = 4, KM_EULER_CORR = 5 };
+// the corrector variants add h * R_t[x,:] to the rates; the Euler variants draw ONE categorical per row over
+// {h * rate_s (s != x), max(0, 1 - h * sum)} (sampling.py:278-293) instead of Poisson jump counts
+__host__ __device__ constexpr bool km_corr(int km) { return km == KM_CORR || km == KM_EULER_CORR; }
+__host__ __device__ constexpr bool km_euler(int km) { return km == KM_EULER || km == KM_EULER_CORR; }
 
 // per-row hand-over producer -> count warp -> sampler: rate scale, state, jump count K and the uniforms of picks 0..10
 // (pick uniforms beyond that are regenerated by the sampler; rare)
@@ -334,7 +338,7 @@ __device__ long long g_trace[2][TRACE_ROLES][TRACE_TILES][TRACE_EVENTS];
 #endif
 
 
-// TAULDR: tauLDR rates (else SDDM reverse_prob); KM: KM_JUMP / KM_CORR (corrector adds R_t[x,:]) / KM_RATES / KM_DRIFT
+// TAULDR: tauLDR rates (else SDDM reverse_prob); KM: KM_JUMP / KM_CORR / KM_RATES / KM_DRIFT / KM_EULER / KM_EULER_CORR
 template <bool TAULDR, int KM>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step_tc_kernel(const Args a) {
   extern __shared__ uint8_t smem_raw[];
@@ -540,7 +544,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       }
       const float rs = __frcp_rn(sum);
       if (pw == 0 && lane == 0 && ps == 1) TRACE(0, i, 7);
-      const float rz = (!TAULDR || KM == KM_CORR) ? __ldg(rowsumZ + x) : 0.f;
+      const float rz = (!TAULDR || km_corr(KM)) ? __ldg(rowsumZ + x) : 0.f;
       float c1, c0;
       if (TAULDR) {
         c1 = hb * rs;                                            // lam_s = D_s * c1 * Rb[s,x]
@@ -551,7 +555,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         c0 = hb * 1e-35f * inv;
       }
       float lam_tot = fmaf(c1, dotg, c0 * rz);
-      if (KM == KM_CORR) lam_tot = fmaf(hb, rz, lam_tot);
+      if (km_corr(KM)) lam_tot = fmaf(hb, rz, lam_tot);
       // k = 64c + 4*l16 .. +3 lives in K block c, 16-byte chunk l16/2 (XOR-swizzled by the row), half l16&1
       const uint32_t off = (uint32_t)r * 128 + (uint32_t)((((l16 >> 1) ^ (r & 7)) << 4) | ((l16 & 1) << 3));
 #pragma unroll
@@ -606,6 +610,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       if (si.valid) {
         if (KM == KM_RATES || KM == KM_DRIFT) {
           si.K = 1;
+        } else if (km_euler(KM)) {   // one categorical draw per row: the per-row uniform of the Euler stream
+          si.K = 1;
+          si.w[0] = philox_row_word((uint64_t)(a.row_offset + g0 + lane), 0, a.offset, STREAM_ROW, a.seed);
         } else {
           const Philox4 p0 = philox_rowjump((uint64_t)(a.row_offset + g0 + lane), 0, a.offset, a.seed);
 #ifdef CTDD_EXP_NOSAMPLE   // diagnostic build: no row ever jumps (isolates producer + MMA + phase A)
@@ -841,7 +848,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
             e0[u] = __ldg(reinterpret_cast<const float4*>(tabE + xo));
             e1[u] = __ldg(reinterpret_cast<const float4*>(tabE + xo + 4));
 #endif
-            if (KM == KM_CORR) {
+            if (km_corr(KM)) {
               c0v[u] = __ldg(reinterpret_cast<const float4*>(tabC + xo));
               c1v[u] = __ldg(reinterpret_cast<const float4*>(tabC + xo + 4));
             }
@@ -855,7 +862,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
             // lam_s for s = 8*lane .. 8*lane+7 (zero at s == x through the zero-diagonal tables)
 #pragma unroll
             for (int e = 0; e < 8; ++e) d[u][e] = fmaf(dv[e], si[u].c1, si[u].c0) * ev[e];
-            if (KM == KM_CORR) {
+            if (km_corr(KM)) {
               const float cv[8] = {c0v[u].x, c0v[u].y, c0v[u].z, c0v[u].w, c1v[u].x, c1v[u].y, c1v[u].z, c1v[u].w};
 #pragma unroll
               for (int e = 0; e < 8; ++e) d[u][e] = fmaf(hb, cv[e], d[u][e]);
@@ -881,6 +888,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
             total[u] = __shfl_sync(0xffffffffu, incl[u], 31);
 #pragma unroll
             for (int e = 0; e < 8; ++e) d[u][e] += excl;
+            if (km_euler(KM)) {   // stay-probability max(0, 1 - sum) enters the cumulative sums at position x
+              const float diag = fmaxf(0.f, 1.0f - total[u]);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) d[u][e] += (8 * lane + e >= si[u].x) ? diag : 0.f;
+              total[u] += diag;
+            }
             if (u == 0 || two) {
               *reinterpret_cast<float4*>(gp[u] + 8 * lane) = make_float4(d[u][0], d[u][1], d[u][2], d[u][3]);
               *reinterpret_cast<float4*>(gp[u] + 8 * lane + 4) = make_float4(d[u][4], d[u][5], d[u][6], d[u][7]);
@@ -942,7 +955,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
             const long long g = g0 + warp * ROWS_PER_SAMPLER + rrow[u];
             const int x = u ? si[1].x : si[0].x;
             const int xb = a.x_base ? a.x_base[g] : x;
-            a.x_out[g] = finalize_jump(xb, x, u ? jump[1] : jump[0], u ? K1 : K0, a.reject_multi, S, stt);
+            if (km_euler(KM)) {   // the pick IS the new state (jump holds pick - x)
+              const int xn = x + (u ? jump[1] : jump[0]);
+              a.x_out[g] = xn;
+              stt.changed_base += (xn != xb);
+              stt.changed_eval += (xn != x);
+            } else {
+              a.x_out[g] = finalize_jump(xb, x, u ? jump[1] : jump[0], u ? K1 : K0, a.reject_multi, S, stt);
+            }
           }
         }
       }
@@ -1038,7 +1058,8 @@ bool tc_supports(const ctdd_step_params* p) {
   if (p->S != tc::S) return false;
   if (!(p->branch == CTDD_BRANCH_TAULDR || p->branch == CTDD_BRANCH_SDDM_REVERSE_PROB)) return false;
   if (!(p->mode == CTDD_MODE_TAU_LEAP || p->mode == CTDD_MODE_TAU_LEAP_CORR || p->mode == CTDD_MODE_MIDPOINT_JUMP ||
-        p->mode == CTDD_MODE_MIDPOINT_DRIFT || p->mode == CTDD_MODE_RATES_ONLY))
+        p->mode == CTDD_MODE_MIDPOINT_DRIFT || p->mode == CTDD_MODE_EULER || p->mode == CTDD_MODE_EULER_CORR ||
+        p->mode == CTDD_MODE_RATES_ONLY))
     return false;
   if (!p->tc_tables || !p->tc_static) return false;
   if ((p->ld_logits & 3) || (p->batch_stride_logits & 3) || (reinterpret_cast<uintptr_t>(p->logits) & 15)) return false;
@@ -1059,15 +1080,17 @@ int launch_step_tc(const ctdd_step_params* p, cudaStream_t st) {
   static bool attr_set = false;
   const size_t smem_bytes = sizeof(Smem) + 1024;
   typedef void (*kern_t)(const Args);
-  static const kern_t kerns[2][4] = {
-      {step_tc_kernel<false, KM_JUMP>, step_tc_kernel<false, KM_CORR>, step_tc_kernel<false, KM_RATES>, step_tc_kernel<false, KM_DRIFT>},
-      {step_tc_kernel<true, KM_JUMP>, step_tc_kernel<true, KM_CORR>, step_tc_kernel<true, KM_RATES>, step_tc_kernel<true, KM_DRIFT>}};
+  static const kern_t kerns[2][6] = {
+      {step_tc_kernel<false, KM_JUMP>, step_tc_kernel<false, KM_CORR>, step_tc_kernel<false, KM_RATES>, step_tc_kernel<false, KM_DRIFT>,
+       step_tc_kernel<false, KM_EULER>, step_tc_kernel<false, KM_EULER_CORR>},
+      {step_tc_kernel<true, KM_JUMP>, step_tc_kernel<true, KM_CORR>, step_tc_kernel<true, KM_RATES>, step_tc_kernel<true, KM_DRIFT>,
+       step_tc_kernel<true, KM_EULER>, step_tc_kernel<true, KM_EULER_CORR>}};
   if (!attr_set) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     for (int i = 0; i < 2; ++i)
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < 6; ++j)
         if (cudaFuncSetAttribute(kerns[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
           set_error("ctdd_reverse_step: cannot reserve %zu bytes of shared memory for the tcgen05 kernel", smem_bytes);
           cudaGetLastError();
@@ -1094,6 +1117,8 @@ int launch_step_tc(const ctdd_step_params* p, cudaStream_t st) {
   if (p->mode == CTDD_MODE_RATES_ONLY) kj = KM_RATES;
   else if (p->mode == CTDD_MODE_TAU_LEAP_CORR) kj = KM_CORR;
   else if (p->mode == CTDD_MODE_MIDPOINT_DRIFT) kj = KM_DRIFT;
+  else if (p->mode == CTDD_MODE_EULER) kj = KM_EULER;
+  else if (p->mode == CTDD_MODE_EULER_CORR) kj = KM_EULER_CORR;
   kerns[ki][kj]<<<2 * pairs, NUM_THREADS, smem_bytes, st>>>(a);
   CTDD_CHECK_LAUNCH("step_tc_kernel");
   return 0;

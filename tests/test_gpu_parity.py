@@ -151,9 +151,7 @@ def test_step_modes_match_oracle(sc, impl_i):
 
     def run(mode, offset, reject=False, x_base=None):
         stats = torch.zeros(8, dtype=torch.int64, device="cuda")
-        use = impl
-        if impl == nat.IMPL_TC and mode in (nat.MODE_EULER, nat.MODE_EULER_CORR):
-            use = nat.IMPL_AUTO   # these modes run on the CUDA-core path at S=256
+        use = impl            # every update mode runs on the tcgen05 path at S=256
         out = ops.reverse_step(mode, branch, lg, xe, tb["Q"], tb["QT"], tb["Rb"], tb["RbT"], tb["beta"], h, 1e-9,
                                N=N, D=D, S=S, impl=use, tc_tables=tct, tc_static=tcs,
                                reject_multi=reject, seed=seed, offset=offset, x_base=x_base, stats=stats)
