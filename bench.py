@@ -291,6 +291,68 @@ def run_ours(args, w, rank, world, local_rank):
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_ms = float(t_e.item())
 
+    # ---- the sampler CLASS end to end (the reference-facing API): TauL.sample(model, B) with a stub network that returns
+    # resident logits (network cost excluded on both sides); includes q_{t|0} / table builds for the schedule,
+    # the initial samples, one kernel launch per step, the statistics read-back and the final .cpu() of the samples
+    loop = None
+    if w["mode"] == "tau_leap":
+        import torch.nn as nn
+        from ctdd_b200.lib.sampling import sampling_utils
+        import ctdd_b200.lib.sampling.sampling  # noqa: F401
+        loop_steps = w["num_steps"]     # the whole schedule: the step length h decides the jump rates, a short schedule is not representative
+        mcfg = dict(w["model"], concat_dim=D)
+        mcfg.setdefault("Q_sigma", 20.0)
+        scfg = make_config(data=dict(S=S, shape=[D], name="DiscreteCIFAR10"), model=mcfg, training=dict(max_t=w["max_t"]),
+                           sampler=dict(name="TauL", num_steps=loop_steps, min_t=w["min_t"], eps_ratio=1e-9,
+                                        initial_dist="gaussian" if S > 8 else "uniform", num_corrector_steps=0,
+                                        corrector_step_size_multiplier=1.5, corrector_entry_time=0.0, is_ordinal=w["ordinal"]),
+                           loss=dict(name="CTElboLambda", eps_ratio=1e-9, logit_type="reverse_prob"), device=str(dev))
+        mixin = getattr(fm, MIXIN[w["fwd"]])
+
+        class Stub(nn.Module, mixin):
+            """Denoiser-like stand-in for the score network: logits[n,d,s] = -(s - x[n,d])^2 / (2 * 8^2), written in place
+            into one resident buffer (three elementwise torch kernels; timed separately as `stub_network_ms`).  The logits
+            must follow the state: with logits that ignore x the reverse rates explode and the run measures nothing real."""
+
+            def __init__(self):
+                nn.Module.__init__(self)
+                mixin.__init__(self, scfg, str(dev))
+                self.out = bufs[0]
+                self.s_row = torch.arange(S, device=dev, dtype=torch.float32).view(1, 1, S)
+
+            def forward(self, x, t):
+                torch.sub(self.s_row, x.unsqueeze(-1).to(torch.float32), out=self.out)
+                self.out.square_().mul_(-1.0 / 128.0)
+                return self.out
+
+        stub = Stub()
+        stub.device = str(dev)
+        sampler = sampling_utils.get_sampler(scfg)
+        sampler.seed, sampler.row_offset, sampler.impl = 0xC7DD, row_offset, impl
+        barrier()
+        t0 = time.perf_counter()
+        xs, _ = sampler.sample(stub, B)
+        barrier()
+        loop_ms = (time.perf_counter() - t0) * 1e3 / loop_steps
+        t_l = torch.tensor([loop_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_l, op=dist.ReduceOp.MAX)
+        loop_ms = float(t_l.item())
+        # the stub network alone, same call pattern
+        xs_dev = torch.from_numpy(np.asarray(xs)).to(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stub(xs_dev, None)
+        e0.record()
+        for _ in range(4):
+            stub(xs_dev, None)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        stub_ms = e0.elapsed_time(e1) / 4
+        loop = {"api": "TauL.sample(model, B), whole schedule, stub network whose logits follow the state; includes the "
+                       "q_{t|0} / table build for every time point and the final read-back", "steps": loop_steps,
+                "ms_per_step": loop_ms, "stub_network_ms": stub_ms,
+                "samples_per_s": world * B / (loop_steps * loop_ms * 1e-3)}
+
     if rank != 0:
         return
     pk = peaks()
@@ -324,7 +386,8 @@ def run_ours(args, w, rank, world, local_rank):
                                f"(TauL predictor, lib/sampling/sampling.py:119-160)",
                    "l2": "inputs larger than L2 (2 alternating logits buffers)" if flush is None else "L2 flushed between timed steps",
                    "kernels": args.kernels, "times": "steps spread over the schedule max_t..min_t",
-                   "samples_per_s_at_num_steps": world * B / (w["num_steps"] * ms * 1e-3), "num_steps": w["num_steps"]},
+                   "samples_per_s_at_num_steps": world * B / (w["num_steps"] * ms * 1e-3), "num_steps": w["num_steps"],
+                   "sampler_loop": loop},
         "roofline": roof,
         "e2e": {"value": world * fl / (e2e_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(B * D * S * 4 + B * D * 4), "d2h_bytes_per_step": int(B * D * 4),
