@@ -1,23 +1,29 @@
 // tcgen05 reverse-step kernel for S == 256 (configs C3/C4/C5): the (N*D x S)(S x S) contraction of
 // lib/sampling/sampling.py:57 on 5th-generation tensor cores, fused with softmax, the q_{t|0} denominators, the
-// forward-rate multiply and the Philox tau-leap / midpoint-drift state update (sampling.py:127-160, :423-503).
+// forward-rate multiply and the Philox state update of every sampler (tau-leap / corrector sampling.py:127-221,
+// midpoint :423-503, Euler :278-341, rates only :31-78).
 //
-// One CTA PAIR (thread-block cluster of 2, tcgen05 cta_group::2) owns a sequence of 128-row tiles:
-//   D[s, row] = sum_k Q^T[s, k] * a[row, k]        M = 256 states (128 per CTA), N = 128 rows, K = 256
+// One CTA PAIR (thread-block cluster of 2, tcgen05 cta_group::2) owns a sequence of 64-row tiles:
+//   D[s, row] = sum_k Q^T[s, k] * a[row, k]        M = 256 states (128 per CTA), N = 64 rows, K = 256
 //   * M side = state s. Each CTA keeps ITS 128-state half of Q^T (bf16 hi + mid split, 2 x 128 TMEM columns)
-//     resident in tensor memory as the A operand (TS form) for the whole kernel.
-//   * N side = data rows. Each CTA's producer warps (one warp per row) build 64 of the tile's 128 rows: fp32 logits
-//     straight from HBM with coalesced 128-bit loads, row softmax by shuffles, gathered reciprocal denominators
-//     1/(Q[k,x]+eps), bf16 hi/mid split, K-major 128B-swizzled smem stage.  Every row is produced exactly once.
-//     The producer also computes the row's TOTAL jump rate from a precomputed table dot product
-//     (Lambda = c * sum_k e_k G[x][k], G = (Q Rbz)[k,x] / (Q[k,x]+eps)) and draws the row's jump count K.
-//   * 3 tensor passes  Qh*ah + Qh*am + Qm*ah  accumulate in fp32 TMEM (2 accumulators x 128 columns per CTA).
-//   * Epilogue: each CTA reads its 128 states x 128 rows with tcgen05.ld and scatters them (local st.shared /
-//     remote st.shared::cluster) into the [row][state] gather buffer of the CTA that OWNS the row, so that each
-//     owner sees all 256 states of its 64 rows.  The same warps then run the row sampler (one warp per row):
-//     lam_s = D_s * c * Rbz[s,x], warp prefix sum, K inverse-CDF picks (superposition map of ctdd_common.cuh),
-//     clamp, rejection, statistics, x_out.  Rows with K == 0 cost one store.
-// Warp roles per CTA: 8 epilogue/sampler warps, 1 MMA-issue warp (leader CTA only issues), 8 producer warps.
+//     resident in tensor memory as the A operand (TS form) for the whole kernel; 4 accumulators of 64 columns.
+//   * N side = data rows. Each CTA's 8 producer warps build 32 of the tile's 64 rows, two rows per pass with 16 lanes
+//     per row: raw fp32 logits arrive through a per-warp smem ring filled by cp.async.bulk (HBM -> L2 prefetch eight
+//     tiles ahead), row softmax by half-warp butterflies, gathered reciprocal denominators 1/(Q[k,x]+eps), bf16 hi/mid
+//     split, K-major 128B-swizzled smem stage.  Every row is produced exactly once.  The producer also computes the
+//     row's TOTAL jump rate as one table dot product (Lambda = c * sum_k e_k G[x][k], G = (Q Rbz)[k,x] / (Q[k,x]+eps)).
+//   * Count warp (lane = row): total jump count K ~ Poisson(Lambda) and the uniforms of the first 11 picks.
+//   * 3 tensor passes  Qh*ah + Qh*am + Qm*ah  accumulate in fp32 TMEM (48 tcgen05.mma per tile).
+//   * Epilogue phase A: each CTA reads its 128 states x 64 rows with tcgen05.ld and scatters them (local st.shared /
+//     remote st.async with mbarrier complete_tx) into the [row][state] gather buffer of the CTA that OWNS the row, so
+//     that each owner sees all 256 states of its 32 rows.  Two gather buffers: phase A of tile i+1 runs before the
+//     sampling of tile i.
+//   * Row sampler (the same 8 warps, one warp per row, two rows in flight): lam_s = D_s * c * Rbz[s,x], warp prefix
+//     sum, K inverse-CDF picks (superposition map of ctdd_common.cuh), clamp, rejection, statistics, x_out.  Rows with
+//     K == 0 are settled by one lane.
+// Warp roles per CTA (5 warpgroups, setmaxnreg 104 / 64): 8 epilogue/sampler warps, 8 producer warps, and a light
+// group with the MMA-issue warp (leader CTA issues; the partner's relays its producers' arrivals), the count warp and
+// 2 idle warps.  profiles/r1_step_tc_summary.md has the measured per-role timeline.
 #include "ctdd_common.cuh"
 #include <cuda_bf16.h>
 
