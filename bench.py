@@ -57,13 +57,48 @@ def synth_logits(B, D, S, seed, device, x0=None):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons of this rank's GPU during the timed region."""
+    """Samples SM clock and throttle reasons of this rank's GPU DURING the timed region: NVML (the library behind
+    nvidia-smi) polled every 2 ms from a thread; falls back to an `nvidia-smi -lms` subprocess when pynvml is missing."""
+
+    NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         self.index, self.rows, self._stop = index, [], threading.Event()
-        self.proc = None
+        self.proc = self.nvml = self.t = None
+
+    def _poll_nvml(self):
+        nv, h = self.nvml
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((float(sm), float(mx), int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def __enter__(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber devices: resolve through the PCI bus id torch reports
+            try:
+                bus = torch.cuda.get_device_properties(self.index).pci_bus_id
+                dom = torch.cuda.get_device_properties(self.index).pci_domain_id
+                dev = torch.cuda.get_device_properties(self.index).pci_device_id
+                h = nv.nvmlDeviceGetHandleByPciBusId(f"{dom:08x}:{bus:02x}:{dev:02x}.0")
+            except Exception:
+                h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml = (nv, h)
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.t.start()
+            return self
+        except Exception:
+            self.nvml = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
@@ -76,10 +111,18 @@ class ClockSampler:
         return self
 
     def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        bits = {v: k for k, v in self.NAMES.items()}
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            c = [x.strip() for x in line.split(",")]
+            try:
+                rs = sum(bits[n] for n, v in zip(names, c[3:7]) if v.lower().startswith("active"))
+                self.rows.append((float(c[0]), float(c[1]), rs))
+            except Exception:
+                continue
 
     def __exit__(self, *a):
+        self._stop.set()
         if self.proc is not None:
             time.sleep(0.15)
             self.proc.terminate()
@@ -87,21 +130,16 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
+        elif self.t is not None:
+            self.t.join(timeout=1)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except Exception:
-                continue
-            for n, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        if not sm:
+        if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        sm = [r[0] for r in self.rows]
+        reasons = sorted({n for r in self.rows for bit, n in self.NAMES.items() if r[2] & bit})
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(r[1] for r in self.rows)), "reasons": reasons,
+                "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def peaks():
