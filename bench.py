@@ -222,6 +222,8 @@ def run_ours(args, w, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     S, D, B = w["S"], w["D"], w["B"]
+    if args.batch:
+        B = args.batch          # diagnostic: other batch sizes of the same workload (the bench line names the B it ran)
     K, W = args.steps, args.warmup
     cfg = make_config(data=dict(S=S), model=dict(w["model"], Q_sigma=w["model"].get("Q_sigma", 20.0)), device=str(dev))
     model = getattr(fm, MIXIN[w["fwd"]])(cfg, str(dev))
@@ -454,6 +456,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch of the workload (diagnostic)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = WORKLOADS[args.workload]
