@@ -1,0 +1,60 @@
+"""CPU: the drop-in boundary — registry names, call conventions, and INTEGRATION.md option (ii) against the
+real reference when it is mounted (build container only; the GPU box does not have /root/reference)."""
+import inspect
+import os
+
+import pytest
+
+
+def test_registries_hold_the_reference_names():
+    from ctdd_b200.lib.sampling import sampling_utils as su
+    from ctdd_b200.lib.losses import losses_utils as lu
+    import ctdd_b200.lib.sampling.sampling  # noqa: F401
+    import ctdd_b200.lib.losses.losses  # noqa: F401
+    for name in ("TauL", "LBJF", "MidPointTauL", "PCTauL", "ConditionalTauLeaping", "ConditionalPCTauLeaping", "ExactSampling"):
+        assert name in su._SAMPLERS, name
+    for name in ("CTElbo", "NLL", "CTElboLambda", "CondCTElbo", "CatRM", "CatRMNLL", "ScoreElbo", "SDDMElbo", "NLLOriginal"):
+        assert name in lu._LOSSES, name
+    with pytest.raises(ValueError):                 # duplicate registration is an error, as in the reference
+        su.register_sampler(su._SAMPLERS["TauL"])
+    with pytest.raises(ValueError):
+        lu.register_loss(lu._LOSSES["CTElbo"])
+
+
+def test_sampler_and_loss_signatures_match_the_reference_conventions():
+    from ctdd_b200.lib.sampling import sampling as s
+    from ctdd_b200.lib.losses import losses as l
+    assert list(inspect.signature(s.TauL.sample).parameters) == ["self", "model", "N"]
+    assert list(inspect.signature(s.ConditionalTauLeaping.sample).parameters) == ["self", "model", "N", "conditioner"]
+    assert list(inspect.signature(s.get_initial_samples).parameters)[:6] == ["N", "D", "device", "S", "initial_dist", "initial_dist_std"]
+    for cls in (l.CTElbo, l.CatRM, l.SDDMElbo, l.ScoreElbo, l.CatRMNLL, l.NLLOriginal):
+        assert len(inspect.signature(cls.calc_loss).parameters) >= 3     # (self, a, b[, label/writer]): both orders accepted
+
+
+def test_no_cpu_fallback_is_offered():
+    """Host tensors are refused instead of being routed to a CPU path."""
+    import torch
+    from ctdd_b200 import _native as nat
+    with pytest.raises(RuntimeError):
+        nat.ptr(torch.zeros(4))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/TAUnSDDM"), reason="reference not mounted")
+def test_install_into_reference_overwrites_the_reference_registries():
+    from oracle import ref_harness as rh
+    ref = rh.import_reference()
+    import ctdd_b200
+    before = ref.su._SAMPLERS["TauL"]
+    samplers, losses = ctdd_b200.install_into_reference()
+    from ctdd_b200.lib.sampling import sampling as ours
+    assert ref.su._SAMPLERS["TauL"] is ours.TauL and ref.su._SAMPLERS["TauL"] is not before
+    assert "CTElbo" in losses and ref.lu._LOSSES["CTElbo"].__module__.startswith("ctdd_b200")
+    # put the reference classes back so that other tests that drive the reference see the original registry
+    import lib.sampling.sampling as rs
+    import lib.losses.losses as rl
+    for name in list(ref.su._SAMPLERS):
+        if hasattr(rs, name):
+            ref.su._SAMPLERS[name] = getattr(rs, name)
+    for name in list(ref.lu._LOSSES):
+        if hasattr(rl, name):
+            ref.lu._LOSSES[name] = getattr(rl, name)
