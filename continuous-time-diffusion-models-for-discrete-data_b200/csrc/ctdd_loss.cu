@@ -330,11 +330,13 @@ int run_loss(const ctdd_loss_params* p, void* stream, bool bwd) {
   const int S = p->S;
   const size_t smem = (size_t)3 * ROWS * S * sizeof(float);
   if (smem > 200 * 1024) { set_error("ctdd_loss: S=%d too large", S); return 2; }
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr_done = 0ull;   // function attributes live in the device's context: a bit per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !((attr_done >> dev) & 1ull)) {
     cudaFuncSetAttribute(loss_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(loss_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr = true;
+    if (dev >= 0 && dev < 64) attr_done |= 1ull << dev;
   }
   Args a;
   a.kind = p->kind; a.logit_type = p->logit_type; a.crm_type = p->crm_type; a.B = p->B; a.D = p->D; a.S = S;

@@ -447,10 +447,12 @@ int launch_step_simt(const ctdd_step_params* p, cudaStream_t st) {
   }
   const size_t smem = (size_t)2 * BLK_ROWS * S * sizeof(float);
   if (smem > 200 * 1024) { set_error("ctdd_reverse_step: S=%d too large for the block path", S); return 2; }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_done = 0ull;   // function attributes live in the device's context: a bit per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !((attr_done >> dev) & 1ull)) {
     cudaFuncSetAttribute(step_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_done |= 1ull << dev;
   }
   int threads = ((S + 31) / 32) * 32;
   if (threads > 256) threads = 256;

@@ -1082,8 +1082,12 @@ long long tc_workspace_bytes(long long rows, int S) {
 
 int launch_step_tc(const ctdd_step_params* p, cudaStream_t st) {
   using namespace tc;
-  static int num_sms = 0;
-  static bool attr_set = false;
+  // per-device one-time setup (function attributes live in the device's context): a bit per device ordinal
+  static int num_sms[64] = {0};
+  static unsigned long long attr_done = 0ull;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool attr_set = dev >= 0 && dev < 64 && ((attr_done >> dev) & 1ull);
   const size_t smem_bytes = sizeof(Smem) + 1024;
   typedef void (*kern_t)(const Args);
   static const kern_t kerns[2][6] = {
@@ -1092,9 +1096,7 @@ int launch_step_tc(const ctdd_step_params* p, cudaStream_t st) {
       {step_tc_kernel<true, KM_JUMP>, step_tc_kernel<true, KM_CORR>, step_tc_kernel<true, KM_RATES>, step_tc_kernel<true, KM_DRIFT>,
        step_tc_kernel<true, KM_EULER>, step_tc_kernel<true, KM_EULER_CORR>}};
   if (!attr_set) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&num_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
     for (int i = 0; i < 2; ++i)
       for (int j = 0; j < 6; ++j)
         if (cudaFuncSetAttribute(kerns[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
@@ -1102,7 +1104,7 @@ int launch_step_tc(const ctdd_step_params* p, cudaStream_t st) {
           cudaGetLastError();
           return 1;
         }
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_done |= 1ull << dev;
   }
   Args a;
   a.branch = p->branch; a.D = p->D; a.reject_multi = p->reject_multi;
@@ -1115,7 +1117,7 @@ int launch_step_tc(const ctdd_step_params* p, cudaStream_t st) {
   a.x_out = p->x_out; a.rr_out = p->rr_out; a.ratio_out = p->ratio_out;
   a.stats = reinterpret_cast<unsigned long long*>(p->stats_out);
   a.num_tiles = (int)((a.rows + NT - 1) / NT);
-  int pairs = num_sms / 2;                           // one CTA pair (cluster of 2) per TPC
+  int pairs = num_sms[dev & 63] / 2;                 // one CTA pair (cluster of 2) per TPC
   if (pairs > a.num_tiles) pairs = a.num_tiles;
   if (pairs < 1) pairs = 1;
   const int ki = (p->branch == CTDD_BRANCH_TAULDR) ? 1 : 0;
