@@ -336,3 +336,50 @@ def test_free_running_histograms_tc_vs_simt():
     kl = 0.5 * ((p * np.log(p / q)).sum(axis=1) + (q * np.log(q / p)).sum(axis=1))
     assert kl.mean() < 1e-3, kl
     assert kl.max() < 3e-3, kl
+
+
+def test_full_size_c4_properties():
+    """BASELINE.json's full C4 size (B=1024, D=3072, S=256: 3.1 M rows, 3.2 GB of logits) through size-independent
+    properties: states stay in range, the statistics counters equal what the output shows, the run is deterministic in
+    (seed, offset), batch sharding with row offsets reproduces the single launch bit for bit, and two 4096-row slices
+    agree with the CUDA-core path run on just those rows (Philox is keyed on the global row)."""
+    from ctdd_b200 import ops
+    nat = _nat()
+    N, D, S, t, h = 1024, 3072, 256, 0.3, 0.99 / 1000
+    fp = oracle_forward("gauss256")
+    tb = _tables(fp, t)
+    branch = nat.BRANCH_TAULDR
+    _, tct, tcs = _tc(tb, branch, S, nat.IMPL_AUTO)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x0 = torch.randint(0, S, (N, D), generator=g, device="cuda")
+    logits = torch.randn((N, D, S), generator=g, device="cuda")
+    logits -= (torch.arange(S, device="cuda", dtype=torch.float32).view(1, 1, S) - x0.unsqueeze(-1).float()) ** 2 / 128.0
+    x = torch.clamp(x0 + torch.randint(-3, 4, x0.shape, generator=g, device="cuda"), 0, S - 1).to(torch.int32)
+    common = dict(D=D, S=S, tc_tables=tct, tc_static=tcs, seed=99, offset=4)
+    args = (branch,)
+    tabs = (tb["Q"], tb["QT"], tb["Rb"], tb["RbT"], tb["beta"], h, 1e-9)
+
+    def run(lg, xs, n, impl, row_offset=0, seed=99, stats=None):
+        kw = dict(common)
+        kw["seed"] = seed
+        if impl == nat.IMPL_SIMT:
+            kw["tc_tables"] = kw["tc_static"] = None
+        return ops.reverse_step(nat.MODE_TAU_LEAP, branch, lg, xs, *tabs, N=n, impl=impl, row_offset=row_offset, stats=stats, **kw)["x"]
+
+    st = torch.zeros(8, dtype=torch.int64, device="cuda")
+    full = run(logits, x, N, nat.IMPL_TC, stats=st)
+    assert full.shape == (N, D) and int(full.min()) >= 0 and int(full.max()) < S
+    changed = int((full != x).sum())
+    assert int(st[nat.STAT_CHANGED_BASE]) == changed == int(st[nat.STAT_CHANGED_EVAL])
+    assert 0.2 * N * D < int(st[nat.STAT_ROWS_JUMPED]) < 0.8 * N * D and int(st[nat.STAT_ROWS_MULTI]) <= int(st[nat.STAT_ROWS_JUMPED])
+    assert changed <= int(st[nat.STAT_ROWS_JUMPED])
+    assert torch.equal(full, run(logits, x, N, nat.IMPL_TC))                       # deterministic
+    assert not torch.equal(full, run(logits, x, N, nat.IMPL_TC, seed=100))         # and a function of the seed
+    half = N // 2                                                                  # sharding invariance at full size
+    lo = run(logits[:half], x[:half], half, nat.IMPL_TC)
+    hi = run(logits[half:], x[half:], half, nat.IMPL_TC, row_offset=half * D)
+    assert torch.equal(full, torch.cat([lo, hi]))
+    for n0 in (0, 771):                                                            # slices vs the CUDA-core path
+        sl = slice(n0, n0 + 2)                                                     # 2 samples = 6144 rows
+        ref = run(logits[sl].contiguous(), x[sl].contiguous(), 2, nat.IMPL_SIMT, row_offset=n0 * D)
+        assert mismatch_fraction(full[sl].cpu().numpy(), ref.cpu().numpy()) <= 2e-3
