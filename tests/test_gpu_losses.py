@@ -134,3 +134,62 @@ def test_loss_accepts_both_argument_orders_and_4d_minibatch(golden):
     with pytest.raises(KeyError):
         cfg.loss.name = "NoSuchLoss"
         losses_utils.get_loss(cfg)
+
+
+@pytest.mark.parametrize("cls,over", [("CatRMNLL", dict(logit_type="reverse_prob", loss_type="rm", nll_weight=0.01)),
+                                      ("CTElbo", dict(nll_weight=0.001)),
+                                      ("SDDMElbo", dict(logit_type="reverse_prob", nll_weight=0.01))],
+                         ids=["CatRMNLL", "CTElbo", "SDDMElbo"])
+def test_losses_at_c3_size_match_the_oracle(cls, over):
+    """BASELINE.json config C3 (S=256, D=784, B=64): loss value vs the CPU oracle on the same time draw and injected
+    noising uniforms (1e-4 relative), d loss / d w vs the oracle's autograd (2e-3 of the largest entry: fp32 sums over
+    50 k rows in different orders), and the shift invariance every softmax-composed loss has: the logit gradient of each
+    (b, d) row sums to zero."""
+    from ctdd_b200 import make_config
+    from ctdd_b200.lib.models import forward_model as fm
+    from ctdd_b200.lib.losses import losses_utils
+    import ctdd_b200.lib.losses.losses  # noqa: F401
+    from oracle import loss_oracle as lo
+    B, D, S, seed = 64, 784, 256, 321
+    case = ("c3", cls, "gauss256", B, D, over, 1.0, seed, 0)
+    cfg = cases.loss_cfg(make_config, case, device="cuda")
+    g = np.random.Generator(np.random.PCG64(seed))
+    x0 = torch.from_numpy(g.integers(0, S, (B, D)))
+    ts = torch.from_numpy(g.uniform(0.02, 0.98, B).astype(np.float32))
+    fp = oracle_forward("gauss256")
+    Q = fp.transition(ts)
+    seen = []
+
+    class M(rh.StubNet, fm.GaussianTargetRate):
+        def __init__(self):
+            rh.StubNet.__init__(self, S, D, seed, 1.0, 3.0)
+            fm.GaussianTargetRate.__init__(self, cfg, "cuda")
+
+        def forward(self, x, t):
+            out = self.net(x, t)
+            out.retain_grad()
+            seen.append(out)
+            return out
+
+    m = M().to("cuda")
+    m.device = "cuda"
+    Qd, QTd = Q.cuda().contiguous(), Q.transpose(1, 2).contiguous().cuda()
+    m._build_qt0 = lambda d_int, inverse=True, want_transpose=False: (Qd, QTd) if want_transpose else Qd
+    loss_obj = losses_utils.get_loss(cfg)
+    loss_obj.ts_override, loss_obj.seed = ts.cuda(), seed
+    state = {"model": m, "optimizer": None, "n_iter": 0}
+    loss = loss_obj.calc_loss(x0.cuda(), state) if cls in cases.LOSS_MINIBATCH_FIRST else loss_obj.calc_loss(state, x0.cuda())
+    loss.backward()
+    # oracle on the CPU
+    net = rh.StubNet(S, D, seed, 1.0, 3.0)
+    L = cfg.loss
+    want = lo.loss_value(cls, fp, lambda x, t, label=None: net.net(x, t), x0, ts, seed=seed, eps=L.eps_ratio,
+                         nll_weight=L.nll_weight, logit_type=L.logit_type, loss_type=L.loss_type, ce_coeff=L.ce_coeff,
+                         one_forward_pass=L.one_forward_pass)
+    want.backward()
+    np.testing.assert_allclose(loss.item(), want.item(), rtol=1e-4)
+    gw, ow = m.w.grad.cpu().numpy(), net.w.grad.numpy()
+    assert np.abs(gw - ow).max() <= 2e-3 * np.abs(ow).max() + 1e-12
+    gl = seen[0].grad
+    rowsum = gl.sum(-1).abs().max().item()
+    assert rowsum <= 2e-5 * gl.abs().max().item() * S ** 0.5 + 1e-12, rowsum
