@@ -253,6 +253,23 @@ __device__ __forceinline__ float4 ld_stream(const float* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
+// explicit shared-space accesses (the compiler emits generic LD/ST for pointers it cannot prove to be shared)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -715,9 +732,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + TM_ACC + b * NT + owner * NH, acc);
       tmem_ld_wait();
       if (owner == rank) {
-        float* dst = &sm.gather[gb][0][s_mine];
+        const uint32_t dst = smem_u32(&sm.gather[gb][0][s_mine]);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) dst[j * S] = __uint_as_float(acc[j]);
+        for (int j = 0; j < 32; ++j) sts32(dst + (uint32_t)j * (S * 4), __uint_as_float(acc[j]));
       } else {
         // the partner's barrier counts these bytes as they land: nothing to fence, nothing to wait for here
         const uint32_t dst = gather_dst + (uint32_t)gb * (NH * S * 4);
@@ -779,9 +796,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
           const SideHead si = *reinterpret_cast<const SideHead*>(&sm.side[slot][r]);
           const long long g = g0 + r;
           const int x = si.x;
-          const float* grow_p = &sm.gather[gb][r][0];
-          const float4 d0 = *reinterpret_cast<const float4*>(grow_p + 8 * lane);
-          const float4 d1 = *reinterpret_cast<const float4*>(grow_p + 8 * lane + 4);
+          const uint32_t grow_p = smem_u32(&sm.gather[gb][r][0]);
+          const float4 d0 = lds128(grow_p + 32 * lane);
+          const float4 d1 = lds128(grow_p + 32 * lane + 16);
           const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
           const size_t xo = (size_t)x << 8;
           if constexpr (KM == KM_RATES) {
@@ -835,14 +852,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
           rrow[1] = two ? __ffs(todo) - 1 : rrow[0];
           todo &= todo - 1;   // no-op when todo == 0
           SideHead si[2];
-          float* gp[2];
+          uint32_t gp[2];   // shared-space address of the row's gather slot
           float d[2][8];
           float total[2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const int r = warp * ROWS_PER_SAMPLER + rrow[u];
             si[u] = *reinterpret_cast<const SideHead*>(&sm.side[slot][r]);
-            gp[u] = &sm.gather[gb][r][0];
+            gp[u] = smem_u32(&sm.gather[gb][r][0]);
           }
           float4 e0[2], e1[2], c0v[2], c1v[2];
 #pragma unroll
@@ -861,8 +878,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
           }
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            const float4 d0 = *reinterpret_cast<const float4*>(gp[u] + 8 * lane);
-            const float4 d1 = *reinterpret_cast<const float4*>(gp[u] + 8 * lane + 4);
+            const float4 d0 = lds128(gp[u] + 32 * lane);
+            const float4 d1 = lds128(gp[u] + 32 * lane + 16);
             const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
             const float ev[8] = {e0[u].x, e0[u].y, e0[u].z, e0[u].w, e1[u].x, e1[u].y, e1[u].z, e1[u].w};
             // lam_s for s = 8*lane .. 8*lane+7 (zero at s == x through the zero-diagonal tables)
@@ -901,8 +918,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
               total[u] += diag;
             }
             if (u == 0 || two) {
-              *reinterpret_cast<float4*>(gp[u] + 8 * lane) = make_float4(d[u][0], d[u][1], d[u][2], d[u][3]);
-              *reinterpret_cast<float4*>(gp[u] + 8 * lane + 4) = make_float4(d[u][4], d[u][5], d[u][6], d[u][7]);
+              sts128(gp[u] + 32 * lane, make_float4(d[u][0], d[u][1], d[u][2], d[u][3]));
+              sts128(gp[u] + 32 * lane + 16, make_float4(d[u][4], d[u][5], d[u][6], d[u][7]));
             }
           }
           __syncwarp();
@@ -934,17 +951,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
 #ifdef CTDD_EXP_NOSEARCH    // diagnostic build: no search
               lo[u] = (target[u] > 1e30f) ? 1 : 0;
 #else
-              const float* P = gp[u];
+              const uint32_t P = gp[u];
               const float T = target[u];
               int c1 = 0;
 #pragma unroll
-              for (int m = 0; m < 7; ++m) c1 += (P[32 * m + 31] <= T) ? 1 : 0;
-              const float* P1 = P + 32 * c1;
+              for (int m = 0; m < 7; ++m) c1 += (lds32(P + 4 * (32 * m + 31)) <= T) ? 1 : 0;
+              const uint32_t P1 = P + 128 * c1;
               int c2 = 0;
 #pragma unroll
-              for (int n = 0; n < 7; ++n) c2 += (P1[4 * n + 3] <= T) ? 1 : 0;
-              const float* P2 = P1 + 4 * c2;
-              const int c3 = ((P2[0] <= T) ? 1 : 0) + ((P2[1] <= T) ? 1 : 0) + ((P2[2] <= T) ? 1 : 0);
+              for (int n = 0; n < 7; ++n) c2 += (lds32(P1 + 4 * (4 * n + 3)) <= T) ? 1 : 0;
+              const uint32_t P2 = P1 + 16 * c2;
+              const int c3 = ((lds32(P2) <= T) ? 1 : 0) + ((lds32(P2 + 4) <= T) ? 1 : 0) + ((lds32(P2 + 8) <= T) ? 1 : 0);
               lo[u] = 32 * c1 + 4 * c2 + c3;
 #endif
             }
