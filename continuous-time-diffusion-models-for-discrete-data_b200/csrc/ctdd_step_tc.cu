@@ -267,6 +267,9 @@ __device__ __forceinline__ float lds32(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
 __device__ __forceinline__ void sts32(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
@@ -498,20 +501,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         mbar_wait(&sm.empty[st], st_par);
         if (pw == 0 && lane == 0) TRACE(0, i, 1);
       }
-      uint8_t* stage = sm.stage[st];
+      const uint32_t stage_s = smem_u32(sm.stage[st]);
       mbar_wait(&sm.lring_full[pw][rslot], ring_par);
       if (pw == 0 && lane == 0) TRACE(0, i, 5 + (ps & 1));
       const int r = ROWS_PER_PROD * pw + 2 * ps + half;
 #ifdef CTDD_EXP_NOPRODUCE   // diagnostic build: producers only run the barrier protocol (isolates MMA + phase A + samplers)
       const float c1 = 1e-6f, c0 = 0.f, lam_tot = CTDD_EXP_NOPRODUCE;
-      (void)stage; (void)r; (void)ok;
+      (void)stage_s; (void)r; (void)ok;
 #else
       float v[16];
       {
-        const float4* src = reinterpret_cast<const float4*>(&sm.lring[pw][rslot][half][4 * l16]);
+        const uint32_t src = smem_u32(&sm.lring[pw][rslot][half][4 * l16]);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const float4 q4 = src[16 * c];
+          const float4 q4 = lds128(src + 256 * c);
           v[4 * c] = q4.x; v[4 * c + 1] = q4.y; v[4 * c + 2] = q4.z; v[4 * c + 3] = q4.w;
         }
       }
@@ -587,8 +590,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         split2(v[4 * c], v[4 * c + 1], h0, m0);
         split2(v[4 * c + 2], v[4 * c + 3], h1, m1);
         if (!ok) h0 = m0 = h1 = m1 = 0u;
-        *reinterpret_cast<uint2*>(stage + c * KBLOCK_BYTES + off) = make_uint2(h0, h1);
-        *reinterpret_cast<uint2*>(stage + SPLIT_BYTES + c * KBLOCK_BYTES + off) = make_uint2(m0, m1);
+        sts64(stage_s + c * KBLOCK_BYTES + off, h0, h1);
+        sts64(stage_s + SPLIT_BYTES + c * KBLOCK_BYTES + off, m0, m1);
       }
 #endif
       // row scalars for the count warp and the samplers (one lane per half-warp)
