@@ -871,21 +871,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
 #ifdef CTDD_EXP_NOTABE      // diagnostic build: no rate-table gather in the sampler
             e0[u] = make_float4(1.f, 1.f, 1.f, 1.f); e1[u] = e0[u]; (void)xo;
 #else
-            e0[u] = __ldg(reinterpret_cast<const float4*>(tabE + xo));
-            e1[u] = __ldg(reinterpret_cast<const float4*>(tabE + xo + 4));
+            // lane owns states 4*lane .. +3 (elements 0-3) and 128 + 4*lane .. +3 (elements 4-7): every 128-bit access of
+            // the warp to a gather row is then one contiguous 512-byte run (no bank conflicts)
+            e0[u] = __ldg(reinterpret_cast<const float4*>(tabE - 4 * lane + xo));
+            e1[u] = __ldg(reinterpret_cast<const float4*>(tabE - 4 * lane + xo + 128));
 #endif
             if (km_corr(KM)) {
-              c0v[u] = __ldg(reinterpret_cast<const float4*>(tabC + xo));
-              c1v[u] = __ldg(reinterpret_cast<const float4*>(tabC + xo + 4));
+              c0v[u] = __ldg(reinterpret_cast<const float4*>(tabC - 4 * lane + xo));
+              c1v[u] = __ldg(reinterpret_cast<const float4*>(tabC - 4 * lane + xo + 128));
             }
           }
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            const float4 d0 = lds128(gp[u] + 32 * lane);
-            const float4 d1 = lds128(gp[u] + 32 * lane + 16);
+            const float4 d0 = lds128(gp[u] + 16 * lane);
+            const float4 d1 = lds128(gp[u] + 512 + 16 * lane);
             const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
             const float ev[8] = {e0[u].x, e0[u].y, e0[u].z, e0[u].w, e1[u].x, e1[u].y, e1[u].z, e1[u].w};
-            // lam_s for s = 8*lane .. 8*lane+7 (zero at s == x through the zero-diagonal tables)
+            // lam_s (zero at s == x through the zero-diagonal tables)
 #pragma unroll
             for (int e = 0; e < 8; ++e) d[u][e] = fmaf(dv[e], si[u].c1, si[u].c0) * ev[e];
             if (km_corr(KM)) {
@@ -893,36 +895,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
 #pragma unroll
               for (int e = 0; e < 8; ++e) d[u][e] = fmaf(hb, cv[e], d[u][e]);
             }
-            // inclusive prefix sums over the 256 states: in-lane, then across lanes
+            // inclusive prefix sums over the 256 states: in-lane per 4-state group, then across lanes per half
 #pragma unroll
-            for (int e = 1; e < 8; ++e) d[u][e] += d[u][e - 1];
+            for (int e = 1; e < 4; ++e) { d[u][e] += d[u][e - 1]; d[u][4 + e] += d[u][3 + e]; }
           }
-          float incl[2] = {d[0][7], d[1][7]};
+          float incl[2][2] = {{d[0][3], d[0][7]}, {d[1][3], d[1][7]}};   // [row][half]
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) {
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              const float n = __shfl_up_sync(0xffffffffu, incl[u], o);
-              if (lane >= o) incl[u] += n;
-            }
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf) {
+                const float n = __shfl_up_sync(0xffffffffu, incl[u][hf], o);
+                if (lane >= o) incl[u][hf] += n;
+              }
           }
           __syncwarp();
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            float excl = __shfl_up_sync(0xffffffffu, incl[u], 1);
-            if (lane == 0) excl = 0.f;
-            total[u] = __shfl_sync(0xffffffffu, incl[u], 31);
+            float excl_a = __shfl_up_sync(0xffffffffu, incl[u][0], 1);
+            float excl_b = __shfl_up_sync(0xffffffffu, incl[u][1], 1);
+            const float tot_a = __shfl_sync(0xffffffffu, incl[u][0], 31);
+            const float tot_b = __shfl_sync(0xffffffffu, incl[u][1], 31);
+            if (lane == 0) { excl_a = 0.f; excl_b = 0.f; }
+            excl_b += tot_a;
+            total[u] = tot_a + tot_b;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) d[u][e] += excl;
+            for (int e = 0; e < 4; ++e) { d[u][e] += excl_a; d[u][4 + e] += excl_b; }
             if (km_euler(KM)) {   // stay-probability max(0, 1 - sum) enters the cumulative sums at position x
               const float diag = fmaxf(0.f, 1.0f - total[u]);
 #pragma unroll
-              for (int e = 0; e < 8; ++e) d[u][e] += (8 * lane + e >= si[u].x) ? diag : 0.f;
+              for (int e = 0; e < 4; ++e) {
+                d[u][e] += (4 * lane + e >= si[u].x) ? diag : 0.f;
+                d[u][4 + e] += (128 + 4 * lane + e >= si[u].x) ? diag : 0.f;
+              }
               total[u] += diag;
             }
             if (u == 0 || two) {
-              sts128(gp[u] + 32 * lane, make_float4(d[u][0], d[u][1], d[u][2], d[u][3]));
-              sts128(gp[u] + 32 * lane + 16, make_float4(d[u][4], d[u][5], d[u][6], d[u][7]));
+              sts128(gp[u] + 16 * lane, make_float4(d[u][0], d[u][1], d[u][2], d[u][3]));
+              sts128(gp[u] + 512 + 16 * lane, make_float4(d[u][4], d[u][5], d[u][6], d[u][7]));
             }
           }
           __syncwarp();
