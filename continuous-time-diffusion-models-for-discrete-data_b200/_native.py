@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libctdd_b200.so")
 BRANCH_TAULDR, BRANCH_SDDM_DIRECT, BRANCH_SDDM_REVERSE_PROB, BRANCH_SDDM_REVERSE_LOGSCALE = 0, 1, 2, 3
 MODE_TAU_LEAP, MODE_TAU_LEAP_CORR, MODE_MIDPOINT_DRIFT, MODE_MIDPOINT_JUMP, MODE_EULER, MODE_EULER_CORR, MODE_RATES_ONLY, MODE_EXACT = range(8)
 IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+HEAD_LOGITS, HEAD_LOGISTIC, HEAD_LOGISTIC_FIX = 0, 1, 2
 STAT_CHANGED_BASE, STAT_NONZERO_JUMP, STAT_CHANGED_EVAL, STAT_ROWS_JUMPED, STAT_ROWS_MULTI = 0, 1, 2, 3, 4
 STAT_COUNT = 8
 LOSS_CTELBO, LOSS_CRM, LOSS_SDDM = 0, 1, 2
@@ -47,6 +48,7 @@ class StepParams(ctypes.Structure):
         ("seed", c_uint64), ("offset", c_uint64),
         ("x_out", c_void_p), ("rr_out", c_void_p), ("ratio_out", c_void_p),
         ("stats_out", c_void_p), ("workspace", c_void_p),
+        ("head", c_int32), ("head_mu", c_void_p), ("head_log_scale", c_void_p), ("head_batch_stride", c_int64),
     ]
 
 
@@ -93,6 +95,8 @@ def lib() -> ctypes.CDLL:
     L.ctdd_prep_tc_tables.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_void_p]
     L.ctdd_sample_categorical_shared.argtypes = [c_void_p, c_int, c_int64, c_int64, c_uint64, c_uint64, c_void_p, c_void_p]
     L.ctdd_noise_xt.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p]
+    L.ctdd_logistic_logits.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_int, c_void_p, c_void_p]
+    L.ctdd_logistic_logits.restype = c_int
     L.ctdd_loss_workspace_bytes.argtypes = [c_int, c_int, c_int]
     L.ctdd_loss_workspace_bytes.restype = c_int64
     L.ctdd_loss_forward.argtypes = [ctypes.POINTER(LossParams), c_void_p]

@@ -121,6 +121,10 @@ struct Args {
   float* ratio_out;
   unsigned long long* stats;
   int num_tiles;
+  int head_fix;              // fused truncated-logistic head (HEAD kernels): fix_logistic
+  const float* head_mu;
+  const float* head_ls;
+  long long head_bs;         // elements between consecutive n
 };
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -349,6 +353,56 @@ __device__ __forceinline__ int warp_sum_int(int v) {
   return v;
 }
 
+// Softmax numerators of the truncated-logistic head (reference lib/models/models.py:28-74, :248-282) for the 16 states
+// k = 64c + 4*l16 .. +3 (c = 0..3) of one row.  With z_j = (edge_j - mu) * exp(2 - log_scale), u = sigmoid(z),
+// v = sigmoid(-z) and kappa = 1 - exp(-(z_{j+1} - z_j)):   exp(logits_1[s]) = u_{s+1} * (kappa * v_s + 1e-6)  and the
+// fix_logistic variant exp(min(logits_1, logits_2)[s]) = kappa * u_{s+1} * v_s + 1e-6 * min(u_{s+1}, v_s)  (identities,
+// not approximations; no cancellation, unlike the 1 - exp(.) of the reference's log_minus_exp).  Rows whose edges all lie
+// on one side of mu (|mu| > 1: outside what tanh emits, but legal input) are rescaled by exp(+-c) so that the numerators
+// cannot all underflow; softmax is invariant to the common factor.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void head_numerators(float mu, float ls, bool fix, int l16, float (&P)[16]) {
+  constexpr float L2E = 1.4426950408889634f, BW = 2.0f / S, EPS = 1e-6f;
+  const float inv = expf(2.0f - ls);
+  const float kap = -expm1f(-inv * BW);
+  const float z_first = (-1.0f - mu) * inv, z_last = (1.0f - mu) * inv;
+  float c = 0.f;
+  if (z_last < 0.f) c = -z_last; else if (fix && z_first > 0.f) c = -z_first;
+  const float A = c > 0.f ? expf(-c) : 1.0f, B = c < 0.f ? expf(c) : 1.0f;
+  // exponent (base 2) of e_j = exp(-z_j - c) for edge j = 64c + 4*l16 + k:  t_c * sc + off[k]
+  const float sc = -inv * L2E;
+  float off[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) off[k] = fmaf((float)k * BW, sc, -c * L2E);
+  // select of the 1e-6 term:  no fix / c > 0 -> u,  fix and c == 0 -> min(u, v),  fix and c < 0 -> v
+  const float bu = (fix && c < 0.f) ? 3.0e38f : 0.f;
+  const float bv = (!fix || c > 0.f) ? 3.0e38f : 0.f;
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    const float t = (fmaf((float)(64 * cc + 4 * l16), BW, -1.0f)) - mu;       // edge - mu (the edge is exact in fp32)
+    float u[5], vv[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const float e = ex2_approx(fminf(fmaf(t, sc, off[k]), 126.0f));
+      u[k] = rcp_approx(fmaf(B, e, A));
+      vv[k] = e * u[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (fix) {
+        const float m = fminf(fmaxf(u[k + 1], bu), fmaxf(vv[k], bv));
+        P[4 * cc + k] = fmaf(kap * u[k + 1], vv[k], EPS * m);
+      } else {
+        P[4 * cc + k] = u[k + 1] * fmaf(kap, vv[k], EPS);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- the kernel
 #ifdef CTDD_TC_TRACE
 // diagnostic build only (CTDD_TRACE=1 python build.py): per-tile clock stamps of one CTA's roles, read back with
@@ -364,8 +418,9 @@ __device__ long long g_trace[2][TRACE_ROLES][TRACE_TILES][TRACE_EVENTS];
 #endif
 
 
-// TAULDR: tauLDR rates (else SDDM reverse_prob); KM: KM_JUMP / KM_CORR / KM_RATES / KM_DRIFT / KM_EULER / KM_EULER_CORR
-template <bool TAULDR, int KM>
+// TAULDR: tauLDR rates (else SDDM reverse_prob); KM: KM_JUMP / KM_CORR / KM_RATES / KM_DRIFT / KM_EULER / KM_EULER_CORR;
+// HEAD: the rows' softmax numerators come from the truncated-logistic head (mu, log_scale per row) instead of logits
+template <bool TAULDR, int KM, bool HEAD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step_tc_kernel(const Args a) {
   extern __shared__ uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -451,10 +506,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     int f_left = npass, f_ps = 0, f_slot = 0;
     // lane 0 starts the bulk copy of the next row pair (rows past the end are replaced by row 0: never used; adjacent
     // rows of a contiguous logits tensor travel as one 2 KB copy); every lane fetches the state of its half's row
+    float f_mu = 0.f, f_ls = 0.f;        // HEAD: head parameters of the row fetch() just visited
     auto fetch = [&]() -> int {
       int xv = -1;
       if (f_left > 0) {
-        if (lane == 0) {
+        if (HEAD) {
+          const long long g = gf + half;
+          if (g < a.rows) {
+            long long src = g;
+            if (a.head_bs != (long long)a.D) {
+              const long long n = g / a.D;
+              src = n * a.head_bs + (g - n * a.D);
+            }
+            f_mu = __ldg(a.head_mu + src);
+            f_ls = __ldg(a.head_ls + src);
+          }
+        } else if (lane == 0) {
           uint64_t* bar = &sm.lring_full[pw][f_slot];
           mbar_arrive_expect_tx(bar, 2 * S * 4);
           if (contiguous && gf + 1 < a.rows) {
@@ -468,7 +535,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
           }
         }
         if (gf + half < a.rows) xv = __ldg(a.x_eval + gf + half);
-        if (contiguous && f_ps == 0 && lane == 0) {   // pull this warp's 4 rows of a later tile from HBM into L2
+        if (!HEAD && contiguous && f_ps == 0 && lane == 0) {   // pull this warp's 4 rows of a later tile from HBM into L2
           const long long r0 = gf + (long long)PREFETCH_TILES * npairs * NT;
           if (r0 + ROWS_PER_PROD <= a.rows) l2_prefetch_bulk(a.logits + r0 * S, ROWS_PER_PROD * S * 4);
         }
@@ -479,7 +546,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       return xv;
     };
 
-    int x_cur = fetch(), x_n1 = fetch();
+    int x_cur = fetch();
+    float mu_cur = f_mu, ls_cur = f_ls;
+    int x_n1 = fetch();
+    float mu_n1 = f_mu, ls_n1 = f_ls;
     float4 t4[4], g4[4];
     {
       const size_t xo = (size_t)(x_cur < 0 ? 0 : x_cur) << 8;
@@ -502,7 +572,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         if (pw == 0 && lane == 0) TRACE(0, i, 1);
       }
       const uint32_t stage_s = smem_u32(sm.stage[st]);
-      mbar_wait(&sm.lring_full[pw][rslot], ring_par);
+      if (!HEAD) mbar_wait(&sm.lring_full[pw][rslot], ring_par);
       if (pw == 0 && lane == 0) TRACE(0, i, 5 + (ps & 1));
       const int r = ROWS_PER_PROD * pw + 2 * ps + half;
 #ifdef CTDD_EXP_NOPRODUCE   // diagnostic build: producers only run the barrier protocol (isolates MMA + phase A + samplers)
@@ -510,21 +580,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       (void)stage_s; (void)r; (void)ok;
 #else
       float v[16];
-      {
+      float ml = 0.f;
+      if (HEAD) {
+        head_numerators(mu_cur, ls_cur, a.head_fix != 0, l16, v);
+      } else {
         const uint32_t src = smem_u32(&sm.lring[pw][rslot][half][4 * l16]);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const float4 q4 = lds128(src + 256 * c);
           v[4 * c] = q4.x; v[4 * c + 1] = q4.y; v[4 * c + 2] = q4.z; v[4 * c + 3] = q4.w;
         }
+        float m4[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) m4[c] = fmaxf(fmaxf(v[4 * c], v[4 * c + 1]), fmaxf(v[4 * c + 2], v[4 * c + 3]));
+        float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        ml = -m * 1.4426950408889634f;
       }
-      float m4[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) m4[c] = fmaxf(fmaxf(v[4 * c], v[4 * c + 1]), fmaxf(v[4 * c + 2], v[4 * c + 3]));
-      float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-      const float ml = -m * 1.4426950408889634f;
       // four independent accumulation chains of packed pairs
       float2 sum2[4], dot2[4], dotg2[4];
       const float2 l2e2 = make_float2(1.4426950408889634f, 1.4426950408889634f), ml2 = make_float2(ml, ml);
@@ -535,8 +608,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         for (int e = 0; e < 4; e += 2) {
           const float2 tq = e == 0 ? make_float2(t4[c].x, t4[c].y) : make_float2(t4[c].z, t4[c].w);
           const float2 gq = e == 0 ? make_float2(g4[c].x, g4[c].y) : make_float2(g4[c].z, g4[c].w);
-          const float2 arg = ffma2(make_float2(v[4 * c + e], v[4 * c + e + 1]), l2e2, ml2);
-          const float2 ex = make_float2(ex2_approx(arg.x), ex2_approx(arg.y));     // exp(v - max)
+          float2 ex = make_float2(v[4 * c + e], v[4 * c + e + 1]);                 // HEAD: already the numerators
+          if (!HEAD) {
+            const float2 arg = ffma2(ex, l2e2, ml2);
+            ex = make_float2(ex2_approx(arg.x), ex2_approx(arg.y));                // exp(v - max)
+          }
           sum2[c] = fadd2(sum2[c], ex);
           dotg2[c] = ffma2(ex, gq, dotg2[c]);
           if (!TAULDR) dot2[c] = ffma2(ex, tq, dot2[c]);
@@ -604,7 +680,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       if (++rslot == LRING) { rslot = 0; ring_par ^= 1u; }
       __syncwarp();            // every lane is done with this pass's ring slot: refill it for the pass after next
       x_cur = x_n1;
+      if (HEAD) { mu_cur = mu_n1; ls_cur = ls_n1; }
       x_n1 = fetch();
+      if (HEAD) { mu_n1 = f_mu; ls_n1 = f_ls; }
       if (pw == 0 && lane == 0) TRACE(0, i, 2 + (ps & 1));
       if (++ps == PASSES) {     // last pass of the tile
         fence_proxy_async();
@@ -1099,7 +1177,9 @@ bool tc_supports(const ctdd_step_params* p) {
         p->mode == CTDD_MODE_RATES_ONLY))
     return false;
   if (!p->tc_tables || !p->tc_static) return false;
-  if ((p->ld_logits & 3) || (p->batch_stride_logits & 3) || (reinterpret_cast<uintptr_t>(p->logits) & 15)) return false;
+  if (p->head == CTDD_HEAD_LOGITS &&
+      ((p->ld_logits & 3) || (p->batch_stride_logits & 3) || (reinterpret_cast<uintptr_t>(p->logits) & 15)))
+    return false;
   if (p->mode == CTDD_MODE_RATES_ONLY &&
       ((reinterpret_cast<uintptr_t>(p->rr_out) & 15) || (reinterpret_cast<uintptr_t>(p->ratio_out) & 15)))
     return false;
@@ -1121,14 +1201,15 @@ int launch_step_tc(const ctdd_step_params* p, cudaStream_t st) {
   const bool attr_set = dev >= 0 && dev < 64 && ((attr_done >> dev) & 1ull);
   const size_t smem_bytes = sizeof(Smem) + 1024;
   typedef void (*kern_t)(const Args);
-  static const kern_t kerns[2][6] = {
-      {step_tc_kernel<false, KM_JUMP>, step_tc_kernel<false, KM_CORR>, step_tc_kernel<false, KM_RATES>, step_tc_kernel<false, KM_DRIFT>,
-       step_tc_kernel<false, KM_EULER>, step_tc_kernel<false, KM_EULER_CORR>},
-      {step_tc_kernel<true, KM_JUMP>, step_tc_kernel<true, KM_CORR>, step_tc_kernel<true, KM_RATES>, step_tc_kernel<true, KM_DRIFT>,
-       step_tc_kernel<true, KM_EULER>, step_tc_kernel<true, KM_EULER_CORR>}};
+#define CTDD_TC_ROW(T, H)                                                                                          \
+  {step_tc_kernel<T, KM_JUMP, H>, step_tc_kernel<T, KM_CORR, H>, step_tc_kernel<T, KM_RATES, H>,                  \
+   step_tc_kernel<T, KM_DRIFT, H>, step_tc_kernel<T, KM_EULER, H>, step_tc_kernel<T, KM_EULER_CORR, H>}
+  static const kern_t kerns[4][6] = {CTDD_TC_ROW(false, false), CTDD_TC_ROW(true, false), CTDD_TC_ROW(false, true),
+                                     CTDD_TC_ROW(true, true)};
+#undef CTDD_TC_ROW
   if (!attr_set) {
     cudaDeviceGetAttribute(&num_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 4; ++i)
       for (int j = 0; j < 6; ++j)
         if (cudaFuncSetAttribute(kerns[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
           set_error("ctdd_reverse_step: cannot reserve %zu bytes of shared memory for the tcgen05 kernel", smem_bytes);
@@ -1147,11 +1228,13 @@ int launch_step_tc(const ctdd_step_params* p, cudaStream_t st) {
   a.RbT = p->RbT; a.Rb = p->Rb; a.beta = p->beta; a.h = p->h; a.seed = p->seed; a.offset = p->offset;
   a.x_out = p->x_out; a.rr_out = p->rr_out; a.ratio_out = p->ratio_out;
   a.stats = reinterpret_cast<unsigned long long*>(p->stats_out);
+  a.head_fix = p->head == CTDD_HEAD_LOGISTIC_FIX;
+  a.head_mu = p->head_mu; a.head_ls = p->head_log_scale; a.head_bs = p->head_batch_stride;
   a.num_tiles = (int)((a.rows + NT - 1) / NT);
   int pairs = num_sms[dev & 63] / 2;                 // one CTA pair (cluster of 2) per TPC
   if (pairs > a.num_tiles) pairs = a.num_tiles;
   if (pairs < 1) pairs = 1;
-  const int ki = (p->branch == CTDD_BRANCH_TAULDR) ? 1 : 0;
+  const int ki = ((p->branch == CTDD_BRANCH_TAULDR) ? 1 : 0) + (p->head != CTDD_HEAD_LOGITS ? 2 : 0);
   int kj = KM_JUMP;
   if (p->mode == CTDD_MODE_RATES_ONLY) kj = KM_RATES;
   else if (p->mode == CTDD_MODE_TAU_LEAP_CORR) kj = KM_CORR;

@@ -29,6 +29,12 @@ def _seed_from_torch() -> int:
     return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
 
 
+def _dense(out, S):
+    """A model evaluated without gradients may hand back its truncated-logistic head un-expanded (ops.LogisticHead);
+    the loss terms need the logits tensor."""
+    return out.logits(S) if isinstance(out, ops.LogisticHead) else out
+
+
 def _split_args(a, b):
     """Accept (state, minibatch) or (minibatch, state)."""
     return (a, b) if isinstance(a, dict) else (b, a)
@@ -77,14 +83,14 @@ class _CTElboFamily(_LossBase):
         """-> (neg_elbo, nll) as 0-dim tensors (reference losses.py:108-284)."""
         model = state["model"]
         c = self._prepare(model, minibatch, self.max_t)
-        logits = model(c["xt"].long(), c["ts"], *model_args)
+        logits = _dense(model(c["xt"].long(), c["ts"], *model_args), model.S)
         kw = dict(Q=c["Q"], QT=c["QT"], Rb=c["Rb"], beta=c["beta"], x0=c["x0"], eps=self.ratio_eps)
         if self.one_forward_pass:
             reg, outer, norm, _, ce = ops.loss_terms(logits, nat.LOSS_CTELBO, xt=c["x_tilde"], x_tilde=c["x_tilde"], **kw)
         else:
             # reg term at x_t with p(x_t); signal term at x~ with a second forward pass (losses.py:114-118, :157-160)
             reg, _, _, _, ce = ops.loss_terms(logits, nat.LOSS_CTELBO, xt=c["xt"], x_tilde=c["x_tilde"], **kw)
-            logits_sig = model(c["x_tilde"].long(), c["ts"], *model_args)
+            logits_sig = _dense(model(c["x_tilde"].long(), c["ts"], *model_args), model.S)
             _, outer, norm, _, _ = ops.loss_terms(logits_sig, nat.LOSS_CTELBO, xt=c["x_tilde"], x_tilde=c["x_tilde"], **kw)
         neg_elbo = torch.mean(-outer / norm) + torch.mean(reg)
         nll = torch.sum(ce) / (c["B"] * c["D"])
@@ -147,7 +153,7 @@ class CondCTElbo(_LossBase):
         kw = dict(Q=c["Q"], QT=c["QT"], Rb=c["Rb"], beta=c["beta"], x0=c["x0"], eps=self.ratio_eps)
 
         def sliced(x):
-            return model(torch.concat((cond, x.long()), dim=1), c["ts"])[:, cd:, :].contiguous()
+            return _dense(model(torch.concat((cond, x.long()), dim=1), c["ts"]), model.S)[:, cd:, :].contiguous()
 
         if self.one_forward_pass:
             logits = sliced(c["x_tilde"])
@@ -176,7 +182,7 @@ class _SDDMFamily(_LossBase):
             raise NotImplementedError("one_forward_pass=False is broken in the reference for ScoreElbo/SDDMElbo "
                                       "(undefined logits_sig, losses.py:1386-1390); only True is supported")
         c = self._prepare(model, minibatch, 1.0, clamp_max=0.99999)
-        logits = model(c["x_tilde"].long(), c["ts"])
+        logits = _dense(model(c["x_tilde"].long(), c["ts"]), model.S)
         branch = nat.branch_for(self.cfg.loss.name, self.cfg.loss.logit_type)
         if branch == nat.BRANCH_SDDM_REVERSE_LOGSCALE:
             return _sddm_terms_torch(self.cfg, model, c, logits, self.ratio_eps)
@@ -241,7 +247,7 @@ class _CatRMFamily(_LossBase):
         if self.cfg.loss.loss_type not in _CRM_TYPES:
             raise ValueError("Unknown loss_type: %s" % self.cfg.loss.loss_type)
         c = self._prepare(model, minibatch, t_hi, clamp_max=clamp_max, want_tilde=False)
-        logits = model(c["xt"].long(), c["ts"])
+        logits = _dense(model(c["xt"].long(), c["ts"]), model.S)
         branch = nat.branch_for(self.cfg.loss.name, self.cfg.loss.logit_type)
         if branch == nat.BRANCH_SDDM_REVERSE_LOGSCALE:
             ll_all, ll_xt = model_utils.get_logprob_with_logits(self.cfg, model, c["xt"], c["ts"], logits)
@@ -307,5 +313,5 @@ class NLLOriginal(_LossBase):
         state, minibatch = _split_args(a, b)
         model = state["model"]
         c = self._prepare(model, minibatch, 1.0, want_tilde=False)
-        logits = model(c["xt"].long(), c["ts"], label)
+        logits = _dense(model(c["xt"].long(), c["ts"], label), model.S)
         return F.cross_entropy(logits.permute(0, 2, 1), c["x0"].long())

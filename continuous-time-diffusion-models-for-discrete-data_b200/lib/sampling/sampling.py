@@ -87,10 +87,15 @@ class StepEngine:
         `draws=False` marks an evaluation that consumes no randomness (midpoint drift, rates only): the Philox
         call counter is not advanced. `stats` overrides the row of self.stats the counters are added to."""
         N, D, S = self.N, self.D, self.S
-        off_elems, bstride = 0, None
+        off_elems, bstride, head = 0, None, None
         if logits_view is not None:  # (full model output, c): rows live at full[:, c:, :]
             logits, c = logits_view
-            off_elems, bstride = c * S, logits.shape[1] * S
+            if isinstance(logits, ops.LogisticHead):
+                logits = logits.slice_dims(c)
+            else:
+                off_elems, bstride = c * S, logits.shape[1] * S
+        if isinstance(logits, ops.LogisticHead):   # truncated-logistic output head: fused into the step kernel
+            head, logits = logits.as_tuple(), None
         row = self.call if self.call < self.stats.shape[0] else self.stats.shape[0] - 1
         out = ops.reverse_step(
             mode, self.branch, logits, x_eval, self.Q[tidx], self.QT[tidx], self.Rb, self.RbT, self.beta[tidx], h,
@@ -99,7 +104,7 @@ class StepEngine:
             tc_tables=(self.tc_tables[tidx] if self.tc_tables is not None else None), tc_static=self.tc_static,
             workspace=self.workspace,
             stats=(stats if stats is not None else self.stats[row]), want_rr=want_rr, want_ratio=want_ratio,
-            logits_offset_elems=off_elems, batch_stride=bstride)
+            logits_offset_elems=off_elems, batch_stride=bstride, head=head)
         x_out = out["x"]
         if want_rr or want_ratio:
             self.last_rates = (out["rr"], out["ratio"])
@@ -131,8 +136,14 @@ def _branch_of(cfg):
     return nat.branch_for(name, None if name in nat.TAULDR_LOSSES else cfg.loss.logit_type)
 
 
+def _dense(logits, S):
+    """Logits tensor of a model output (materialises a LogisticHead)."""
+    return logits.logits(S) if isinstance(logits, ops.LogisticHead) else logits
+
+
 def _final_argmax(model, x, min_t, N, device):
-    p_0gt = F.softmax(model(x.long(), min_t * torch.ones((N,), device=device)), dim=2)
+    out = model(x.long(), min_t * torch.ones((N,), device=device))
+    p_0gt = F.softmax(_dense(out, getattr(model, "S", None)), dim=2)
     return torch.max(p_0gt, dim=2)[1]
 
 
@@ -383,7 +394,7 @@ class ConditionalTauLeaping(_SamplerBase):
                 full = model(torch.concat((conditioner, x.long()), dim=1), eng.t_ones(idx))
                 x, _ = eng.step(nat.MODE_TAU_LEAP, full, x, idx, h, False, logits_view=(full, condition_dim))
             full = model(torch.concat((conditioner, x.long()), dim=1), scfg.min_t * torch.ones((N,), device=device))
-            x_0max = torch.max(F.softmax(full, dim=2)[:, condition_dim:, :], dim=2)[1]
+            x_0max = torch.max(F.softmax(_dense(full, S), dim=2)[:, condition_dim:, :], dim=2)[1]
             output = torch.concat((conditioner, x_0max), dim=1)
             return output.detach().cpu().numpy().astype(int)
 
@@ -410,7 +421,7 @@ class ConditionalPCTauLeaping(_SamplerBase):
                             reject=bool(scfg.reject_multiple_jumps), init_std=init_std, seed=self.seed,
                             row_offset=self.row_offset, impl=self.impl)
             full = model(torch.concat((conditioner, x.long()), dim=1), scfg.min_t * torch.ones((N,), device=device))
-            x_0max = torch.max(F.softmax(full, dim=2)[:, condition_dim:, :], dim=2)[1]
+            x_0max = torch.max(F.softmax(_dense(full, S), dim=2)[:, condition_dim:, :], dim=2)[1]
             output = torch.concat((conditioner, x_0max), dim=1)
             return output.detach().cpu().numpy().astype(int)
 
@@ -464,7 +475,7 @@ class ExactSampling(_SamplerBase):
             stats = torch.zeros((len(ts) - 1, nat.STAT_COUNT), dtype=torch.int64, device=device)
             x = get_initial_samples(N, D, device, S, self.initial_dist, initial_dist_std, seed, self.row_offset)
             for idx, t in enumerate(ts[0:-1]):
-                logits = model(x.long(), float(t) * torch.ones((N,), device=device))
+                logits = _dense(model(x.long(), float(t) * torch.ones((N,), device=device)), S)
                 x = ops.reverse_step(nat.MODE_EXACT, nat.BRANCH_SDDM_REVERSE_PROB, logits, x, Q[idx], QT[idx], Rb, WT[idx],
                                      0.0, 0.0, 0.0, N=N, D=D, S=S, seed=seed, offset=idx, row_offset=self.row_offset,
                                      impl=nat.IMPL_SIMT, stats=stats[idx])["x"]

@@ -46,12 +46,29 @@ def prep_tc_static(Rb):
 def reverse_step(mode, branch, logits, x_eval, Q, QT, Rb, RbT, beta, h, eps, *, N, D, S, x_base=None,
                  reject_multi=False, seed=0, offset=0, row_offset=0, impl=nat.IMPL_AUTO, tc_tables=None, tc_static=None,
                  workspace=None, stats=None, want_rr=False, want_ratio=False, logits_offset_elems=0,
-                 batch_stride=None):
-    """One fused reverse-rate evaluation (+ state update). Returns dict(x=..., rr=..., ratio=...)."""
+                 batch_stride=None, head=None):
+    """One fused reverse-rate evaluation (+ state update). Returns dict(x=..., rr=..., ratio=...).
+
+    `head=(mu, log_scale, fix_logistic)` replaces `logits` (pass None) by the parameters of the truncated-logistic
+    output head (reference lib/models/models.py:248-282): mu / log_scale are (N, D)-shaped fp32 views whose batch
+    stride may exceed D (the two torch.chunk halves of a (B, 2C, H, W) network output).  On the tcgen05 path the
+    logits are never materialised; elsewhere they are built once with `logistic_logits`."""
     dev = x_eval.device
-    if logits.dtype != torch.float32:
-        logits = logits.float()
-    logits = logits.contiguous()
+    head_kind, head_mu, head_ls, head_bs = nat.HEAD_LOGITS, None, None, 0
+    if head is not None:
+        mu, ls, fix = head
+        mu, ls, head_bs = _head_views(mu, ls, N, D)
+        use_tc = S == 256 and tc_tables is not None and impl != nat.IMPL_SIMT and mode != nat.MODE_EXACT and \
+            branch in (nat.BRANCH_TAULDR, nat.BRANCH_SDDM_REVERSE_PROB)
+        if use_tc:
+            head_kind, head_mu, head_ls = (nat.HEAD_LOGISTIC_FIX if fix else nat.HEAD_LOGISTIC), mu, ls
+            logits = None
+        else:
+            logits = logistic_logits(mu, ls, S, fix)
+    if logits is not None:
+        if logits.dtype != torch.float32:
+            logits = logits.float()
+        logits = logits.contiguous()
     x_out = torch.empty((N, D), dtype=torch.int32, device=dev) if mode != nat.MODE_RATES_ONLY else None
     rr = torch.empty((N, D, S), dtype=torch.float32, device=dev) if want_rr else None
     ratio = torch.empty((N, D, S), dtype=torch.float32, device=dev) if want_ratio else None
@@ -60,16 +77,83 @@ def reverse_step(mode, branch, logits, x_eval, Q, QT, Rb, RbT, beta, h, eps, *, 
         workspace = torch.empty((ws,), dtype=torch.uint8, device=dev) if ws > 0 else None
     p = nat.StepParams(
         mode=mode, branch=branch, impl=impl, N=N, D=D, S=S, row_offset=int(row_offset),
-        logits=nat.ptr(logits) + 4 * int(logits_offset_elems), ld_logits=S,
+        logits=(nat.ptr(logits) + 4 * int(logits_offset_elems)) if logits is not None else None, ld_logits=S,
         batch_stride_logits=(int(batch_stride) if batch_stride is not None else D * S),
         x_eval=nat.ptr(x_eval), x_base=nat.ptr(x_base),
         Q=nat.ptr(Q), QT=nat.ptr(QT), Rb=nat.ptr(Rb), RbT=nat.ptr(RbT), tc_tables=nat.ptr(tc_tables), tc_static=nat.ptr(tc_static),
         beta=float(beta), h=float(h), eps=float(eps), reject_multi=1 if reject_multi else 0,
         seed=int(seed), offset=int(offset),
         x_out=nat.ptr(x_out), rr_out=nat.ptr(rr), ratio_out=nat.ptr(ratio),
-        stats_out=(stats.data_ptr() if stats is not None else None), workspace=nat.ptr(workspace))
+        stats_out=(stats.data_ptr() if stats is not None else None), workspace=nat.ptr(workspace),
+        head=head_kind, head_mu=(head_mu.data_ptr() if head_mu is not None else None),
+        head_log_scale=(head_ls.data_ptr() if head_ls is not None else None), head_batch_stride=int(head_bs))
     nat.check(nat.lib().ctdd_reverse_step(p, nat.stream()), "ctdd_reverse_step")
     return {"x": x_out, "rr": rr, "ratio": ratio}
+
+
+class LogisticHead:
+    """What a model's forward may return instead of (N, D, S) logits when its output layer is the truncated-logistic
+    head (reference lib/models/models.py:248-282, cfg.model.model_output == 'logistic_pars'): the two numbers per
+    dimension the network emits.  The samplers hand them to the fused reverse step, so the logits are never
+    materialised; `.logits(S)` builds them (one kernel) for the callers that need the tensor (final argmax)."""
+
+    def __init__(self, mu, log_scale, fix_logistic=False):
+        if mu.shape != log_scale.shape:
+            raise ValueError(f"mu {tuple(mu.shape)} and log_scale {tuple(log_scale.shape)} differ in shape")
+        self.mu, self.log_scale, self.fix_logistic = mu, log_scale, bool(fix_logistic)
+
+    def flat(self):
+        """(N, D) views (no copy for contiguous tensors or torch.chunk halves)."""
+        N = self.mu.shape[0]
+        return self.mu.reshape(N, -1) if self.mu[0].is_contiguous() else self.mu.contiguous().view(N, -1), \
+            self.log_scale.reshape(N, -1) if self.log_scale[0].is_contiguous() else self.log_scale.contiguous().view(N, -1)
+
+    def slice_dims(self, c):
+        """The head of dimensions c.. (conditional samplers keep the first c dimensions fixed)."""
+        mu, ls = self.flat()
+        return LogisticHead(mu[:, c:], ls[:, c:], self.fix_logistic)
+
+    def logits(self, S):
+        mu, ls = self.flat()
+        return logistic_logits(mu, ls, S, self.fix_logistic)
+
+    def as_tuple(self):
+        mu, ls = self.flat()
+        return mu, ls, self.fix_logistic
+
+
+def _head_views(mu, ls, N, D):
+    """(mu, log_scale) as fp32 CUDA tensors addressable as base[n * batch_stride + d]; returns (mu, ls, batch_stride).
+    Accepts (N, D) or (N, C, H, W) tensors, contiguous or the two halves of torch.chunk(out, 2, dim=1)."""
+    def flat(t):
+        if not t.is_cuda:
+            raise RuntimeError("ctdd_b200 kernels need CUDA tensors; got a host tensor (there is no CPU fallback)")
+        if t.dtype != torch.float32:
+            t = t.float()
+        if t.shape[0] != N or t.numel() != N * D:
+            raise ValueError(f"head tensor of shape {tuple(t.shape)} does not hold N={N} x D={D} values")
+        inner = t[0]
+        if N > 1 and not inner.is_contiguous():
+            t = t.contiguous()
+        elif N == 1 and not t.is_contiguous():
+            t = t.contiguous()
+        return t, (t.stride(0) if N > 1 else D)
+    mu, bs_mu = flat(mu)
+    ls, bs_ls = flat(ls)
+    if bs_mu != bs_ls:
+        mu, ls, bs_mu = mu.contiguous(), ls.contiguous(), D
+    return mu, ls, bs_mu
+
+
+def logistic_logits(mu, log_scale, S, fix_logistic=False):
+    """Truncated-logistic head -> (N, D, S) fp32 logits in one pass (replaces sample_logistic, models.py:28-74)."""
+    N = mu.shape[0]
+    D = mu.numel() // N
+    mu, ls, bs = _head_views(mu, log_scale, N, D)
+    out = torch.empty((N, D, S), dtype=torch.float32, device=mu.device)
+    nat.check(nat.lib().ctdd_logistic_logits(mu.data_ptr(), ls.data_ptr(), N, D, int(bs), S, 1 if fix_logistic else 0,
+                                             nat.ptr(out), nat.stream()), "ctdd_logistic_logits")
+    return out
 
 
 def sample_categorical_shared(probs, rows, seed, offset=0, row_offset=0):

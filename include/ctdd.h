@@ -130,7 +130,28 @@ typedef struct ctdd_step_params {
   float* ratio_out;      /* [N*D,S] ratio, or NULL */
   int64_t* stats_out;    /* [CTDD_STAT_COUNT] or NULL */
   void* workspace;       /* >= ctdd_step_workspace_bytes(N*D, S) bytes, or NULL when that is 0 (it is 0 today) */
+  /* Output head of the network (appended fields; zero-initialised = dense logits).  With CTDD_HEAD_LOGISTIC[_FIX] the
+   * caller passes the two numbers per dimension the U-Net emits (lib/networks/unet.py:450-452) instead of the (N,D,S)
+   * logits tensor and `logits` may be NULL: the kernel evaluates the truncated-logistic head
+   * (lib/models/models.py:28-74, :248-282) on the fly, so the logits never exist in memory.  tcgen05 path (S == 256)
+   * only; for other shapes materialise them with ctdd_logistic_logits first. */
+  int32_t head;                 /* CTDD_HEAD_* */
+  const float* head_mu;         /* row (n,d) at head_mu[n*head_batch_stride + d] */
+  const float* head_log_scale;  /* same addressing */
+  int64_t head_batch_stride;    /* elements between consecutive n (2*D for the two halves of a torch.chunk'ed (B,2C,H,W)) */
 } ctdd_step_params;
+
+enum {
+  CTDD_HEAD_LOGITS = 0,        /* dense logits */
+  CTDD_HEAD_LOGISTIC = 1,      /* model.model_output == 'logistic_pars', fix_logistic False */
+  CTDD_HEAD_LOGISTIC_FIX = 2   /* fix_logistic True: min with the mirrored evaluation (models.py:66-70) */
+};
+
+/* logits[n,d,s] of the truncated-logistic head: log-mass of Logistic(mu, exp(log_scale - 2)) on bin s of [-1,1] cut into
+ * S bins, with the reference's 1e-6 guard.  Replaces sample_logistic lib/models/models.py:28-74 (one pass instead of ~20
+ * elementwise passes over (N,D,S)).  Values agree with the reference to its own fp32 noise; see DESIGN.md. */
+int ctdd_logistic_logits(const float* mu, const float* log_scale, int N, int D, int64_t batch_stride, int S,
+                         int fix_logistic, float* logits_out, void* stream);
 
 int64_t ctdd_step_workspace_bytes(int64_t rows, int S, int impl);
 int ctdd_reverse_step(const ctdd_step_params* p, void* stream);

@@ -88,6 +88,26 @@ class StubNet(nn.Module):
         return out + self.w
 
 
+class HeadStubNet(nn.Module):
+    """(mu, log_scale) per dimension, shaped like the U-Net's `logistic_pars` output (lib/networks/unet.py:450-452):
+    mu = tanh(loc + normalised input), log_scale growing with the noise level."""
+
+    def __init__(self, S: int, D: int, seed: int):
+        super().__init__()
+        g = np.random.Generator(np.random.PCG64(seed))
+        self.S_states = S
+        self.register_buffer("loc_d", torch.from_numpy((0.2 * g.standard_normal(D)).astype(np.float32)))
+        self.register_buffer("ls_d", torch.from_numpy((0.3 * g.standard_normal(D)).astype(np.float32)))
+        self.w = nn.Parameter(torch.zeros(1))
+
+    def head_params(self, x, t):
+        tt = t.view(-1, 1).to(torch.float32)
+        xn = (x.to(torch.float32) + 0.5) * (2.0 / self.S_states) - 1.0
+        mu = torch.tanh(xn + self.loc_d * tt + self.w)
+        log_scale = -1.2 + 2.0 * tt + self.ls_d + 0.0 * mu
+        return mu, log_scale
+
+
 def make_ref_model(ref, mixin_name: str, cfg, S: int, D: int, seed: int, scale: float = 0.5, width: float = None):
     mixin = getattr(ref.fm, mixin_name)
 

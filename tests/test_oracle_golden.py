@@ -53,13 +53,18 @@ def test_reverse_rates_match_reference(golden, case):
     np.testing.assert_allclose(ratio.numpy(), g[f"{name}/ratio"], rtol=2e-5, atol=1e-30)
 
 
-def _run_oracle_sampler(case):
+def _run_oracle_sampler(case, head=False):
     name, cls, fwd, N, D, loss_name, logit_type, stub, over, max_t, seed = case
     cfg = cases.sampler_cfg(rh.make_cfg, case)
     S, sc = cfg.data.S, cfg.sampler
     fp = oracle_forward(fwd)
-    net = rh.StubNet(S, D, seed, stub[0], stub[1])
-    model = lambda x, t: net.net(x, t)
+    if head:        # stub network emitting (mu, log_scale) + the oracle's truncated-logistic head; `stub` = fix_logistic
+        from oracle import head_oracle as ho
+        hnet = rh.HeadStubNet(S, D, seed)
+        model = lambda x, t: ho.truncated_logistic_logits(*hnet.head_params(x, t), S, stub)
+    else:
+        net = rh.StubNet(S, D, seed, stub[0], stub[1])
+        model = lambda x, t: net.net(x, t)
     lt = logit_type or "reverse_prob"
     common = dict(min_t=sc.min_t, num_steps=sc.num_steps, initial_dist=sc.initial_dist, seed=seed)
     if cls == "TauL":
