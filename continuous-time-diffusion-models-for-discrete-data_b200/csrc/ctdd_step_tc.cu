@@ -403,6 +403,39 @@ __device__ __forceinline__ void head_numerators(float mu, float ls, bool fix, in
   }
 }
 
+// First index whose inclusive prefix sum (256 floats at shared address P) exceeds T, for NB independent (P, T) pairs per
+// lane: three rounds of INDEPENDENT loads (7 splitters of stride 32, 7 of stride 4, 3 neighbours) instead of eight
+// dependent binary-search steps; the rounds of the NB searches are interleaved.
+template <int NB>
+__device__ __forceinline__ void prefix_search(const uint32_t (&P)[NB], const float (&T)[NB], int (&lo)[NB]) {
+#ifdef CTDD_EXP_NOSEARCH    // diagnostic build: no search
+#pragma unroll
+  for (int b = 0; b < NB; ++b) lo[b] = (T[b] > 1e30f) ? 1 : 0;
+#else
+  int c1[NB], c2[NB];
+  uint32_t P1[NB], P2[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    c1[b] = 0;
+#pragma unroll
+    for (int m = 0; m < 7; ++m) c1[b] += (lds32(P[b] + 4 * (32 * m + 31)) <= T[b]) ? 1 : 0;
+    P1[b] = P[b] + 128 * c1[b];
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    c2[b] = 0;
+#pragma unroll
+    for (int n = 0; n < 7; ++n) c2[b] += (lds32(P1[b] + 4 * (4 * n + 3)) <= T[b]) ? 1 : 0;
+    P2[b] = P1[b] + 16 * c2[b];
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const int c3 = ((lds32(P2[b]) <= T[b]) ? 1 : 0) + ((lds32(P2[b] + 4) <= T[b]) ? 1 : 0) + ((lds32(P2[b] + 8) <= T[b]) ? 1 : 0);
+    lo[b] = 32 * c1[b] + 4 * c2[b] + c3;
+  }
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------- the kernel
 #ifdef CTDD_TC_TRACE
 // diagnostic build only (CTDD_TRACE=1 python build.py): per-tile clock stamps of one CTA's roles, read back with
@@ -1015,50 +1048,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
             }
           }
           __syncwarp();
-          // K picks, one per lane: first state whose prefix sum exceeds v * total
+          // K0 + K1 picks, one per lane (row 0's picks first): first state whose prefix sum exceeds v * total
           const int K0 = si[0].K, K1 = two ? si[1].K : 0;
-          const int Kmax = K0 > K1 ? K0 : K1;
+          const int Kt = K0 + K1;
           int jump[2] = {0, 0};
-          for (int base = 0; base < Kmax; base += 32) {
-            const int j = base + lane;
-            float target[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              uint32_t w = sm.side[slot][warp * ROWS_PER_SAMPLER + rrow[u]].w[j < SIDE_PICKS ? j : 0];
-              if (si[u].K > SIDE_PICKS && base < si[u].K) {   // warp-uniform
-                const int jj = j >= 3 ? j - 3 : 0;
-                const long long g = g0 + warp * ROWS_PER_SAMPLER + rrow[u];
-                const Philox4 pc = philox_rowjump((uint64_t)(a.row_offset + g), 1u + (uint32_t)(jj >> 2), a.offset, a.seed);
-                if (j >= SIDE_PICKS) w = philox_word(pc, jj & 3);
-              }
-              // lanes without a pick get a target below every prefix sum: they all walk the same (broadcast) addresses
-              // instead of scattering 32 random shared-memory reads per step over the banks
-              target[u] = (j < (u ? K1 : K0)) ? fminf(u32_to_unit(w), 0.99999994f) * total[u] : -1.0f;
+          for (int base = 0; base < Kt; base += 32) {
+            const int idx = base + lane;
+            const int u = idx >= K0 ? 1 : 0;          // row of this lane's pick
+            const int j = u ? idx - K0 : idx;         // pick number within the row
+            const bool active = idx < Kt;
+            const int rsel = warp * ROWS_PER_SAMPLER + rrow[u];
+            uint32_t w = sm.side[slot][rsel].w[j < SIDE_PICKS ? j : 0];
+            if (active && j >= SIDE_PICKS) {          // more picks than the count warp prepared (large rates only)
+              const int jj = j - 3;
+              const Philox4 pc = philox_rowjump((uint64_t)(a.row_offset + g0 + rsel), 1u + (uint32_t)(jj >> 2), a.offset, a.seed);
+              w = philox_word(pc, jj & 3);
             }
-            // first prefix sum above the target in three rounds of INDEPENDENT loads (7 splitters of stride 32, 7 of
-            // stride 4, 3 neighbours) instead of eight dependent binary-search steps
-            int lo[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-#ifdef CTDD_EXP_NOSEARCH    // diagnostic build: no search
-              lo[u] = (target[u] > 1e30f) ? 1 : 0;
-#else
-              const uint32_t P = gp[u];
-              const float T = target[u];
-              int c1 = 0;
-#pragma unroll
-              for (int m = 0; m < 7; ++m) c1 += (lds32(P + 4 * (32 * m + 31)) <= T) ? 1 : 0;
-              const uint32_t P1 = P + 128 * c1;
-              int c2 = 0;
-#pragma unroll
-              for (int n = 0; n < 7; ++n) c2 += (lds32(P1 + 4 * (4 * n + 3)) <= T) ? 1 : 0;
-              const uint32_t P2 = P1 + 16 * c2;
-              const int c3 = ((lds32(P2) <= T) ? 1 : 0) + ((lds32(P2 + 4) <= T) ? 1 : 0) + ((lds32(P2 + 8) <= T) ? 1 : 0);
-              lo[u] = 32 * c1 + 4 * c2 + c3;
-#endif
-            }
-            jump[0] += (j < K0) ? (lo[0] - si[0].x) : 0;
-            jump[1] += (j < K1) ? (lo[1] - si[1].x) : 0;
+            // lanes without a pick get a target below every prefix sum: they all walk the same (broadcast) addresses
+            // instead of scattering random shared-memory reads over the banks
+            const uint32_t P[1] = {u ? gp[1] : gp[0]};
+            const float T[1] = {active ? fminf(u32_to_unit(w), 0.99999994f) * (u ? total[1] : total[0]) : -1.0f};
+            int lo[1];
+            prefix_search<1>(P, T, lo);
+            const int dj = active ? lo[0] - (u ? si[1].x : si[0].x) : 0;
+            jump[0] += u ? 0 : dj;
+            jump[1] += u ? dj : 0;
           }
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) {

@@ -145,12 +145,15 @@ def _head_views(mu, ls, N, D):
     return mu, ls, bs_mu
 
 
-def logistic_logits(mu, log_scale, S, fix_logistic=False):
+def logistic_logits(mu, log_scale, S, fix_logistic=False, out=None):
     """Truncated-logistic head -> (N, D, S) fp32 logits in one pass (replaces sample_logistic, models.py:28-74)."""
     N = mu.shape[0]
     D = mu.numel() // N
     mu, ls, bs = _head_views(mu, log_scale, N, D)
-    out = torch.empty((N, D, S), dtype=torch.float32, device=mu.device)
+    if out is None:
+        out = torch.empty((N, D, S), dtype=torch.float32, device=mu.device)
+    elif out.shape != (N, D, S) or out.dtype != torch.float32:
+        raise ValueError(f"out must be a float32 ({N}, {D}, {S}) tensor")
     nat.check(nat.lib().ctdd_logistic_logits(mu.data_ptr(), ls.data_ptr(), N, D, int(bs), S, 1 if fix_logistic else 0,
                                              nat.ptr(out), nat.stream()), "ctdd_logistic_logits")
     return out
