@@ -97,6 +97,9 @@ def lib() -> ctypes.CDLL:
     L.ctdd_noise_xt.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p]
     L.ctdd_logistic_logits.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_int, c_void_p, c_void_p]
     L.ctdd_logistic_logits.restype = c_int
+    L.ctdd_logistic_logits_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_int, c_void_p,
+                                                c_void_p, c_void_p]
+    L.ctdd_logistic_logits_backward.restype = c_int
     L.ctdd_loss_workspace_bytes.argtypes = [c_int, c_int, c_int]
     L.ctdd_loss_workspace_bytes.restype = c_int64
     L.ctdd_loss_forward.argtypes = [ctypes.POINTER(LossParams), c_void_p]

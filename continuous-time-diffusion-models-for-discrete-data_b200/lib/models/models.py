@@ -8,8 +8,10 @@ lib/networks/unet.py:450-452) into an (B, D, S) logits tensor with ~20 elementwi
   samplers pass straight into the fused reverse-step kernel: the logits never exist in memory;
 * `sample_logistic(...)` is the reference's function with the same signature, backed by one CUDA pass
   (`ctdd_logistic_logits`) when no gradient is required;
-* with gradients enabled (training) the head is part of the network's autograd graph and is evaluated with differentiable
-  torch ops in the cancellation-free closed form the kernels use.
+* with gradients enabled (training) the head is one `autograd.Function`: the same forward kernel, and a backward kernel
+  (`ctdd_logistic_logits_backward`) that recomputes the head from (mu, log_scale) and reads the incoming (B, D, S) gradient
+  once — instead of autograd through ~20 saved (B, D, S) tensors.  `_logistic_logits_torch` keeps the same closed form in
+  differentiable torch ops for host tensors / double precision checks.
 """
 from __future__ import annotations
 
@@ -25,8 +27,15 @@ def log_minus_exp(a, b, eps=1e-6):
 
 
 def _logistic_logits_autograd(mu, log_scale, S, fix_logistic):
-    """Differentiable head: log(u_{s+1} (kappa v_s + 1e-6)) with u = sigmoid(z), v = sigmoid(-z) at the bin edges
-    (identical in exact arithmetic to the reference's logsigmoid / log_minus_exp chain; see csrc/ctdd_head.cu)."""
+    """Differentiable head on the training path: CUDA forward + backward kernels for fp32 CUDA tensors."""
+    if mu.is_cuda and mu.dtype == torch.float32 and log_scale.dtype == torch.float32:
+        return ops.logistic_logits_autograd(mu, log_scale, S, fix_logistic).view(*mu.shape, S)
+    return _logistic_logits_torch(mu, log_scale, S, fix_logistic)
+
+
+def _logistic_logits_torch(mu, log_scale, S, fix_logistic):
+    """The head in differentiable torch ops: log(u_{s+1} (kappa v_s + 1e-6)) with u = sigmoid(z), v = sigmoid(-z) at the
+    bin edges (identical in exact arithmetic to the reference's logsigmoid / log_minus_exp chain; see csrc/ctdd_head.cu)."""
     mu = mu.unsqueeze(-1)
     inv = torch.exp(2.0 - log_scale).unsqueeze(-1)
     edges = torch.linspace(-1.0, 1.0, S + 1, device=mu.device, dtype=mu.dtype)

@@ -91,6 +91,38 @@ def reverse_step(mode, branch, logits, x_eval, Q, QT, Rb, RbT, beta, h, eps, *, 
     return {"x": x_out, "rr": rr, "ratio": ratio}
 
 
+class _LogisticLogitsFn(torch.autograd.Function):
+    """Differentiable truncated-logistic head: forward `ctdd_logistic_logits`, backward `ctdd_logistic_logits_backward`
+    (recomputes the head from its two inputs; nothing of size (N, D, S) is saved)."""
+
+    @staticmethod
+    def forward(ctx, mu, log_scale, S, fix_logistic):
+        N = mu.shape[0]
+        D = mu.numel() // N
+        mu_c = mu.detach().reshape(N, D).contiguous().float()
+        ls_c = log_scale.detach().reshape(N, D).contiguous().float()
+        ctx.save_for_backward(mu_c, ls_c)
+        ctx.meta = (S, bool(fix_logistic), tuple(mu.shape), mu.dtype, log_scale.dtype)
+        return logistic_logits(mu_c, ls_c, S, fix_logistic)
+
+    @staticmethod
+    def backward(ctx, grad_logits):
+        mu_c, ls_c = ctx.saved_tensors
+        S, fix, shape, dt_mu, dt_ls = ctx.meta
+        N, D = mu_c.shape
+        g = grad_logits.contiguous().float()
+        dmu, dls = torch.empty_like(mu_c), torch.empty_like(ls_c)
+        nat.check(nat.lib().ctdd_logistic_logits_backward(mu_c.data_ptr(), ls_c.data_ptr(), nat.ptr(g), N, D, D, S,
+                                                          1 if fix else 0, dmu.data_ptr(), dls.data_ptr(), nat.stream()),
+                  "ctdd_logistic_logits_backward")
+        return dmu.view(shape).to(dt_mu), dls.view(shape).to(dt_ls), None, None
+
+
+def logistic_logits_autograd(mu, log_scale, S, fix_logistic=False):
+    """(N, D, S) logits of the head, differentiable w.r.t. mu and log_scale (training path)."""
+    return _LogisticLogitsFn.apply(mu, log_scale, S, fix_logistic)
+
+
 class LogisticHead:
     """What a model's forward may return instead of (N, D, S) logits when its output layer is the truncated-logistic
     head (reference lib/models/models.py:248-282, cfg.model.model_output == 'logistic_pars'): the two numbers per

@@ -152,6 +152,12 @@ enum {
  * elementwise passes over (N,D,S)).  Values agree with the reference to its own fp32 noise; see DESIGN.md. */
 int ctdd_logistic_logits(const float* mu, const float* log_scale, int N, int D, int64_t batch_stride, int S,
                          int fix_logistic, float* logits_out, void* stream);
+/* Backward of the head w.r.t. its two inputs: grad_mu[n,d] = sum_s grad_logits[n,d,s] * dlogits/dmu (same for log_scale),
+ * written at the addressing of mu / log_scale.  Replaces autograd through the ~20 saved (N,D,S) tensors of the
+ * reference's formula chain (models.py:44-72); recomputes the head from (mu, log_scale), reads grad_logits once. */
+int ctdd_logistic_logits_backward(const float* mu, const float* log_scale, const float* grad_logits, int N, int D,
+                                  int64_t batch_stride, int S, int fix_logistic, float* grad_mu, float* grad_log_scale,
+                                  void* stream);
 
 int64_t ctdd_step_workspace_bytes(int64_t rows, int S, int impl);
 int ctdd_reverse_step(const ctdd_step_params* p, void* stream);

@@ -250,9 +250,36 @@ def test_samplers_with_fused_head_match_reference_fixtures(golden, case):
     assert mismatch_fraction(res[0], want) <= 0.011
 
 
+@pytest.mark.parametrize("S", [256, 32, 5])
+def test_head_backward_kernel_matches_fp64_autograd(S):
+    """d loss / d mu and d loss / d log_scale through the CUDA backward kernel against fp64 autograd of the reference
+    formulas (oracle), for a random upstream gradient; the reference's own fp32 autograd is the noise yardstick."""
+    from ctdd_b200 import ops
+    N, D = 6, 50
+    mu, ls = ho.head_inputs(N * D, 21 + S, -2.5, 2.5)
+    g = torch.randn((N, D, S), generator=torch.Generator().manual_seed(5))
+    for fix in (False, True):
+        m64 = mu.double().view(N, D).requires_grad_(True)
+        l64 = ls.double().view(N, D).requires_grad_(True)
+        gm64, gl64 = torch.autograd.grad((ho.truncated_logistic_logits(m64, l64, S, fix) * g.double()).sum(), (m64, l64))
+        m32 = mu.view(N, D).clone().requires_grad_(True)
+        l32 = ls.view(N, D).clone().requires_grad_(True)
+        gm32, gl32 = torch.autograd.grad((ho.truncated_logistic_logits(m32, l32, S, fix) * g).sum(), (m32, l32))
+        mc = mu.view(N, D).cuda().requires_grad_(True)
+        lc = ls.view(N, D).cuda().requires_grad_(True)
+        out = ops.logistic_logits_autograd(mc, lc, S, fix)
+        assert out.shape == (N, D, S)
+        gm, gl = torch.autograd.grad((out * g.cuda()).sum(), (mc, lc))
+        for got, want, ref32 in ((gm, gm64, gm32), (gl, gl64, gl32)):
+            scale = float(want.abs().max())
+            ref_err = float((ref32.double() - want).abs().max())
+            err = float((got.cpu().double() - want).abs().max())
+            assert err <= max(1e-4 * scale, 2.0 * ref_err), (S, fix, err, ref_err, scale)
+
+
 def test_head_training_path_is_differentiable_and_matches_kernel():
-    """With gradients enabled the head stays in the autograd graph (torch ops, closed form); its values agree with the
-    CUDA kernel and the reference formulas, and sample_logistic keeps the reference's signature / layout."""
+    """With gradients enabled the head is one autograd.Function (CUDA forward + backward); its values agree with the
+    no-grad kernel and the reference formulas, and sample_logistic keeps the reference's signature / layout."""
     from ctdd_b200.lib.models import models
     S = 256
     mu, ls = ho.head_inputs(2 * 3 * 4 * 4, 4, -2.0, 2.0)

@@ -56,5 +56,52 @@ def main():
               f"fused {t_fused:6.3f} ms | states differing fused vs dense {diff:.2e} | changed {float((xa != x).float().mean()):.3f}")
 
 
+def train_path(B=128):
+    """Training path of the head at a C5-like batch: forward + backward through the reference's formula chain in torch
+    (autograd saves ~20 (B,D,S) tensors) against the CUDA forward/backward pair."""
+    import torch.nn.functional as F
+    D, S = 3072, 256
+    g = torch.Generator(device="cuda").manual_seed(2)
+    mu0 = torch.tanh(torch.randn((B, D), device="cuda", generator=g))
+    ls0 = torch.randn((B, D), device="cuda", generator=g)
+    up = torch.randn((B, D, S), device="cuda", generator=g)
+
+    def ref_formula(mu, log_scale):        # the op sequence of sample_logistic (lib/models/models.py:44-72), fix_logistic False
+        mu, log_scale = mu.unsqueeze(-1), log_scale.unsqueeze(-1)
+        inv_scale = torch.exp(-(log_scale - 2))
+        bw = 2.0 / S
+        centers = torch.linspace(-1.0 + bw / 2, 1.0 - bw / 2, S, device="cuda").view(1, 1, S)
+        left = (centers - bw / 2 - mu) * inv_scale
+        right = (centers + bw / 2 - mu) * inv_scale
+        a, b = F.logsigmoid(right), F.logsigmoid(left)
+        return a + torch.log1p(-torch.exp(b - a) + 1e-6)
+
+    def run(fn):
+        mu, ls = mu0.clone().requires_grad_(True), ls0.clone().requires_grad_(True)
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        for _ in range(2):
+            (fn(mu, ls) * up).sum().backward()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            mu.grad = None
+            ls.grad = None
+            (fn(mu, ls) * up).sum().backward()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 5, (torch.cuda.max_memory_allocated() - base) / 2 ** 30, mu.grad.clone(), ls.grad.clone()
+
+    t_ref, m_ref, gm_r, gl_r = run(ref_formula)
+    t_our, m_our, gm_o, gl_o = run(lambda mu, ls: ops.logistic_logits_autograd(mu, ls, S, False))
+    print(f"train path B={B}: torch formula chain fwd+bwd {t_ref:.2f} ms, peak extra memory {m_ref:.2f} GiB | "
+          f"CUDA fwd+bwd kernels {t_our:.2f} ms, {m_our:.2f} GiB | "
+          f"grad agreement mu {float((gm_r - gm_o).abs().max() / gm_r.abs().max()):.1e} ls {float((gl_r - gl_o).abs().max() / gl_r.abs().max()):.1e}")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "train":
+        train_path(int(sys.argv[2]) if len(sys.argv) > 2 else 128)
+    else:
+        main()
