@@ -100,6 +100,9 @@ def lib() -> ctypes.CDLL:
     L.ctdd_logistic_logits_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_int, c_void_p,
                                                 c_void_p, c_void_p]
     L.ctdd_logistic_logits_backward.restype = c_int
+    L.ctdd_ema_chunk_elems.restype = c_int64
+    L.ctdd_ema_update.argtypes = [c_void_p, c_int, c_float, c_void_p]
+    L.ctdd_ema_update.restype = c_int
     L.ctdd_loss_workspace_bytes.argtypes = [c_int, c_int, c_int]
     L.ctdd_loss_workspace_bytes.restype = c_int64
     L.ctdd_loss_forward.argtypes = [ctypes.POINTER(LossParams), c_void_p]

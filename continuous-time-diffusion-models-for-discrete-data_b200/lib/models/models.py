@@ -66,3 +66,93 @@ class TruncatedLogisticHead:
         if torch.is_grad_enabled() and (mu.requires_grad or log_scale.requires_grad):
             return _logistic_logits_autograd(mu, log_scale, self.S, self.fix_logistic).view(B, D, self.S)
         return ops.LogisticHead(mu, log_scale, self.fix_logistic)
+
+
+class EMA:
+    """Exponential moving average of the trainable parameters — the reference's mixin (lib/models/models.py:729-826),
+    same attributes, methods, state-dict keys and error behaviour.  Inherit it FIRST so its state_dict functions win.
+
+    `update_ema` is the only hot method (once per optimiser step): the reference runs three torch kernels per parameter
+    tensor from a Python loop; here one `ctdd_ema_update` launch walks a device table of every (shadow, parameter) pair.
+    The result is bitwise the reference's (same fp32 roundings)."""
+
+    def __init__(self, cfg):
+        self.decay = cfg.model.ema_decay
+        self.device = cfg.device
+        if self.decay < 0.0 or self.decay > 1.0:
+            raise ValueError("Decay must be between 0 and 1")
+        self.shadow_params = []
+        self.collected_params = []
+        self.num_updates = 0
+        self._ema_table = None
+
+    def _trainable(self):
+        return [p for p in self.parameters() if p.requires_grad]
+
+    def init_ema(self):
+        self.shadow_params = [p.clone().detach() for p in self._trainable()]
+        self._ema_table = None
+
+    def update_ema(self):
+        if len(self.shadow_params) == 0:
+            raise ValueError("Shadow params not initialized before first ema update!")
+        self.num_updates += 1
+        decay = min(self.decay, (1 + self.num_updates) / (10 + self.num_updates))
+        params = self._trainable()
+        shadows = self.shadow_params
+        if any(s.device != p.device for s, p in zip(shadows, params)):
+            # the reference moves both to cfg.device on the fly (and so updates a copy); keep the shadows with the model
+            self.shadow_params = shadows = [s.to(p.device) for s, p in zip(shadows, params)]
+        table = getattr(self, "_ema_table", None)
+        if table is None or not table.matches(shadows, params):
+            table = self._ema_table = ops.EmaTable(shadows, [p.data for p in params])
+        with torch.no_grad():
+            table.update(1.0 - decay)
+
+    def state_dict(self, *args, **kwargs):
+        sd = torch.nn.Module.state_dict(self, *args, **kwargs)
+        sd["ema_decay"] = self.decay
+        sd["ema_num_updates"] = self.num_updates
+        sd["ema_shadow_params"] = self.shadow_params
+        return sd
+
+    def move_shadow_params_to_model_params(self):
+        for s_param, param in zip(self.shadow_params, self._trainable()):
+            param.data.copy_(s_param.data)
+
+    def move_model_params_to_collected_params(self):
+        self.collected_params = [param.clone() for param in self.parameters()]
+
+    def move_collected_params_to_model_params(self):
+        for c_param, param in zip(self.collected_params, self.parameters()):
+            param.data.copy_(c_param.data)
+
+    def load_state_dict(self, state_dict, *args, **kwargs):
+        missing, unexpected = torch.nn.Module.load_state_dict(self, state_dict, strict=False)
+        if len(missing) > 0:
+            print("Missing keys: ", missing)
+            raise ValueError
+        if sorted(unexpected) != ["ema_decay", "ema_num_updates", "ema_shadow_params"]:
+            print("Unexpected keys: ", unexpected)
+            raise ValueError
+        self.decay = state_dict["ema_decay"]
+        self.num_updates = state_dict["ema_num_updates"]
+        self.shadow_params = state_dict["ema_shadow_params"]
+        self._ema_table = None
+
+    def train(self, mode=True):
+        if self.training == mode:
+            print("Dont call model.train() with the same mode twice! Otherwise EMA parameters may overwrite original parameters")
+            print("Current model training mode: ", self.training)
+            print("Requested training mode: ", mode)
+            raise ValueError
+        torch.nn.Module.train(self, mode)
+        if mode:
+            if len(self.collected_params) > 0:
+                self.move_collected_params_to_model_params()
+            else:
+                print("model.train(True) called but no ema collected parameters!")
+        else:
+            self.move_model_params_to_collected_params()
+            self.move_shadow_params_to_model_params()
+        return self

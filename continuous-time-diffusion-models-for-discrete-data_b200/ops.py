@@ -191,6 +191,50 @@ def logistic_logits(mu, log_scale, S, fix_logistic=False, out=None):
     return out
 
 
+class EmaTable:
+    """Device table of (shadow, param, n) chunk records for `ctdd_ema_update` — every trainable tensor of a model is
+    updated in ONE launch (replaces the per-parameter loop of EMA.update_ema, reference lib/models/models.py:745-758).
+
+    The table is built once and rebuilt only when a tensor moved (load_state_dict replaces the shadow list, `.to()`
+    re-allocates parameters): `matches()` compares the recorded data pointers."""
+
+    def __init__(self, shadows, params):
+        if len(shadows) != len(params):
+            raise ValueError("EMA: shadow and parameter lists differ in length")
+        chunk = int(nat.lib().ctdd_ema_chunk_elems())
+        recs, dev = [], None
+        for s, p in zip(shadows, params):
+            if s.shape != p.shape:
+                raise ValueError(f"EMA: shadow {tuple(s.shape)} vs parameter {tuple(p.shape)}")
+            if s.dtype != torch.float32 or p.dtype != torch.float32:
+                raise RuntimeError("ctdd_ema_update handles float32 parameters only")
+            nat.ptr(s), nat.ptr(p)          # CUDA + contiguous, or raise: there is no CPU path
+            if dev is None:
+                dev = s.device
+            if s.device != dev or p.device != dev:
+                raise RuntimeError("EMA: all shadow tensors and parameters must live on one device")
+            n, sp, pp = s.numel(), s.data_ptr(), p.data_ptr()
+            for o in range(0, n, chunk):
+                recs.append((sp + 4 * o, pp + 4 * o, min(chunk, n - o)))
+        self.key = self._key(shadows, params)
+        self.n_chunks = len(recs)
+        self.elements = sum(r[2] for r in recs)
+        self.table = (torch.tensor(recs, dtype=torch.int64).to(dev) if recs else None)
+
+    @staticmethod
+    def _key(shadows, params):
+        return tuple(t.data_ptr() for t in shadows) + tuple(t.data_ptr() for t in params)
+
+    def matches(self, shadows, params):
+        return self.key == self._key(shadows, params)
+
+    def update(self, one_minus_decay):
+        """shadow <- shadow - one_minus_decay * (shadow - param), in place, on the current stream."""
+        if self.n_chunks:
+            nat.check(nat.lib().ctdd_ema_update(self.table.data_ptr(), self.n_chunks, float(one_minus_decay), nat.stream()),
+                      "ctdd_ema_update")
+
+
 def sample_categorical_shared(probs, rows, seed, offset=0, row_offset=0):
     x = torch.empty((rows,), dtype=torch.int32, device=probs.device)
     nat.check(nat.lib().ctdd_sample_categorical_shared(nat.ptr(probs.contiguous()), probs.shape[0], rows, row_offset,

@@ -188,6 +188,16 @@ int ctdd_noise_xt(const float* Q, const float* Rb, const float* beta, const int3
                   int S, int64_t batch_offset, uint64_t seed, uint64_t offset, int32_t* xt_out,
                   int32_t* x_tilde_out, void* stream);
 
+/* ---- training-step plumbing --------------------------------------------------------------------
+ * EMA of the model parameters, every trainable tensor in one launch:
+ *   shadow <- shadow - one_minus_decay * (shadow - param)        EMA.update_ema  lib/models/models.py:745-758
+ * (the reference loops over the parameters in Python).  chunk_table: device array of n_chunks records
+ * {float* shadow; const float* param; int64_t n;} (24 bytes each), a tensor cut into pieces of at most
+ * ctdd_ema_chunk_elems() elements.  Same roundings as the reference's torch expression (bitwise equal results). */
+#define CTDD_EMA_CHUNK 32768
+int64_t ctdd_ema_chunk_elems(void);
+int ctdd_ema_update(const void* chunk_table, int n_chunks, float one_minus_decay, void* stream);
+
 /* ---- loss terms -------------------------------------------------------------------------------
  * All per-sample reductions are returned as [B] vectors; the (tiny) final means/weights are combined by
  * the Python loss classes exactly as lib/losses/losses.py does, so one kernel serves every loss class.
