@@ -100,6 +100,14 @@ def lib() -> ctypes.CDLL:
     L.ctdd_logistic_logits_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_int, c_int, c_void_p,
                                                 c_void_p, c_void_p]
     L.ctdd_logistic_logits_backward.restype = c_int
+    L.ctdd_pair_partials.argtypes = [c_int, c_int]
+    L.ctdd_pair_partials.restype = c_int64
+    L.ctdd_pair_similarity.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_void_p]
+    L.ctdd_pair_similarity.restype = c_int
+    L.ctdd_pair_similarity_sum.argtypes = [c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    L.ctdd_pair_similarity_sum.restype = c_int
+    L.ctdd_state_histogram.argtypes = [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]
+    L.ctdd_state_histogram.restype = c_int
     L.ctdd_ema_chunk_elems.restype = c_int64
     L.ctdd_ema_update.argtypes = [c_void_p, c_int, c_float, c_void_p]
     L.ctdd_ema_update.restype = c_int

@@ -191,6 +191,60 @@ def logistic_logits(mu, log_scale, S, fix_logistic=False, out=None):
     return out
 
 
+def _as_f32_rows(x):
+    if x.dim() != 2:
+        x = x.reshape(x.shape[0], -1)
+    return x.to(torch.float32).contiguous()
+
+
+def pair_similarity(x, y, bd=0.1, hamming=False):
+    """(N, M) matrix exp(-bd * sum_d |x_d - y_d|) (or D - sum_d |.| with hamming=True), metrics.py:6-22."""
+    x, y = _as_f32_rows(x), _as_f32_rows(y)
+    if x.shape[1] != y.shape[1]:
+        raise ValueError("pair_similarity: x and y differ in the number of dimensions")
+    K = torch.empty((x.shape[0], y.shape[0]), dtype=torch.float32, device=x.device)
+    if K.numel():
+        nat.check(nat.lib().ctdd_pair_similarity(nat.ptr(x), x.shape[0], nat.ptr(y), y.shape[0], x.shape[1], float(bd),
+                                                 1 if hamming else 0, nat.ptr(K), nat.stream()), "ctdd_pair_similarity")
+    return K
+
+
+def pair_similarity_sums(x, y, bd=0.1, hamming=False):
+    """float64 tensor (3,): sum_{i != j} k(x_i, x_j), sum_{i != j} k(y_i, y_j), sum_{i, j} k(x_i, y_j) — the three sums
+    of binary_mmd (metrics.py:25-48), no (N, M) or (N, M, D) tensor."""
+    x, y = _as_f32_rows(x), _as_f32_rows(y)
+    if x.shape[1] != y.shape[1]:
+        raise ValueError("pair_similarity_sums: x and y differ in the number of dimensions")
+    nat.ptr(x), nat.ptr(y)
+    L = nat.lib()
+    N, M, D = x.shape[0], y.shape[0], x.shape[1]
+    out = torch.empty(3, dtype=torch.float64, device=x.device)
+    scratch = torch.empty(max(1, int(L.ctdd_pair_partials(max(N, M), max(N, M)))), dtype=torch.float64, device=x.device)
+    for slot, (a, na, b, nb, self_) in enumerate(((x, N, x, N, 1), (y, M, y, M, 1), (x, N, y, M, 0))):
+        nat.check(L.ctdd_pair_similarity_sum(a.data_ptr(), na, b.data_ptr(), nb, D, float(bd), self_, 1 if hamming else 0,
+                                             scratch.data_ptr(), out.data_ptr() + 8 * slot, nat.stream()),
+                  "ctdd_pair_similarity_sum")
+    return out
+
+
+def state_histogram(x, S, counts=None):
+    """Per-dimension state counts of samples x (N, D) -> int32 (D, S); pass `counts` (from an earlier call) to accumulate.
+    Raises if any state lies outside [0, S)."""
+    if x.dim() != 2:
+        x = x.reshape(x.shape[0], -1)
+    x = x.to(torch.int32).contiguous()
+    N, D = x.shape
+    buf = torch.zeros(D * S + 1, dtype=torch.int32, device=x.device)
+    nat.check(nat.lib().ctdd_state_histogram(nat.ptr(x), N, D, S, nat.ptr(buf), nat.stream()), "ctdd_state_histogram")
+    if int(buf[-1]) != 0:
+        raise ValueError(f"state_histogram: {int(buf[-1])} states outside [0, {S})")
+    h = buf[:-1].view(D, S)
+    if counts is not None:
+        counts += h
+        return counts
+    return h
+
+
 class EmaTable:
     """Device table of (shadow, param, n) chunk records for `ctdd_ema_update` — every trainable tensor of a model is
     updated in ONE launch (replaces the per-parameter loop of EMA.update_ema, reference lib/models/models.py:745-758).

@@ -198,6 +198,23 @@ int ctdd_noise_xt(const float* Q, const float* Rb, const float* beta, const int3
 int64_t ctdd_ema_chunk_elems(void);
 int ctdd_ema_update(const void* chunk_table, int n_chunks, float one_minus_decay, void* stream);
 
+/* ---- evaluation metrics ------------------------------------------------------------
+ * Pair similarities of two sample sets X (N, D), Y (M, D), fp32 row-major (the reference casts to float32 first):
+ *   k(x, y) = exp(-bd * sum_d |x_d - y_d|)      binary_exp_hamming_sim  lib/datasets/metrics.py:14-22, lib/utils/utils.py:101-105
+ *   k(x, y) = D - sum_d |x_d - y_d|             binary_hamming_sim      lib/datasets/metrics.py:6-10     (hamming_sim != 0)
+ * ctdd_pair_similarity writes the (N, M) matrix K.  ctdd_pair_similarity_sum writes ONE double to `out`: the sum of k
+ * over all pairs, or with self != 0 (needs X == Y, N == M) over the pairs i != j — the three sums of binary_mmd
+ * (metrics.py:25-48) without the (N, M, D) difference tensor.  `partials` is caller scratch of ctdd_pair_partials(N, M)
+ * doubles; the reduction order is fixed (deterministic).  N == 0 or M == 0 gives 0. */
+int64_t ctdd_pair_partials(int N, int M);
+int ctdd_pair_similarity(const float* X, int N, const float* Y, int M, int D, float bd, int hamming_sim, float* K, void* stream);
+int ctdd_pair_similarity_sum(const float* X, int N, const float* Y, int M, int D, float bd, int self, int hamming_sim,
+                             double* partials, double* out, void* stream);
+/* Per-dimension state counts of a sample set x (N, D) int32: counts[d*S + s] += #{n : x[n,d] == s}; counts has D*S + 1
+ * entries, the last one counts out-of-range states (a correct sampler leaves it 0).  The caller zeroes counts; successive
+ * calls accumulate (batch sharding).  S <= 8192.  Used for the per-dimension histogram / KL check of the reverse process. */
+int ctdd_state_histogram(const int32_t* x, int64_t N, int D, int S, int32_t* counts, void* stream);
+
 /* ---- loss terms -------------------------------------------------------------------------------
  * All per-sample reductions are returned as [B] vectors; the (tiny) final means/weights are combined by
  * the Python loss classes exactly as lib/losses/losses.py does, so one kernel serves every loss class.
