@@ -2,16 +2,19 @@
 //   CTDD_LOSS_CTELBO  tauLDR CT-ELBO   losses.py:108-286  (CTElbo, NLL, CTElboLambda, CondCTElbo)
 //   CTDD_LOSS_SDDM    SDDM ELBO        losses.py:1345-1500 (ScoreElbo), :389-544 (SDDMElbo)
 //   CTDD_LOSS_CRM     ratio matching   losses.py:794-890 (CatRM), :1146-1242 (CatRMNLL)
-// One CTA owns 8 rows (b, d..d+7) of ONE sample, so the per-sample q_{t|0} is shared by the CTA; threads span the
-// state axis. The (rows x S)(S x S) contractions against the per-sample Q run on CUDA cores in this round
+// One CTA owns ROWS rows (b, d..d+ROWS-1) of ONE sample, so the per-sample q_{t|0} is shared by the CTA; threads span
+// the state axis. The (rows x S)(S x S) contractions against the per-sample Q run on CUDA cores in this round
 // (2*B*D*S^2 FLOP forward, 4*B*D*S^2 backward: the backward recomputes u instead of saving a (B,D,S) tensor).
+// S == 256 uses ROWS = 32 and a 16-row x 2-state register tile per thread: each Q element fetched from L2 feeds 16 FMAs
+// and each 128-bit shared-memory operand load 8 (the ROWS = 8 / one-state-per-thread form streamed the 256 KB per-sample
+// Q once per 8 rows and was L2-bandwidth bound at ~15 TFLOP/s); other S keep ROWS = 8.  The k order of every dot
+// product is the same in both forms, so the results are bit-identical.
 // Per-sample reductions are returned as [B] vectors; the final means / weights are combined by the Python classes.
 #include "ctdd_common.cuh"
 
 namespace ctdd {
 namespace loss {
 
-constexpr int ROWS = 8;
 
 struct Args {
   int kind, logit_type, crm_type, B, D, S;
@@ -25,6 +28,8 @@ struct Args {
   const int* x_tilde;  // CTELBO: signal-term state; SDDM: == xt
   const float* G;      // CTELBO: [B][x][k] = beta * sum_s Rb[s,x][s!=x] Q[k,s] / (Q[k,x]+eps)
   const float* baseZ;  // [B] sum_d z_b[x_tilde_d]
+  const float* RbT;    // [x][s] = Rb[s][x]: the per-(row, s) terms read a COLUMN of Rb per row (coalesced through the transpose)
+  const float* RbD;    // [s] = Rb[s][s]
   float eps;
   float* out_a; float* out_b; float* out_c; float* out_d; float* out_nll;
   const float* ga; const float* gb; const float* gd; const float* gn;
@@ -76,14 +81,84 @@ __global__ void basez_kernel(const float* __restrict__ Rb, const float* __restri
   }
 }
 
-template <bool BWD>
-__global__ void __launch_bounds__(256) loss_kernel(const Args a) {
+// out[r][c] = epi(r, c, sum_j in[r][j] * M[j][c]) for the CTA's ROWS rows; `in` / `out` are [ROWS][S] shared-memory
+// arrays, M a row-major S x S matrix in global memory (L2-resident).  The j order is sequential in every variant.
+// RbT[x][s] = Rb[s][x], RbD[s] = Rb[s][s] (built by the forward call into the workspace)
+__global__ void __launch_bounds__(256) rb_tables_kernel(const float* __restrict__ Rb, int S, float* __restrict__ RbT,
+                                                        float* __restrict__ RbD) {
+  __shared__ float tile[16][17];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int x = blockIdx.x * 16 + tx, y = blockIdx.y * 16 + ty;
+  tile[ty][tx] = (x < S && y < S) ? Rb[(size_t)y * S + x] : 0.f;
+  __syncthreads();
+  const int ox = blockIdx.y * 16 + tx, oy = blockIdx.x * 16 + ty;
+  if (ox < S && oy < S) RbT[(size_t)oy * S + ox] = tile[tx][ty];
+  if (blockIdx.x == blockIdx.y && ty == tx && x < S) RbD[x] = tile[ty][tx];
+}
+
+template <int ROWS, class Epi>
+__device__ __forceinline__ void rows_times_matrix(const float* __restrict__ in, const float* __restrict__ M, int S, Epi epi) {
+  const int tid = threadIdx.x, nth = blockDim.x;
+  if (ROWS == 32 && S == 256 && nth == 256) {
+    // 16 rows x 2 adjacent columns per thread; a warp reads one 256-byte run of M per j and broadcasts the operand
+    constexpr int RT = 16;
+    const int c = 2 * (tid & 127), r0 = RT * (tid >> 7);
+    float acc0[RT], acc1[RT];
+#pragma unroll
+    for (int r = 0; r < RT; ++r) acc0[r] = acc1[r] = 0.f;
+    const float* mp = M + c;
+    const float* ip = in + r0 * 256;
+#pragma unroll 1
+    for (int j = 0; j < 256; j += 4) {
+      const float2 q0 = __ldg(reinterpret_cast<const float2*>(mp + (size_t)j * 256));
+      const float2 q1 = __ldg(reinterpret_cast<const float2*>(mp + (size_t)(j + 1) * 256));
+      const float2 q2 = __ldg(reinterpret_cast<const float2*>(mp + (size_t)(j + 2) * 256));
+      const float2 q3 = __ldg(reinterpret_cast<const float2*>(mp + (size_t)(j + 3) * 256));
+#pragma unroll
+      for (int r = 0; r < RT; ++r) {
+        const float4 av = *reinterpret_cast<const float4*>(ip + r * 256 + j);
+        acc0[r] = fmaf(av.w, q3.x, fmaf(av.z, q2.x, fmaf(av.y, q1.x, fmaf(av.x, q0.x, acc0[r]))));
+        acc1[r] = fmaf(av.w, q3.y, fmaf(av.z, q2.y, fmaf(av.y, q1.y, fmaf(av.x, q0.y, acc1[r]))));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RT; ++r) { epi(r0 + r, c, acc0[r]); epi(r0 + r, c + 1, acc1[r]); }
+    return;
+  }
+  const bool vec4 = (S & 3) == 0;   // rows of the smem operands are 16-byte aligned only then
+  for (int c = tid; c < S; c += nth) {
+    for (int rb = 0; rb < ROWS; rb += 8) {
+      float acc[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+      int j = 0;
+      for (; vec4 && j + 4 <= S; j += 4) {   // 4 contraction steps per 128-bit shared-memory load of every row's operand
+        const float q0 = __ldg(M + (size_t)j * S + c), q1 = __ldg(M + (size_t)(j + 1) * S + c);
+        const float q2 = __ldg(M + (size_t)(j + 2) * S + c), q3 = __ldg(M + (size_t)(j + 3) * S + c);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const float4 av = *reinterpret_cast<const float4*>(in + (rb + r) * S + j);
+          acc[r] = fmaf(av.w, q3, fmaf(av.z, q2, fmaf(av.y, q1, fmaf(av.x, q0, acc[r]))));
+        }
+      }
+      for (; j < S; ++j) {
+        const float q = __ldg(M + (size_t)j * S + c);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) acc[r] = fmaf(in[(rb + r) * S + j], q, acc[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) epi(rb + r, c, acc[r]);
+    }
+  }
+}
+
+template <bool BWD, int ROWS>
+__global__ void __launch_bounds__(256, ROWS == 32 ? 2 : 1) loss_kernel(const Args a) {
   extern __shared__ __align__(16) float smem[];
   const int S = a.S;
-  const bool vec4 = (S & 3) == 0;   // rows of the smem operands are 16-byte aligned only then
-  float* sP = smem;                 // [8][S] softmax p
-  float* sA = smem + ROWS * S;      // [8][S] GEMM operand (p * a, or p), later dp
-  float* sU = smem + 2 * ROWS * S;  // [8][S] u, later the s-space cotangent
+  float* sP = smem;                 // [ROWS][S] softmax p
+  float* sA = smem + ROWS * S;      // [ROWS][S] GEMM operand (p * a, or p), later dp
+  float* sU = smem + 2 * ROWS * S;  // [ROWS][S] u, later the s-space cotangent
   __shared__ int s_x0[ROWS], s_xr[ROWS], s_xt[ROWS];
   __shared__ float s_llx[ROWS], s_lse[ROWS], s_row_a[ROWS], s_row_b[ROWS], s_row_c[ROWS], s_row_d[ROWS], s_row_n[ROWS];
   const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nth >> 5;
@@ -124,28 +199,7 @@ __global__ void __launch_bounds__(256) loss_kernel(const Args a) {
   __syncthreads();
   // 2. u[r][s] = sum_k A[r][k] Q[k][s]
   if (!direct) {
-    for (int s = tid; s < S; s += nth) {
-      float acc[ROWS];
-#pragma unroll
-      for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
-      int k = 0;
-      for (; vec4 && k + 4 <= S; k += 4) {   // 4 contraction steps per 128-bit shared-memory load of every row's operand
-        const float q0 = __ldg(Q + (size_t)k * S + s), q1 = __ldg(Q + (size_t)(k + 1) * S + s);
-        const float q2 = __ldg(Q + (size_t)(k + 2) * S + s), q3 = __ldg(Q + (size_t)(k + 3) * S + s);
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-          const float4 av = *reinterpret_cast<const float4*>(sA + r * S + k);
-          acc[r] = fmaf(av.w, q3, fmaf(av.z, q2, fmaf(av.y, q1, fmaf(av.x, q0, acc[r]))));
-        }
-      }
-      for (; k < S; ++k) {
-        const float q = __ldg(Q + (size_t)k * S + s);
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) acc[r] = fmaf(sA[r * S + k], q, acc[r]);
-      }
-#pragma unroll
-      for (int r = 0; r < ROWS; ++r) sU[r * S + s] = acc[r];
-    }
+    rows_times_matrix<ROWS>(sA, Q, S, [&](int r, int c, float v) { sU[r * S + c] = v; });
   } else {
     for (int s = tid; s < S; s += nth)
 #pragma unroll
@@ -174,10 +228,11 @@ __global__ void __launch_bounds__(256) loss_kernel(const Args a) {
       const float den = Q[(size_t)x0 * S + xt] + a.eps;
       const float zt = -beta * a.Rb[(size_t)xt * S + xt];
       const float* Gr = a.G + ((size_t)b * S + xr) * S;
+      const float* rcol = a.RbT + (size_t)xt * S;      // Rb[., xt]
       for (int s = lane; s < S; s += 32) {
         const float u = sU[r * S + s];
-        const float w = (s == xt) ? 0.f : beta * a.Rb[(size_t)s * S + xt] * Q[(size_t)x0 * S + s] / den;
-        const float Z = baseZ - zt + (-beta * a.Rb[(size_t)s * S + s]);
+        const float w = (s == xt) ? 0.f : beta * rcol[s] * Q[(size_t)x0 * S + s] / den;
+        const float Z = baseZ - zt + (-beta * a.RbD[s]);
         rb += w * logf(u + a.eps);
         rc += w / Z;
         ra += sP[r * S + s] * Gr[s];                 // reg: sum_k p_k G[x_reg][k]   (index s doubles as k)
@@ -187,15 +242,16 @@ __global__ void __launch_bounds__(256) loss_kernel(const Args a) {
       const float llx = s_llx[r];
       const float den = Q[(size_t)x0 * S + xr] + a.eps;
       const float zt = -beta * a.Rb[(size_t)xr * S + xr];
+      const float* rcol = a.RbT ? a.RbT + (size_t)xr * S : nullptr;      // Rb[., xr] (SDDM only)
       for (int s = lane; s < S; s += 32) {
         const float uraw = sU[r * S + s];
         const float ll = direct ? uraw : logf(uraw + 1e-35f);
         float dll = 0.f;
         if (a.kind == CTDD_LOSS_SDDM) {
-          const float rs = (s == xr) ? 0.f : beta * a.Rb[(size_t)s * S + xr];
+          const float rs = (s == xr) ? 0.f : beta * rcol[s];
           const float e = expf(ll - llx);
           const float w = (s == xr) ? 0.f : rs * Q[(size_t)x0 * S + s] / den;
-          const float Z = baseZ - zt + (-beta * a.Rb[(size_t)s * S + s]);
+          const float Z = baseZ - zt + (-beta * a.RbD[s]);
           ra += e * rs;
           rb += w * (ll - llx);
           rc += w / Z;
@@ -209,7 +265,7 @@ __global__ void __launch_bounds__(256) loss_kernel(const Args a) {
           } else if (a.crm_type == 2) {   // elbo
             if (s != xr) {
               const float e = expf(ll - llx);
-              const float qsx = Q[(size_t)s * S + xr], qxs = Q[(size_t)xr * S + s];
+              const float qsx = QT[(size_t)xr * S + s], qxs = Q[(size_t)xr * S + s];   // Q[s][xr] through the transpose
               ra += e * qsx - (llx - ll) * qxs;
               wsum += e * qsx + qxs;
               dll = ga * (e * qsx + qxs);
@@ -256,34 +312,17 @@ __global__ void __launch_bounds__(256) loss_kernel(const Args a) {
   }
   // 4. dp[r][k] = a[k] * sum_s V[r][s] Q[k][s]  (+ reg part)  — threads over k, QT[s][k] coalesced
   const float gn = a.gn[b];
-  for (int k = tid; k < S; k += nth) {
-    float acc[ROWS];
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
-    if (!direct) {
-      int s = 0;
-      for (; vec4 && s + 4 <= S; s += 4) {
-        const float q0 = __ldg(QT + (size_t)s * S + k), q1 = __ldg(QT + (size_t)(s + 1) * S + k);
-        const float q2 = __ldg(QT + (size_t)(s + 2) * S + k), q3 = __ldg(QT + (size_t)(s + 3) * S + k);
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-          const float4 uv = *reinterpret_cast<const float4*>(sU + r * S + s);
-          acc[r] = fmaf(uv.w, q3, fmaf(uv.z, q2, fmaf(uv.y, q1, fmaf(uv.x, q0, acc[r]))));
-        }
-      }
-      for (; s < S; ++s) {
-        const float q = __ldg(QT + (size_t)s * S + k);
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) acc[r] = fmaf(sU[r * S + s], q, acc[r]);
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-      float dp = acc[r];
-      if (ctelbo) {
-        dp = dp / (QT[(size_t)s_xt[r] * S + k] + a.eps) + a.ga[b] * a.G[((size_t)b * S + s_xr[r]) * S + k];
-      }
+  {
+    const float ga_b = a.ga[b];
+    auto store_dp = [&](int r, int k, float dp) {
+      if (ctelbo) dp = dp / (QT[(size_t)s_xt[r] * S + k] + a.eps) + ga_b * a.G[((size_t)b * S + s_xr[r]) * S + k];
       sA[r * S + k] = dp;
+    };
+    if (!direct) {
+      rows_times_matrix<ROWS>(sU, QT, S, store_dp);
+    } else {
+      for (int k = tid; k < S; k += nth)
+        for (int r = 0; r < ROWS; ++r) store_dp(r, k, 0.f);
     }
   }
   __syncthreads();
@@ -328,22 +367,28 @@ int run_loss(const ctdd_loss_params* p, void* stream, bool bwd) {
   if (!bwd && (!p->out_a || !p->out_b || !p->out_c || !p->out_d || !p->out_nll)) { set_error("ctdd_loss_forward: null output pointer"); return 2; }
   cudaStream_t st = (cudaStream_t)stream;
   const int S = p->S;
+  const int ROWS = (S == 256) ? 32 : 8;
   const size_t smem = (size_t)3 * ROWS * S * sizeof(float);
   if (smem > 200 * 1024) { set_error("ctdd_loss: S=%d too large", S); return 2; }
   static unsigned long long attr_done = 0ull;   // function attributes live in the device's context: a bit per device
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !((attr_done >> dev) & 1ull)) {
-    cudaFuncSetAttribute(loss_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(loss_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(loss_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(loss_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(loss_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(loss_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (dev >= 0 && dev < 64) attr_done |= 1ull << dev;
   }
   Args a;
   a.kind = p->kind; a.logit_type = p->logit_type; a.crm_type = p->crm_type; a.B = p->B; a.D = p->D; a.S = S;
   a.logits = p->logits; a.Q = p->Q; a.QT = p->QT; a.Rb = p->Rb; a.beta = p->beta;
   a.x0 = p->x0; a.xt = p->xt; a.x_tilde = p->x_tilde; a.eps = p->eps;
+  // workspace: [G: B*S*S, CTELBO only][baseZ: B][RbT: S*S][RbD: S]
   a.G = reinterpret_cast<const float*>(p->workspace);
   a.baseZ = p->workspace ? reinterpret_cast<const float*>(p->workspace) + (p->kind == CTDD_LOSS_CTELBO ? (size_t)p->B * S * S : 0) : nullptr;
+  a.RbT = (a.baseZ && p->kind != CTDD_LOSS_CRM) ? a.baseZ + p->B : nullptr;
+  a.RbD = a.RbT ? a.RbT + (size_t)S * S : nullptr;
   a.out_a = p->out_a; a.out_b = p->out_b; a.out_c = p->out_c; a.out_d = p->out_d; a.out_nll = p->out_nll;
   a.ga = p->ga; a.gb = p->gb; a.gd = p->gd; a.gn = p->gn; a.grad = p->grad_logits;
   if (p->kind != CTDD_LOSS_CRM) {
@@ -355,6 +400,9 @@ int run_loss(const ctdd_loss_params* p, void* stream, bool bwd) {
         ctelbo_table_kernel<<<grid, block, 0, st>>>(p->QT, p->Rb, p->beta, S, p->eps, const_cast<float*>(a.G));
         CTDD_CHECK_LAUNCH("ctelbo_table_kernel");
       }
+      const int rt = (S + 15) / 16;
+      rb_tables_kernel<<<dim3(rt, rt), 256, 0, st>>>(p->Rb, S, const_cast<float*>(a.RbT), const_cast<float*>(a.RbD));
+      CTDD_CHECK_LAUNCH("rb_tables_kernel");
       basez_kernel<<<p->B, 256, 0, st>>>(p->Rb, p->beta, p->x_tilde ? p->x_tilde : p->xt, p->D, S, const_cast<float*>(a.baseZ));
       CTDD_CHECK_LAUNCH("basez_kernel");
     }
@@ -363,16 +411,21 @@ int run_loss(const ctdd_loss_params* p, void* stream, bool bwd) {
   if (threads > 256) threads = 256;
   if (threads < 64) threads = 64;
   dim3 grid((p->D + ROWS - 1) / ROWS, p->B);
-  if (bwd) loss_kernel<true><<<grid, threads, smem, st>>>(a);
-  else loss_kernel<false><<<grid, threads, smem, st>>>(a);
+  if (ROWS == 32) {
+    if (bwd) loss_kernel<true, 32><<<grid, threads, smem, st>>>(a);
+    else loss_kernel<false, 32><<<grid, threads, smem, st>>>(a);
+  } else {
+    if (bwd) loss_kernel<true, 8><<<grid, threads, smem, st>>>(a);
+    else loss_kernel<false, 8><<<grid, threads, smem, st>>>(a);
+  }
   CTDD_CHECK_LAUNCH("loss_kernel");
   return 0;
 }
 }  // namespace
 
 extern "C" int64_t ctdd_loss_workspace_bytes(int kind, int B, int S) {
-  if (kind == CTDD_LOSS_CTELBO) return ((int64_t)B * S * S + B) * 4;
-  if (kind == CTDD_LOSS_SDDM) return (int64_t)B * 4;
+  if (kind == CTDD_LOSS_CTELBO) return ((int64_t)B * S * S + B + (int64_t)S * S + S) * 4;
+  if (kind == CTDD_LOSS_SDDM) return ((int64_t)B + (int64_t)S * S + S) * 4;
   return 0;
 }
 extern "C" int ctdd_loss_forward(const ctdd_loss_params* p, void* stream) { return run_loss(p, stream, false); }

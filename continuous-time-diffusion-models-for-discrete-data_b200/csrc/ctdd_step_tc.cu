@@ -791,7 +791,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         const uint64_t bd0 = make_b_desc(smem_u32(sm.stage[st]));
         const uint32_t bd_lo = (uint32_t)bd0, bd_hi = (uint32_t)(bd0 >> 32);
 #pragma unroll 1
-        for (int pass = 0; pass < 3; ++pass) {
+#ifndef CTDD_EXP_PASSES
+#define CTDD_EXP_PASSES 3     // diagnostic builds issue fewer tensor passes (wrong numerics, timing only)
+#endif
+        for (int pass = 0; pass < CTDD_EXP_PASSES; ++pass) {
           const uint32_t a_tmem = tmem + (pass == 2 ? TM_QM : TM_QH);
           const uint32_t lo = bd_lo + (pass == 1 ? (uint32_t)(SPLIT_BYTES >> 4) : 0u);
 #pragma unroll
