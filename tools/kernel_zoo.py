@@ -108,7 +108,7 @@ def forward_process():
 
         def run_q():
             model._build_qt0(model._transition_delta(ts), inverse=True, want_transpose=True)
-        report("qt0_eig_kernel + qt0_finish_kernel", f"q_t|0 for B={B} distinct times, S=256 (Q and Q^T)", timed(run_q),
+        report("qt0_fused_kernel", f"q_t|0 for B={B} distinct times, S=256 (Q and Q^T)", timed(run_q),
                bytes_=8.0 * B * S * S, flop=2.0 * B * S * S * S)
     B = 128
     ts = torch.rand(B, device=dev) * 0.98 + 0.01
