@@ -42,24 +42,53 @@ __device__ __forceinline__ float log1mexp_ref(float v) {  // lib/utils/utils.py:
 }
 
 // G[b][x][k] = beta_b * (sum_s RzT[x][s] * QT_b[s][k]) / (QT_b[x][k] + eps), RzT[x][s] = Rb[s][x] (s != x)
+// 64 x 64 output tile per CTA, 4 x 4 register tile per thread (rows x = x0 + ty + 16a, columns k = k0 + 4tx .. +3);
+// the s order of every dot product is ascending.
 __global__ void __launch_bounds__(256) ctelbo_table_kernel(const float* __restrict__ QT, const float* __restrict__ Rb,
                                                           const float* __restrict__ beta, int S, float eps,
                                                           float* __restrict__ G) {
-  __shared__ float sA[16][17], sB[16][17];
-  const int b = blockIdx.z, tx = threadIdx.x, ty = threadIdx.y;
-  const int x = blockIdx.y * 16 + ty, k = blockIdx.x * 16 + tx;
+  __shared__ __align__(16) float sA[16][64];    // [s][x]
+  __shared__ __align__(16) float sB[16][64];    // [s][k]
+  const int b = blockIdx.z, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int x0 = blockIdx.y * 64, k0 = blockIdx.x * 64;
   const float* qt = QT + (size_t)b * S * S;
-  float acc = 0.f;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
   for (int s0 = 0; s0 < S; s0 += 16) {
-    const int sa = s0 + tx, sb = s0 + ty;
-    sA[ty][tx] = (x < S && sa < S && sa != x) ? Rb[(size_t)sa * S + x] : 0.f;
-    sB[ty][tx] = (sb < S && k < S) ? qt[(size_t)sb * S + k] : 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + 256 * e, sl = idx >> 6, col = idx & 63;
+      const int sg = s0 + sl, x = x0 + col, k = k0 + col;
+      sA[sl][col] = (sg < S && x < S && sg != x) ? Rb[(size_t)sg * S + x] : 0.f;
+      sB[sl][col] = (sg < S && k < S) ? qt[(size_t)sg * S + k] : 0.f;
+    }
     __syncthreads();
 #pragma unroll
-    for (int m = 0; m < 16; ++m) acc = fmaf(sA[ty][m], sB[m][tx], acc);
+    for (int m = 0; m < 16; ++m) {
+      const float4 bv = *reinterpret_cast<const float4*>(&sB[m][4 * tx]);
+      const float bq[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const float av = sA[m][ty + 16 * a];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(av, bq[c], acc[a][c]);
+      }
+    }
     __syncthreads();
   }
-  if (x < S && k < S) G[((size_t)b * S + x) * S + k] = beta[b] * acc / (qt[(size_t)x * S + k] + eps);
+  const float bt = beta[b];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int x = x0 + ty + 16 * a;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int k = k0 + 4 * tx + c;
+      if (x < S && k < S) G[((size_t)b * S + x) * S + k] = bt * acc[a][c] / (qt[(size_t)x * S + k] + eps);
+    }
+  }
 }
 
 __global__ void basez_kernel(const float* __restrict__ Rb, const float* __restrict__ beta, const int* __restrict__ x_tilde,
@@ -185,15 +214,20 @@ __global__ void __launch_bounds__(256, ROWS == 32 ? 2 : 1) loss_kernel(const Arg
     for (int k = lane; k < S; k += 32) m = fmaxf(m, lp[k]);
     m = warp_max(m);
     float sum = 0.f;
-    for (int k = lane; k < S; k += 32) sum += expf(lp[k] - m);
+    for (int k = lane; k < S; k += 32) {      // one exp per element: the numerators are parked in sP
+      const float e = expf(lp[k] - m);
+      sP[r * S + k] = e;
+      sum += e;
+    }
     sum = warp_sum(sum);
     const float lse = m + logf(sum);
     if (lane == 0) { s_lse[r] = lse; s_row_n[r] = lse - lp[s_x0[r]]; }
     const int xt = s_xt[r];
+    const float rsum = 1.f / sum;
     for (int k = lane; k < S; k += 32) {
-      const float p = expf(lp[k] - m) / sum;
+      const float p = sP[r * S + k] * rsum;
       sP[r * S + k] = p;
-      sA[r * S + k] = ctelbo ? p / (QT[(size_t)xt * S + k] + a.eps) : p;
+      sA[r * S + k] = ctelbo ? __fdividef(p, QT[(size_t)xt * S + k] + a.eps) : p;
     }
   }
   __syncthreads();
@@ -209,13 +243,10 @@ __global__ void __launch_bounds__(256, ROWS == 32 ? 2 : 1) loss_kernel(const Arg
   __syncthreads();
   // SDDM / CRM: ll[s] and ll at the evaluation state
   if (!ctelbo) {
-    for (int s = tid; s < S; s += nth)
-#pragma unroll
-      for (int r = 0; r < ROWS; ++r) {
-        float ll = sU[r * S + s];
-        if (!direct) ll = logf(ll + 1e-35f);
-        if (s == s_xr[r]) s_llx[r] = ll;
-      }
+    if (tid < ROWS) {
+      const float ux = sU[tid * S + s_xr[tid]];
+      s_llx[tid] = direct ? ux : logf(ux + 1e-35f);
+    }
     __syncthreads();
   }
   // 3. per-(row, s) terms; row reductions by warp r
@@ -225,36 +256,37 @@ __global__ void __launch_bounds__(256, ROWS == 32 ? 2 : 1) loss_kernel(const Arg
     const float ga = BWD ? a.ga[b] : 0.f, gb = BWD ? a.gb[b] : 0.f, gd = BWD ? a.gd[b] : 0.f;
     float ra = 0.f, rb = 0.f, rc = 0.f, wsum = 0.f;
     if (ctelbo) {
-      const float den = Q[(size_t)x0 * S + xt] + a.eps;
+      const float inv_den = 1.f / (Q[(size_t)x0 * S + xt] + a.eps);   // per row: the per-element divisions become products
       const float zt = -beta * a.Rb[(size_t)xt * S + xt];
       const float* Gr = a.G + ((size_t)b * S + xr) * S;
       const float* rcol = a.RbT + (size_t)xt * S;      // Rb[., xt]
       for (int s = lane; s < S; s += 32) {
         const float u = sU[r * S + s];
-        const float w = (s == xt) ? 0.f : beta * rcol[s] * Q[(size_t)x0 * S + s] / den;
+        const float w = (s == xt) ? 0.f : beta * rcol[s] * Q[(size_t)x0 * S + s] * inv_den;
         const float Z = baseZ - zt + (-beta * a.RbD[s]);
-        rb += w * logf(u + a.eps);
-        rc += w / Z;
+        rb += w * __logf(u + a.eps);
+        rc += __fdividef(w, Z);
         ra += sP[r * S + s] * Gr[s];                 // reg: sum_k p_k G[x_reg][k]   (index s doubles as k)
-        if (BWD) sU[r * S + s] = gb * w / (u + a.eps);  // cotangent of u
+        if (BWD) sU[r * S + s] = __fdividef(gb * w, u + a.eps);  // cotangent of u
       }
     } else {
       const float llx = s_llx[r];
-      const float den = Q[(size_t)x0 * S + xr] + a.eps;
+      const float inv_den = 1.f / (Q[(size_t)x0 * S + xr] + a.eps);
+      const float inv_ex = expf(-llx);          // reverse_prob: exp(ll_s - ll_x) = (u_s + 1e-35) * exp(-ll_x)
       const float zt = -beta * a.Rb[(size_t)xr * S + xr];
       const float* rcol = a.RbT ? a.RbT + (size_t)xr * S : nullptr;      // Rb[., xr] (SDDM only)
       for (int s = lane; s < S; s += 32) {
         const float uraw = sU[r * S + s];
-        const float ll = direct ? uraw : logf(uraw + 1e-35f);
+        const float ll = direct ? uraw : __logf(uraw + 1e-35f);
         float dll = 0.f;
         if (a.kind == CTDD_LOSS_SDDM) {
           const float rs = (s == xr) ? 0.f : beta * rcol[s];
-          const float e = expf(ll - llx);
-          const float w = (s == xr) ? 0.f : rs * Q[(size_t)x0 * S + s] / den;
+          const float e = direct ? __expf(ll - llx) : (uraw + 1e-35f) * inv_ex;
+          const float w = (s == xr) ? 0.f : rs * Q[(size_t)x0 * S + s] * inv_den;
           const float Z = baseZ - zt + (-beta * a.RbD[s]);
           ra += e * rs;
           rb += w * (ll - llx);
-          rc += w / Z;
+          rc += __fdividef(w, Z);
           wsum += w;
           dll = ga * e * rs + gb * w;
         } else {  // CRM
@@ -272,7 +304,7 @@ __global__ void __launch_bounds__(256, ROWS == 32 ? 2 : 1) loss_kernel(const Arg
             }
           }
         }
-        if (BWD) sU[r * S + s] = direct ? dll : dll / (uraw + 1e-35f);   // cotangent of u (or of ll for direct)
+        if (BWD) sU[r * S + s] = direct ? dll : __fdividef(dll, uraw + 1e-35f);   // cotangent of u (or of ll for direct)
       }
     }
     ra = warp_sum(ra); rb = warp_sum(rb); rc = warp_sum(rc); wsum = warp_sum(wsum);
@@ -395,8 +427,8 @@ int run_loss(const ctdd_loss_params* p, void* stream, bool bwd) {
     if (!p->workspace) { set_error("ctdd_loss: workspace required (ctdd_loss_workspace_bytes)"); return 2; }
     if (!bwd) {  // tables are built by the forward call and reused by the backward call (same workspace)
       if (p->kind == CTDD_LOSS_CTELBO) {
-        const int tiles = (S + 15) / 16;
-        dim3 grid(tiles, tiles, p->B), block(16, 16);
+        const int tiles = (S + 63) / 64;
+        dim3 grid(tiles, tiles, p->B), block(256);
         ctelbo_table_kernel<<<grid, block, 0, st>>>(p->QT, p->Rb, p->beta, S, p->eps, const_cast<float*>(a.G));
         CTDD_CHECK_LAUNCH("ctelbo_table_kernel");
       }
