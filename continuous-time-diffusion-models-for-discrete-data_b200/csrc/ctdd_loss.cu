@@ -137,18 +137,25 @@ __device__ __forceinline__ void rows_times_matrix(const float* __restrict__ in, 
     for (int r = 0; r < RT; ++r) acc0[r] = acc1[r] = 0.f;
     const float* mp = M + c;
     const float* ip = in + r0 * 256;
+    // the four matrix rows of step j + 4 are requested before the FMAs of step j (L2 latency off the critical path)
+    float2 q0 = __ldg(reinterpret_cast<const float2*>(mp));
+    float2 q1 = __ldg(reinterpret_cast<const float2*>(mp + 256));
+    float2 q2 = __ldg(reinterpret_cast<const float2*>(mp + 512));
+    float2 q3 = __ldg(reinterpret_cast<const float2*>(mp + 768));
 #pragma unroll 1
     for (int j = 0; j < 256; j += 4) {
-      const float2 q0 = __ldg(reinterpret_cast<const float2*>(mp + (size_t)j * 256));
-      const float2 q1 = __ldg(reinterpret_cast<const float2*>(mp + (size_t)(j + 1) * 256));
-      const float2 q2 = __ldg(reinterpret_cast<const float2*>(mp + (size_t)(j + 2) * 256));
-      const float2 q3 = __ldg(reinterpret_cast<const float2*>(mp + (size_t)(j + 3) * 256));
+      const int jn = (j + 4 < 256) ? j + 4 : j;
+      const float2 n0 = __ldg(reinterpret_cast<const float2*>(mp + (size_t)jn * 256));
+      const float2 n1 = __ldg(reinterpret_cast<const float2*>(mp + (size_t)(jn + 1) * 256));
+      const float2 n2 = __ldg(reinterpret_cast<const float2*>(mp + (size_t)(jn + 2) * 256));
+      const float2 n3 = __ldg(reinterpret_cast<const float2*>(mp + (size_t)(jn + 3) * 256));
 #pragma unroll
       for (int r = 0; r < RT; ++r) {
         const float4 av = *reinterpret_cast<const float4*>(ip + r * 256 + j);
         acc0[r] = fmaf(av.w, q3.x, fmaf(av.z, q2.x, fmaf(av.y, q1.x, fmaf(av.x, q0.x, acc0[r]))));
         acc1[r] = fmaf(av.w, q3.y, fmaf(av.z, q2.y, fmaf(av.y, q1.y, fmaf(av.x, q0.y, acc1[r]))));
       }
+      q0 = n0; q1 = n1; q2 = n2; q3 = n3;
     }
 #pragma unroll
     for (int r = 0; r < RT; ++r) { epi(r0 + r, c, acc0[r]); epi(r0 + r, c + 1, acc1[r]); }
