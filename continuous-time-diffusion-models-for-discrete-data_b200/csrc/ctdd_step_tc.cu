@@ -1077,11 +1077,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
             jump[0] += u ? 0 : dj;
             jump[1] += u ? dj : 0;
           }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            jump[0] += __shfl_xor_sync(0xffffffffu, jump[0], o);
-            jump[1] += __shfl_xor_sync(0xffffffffu, jump[1], o);
-          }
+          jump[0] = __reduce_add_sync(0xffffffffu, jump[0]);     // integer sums: one redux.sync each
+          jump[1] = __reduce_add_sync(0xffffffffu, jump[1]);
           if (lane < 2 && (lane == 0 || two)) {
             const int u = lane;
             const long long g = g0 + warp * ROWS_PER_SAMPLER + rrow[u];
