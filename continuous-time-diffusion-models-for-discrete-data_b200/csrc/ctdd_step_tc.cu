@@ -882,8 +882,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       const int slot = i % RING, gb = i % GBUF;
       if ((warp & 3) == 0 && lane == 0) TRACE(2 + (warp >> 2), i, 5);
       mbar_wait(&sm.side_full[slot], (i / RING) & 1);
-      mbar_wait(&sm.gather_full[gb], (i / GBUF) & 1);
-      if ((warp & 3) == 0 && lane == 0) TRACE(2 + (warp >> 2), i, 6);
       const long long g0 = (long long)tile * NT + (long long)rank * NH;
       // lanes 0..3 settle the rows without a jump in one go; the rest are processed two rows per iteration
       uint32_t todo;
@@ -904,6 +902,46 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         }
         todo = __ballot_sync(0xffffffffu, need);
       }
+      // Jump modes: the rows are processed two at a time, and the side record + rate-table rows (L2 gathers) of the NEXT
+      // pair are requested while the current pair is searched / finalized; the first pair's before the wait for the
+      // accumulator rows.  The table registers are dead between the rate computation and the next iteration.
+      int rrow[2] = {0, 0};
+      bool two = false;
+      SideHead si[2];
+      float4 e0[2], e1[2], c0v[2], c1v[2];
+      auto load_pair = [&]() {
+        rrow[0] = __ffs(todo) - 1;
+        todo &= todo - 1;
+        two = todo != 0;
+        rrow[1] = two ? __ffs(todo) - 1 : rrow[0];
+        todo &= todo - 1;   // no-op when todo == 0
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          si[u] = *reinterpret_cast<const SideHead*>(&sm.side[slot][warp * ROWS_PER_SAMPLER + rrow[u]]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const size_t xo = (size_t)si[u].x << 8;
+#ifdef CTDD_EXP_NOTABE      // diagnostic build: no rate-table gather in the sampler
+          e0[u] = make_float4(1.f, 1.f, 1.f, 1.f); e1[u] = e0[u]; (void)xo;
+#else
+          // lane owns states 4*lane .. +3 (elements 0-3) and 128 + 4*lane .. +3 (elements 4-7): every 128-bit access of
+          // the warp to a gather row is then one contiguous 512-byte run (no bank conflicts)
+          e0[u] = __ldg(reinterpret_cast<const float4*>(tabE - 4 * lane + xo));
+          e1[u] = __ldg(reinterpret_cast<const float4*>(tabE - 4 * lane + xo + 128));
+#endif
+          if (km_corr(KM)) {
+            c0v[u] = __ldg(reinterpret_cast<const float4*>(tabC - 4 * lane + xo));
+            c1v[u] = __ldg(reinterpret_cast<const float4*>(tabC - 4 * lane + xo + 128));
+          }
+        }
+      };
+      bool have = false;
+      if constexpr (!(KM == KM_RATES || KM == KM_DRIFT)) {
+        have = todo != 0;
+        if (have) load_pair();
+      }
+      mbar_wait(&sm.gather_full[gb], (i / GBUF) & 1);
+      if ((warp & 3) == 0 && lane == 0) TRACE(2 + (warp >> 2), i, 6);
       if constexpr (KM == KM_RATES || KM == KM_DRIFT) {
 #pragma unroll 1
         while (todo) {
@@ -961,40 +999,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       } else {
         // jump modes: two rows in flight per iteration (independent dependency chains hide the shuffle / smem latency)
 #pragma unroll 1
-        while (todo) {
-          int rrow[2];
-          rrow[0] = __ffs(todo) - 1;
-          todo &= todo - 1;
-          const bool two = todo != 0;
-          rrow[1] = two ? __ffs(todo) - 1 : rrow[0];
-          todo &= todo - 1;   // no-op when todo == 0
-          SideHead si[2];
+        while (have) {
+          // the current pair's identifiers survive the preload of the next pair
+          const int rc0 = rrow[0], rc1 = rrow[1];
+          const bool two_c = two;
+          const int xc0 = si[0].x, xc1 = si[1].x;
+          const int K0 = si[0].K, K1 = two_c ? si[1].K : 0;
           uint32_t gp[2];   // shared-space address of the row's gather slot
           float d[2][8];
           float total[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int r = warp * ROWS_PER_SAMPLER + rrow[u];
-            si[u] = *reinterpret_cast<const SideHead*>(&sm.side[slot][r]);
-            gp[u] = smem_u32(&sm.gather[gb][r][0]);
-          }
-          float4 e0[2], e1[2], c0v[2], c1v[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const size_t xo = (size_t)si[u].x << 8;
-#ifdef CTDD_EXP_NOTABE      // diagnostic build: no rate-table gather in the sampler
-            e0[u] = make_float4(1.f, 1.f, 1.f, 1.f); e1[u] = e0[u]; (void)xo;
-#else
-            // lane owns states 4*lane .. +3 (elements 0-3) and 128 + 4*lane .. +3 (elements 4-7): every 128-bit access of
-            // the warp to a gather row is then one contiguous 512-byte run (no bank conflicts)
-            e0[u] = __ldg(reinterpret_cast<const float4*>(tabE - 4 * lane + xo));
-            e1[u] = __ldg(reinterpret_cast<const float4*>(tabE - 4 * lane + xo + 128));
-#endif
-            if (km_corr(KM)) {
-              c0v[u] = __ldg(reinterpret_cast<const float4*>(tabC - 4 * lane + xo));
-              c1v[u] = __ldg(reinterpret_cast<const float4*>(tabC - 4 * lane + xo + 128));
-            }
-          }
+          gp[0] = smem_u32(&sm.gather[gb][warp * ROWS_PER_SAMPLER + rc0][0]);
+          gp[1] = smem_u32(&sm.gather[gb][warp * ROWS_PER_SAMPLER + rc1][0]);
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const float4 d0 = lds128(gp[u] + 16 * lane);
@@ -1045,14 +1060,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
               }
               total[u] += diag;
             }
-            if (u == 0 || two) {
+            if (u == 0 || two_c) {
               sts128(gp[u] + 16 * lane, make_float4(d[u][0], d[u][1], d[u][2], d[u][3]));
               sts128(gp[u] + 512 + 16 * lane, make_float4(d[u][4], d[u][5], d[u][6], d[u][7]));
             }
           }
           __syncwarp();
+          have = todo != 0;
+          if (have) load_pair();      // next pair: side record and table rows in flight during the search below
           // K0 + K1 picks, one per lane (row 0's picks first): first state whose prefix sum exceeds v * total
-          const int K0 = si[0].K, K1 = two ? si[1].K : 0;
           const int Kt = K0 + K1;
           int jump[2] = {0, 0};
           for (int base = 0; base < Kt; base += 32) {
@@ -1060,7 +1076,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
             const int u = idx >= K0 ? 1 : 0;          // row of this lane's pick
             const int j = u ? idx - K0 : idx;         // pick number within the row
             const bool active = idx < Kt;
-            const int rsel = warp * ROWS_PER_SAMPLER + rrow[u];
+            const int rsel = warp * ROWS_PER_SAMPLER + (u ? rc1 : rc0);
             uint32_t w = sm.side[slot][rsel].w[j < SIDE_PICKS ? j : 0];
             if (active && j >= SIDE_PICKS) {          // more picks than the count warp prepared (large rates only)
               const int jj = j - 3;
@@ -1073,16 +1089,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
             const float T[1] = {active ? fminf(u32_to_unit(w), 0.99999994f) * (u ? total[1] : total[0]) : -1.0f};
             int lo[1];
             prefix_search<1>(P, T, lo);
-            const int dj = active ? lo[0] - (u ? si[1].x : si[0].x) : 0;
+            const int dj = active ? lo[0] - (u ? xc1 : xc0) : 0;
             jump[0] += u ? 0 : dj;
             jump[1] += u ? dj : 0;
           }
           jump[0] = __reduce_add_sync(0xffffffffu, jump[0]);     // integer sums: one redux.sync each
           jump[1] = __reduce_add_sync(0xffffffffu, jump[1]);
-          if (lane < 2 && (lane == 0 || two)) {
+          if (lane < 2 && (lane == 0 || two_c)) {
             const int u = lane;
-            const long long g = g0 + warp * ROWS_PER_SAMPLER + rrow[u];
-            const int x = u ? si[1].x : si[0].x;
+            const long long g = g0 + warp * ROWS_PER_SAMPLER + (u ? rc1 : rc0);
+            const int x = u ? xc1 : xc0;
             const int xb = a.x_base ? a.x_base[g] : x;
             if (km_euler(KM)) {   // the pick IS the new state (jump holds pick - x)
               const int xn = x + (u ? jump[1] : jump[0]);
