@@ -875,8 +875,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
 
     if (my_tiles > 0) phase_a(0);
     for (int i = 0; i < my_tiles; ++i) {
-      // the next tile's accumulator is moved first: the cross-CTA hand-shakes of tile i complete in its shadow
-      if (i + 1 < my_tiles) phase_a(i + 1);
       // ---- phase B: sample the rows this CTA owns (warp w: rows 4w .. 4w+3 of the CTA's 32)
       const int tile = pair + i * npairs;
       const int slot = i % RING, gb = i % GBUF;
@@ -940,6 +938,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         have = todo != 0;
         if (have) load_pair();
       }
+      // the next tile's accumulator is moved now: the cross-CTA hand-shakes of tile i and the L2 latency of the first
+      // pair's table rows complete in its shadow
+      if (i + 1 < my_tiles) phase_a(i + 1);
       mbar_wait(&sm.gather_full[gb], (i / GBUF) & 1);
       if ((warp & 3) == 0 && lane == 0) TRACE(2 + (warp >> 2), i, 6);
       if constexpr (KM == KM_RATES || KM == KM_DRIFT) {
