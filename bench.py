@@ -216,7 +216,7 @@ def run_reference(args, w, rank, world):
                          "sample_steps_per_s": n_cpu / t},
         "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -521,7 +521,17 @@ def run_ours(args, w, rank, world, local_rank):
         line["cpu_baseline"] = {"value": flops_per_step(n_cpu, D, S) / tc_ / 1e12, "unit": "TFLOP/s", "cores": os.cpu_count(),
                                 "kind": "port", "sample": f"N={n_cpu} samples x D={D}, {args.cpu_steps} steps of the oracle port",
                                 "ms_per_step": tc_ * 1e3, "sample_steps_per_s": n_cpu / tc_}
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
+
+
+_RESULT_OUT = None
+
+
+def emit(line):
+    """Print the result line on the process's original stdout."""
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(line + "\n")
+    out.flush()
 
 
 def main():
@@ -537,6 +547,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch of the workload (diagnostic)")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 (NCCL prints its version banner
+    # there when NCCL_DEBUG is set) are sent to stderr for the whole run; the result line goes to the saved descriptor
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
