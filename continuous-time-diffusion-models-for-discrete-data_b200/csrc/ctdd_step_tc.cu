@@ -592,6 +592,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         g4[c] = __ldg(reinterpret_cast<const float4*>(tabG + xo + 64 * c));
       }
     }
+    // The row reductions (sum e, sum e*G, sum e*a) and the row scalars of a pass are FINISHED IN THE NEXT PASS: its
+    // per-lane partial sums are carried over, their butterflies run next to the next pass's row-maximum butterfly (three
+    // independent shuffle chains instead of one after the other), and the side record / pre_full arrival follow there.
+    // Only the operand rows (what the MMA waits for) are completed inside the pass itself.
+    float p_sum = 1.f, p_dotg = 0.f, p_dot = 0.f;
+    int p_x = 0, p_r = 0, p_slot = 0;
+    bool p_ok = false, p_have = false, p_close = false;
+    auto finish_prev = [&]() {          // p_sum / p_dotg / p_dot hold the reduced values
+      if (!p_have) return;
+#ifdef CTDD_EXP_NOPRODUCE
+      const float c1 = 1e-6f, c0 = 0.f, lam_tot = CTDD_EXP_NOPRODUCE;
+#else
+      const float rs = __frcp_rn(p_sum);
+      const float rz = (!TAULDR || km_corr(KM)) ? __ldg(rowsumZ + p_x) : 0.f;
+      float c1, c0;
+      if (TAULDR) {
+        c1 = hb * rs;                                            // lam_s = D_s * c1 * Rb[s,x]
+        c0 = 0.f;
+      } else {
+        const float inv = __frcp_rn(fmaf(p_dot, rs, 1e-35f));    // 1 / (pQ[x] + 1e-35)
+        c1 = hb * rs * inv;                                      // lam_s = (D_s * c1 + c0) * Rb[x,s]
+        c0 = hb * 1e-35f * inv;
+      }
+      float lam_tot = fmaf(c1, p_dotg, c0 * rz);
+      if (km_corr(KM)) lam_tot = fmaf(hb, rz, lam_tot);
+#endif
+      // row scalars for the count warp and the samplers (one lane per half-warp)
+      if (l16 == 0) {
+        Side si;
+        si.c1 = c1; si.c0 = c0; si.x = p_x; si.valid = p_ok ? 1 : 0;
+        si.K = 0; si.w[0] = __float_as_uint(lam_tot);
+        sm.side[p_slot][p_r] = si;
+      }
+      if (p_close) {                    // that pass closed its tile: the tile's row scalars are complete now
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.pre_full[p_slot]);
+      }
+      p_have = false;
+    };
     // running state of the compute stream
     int i = 0, ps = 0, st = 0, slot = 0, rslot = 0;
     uint32_t st_par = 1, ring_par = 0;      // parity to wait for on empty[st] / lring_full[rslot]
@@ -609,12 +648,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       if (pw == 0 && lane == 0) TRACE(0, i, 5 + (ps & 1));
       const int r = ROWS_PER_PROD * pw + 2 * ps + half;
 #ifdef CTDD_EXP_NOPRODUCE   // diagnostic build: producers only run the barrier protocol (isolates MMA + phase A + samplers)
-      const float c1 = 1e-6f, c0 = 0.f, lam_tot = CTDD_EXP_NOPRODUCE;
-      (void)stage_s; (void)r; (void)ok;
+      (void)stage_s;
+      finish_prev();
+      const float sum = 1.f, dotg = 0.f, dot = 0.f;
 #else
       float v[16];
       float ml = 0.f;
       if (HEAD) {
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {     // previous pass's reductions: independent of the head arithmetic below
+          p_sum += __shfl_xor_sync(0xffffffffu, p_sum, o);
+          p_dotg += __shfl_xor_sync(0xffffffffu, p_dotg, o);
+          if (!TAULDR) p_dot += __shfl_xor_sync(0xffffffffu, p_dot, o);
+        }
         head_numerators(mu_cur, ls_cur, a.head_fix != 0, l16, v);
       } else {
         const uint32_t src = smem_u32(&sm.lring[pw][rslot][half][4 * l16]);
@@ -628,9 +674,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         for (int c = 0; c < 4; ++c) m4[c] = fmaxf(fmaxf(v[4 * c], v[4 * c + 1]), fmaxf(v[4 * c + 2], v[4 * c + 3]));
         float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        for (int o = 8; o > 0; o >>= 1) {     // this pass's row maximum next to the previous pass's three reductions
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+          p_sum += __shfl_xor_sync(0xffffffffu, p_sum, o);
+          p_dotg += __shfl_xor_sync(0xffffffffu, p_dotg, o);
+          if (!TAULDR) p_dot += __shfl_xor_sync(0xffffffffu, p_dot, o);
+        }
         ml = -m * 1.4426950408889634f;
       }
+      finish_prev();
       // four independent accumulation chains of packed pairs
       float2 sum2[4], dot2[4], dotg2[4];
       const float2 l2e2 = make_float2(1.4426950408889634f, 1.4426950408889634f), ml2 = make_float2(ml, ml);
@@ -671,26 +723,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
           g4[c] = __ldg(reinterpret_cast<const float4*>(tabG + xo + 64 * c));
         }
       }
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) {
-        sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        dotg += __shfl_xor_sync(0xffffffffu, dotg, o);
-        if (!TAULDR) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-      }
-      const float rs = __frcp_rn(sum);
-      if (pw == 0 && lane == 0 && ps == 1) TRACE(0, i, 7);
-      const float rz = (!TAULDR || km_corr(KM)) ? __ldg(rowsumZ + x) : 0.f;
-      float c1, c0;
-      if (TAULDR) {
-        c1 = hb * rs;                                            // lam_s = D_s * c1 * Rb[s,x]
-        c0 = 0.f;
-      } else {
-        const float inv = __frcp_rn(fmaf(dot, rs, 1e-35f));      // 1 / (pQ[x] + 1e-35)
-        c1 = hb * rs * inv;                                      // lam_s = (D_s * c1 + c0) * Rb[x,s]
-        c0 = hb * 1e-35f * inv;
-      }
-      float lam_tot = fmaf(c1, dotg, c0 * rz);
-      if (km_corr(KM)) lam_tot = fmaf(hb, rz, lam_tot);
       // k = 64c + 4*l16 .. +3 lives in K block c, 16-byte chunk l16/2 (XOR-swizzled by the row), half l16&1
       const uint32_t off = (uint32_t)r * 128 + (uint32_t)((((l16 >> 1) ^ (r & 7)) << 4) | ((l16 & 1) << 3));
 #pragma unroll
@@ -703,13 +735,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         sts64(stage_s + SPLIT_BYTES + c * KBLOCK_BYTES + off, m0, m1);
       }
 #endif
-      // row scalars for the count warp and the samplers (one lane per half-warp)
-      if (l16 == 0) {
-        Side si;
-        si.c1 = c1; si.c0 = c0; si.x = x; si.valid = ok ? 1 : 0;
-        si.K = 0; si.w[0] = __float_as_uint(lam_tot);
-        sm.side[slot][r] = si;
-      }
+      // this pass's partial sums and row identity travel to the next pass (finish_prev)
+      p_sum = sum; p_dotg = dotg; p_dot = dot;
+      p_x = x; p_ok = ok; p_r = r; p_slot = slot; p_close = (ps + 1 == PASSES); p_have = true;
       if (++rslot == LRING) { rslot = 0; ring_par ^= 1u; }
       __syncwarp();            // every lane is done with this pass's ring slot: refill it for the pass after next
       x_cur = x_n1;
@@ -720,10 +748,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       if (++ps == PASSES) {     // last pass of the tile
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(full_bar + st);          // operand rows are in place
-          mbar_arrive(&sm.pre_full[slot]);     // row scalars are in place
-        }
+        if (lane == 0) mbar_arrive(full_bar + st);   // operand rows are in place (the row scalars follow in finish_prev)
         if (pw == 0 && lane == 0) TRACE(0, i, 4);
         ps = 0;
         ++i;
@@ -731,6 +756,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         if (++st == STAGES) { st = 0; st_par ^= 1u; }
       }
     }
+    // the last pass's reductions and row scalars
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      p_sum += __shfl_xor_sync(0xffffffffu, p_sum, o);
+      p_dotg += __shfl_xor_sync(0xffffffffu, p_dotg, o);
+      if (!TAULDR) p_dot += __shfl_xor_sync(0xffffffffu, p_dot, o);
+    }
+    finish_prev();
   } else if (warp > COUNT_WARP) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_LIGHT));   // idle warps of the light group
   } else if (warp == COUNT_WARP) {
