@@ -178,7 +178,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // same, for phases completed by arrivals from the partner CTA: acquire at cluster scope once the phase has flipped
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   mbar_wait(bar, parity);
-  asm volatile("fence.acq_rel.cluster;" ::: "memory");
+  // the phase has flipped: one test_wait with acquire semantics at CLUSTER scope (it succeeds at once) orders this
+  // thread after the partner's release-arrive - cheaper than a stand-alone fence.acq_rel.cluster
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
