@@ -488,7 +488,7 @@ def run_ours(args, w, rank, world, local_rank):
         # DRAM bytes of one launch from the committed ncu --set full capture of this kernel at this shape
         # (profiles/r1_step_tc_summary.md: dram__bytes_read.sum + dram__bytes_write.sum); null for other shapes
         if args.workload == "C4" and impl != nat.IMPL_SIMT:
-            roof["traffic"] = 3.305e9      # report r1h (t = 0.5): 3.289 GB read + 0.016 GB written
+            roof["traffic"] = 3.350e9      # report r1i (t = 0.5): 3.334 GB read + 0.016 GB written
         t_floor = max(bytes_step / (pk["hbm"] * 1e9), 3.0 * fl / (pk["tc_burst"] * 1e12))
         roof["t_floor_ms"] = t_floor * 1e3
         roof["frac_of_3pass_floor"] = t_floor / (kern_ms * 1e-3)
