@@ -20,7 +20,12 @@
 //     sampling of tile i.
 //   * Row sampler (the same 8 warps, one warp per row, two rows in flight): lam_s = D_s * c * Rbz[s,x], warp prefix
 //     sum, K inverse-CDF picks (superposition map of ctdd_common.cuh), clamp, rejection, statistics, x_out.  Rows with
-//     K == 0 are settled by one lane.
+//     K == 0 are settled by one lane.  The side record and the R_b table rows (L2 gathers) of the NEXT row pair are requested
+//     while the current pair is searched; the first pair's before phase A of the next tile, which hides their latency.
+//   * Producers finish the row reductions (sum e, sum e*G) and the side record of a pass in the head of the NEXT pass, next
+//     to its row-maximum butterfly; only the operand rows are completed inside the pass.
+//   * The MMA-issue thread acquires the partner CTA's release-arrive with ONE mbarrier.test_wait.acquire.cluster on the
+//     already flipped barrier; a stand-alone fence.acq_rel.cluster there cost 0.2 ms per launch.
 // Warp roles per CTA (5 warpgroups, setmaxnreg 104 / 64): 8 epilogue/sampler warps, 8 producer warps, and a light
 // group with the MMA-issue warp (leader CTA issues; the partner's relays its producers' arrivals), the count warp and
 // 2 idle warps.  profiles/r1_step_tc_summary.md has the measured per-role timeline.
