@@ -58,3 +58,19 @@ def test_install_into_reference_overwrites_the_reference_registries():
     for name in list(ref.lu._LOSSES):
         if hasattr(rl, name):
             ref.lu._LOSSES[name] = getattr(rl, name)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver times next to ours) writes exactly one JSON line to stdout,
+    carrying the metric / unit / config of our arm plus cpu_baseline and a zero-copy e2e block."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "reverse_step_tflops" and d["unit"] == "TFLOP/s"
+    assert d["higher_is_better"] is True and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["value"] > 0
