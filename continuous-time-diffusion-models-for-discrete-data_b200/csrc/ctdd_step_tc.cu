@@ -557,8 +557,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
           const long long g = gf + half;
           if (g < a.rows) {
             long long src = g;
-            if (a.head_bs != (long long)a.D) {
-              const long long n = g / a.D;
+            if (a.head_bs != (long long)a.D) {   // (N, 2D) network output viewed as two (N, D) halves
+              // 32-bit division whenever the row index fits (a 64-bit one is ~100 instructions on the warp's critical path)
+              const long long n = (a.rows <= 0xFFFFFFFFLL) ? (long long)((uint32_t)g / (uint32_t)a.D) : g / a.D;
               src = n * a.head_bs + (g - n * a.D);
             }
             f_mu = __ldg(a.head_mu + src);
