@@ -25,7 +25,7 @@ void count_launch(int n = 1);
 // ------------------------------------------------------------------------------------------------
 // RNG streams (Philox counter word c3)
 enum : uint32_t {
-  STREAM_JUMP = 0,      // per-row tau-leap draws: call 0 word 0 = total count, further words = picks
+  STREAM_JUMP = 0,      // per-row tau-leap draws, per chunk of 32 states: call 0 word 0 = total count, further words = picks
   STREAM_RESERVED = 1,
   STREAM_ROW = 2,       // one 32-bit uniform per row (Euler categorical draw)
   STREAM_INIT = 3,      // initial samples
@@ -65,12 +65,15 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
   return o;
 }
 
-// Tau-leap draws of one GLOBAL row: Philox call c of the row's stream, counter = (c, grow, offset_lo, stream | ...).
-//   call 0 word 0     -> uniform of the row's TOTAL jump count K ~ Poisson(sum_s lam_s)
+// Tau-leap draws of one GLOBAL row: the states are cut into chunks of JUMP_CHUNK consecutive states; chunk q draws its
+// own total and picks from Philox calls (q << 16) + c of the row's stream, counter = (call, grow, offset_lo, stream | ...).
+//   call 0 word 0     -> uniform of the chunk's TOTAL jump count K ~ Poisson(sum of the chunk's lam_s)
 //   call 0 words 1..3 -> uniforms of picks 0..2;  call 1 + (j-3)/4 word (j-3)%4 -> pick j >= 3
 // Each pick chooses its target state ~ Categorical(lam_s / sum) by inverse CDF: S independent Poisson counts through
-// the superposition identity (oracle/rng.py poisson_rows is the op-for-op restatement).
+// the superposition identity, chunks independent of one another (oracle/rng.py poisson_rows is the op-for-op
+// restatement).  One warp of the tensor-path epilogue owns one chunk of a row, so no warp waits for another's total.
 constexpr int JUMP_PICK_CAP = 4096;
+constexpr int JUMP_CHUNK = 32;
 __host__ __device__ __forceinline__ Philox4 philox_rowjump(uint64_t grow, uint32_t call, uint64_t offset, uint64_t seed) {
   return philox4x32_10(call, (uint32_t)grow, (uint32_t)offset,
                        STREAM_JUMP | (((uint32_t)(offset >> 32) & 0xFFFFu) << 8) | (((uint32_t)(grow >> 32) & 0xFFu) << 24),
@@ -165,40 +168,46 @@ __device__ __forceinline__ int inv_cdf(int n, float v, F weight) {
   return last;
 }
 
-// Tau-leap of one row in the oracle's op order (sequential fp32 sums): lam(s) must return the row's rate * h with
-// the entry s == x zeroed, rounded the same way on every call. Returns (sum_j (s_j - x), min(K, cap)).
+// Tau-leap of one row in the oracle's op order (sequential fp32 sums), chunk by chunk (JUMP_CHUNK states share one
+// superposition draw): lam(s) must return the row's rate * h with the entry s == x zeroed, rounded the same way on
+// every call. Returns (sum_j (s_j - x), sum over the chunks of min(K_chunk, cap)).
 template <class F>
 __device__ __forceinline__ int2 tau_leap_row_seq(int S, int x, uint64_t grow, uint64_t offset, uint64_t seed, F lam) {
-  float tot = 0.f;
-  for (int s = 0; s < S; ++s) tot = __fadd_rn(tot, lam(s));
-  const Philox4 p0 = philox_rowjump(grow, 0, offset, seed);
-  int K = poisson_from_unit(tot, u32_to_unit(p0.w[0]));
-  if (K <= 0) return make_int2(0, 0);
-  if (K > JUMP_PICK_CAP) K = JUMP_PICK_CAP;
-  int jump = 0;
-  Philox4 pc = p0;
-  for (int j = 0; j < K; ++j) {
-    uint32_t w;
-    if (j < 3) {
-      w = philox_word(p0, 1 + j);
-    } else {
-      const int i = j - 3;
-      if ((i & 3) == 0) pc = philox_rowjump(grow, 1u + (uint32_t)(i >> 2), offset, seed);
-      w = philox_word(pc, i & 3);
+  int jump = 0, Ksum = 0;
+  for (int c0 = 0, chunk = 0; c0 < S; c0 += JUMP_CHUNK, ++chunk) {
+    const int c1 = (c0 + JUMP_CHUNK < S) ? c0 + JUMP_CHUNK : S;
+    const uint32_t cbase = (uint32_t)chunk << 16;
+    float tot = 0.f;
+    for (int s = c0; s < c1; ++s) tot = __fadd_rn(tot, lam(s));
+    const Philox4 p0 = philox_rowjump(grow, cbase, offset, seed);
+    int K = poisson_from_unit(tot, u32_to_unit(p0.w[0]));
+    if (K <= 0) continue;
+    if (K > JUMP_PICK_CAP) K = JUMP_PICK_CAP;
+    Ksum += K;
+    Philox4 pc = p0;
+    for (int j = 0; j < K; ++j) {
+      uint32_t w;
+      if (j < 3) {
+        w = philox_word(p0, 1 + j);
+      } else {
+        const int i = j - 3;
+        if ((i & 3) == 0) pc = philox_rowjump(grow, cbase + 1u + (uint32_t)(i >> 2), offset, seed);
+        w = philox_word(pc, i & 3);
+      }
+      const float target = __fmul_rn(fminf(u32_to_unit(w), 0.99999994f), tot);
+      float cum = 0.f;
+      int last = c0, pick = -1;
+      for (int s = c0; s < c1; ++s) {
+        const float v = lam(s);
+        cum = __fadd_rn(cum, v);
+        if (v > 0.f) last = s;
+        if (cum > target) { pick = s; break; }
+      }
+      if (pick < 0) pick = last;
+      jump += pick - x;
     }
-    const float target = __fmul_rn(fminf(u32_to_unit(w), 0.99999994f), tot);
-    float cum = 0.f;
-    int last = 0, pick = -1;
-    for (int s = 0; s < S; ++s) {
-      const float v = lam(s);
-      cum = __fadd_rn(cum, v);
-      if (v > 0.f) last = s;
-      if (cum > target) { pick = s; break; }
-    }
-    if (pick < 0) pick = last;
-    jump += pick - x;
   }
-  return make_int2(jump, K);
+  return make_int2(jump, Ksum);
 }
 
 // per-thread statistics counters (CTDD_STAT_* order) and the common end of every jump update

@@ -10,11 +10,13 @@ This module defines that map bit-for-bit the way the CUDA kernels evaluate it:
   * Philox4x32-10 (Salmon et al., SC'11; Random123 constants) keyed on (seed), counter =
     (state s | sub-index, global-row group, call offset, stream id);
   * tau-leap jump counts of one row (poisson_rows): the S independent Poisson(lam_s) counts are drawn through the
-    superposition identity — total K ~ Poisson(sum_s lam_s) by upper-tail inverse CDF on the row's first uniform,
-    then K categorical picks over lam_s / sum by inverse CDF on further uniforms of the same row — which is the
-    same joint law as S independent draws (tests/test_rng_maps.py checks marginals and independence);
-    Philox call c of row g: counter (c, g, offset, STREAM_JUMP); word 0 of call 0 is the total's uniform, words
-    1..3 picks 0..2, call 1 + (j-3)//4 word (j-3)%4 pick j >= 3;
+    superposition identity, chunk by chunk: the states are cut into chunks of 32 consecutive states (one warp of the
+    tensor-path epilogue owns one chunk of a row); per chunk, total K ~ Poisson(sum of the chunk's lam_s) by upper-tail
+    inverse CDF on the chunk's first uniform, then K categorical picks over lam_s / sum by inverse CDF on further
+    uniforms of the same chunk — the same joint law as S independent draws (tests/test_rng_maps.py checks marginals
+    and independence); chunks are independent of one another, so no warp waits for another warp's total;
+    Philox call c of chunk q of row g: counter ((q << 16) + c, g, offset, STREAM_JUMP); word 0 of call 0 is the
+    total's uniform, words 1..3 picks 0..2, call 1 + (j-3)//4 word (j-3)%4 pick j >= 3;
   * per-row uniforms (Euler, initial state, noising): one call serves 4 consecutive rows (word row & 3);
   * v = (word + 0.5) * 2^-32 in fp32; Poisson by upper-tail inverse CDF; categorical by sequential fp32 cumsum.
 """
@@ -24,7 +26,8 @@ import numpy as np
 
 STREAM_JUMP = 0       # per-row tau-leap draws (total count + picks)
 STREAM_RESERVED = 1
-JUMP_PICK_CAP = 4096  # picks evaluated per row (rows whose total exceeds it are clamp-saturated anyway)
+JUMP_PICK_CAP = 4096  # picks evaluated per chunk of a row (rows whose total exceeds it are clamp-saturated anyway)
+JUMP_CHUNK = 32       # consecutive states that share one superposition draw (one warp of the tensor-path epilogue)
 STREAM_ROW = 2
 STREAM_INIT = 3
 STREAM_NOISE_XT = 4
@@ -84,15 +87,15 @@ def rowjump_total_unit(rows: int, row_offset: int, offset: int, seed: int) -> np
     return u32_to_unit(rowjump_words(grow, offset, seed, 0)[:, 0])
 
 
-def rowjump_pick_units(grow: np.ndarray, offset: int, seed: int, npicks: int) -> np.ndarray:
-    """fp32 (len(grow), npicks): pick uniforms j = 0..npicks-1 of the given global rows."""
+def rowjump_pick_units(grow: np.ndarray, offset: int, seed: int, npicks: int, call_base: int = 0) -> np.ndarray:
+    """fp32 (len(grow), npicks): pick uniforms j = 0..npicks-1 of the given global rows (chunk with Philox call base call_base)."""
     grow = np.asarray(grow, dtype=np.uint64)
     out = np.empty((grow.shape[0], npicks), dtype=np.float32)
-    first = rowjump_words(grow, offset, seed, 0)
+    first = rowjump_words(grow, offset, seed, call_base)
     for j in range(min(3, npicks)):
         out[:, j] = u32_to_unit(first[:, 1 + j])
     for c in range(1, 1 + (max(npicks - 3, 0) + 3) // 4):
-        w = rowjump_words(grow, offset, seed, c)
+        w = rowjump_words(grow, offset, seed, call_base + c)
         for i in range(4):
             j = 3 + 4 * (c - 1) + i
             if j < npicks:
@@ -191,31 +194,25 @@ def inv_cdf(weights: np.ndarray, v: np.ndarray) -> np.ndarray:
     return first.astype(np.int64)
 
 
-def poisson_rows(lam: np.ndarray, row_offset: int, offset: int, seed: int):
-    """Jump counts k[r, s] ~ independent Poisson(lam[r, s]) through the superposition map (module docstring).
-
-    lam (rows, S) fp32 >= 0. Returns (counts (rows, S) int64, total (rows,) int64); counts.sum(1) == min(total, cap).
-    Op order = device order of the CUDA-core kernels: sequential fp32 cumsum over s, total = last cumsum entry,
-    K = poisson_from_unit(total, v0), pick j = first s with cum[s] > min(v_j, 1 - 2^-24) * total.
-    """
-    lam = np.ascontiguousarray(lam, dtype=np.float32)
-    rows, S = lam.shape
+def _poisson_chunk(lam: np.ndarray, grow: np.ndarray, call_base: int, offset: int, seed: int):
+    """One chunk of states of poisson_rows: (counts (rows, n) int64, K (rows,) int64); Philox calls call_base + c."""
+    rows, n = lam.shape
     cum = np.cumsum(lam, axis=1, dtype=np.float32)
     tot = cum[:, -1]
-    v0 = rowjump_total_unit(rows, row_offset, offset, seed)
+    v0 = u32_to_unit(rowjump_words(grow, offset, seed, call_base)[:, 0])
     K = poisson_from_unit(tot, v0)
-    counts = np.zeros((rows, S), dtype=np.int64)
+    counts = np.zeros((rows, n), dtype=np.int64)
     idx = np.flatnonzero(K > 0)
     if idx.size == 0:
         return counts, K
     Kc = np.minimum(K[idx], JUMP_PICK_CAP)
     kmax = int(Kc.max())
-    picks = rowjump_pick_units(idx.astype(np.uint64) + np.uint64(row_offset), offset, seed, kmax)
+    picks = rowjump_pick_units(grow[idx], offset, seed, kmax, call_base)
     w = lam[idx]
     c = cum[idx]
     t = tot[idx]
     posw = w > 0
-    last = np.where(posw.any(axis=1), S - 1 - posw[:, ::-1].argmax(axis=1), 0)
+    last = np.where(posw.any(axis=1), n - 1 - posw[:, ::-1].argmax(axis=1), 0)
     for j in range(kmax):
         live = Kc > j
         if not live.any():
@@ -225,4 +222,26 @@ def poisson_rows(lam: np.ndarray, row_offset: int, offset: int, seed: int):
         s_j = np.where(gt.any(axis=1), gt.argmax(axis=1), last)
         li = np.flatnonzero(live)
         np.add.at(counts, (idx[li], s_j[li]), 1)
+    return counts, K
+
+
+def poisson_rows(lam: np.ndarray, row_offset: int, offset: int, seed: int):
+    """Jump counts k[r, s] ~ independent Poisson(lam[r, s]) through the chunked superposition map (module docstring).
+
+    lam (rows, S) fp32 >= 0. Returns (counts (rows, S) int64, total (rows,) int64); counts.sum(1) == sum over the
+    chunks of min(K_chunk, cap).  The S states are cut into chunks of JUMP_CHUNK = 32 consecutive states; every chunk
+    is an independent superposition draw.  Op order = device order of the CUDA-core kernels: sequential fp32 cumsum
+    over the chunk's states, total = last cumsum entry, K = poisson_from_unit(total, v0), pick j = first s with
+    cum[s] > min(v_j, 1 - 2^-24) * total; Philox call index of chunk c = (c << 16) + call.
+    """
+    lam = np.ascontiguousarray(lam, dtype=np.float32)
+    rows, S = lam.shape
+    grow = np.arange(rows, dtype=np.uint64) + np.uint64(row_offset)
+    counts = np.zeros((rows, S), dtype=np.int64)
+    K = np.zeros(rows, dtype=np.int64)
+    for ci, c0 in enumerate(range(0, S, JUMP_CHUNK)):
+        c1 = min(c0 + JUMP_CHUNK, S)
+        kc, Kc = _poisson_chunk(lam[:, c0:c1], grow, ci << 16, offset, seed)
+        counts[:, c0:c1] = kc
+        K += Kc
     return counts, K
