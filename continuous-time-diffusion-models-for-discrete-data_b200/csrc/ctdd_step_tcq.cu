@@ -1,0 +1,767 @@
+// tcgen05 reverse-step kernel for S == 256 (configs C3/C4/C5), every mode except the Euler ones: the (N*D x S)(S x S)
+// contraction of lib/sampling/sampling.py:57 on 5th-generation tensor cores, fused with softmax, the q_{t|0}
+// denominators, the forward-rate multiply and the Philox state update (tau-leap / corrector sampling.py:127-221,
+// midpoint :423-503, rates only :31-78).
+//
+// One CTA PAIR (thread-block cluster of 2, tcgen05 cta_group::2) owns a sequence of 128-row tiles:
+//   D[s, row] = sum_k Q^T[s, k] * a[row, k]        M = 256 states (128 per CTA), N = 128 rows, K = 256
+//   * M side = state s. Each CTA keeps ITS 128-state half of Q^T (bf16 hi + mid split, 2 x 128 TMEM columns) resident
+//     in tensor memory as the A operand (TS form) for the whole kernel; 2 accumulators of 128 columns.  With N = 128
+//     an instruction sits on the 64-cycle floor of the TS form (the A slice is read from tensor memory at 64 B/cycle).
+//   * N side = data rows; each CTA produces 64 rows of a tile.  Producer warps work on two rows per pass, 16 lanes per
+//     row: raw fp32 logits through a per-warp smem ring filled by cp.async.bulk (HBM -> L2 prefetch some tiles ahead),
+//     row softmax by half-warp butterflies, gathered reciprocal denominators 1/(Q[k,x]+eps), bf16 hi/mid split, K-major
+//     128B-swizzled smem stage.  The passes of a tile are dealt round-robin to the producer warps.  The row scalars
+//     (rate scale, state, band of non-zero base rates) go to BOTH CTAs of the pair (st.async into the partner).
+//   * 3 tensor passes  Qh*ah + Qh*am + Qm*ah  accumulate in fp32 TMEM (48 tcgen05.mma of N = 128 per tile).
+//   * Epilogue, lane = state: warp (q, h) reads its 32 states x 32 rows with tcgen05.ld (two batches per tile), gathers
+//     R_b[s, x_row] for all 32 rows at once (32 independent coalesced 128-byte loads in flight; chunks outside the
+//     band of non-zero base rates of x are skipped), forms lam[s, row] and reduces over its 32 states for all 32
+//     rows with a 31-shuffle transposing butterfly, which leaves lane = row.  A warp's 32 states are one CHUNK of the
+//     chunked superposition map (ctdd_common.cuh): each chunk of a row draws its own jump count K ~ Poisson(chunk total)
+//     and its own picks, so no warp ever waits for another warp's total.  Rows with a pick in this chunk (rare per
+//     chunk) are then scanned over the 32 lanes (prefix sums, ballot = first state above the target).
+//   * The per-(row, chunk) results (sum of jumps, jump count / partial drift) are 8 bytes each; they go to the CTA that
+//     produced the row (plain st.shared or st.async + complete_tx), whose two finalizer warps (lane = row) add the 8
+//     chunks, apply the clamp / rejection rule and write x_out coalesced.
+// Nothing but those 8-byte records and the row scalars crosses between the CTAs of a pair.
+// Warp roles per CTA: 8 epilogue warps, NPW producer warps, and a light group with the MMA-issue warp (leader CTA
+// issues; the partner's relays its producers' arrivals), one idle warp and the 2 finalizer warps.
+#include "ctdd_tc_common.cuh"
+
+namespace ctdd {
+namespace tcq {
+using namespace tc;
+
+constexpr int NH = 64;                 // rows of a tile produced and finalized by one CTA
+constexpr int NT = 2 * NH;             // rows per pair tile (= UMMA N)
+constexpr int STAGES = 2;              // smem operand stages (64 KB each)
+constexpr int ACC = 2;                 // TMEM accumulator buffers (NT columns each)
+constexpr int CBUF = 2;                // contribution buffers (epilogue -> finalizer)
+constexpr int RING = 8;                // per-tile row-scalar ring (> STAGES + ACC + CBUF)
+constexpr int NUM_EPI_WARPS = 8;       // warps 0-7: TMEM quadrant w&3, column half w>>2 (= CTA that owns those rows)
+constexpr int FIRST_PROD_WARP = 8;
+#ifndef CTDD_TCQ_NPW
+#define CTDD_TCQ_NPW 12
+#endif
+constexpr int NPW = CTDD_TCQ_NPW;      // producer warps (a multiple of 4: register budgets are per 4-warp group)
+constexpr int MMA_WARP = FIRST_PROD_WARP + NPW;   // light group: MMA issue / relay, idle, 2 finalizer warps
+constexpr int FIN_WARP0 = MMA_WARP + 2;
+constexpr int NUM_THREADS = (FIRST_PROD_WARP + NPW + 4) * 32;
+// setmaxnreg targets.  The registers handed out by .inc are the ones the CTA's own warps released with .dec:
+// 8 * EPI + NPW * PROD + 4 * LIGHT must not exceed (12 + NPW) * (launch allocation), or the .inc never returns.
+constexpr int REGS_LAUNCH = (65536 / NUM_THREADS) & ~7;          // what __launch_bounds__ gives every thread
+constexpr int REGS_LIGHT = 48;
+constexpr int REGS_PROD = NPW == 12 ? 80 : 96;
+constexpr int REGS_EPI = NPW == 12 ? 96 : 112;
+static_assert(NUM_EPI_WARPS * REGS_EPI + NPW * REGS_PROD + 4 * REGS_LIGHT <= (NUM_EPI_WARPS + NPW + 4) * REGS_LAUNCH,
+              "setmaxnreg budget exceeds the launch allocation");
+constexpr int PASSES_PER_TILE = NH / 2;                          // 32 two-row passes per tile and CTA
+constexpr int KBLOCK_BYTES = NH * 128;         // one 64-wide K block of one split: NH rows x 128 B
+constexpr int SPLIT_BYTES = 4 * KBLOCK_BYTES;  // K = 256 -> 4 blocks
+constexpr int STAGE_BYTES = 2 * SPLIT_BYTES;   // hi + mid
+constexpr int TM_QH = 0, TM_QM = 128, TM_ACC = 256;  // TMEM column map (accumulator b at TM_ACC + b * NT)
+constexpr int PREFETCH_TILES = 4;      // HBM -> L2 bulk-prefetch distance (tiles of this pair's sequence)
+constexpr int LRING = 2;               // per-producer-warp ring of raw logits row pairs filled by cp.async.bulk
+constexpr uint32_t IDESC = make_idesc(NT);
+constexpr int NCHUNK = S / JUMP_CHUNK;                           // 8 chunks of 32 states per row
+constexpr uint32_t SCAL_TX_BYTES = NH * 12;                      // row scalars the partner sends per tile
+constexpr uint32_t CONTRIB_TX_BYTES = (NUM_EPI_WARPS / 2) * 2 * 32 * 8;   // records the partner's 4 warps send per tile
+
+struct Smem {
+  alignas(1024) uint8_t stage[STAGES][STAGE_BYTES];
+  alignas(16) float lring[NPW][LRING][2][S];   // raw fp32 logits rows, one pass ahead of their use
+  alignas(16) float2 scal_c[RING][NT];         // (c1, c0) of the tile's rows: rows 0..63 from CTA 0, 64..127 from CTA 1
+  uint32_t scal_x[RING][NT];                   // x | band_lo << 8 | band_hi << 16 | valid << 24
+  alignas(16) int2 contrib[CBUF][NCHUNK][NH];  // per (chunk, row of THIS CTA): (sum of jumps | drift bits, jump count)
+  uint32_t band[S];                            // band of non-zero base rates per state x (this launch's branch / mode)
+  alignas(8) uint64_t full[STAGES];            // leader CTA: its 32 passes + 1 relayed arrival for the partner's 32
+  uint64_t full_local[STAGES];                 // partner CTA: its 32 passes; the partner's idle MMA warp relays the phase
+  uint64_t empty[STAGES];                      // multicast tcgen05.commit
+  uint64_t scal_full[RING];                    // 32 local passes + the partner's bytes (st.async complete_tx)
+  uint64_t lring_full[NPW][LRING];             // cp.async.bulk complete_tx of one row pair
+  uint64_t tmem_full[ACC];                     // multicast tcgen05.commit
+  uint64_t tmem_empty[ACC];                    // used in the leader CTA: 8 local + 8 remote epilogue warps
+  uint64_t contrib_full[CBUF];                 // 4 local epilogue warps + the bytes of the partner's 4 warps
+  uint64_t contrib_free_local[CBUF];           // the 2 local finalizer warps are done with this CTA's buffer
+  uint64_t contrib_free_remote[CBUF];          // the 2 finalizer warps of the PARTNER are done with the partner's buffer
+  uint32_t tmem_base;
+};
+
+static_assert(sizeof(Smem) + 1024 <= 232448, "shared memory budget of one CTA (227 KB) exceeded");
+static_assert(RING > STAGES + ACC + CBUF, "row-scalar ring shorter than the pipeline");
+
+// sum over the warp's 32 lanes of w[j] for all 32 j at once: afterwards w[0] of lane L is the total of index L
+// (31 shuffles instead of 32 x 5; each step halves the number of live indices per lane)
+template <int M>
+__device__ __forceinline__ void transpose_reduce_step(float (&w)[32], int lane) {
+  const bool up = (lane & M) != 0;
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+    const float keep = up ? w[i + M] : w[i];
+    const float send = up ? w[i] : w[i + M];
+    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, M);
+  }
+}
+__device__ __forceinline__ float transpose_reduce(float (&w)[32], int lane) {
+  transpose_reduce_step<16>(w, lane);
+  transpose_reduce_step<8>(w, lane);
+  transpose_reduce_step<4>(w, lane);
+  transpose_reduce_step<2>(w, lane);
+  transpose_reduce_step<1>(w, lane);
+  return w[0];
+}
+// w[r] for a warp-uniform runtime index r, without indexed register access (31 selects)
+__device__ __forceinline__ float select32(const float (&w)[32], int r) {
+  float a[16], b[8], c[4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (r & 16) ? w[i + 16] : w[i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = (r & 8) ? a[i + 8] : a[i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (r & 4) ? b[i + 4] : b[i];
+  const float d0 = (r & 2) ? c[2] : c[0], d1 = (r & 2) ? c[3] : c[1];
+  return (r & 1) ? d1 : d0;
+}
+
+// TAULDR: tauLDR rates (else SDDM reverse_prob); KM: KM_JUMP / KM_CORR / KM_RATES / KM_DRIFT;
+// HEAD: the rows' softmax numerators come from the truncated-logistic head (mu, log_scale per row) instead of logits
+template <bool TAULDR, int KM, bool HEAD>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step_q_kernel(const Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();       // state half owned by this CTA; rank 0 issues the MMAs
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+  const int my_tiles = (a.num_tiles > pair) ? (a.num_tiles - pair + npairs - 1) / npairs : 0;
+  constexpr bool SAMPLES = (KM != KM_RATES);     // contributions + finalizers exist
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&sm.full[i], PASSES_PER_TILE + 1);
+      mbar_init(&sm.full_local[i], PASSES_PER_TILE);
+      mbar_init(&sm.empty[i], 1);
+    }
+    for (int i = 0; i < RING; ++i) mbar_init(&sm.scal_full[i], PASSES_PER_TILE);
+    for (int w = 0; w < NPW; ++w)
+      for (int i = 0; i < LRING; ++i) mbar_init(&sm.lring_full[w][i], 1);
+    for (int i = 0; i < ACC; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], 2 * NUM_EPI_WARPS); }
+    for (int i = 0; i < CBUF; ++i) {
+      mbar_init(&sm.contrib_full[i], NUM_EPI_WARPS / 2);
+      mbar_init(&sm.contrib_free_local[i], 2);
+      mbar_init(&sm.contrib_free_remote[i], 2);
+    }
+    fence_barrier_init();
+  }
+  // band of non-zero base rates of every state (exact zero pattern of the gathered table rows, union for the corrector)
+  for (int x = threadIdx.x; x < S; x += NUM_THREADS) {
+    const int bt = reinterpret_cast<const int*>(a.stat + ST_BANDT_OFF)[x];
+    const int br = reinterpret_cast<const int*>(a.stat + ST_BANDR_OFF)[x];
+    int lo, hi;
+    if (TAULDR && km_corr(KM)) {
+      lo = min(bt & 255, br & 255);
+      hi = max((bt >> 8) & 255, (br >> 8) & 255);
+    } else {
+      const int b = TAULDR ? bt : br;
+      lo = b & 255; hi = (b >> 8) & 255;
+    }
+    if (KM == KM_RATES) { lo = 0; hi = S - 1; }   // the rates output keeps the diagonal: every chunk is read
+    sm.band[x] = (uint32_t)(lo << 8) | (uint32_t)(hi << 16);
+  }
+  if (warp == MMA_WARP) tmem_alloc(&sm.tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  // Q^T half of this CTA -> tensor memory (A operand). Warp q < 4 owns TMEM lanes [32q, 32q+32).
+  if (warp < 4) {
+    const int srow = (int)rank * 128 + warp * 32 + lane;
+#pragma unroll 1
+    for (int split = 0; split < 2; ++split) {
+      const uint4* src = reinterpret_cast<const uint4*>(a.tab + (split ? TAB_QM_OFF : TAB_QH_OFF)) + (size_t)srow * 32;
+#pragma unroll 1
+      for (int c = 0; c < 128; c += 32) {
+        uint32_t r[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 v = __ldg(src + (c >> 2) + i);
+          r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+        }
+        tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + (split ? TM_QM : TM_QH) + c, r);
+      }
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  cluster_sync_all();    // barriers initialised and both A halves resident before any cross-CTA traffic
+  tc_fence_after();
+
+  if (warp >= FIRST_PROD_WARP && warp < MMA_WARP) {
+    if constexpr (REGS_PROD > REGS_LAUNCH) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
+    else if constexpr (REGS_PROD < REGS_LAUNCH) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
+    // ======================================================================== producers: 16 lanes per row, 2 rows per pass
+    const int pw = warp - FIRST_PROD_WARP;
+    const int half = lane >> 4, l16 = lane & 15;
+    // lane owns k = 64c + 4*l16 .. +3 for c = 0..3; each softmax reduction is a 4-step butterfly inside the half-warp
+    // (two independent rows per warp keep the pipes busy).  The raw logits rows arrive through a small smem ring that
+    // cp.async.bulk fills two passes ahead, so no global-memory latency sits on the warp's critical path.
+    const float* tabA = reinterpret_cast<const float*>(a.tab + TAB_A_OFF) + 4 * l16;
+    const float hb = (KM == KM_RATES) ? 1.0f : a.h * a.beta;   // rates-only ignores the step length
+    const bool contiguous = (a.ld == S) && (a.batch_stride == (long long)a.D * S);
+    uint64_t* const full_bar = rank == 0 ? &sm.full[0] : &sm.full_local[0];
+    const long long total_pass = (long long)my_tiles * PASSES_PER_TILE;   // passes of this CTA; warp pw takes pw, pw + NPW, ..
+    const uint32_t scal_c_remote = mapa(smem_u32(&sm.scal_c[0][0]), rank ^ 1u);
+    const uint32_t scal_x_remote = mapa(smem_u32(&sm.scal_x[0][0]), rank ^ 1u);
+    const uint32_t scal_full_remote = mapa(smem_u32(&sm.scal_full[0]), rank ^ 1u);
+
+    auto row_ptr = [&](long long g) -> const float* {
+      if (contiguous) return a.logits + g * S;
+      const uint32_t n = (uint32_t)g / (uint32_t)a.D, d = (uint32_t)g - n * (uint32_t)a.D;
+      return a.logits + (long long)n * a.batch_stride + (long long)d * a.ld;
+    };
+    // first global row of pass P of this CTA
+    auto pass_row = [&](long long P) -> long long {
+      const long long tl = P / PASSES_PER_TILE;
+      return ((long long)pair + tl * npairs) * NT + (long long)rank * NH + 2 * (P - tl * PASSES_PER_TILE);
+    };
+    // Fetch stream (two passes of this warp ahead of the compute stream): lane 0 starts the bulk copy of the row pair
+    // (rows past the end are replaced by row 0: never used; adjacent rows of a contiguous logits tensor travel as one
+    // 2 KB copy); every lane fetches the state of its half's row
+    long long Pf = pw;
+    int f_slot = 0;
+    float f_mu = 0.f, f_ls = 0.f;        // HEAD: head parameters of the row fetch() just visited
+    auto fetch = [&]() -> int {
+      int xv = -1;
+      if (Pf < total_pass) {
+        const long long gf = pass_row(Pf);
+        if (HEAD) {
+          const long long g = gf + half;
+          if (g < a.rows) {
+            long long src = g;
+            if (a.head_bs != (long long)a.D) {   // (N, 2D) network output viewed as two (N, D) halves
+              // 32-bit division whenever the row index fits (a 64-bit one is ~100 instructions on the warp's critical path)
+              const long long n = (a.rows <= 0xFFFFFFFFLL) ? (long long)((uint32_t)g / (uint32_t)a.D) : g / a.D;
+              src = n * a.head_bs + (g - n * a.D);
+            }
+            f_mu = __ldg(a.head_mu + src);
+            f_ls = __ldg(a.head_ls + src);
+          }
+        } else if (lane == 0) {
+          uint64_t* bar = &sm.lring_full[pw][f_slot];
+          mbar_arrive_expect_tx(bar, 2 * S * 4);
+          if (contiguous && gf + 1 < a.rows) {
+            bulk_g2s(&sm.lring[pw][f_slot][0][0], a.logits + gf * S, 2 * S * 4, bar);
+          } else {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              const long long gg = (gf + hf < a.rows) ? gf + hf : 0;
+              bulk_g2s(&sm.lring[pw][f_slot][hf][0], row_ptr(gg), S * 4, bar);
+            }
+          }
+          if (contiguous) {   // pull the same two rows of a later tile from HBM into L2
+            const long long r0 = gf + (long long)PREFETCH_TILES * npairs * NT;
+            if (r0 + 2 <= a.rows) l2_prefetch_bulk(a.logits + r0 * S, 2 * S * 4);
+          }
+        }
+        if (gf + half < a.rows) xv = __ldg(a.x_eval + gf + half);
+        Pf += NPW;
+        f_slot = (f_slot + 1 == LRING) ? 0 : f_slot + 1;
+      }
+      return xv;
+    };
+
+    int x_cur = fetch();
+    float mu_cur = f_mu, ls_cur = f_ls;
+    int x_n1 = fetch();
+    float mu_n1 = f_mu, ls_n1 = f_ls;
+    float4 t4[4];
+    {
+      const size_t xo = (size_t)(x_cur < 0 ? 0 : x_cur) << 8;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) t4[c] = __ldg(reinterpret_cast<const float4*>(tabA + xo + 64 * c));
+    }
+    // The row reductions (sum e, sum e*Q[.,x]) and the row scalars of a pass are FINISHED IN THE NEXT PASS: its per-lane
+    // partial sums are carried over, their butterflies run next to the next pass's row-maximum butterfly, and the
+    // scalar records / scal_full arrival follow there.  Only the operand rows (what the MMA waits for) are completed
+    // inside the pass itself.
+    float p_sum = 1.f, p_dot = 0.f;
+    int p_x = 0, p_r = 0, p_slot = 0;
+    bool p_ok = false, p_have = false, p_first = false;
+    auto finish_prev = [&]() {          // p_sum / p_dot hold the reduced values
+      if (!p_have) return;
+      const float rs = __frcp_rn(p_sum);
+      float c1, c0;
+      if (TAULDR) {
+        c1 = hb * rs;                                            // lam_s = D_s * c1 * Rb[s,x]
+        c0 = 0.f;
+      } else {
+        const float inv = __frcp_rn(fmaf(p_dot, rs, 1e-35f));    // 1 / (pQ[x] + 1e-35)
+        c1 = hb * rs * inv;                                      // lam_s = (D_s * c1 + c0) * Rb[x,s]
+        c0 = hb * 1e-35f * inv;
+      }
+      if (l16 == 0) {   // one lane per half-warp: the row's scalars into BOTH CTAs of the pair
+        const uint32_t sx = (uint32_t)p_x | sm.band[p_x] | (p_ok ? (1u << 24) : 0u);
+        const int idx = p_slot * NT + (int)rank * NH + p_r;
+        (&sm.scal_c[0][0])[idx] = make_float2(c1, c0);
+        (&sm.scal_x[0][0])[idx] = sx;
+        const uint32_t bar = scal_full_remote + (uint32_t)p_slot * 8u;
+        st_async_cluster_v2(scal_c_remote + (uint32_t)idx * 8u, __float_as_uint(c1), __float_as_uint(c0), bar);
+        st_async_cluster_b32(scal_x_remote + (uint32_t)idx * 4u, sx, bar);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        // the first pass of a tile also announces the bytes the partner's producers deliver for this tile
+        if (p_first) mbar_arrive_expect_tx(&sm.scal_full[p_slot], SCAL_TX_BYTES);
+        else mbar_arrive(&sm.scal_full[p_slot]);
+      }
+      p_have = false;
+    };
+    int rslot = 0;
+    uint32_t ring_par = 0;       // parity to wait for on lring_full[rslot]
+    long long last_tl = -1;
+#pragma unroll 1
+    for (long long P = pw; P < total_pass; P += NPW) {
+      const long long tl = P / PASSES_PER_TILE;
+      const int ps = (int)(P - tl * PASSES_PER_TILE);
+      const int st = (int)(tl % STAGES);
+      const int slot = (int)(tl % RING);
+      const bool ok = x_cur >= 0;
+      const int x = ok ? x_cur : 0;
+      if (!HEAD) mbar_wait(&sm.lring_full[pw][rslot], ring_par);
+      const int r = 2 * ps + half;
+      float v[16];
+      float ml = 0.f;
+      if (HEAD) {
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {     // previous pass's reductions: independent of the head arithmetic below
+          p_sum += __shfl_xor_sync(0xffffffffu, p_sum, o);
+          if (!TAULDR) p_dot += __shfl_xor_sync(0xffffffffu, p_dot, o);
+        }
+        head_numerators(mu_cur, ls_cur, a.head_fix != 0, l16, v);
+      } else {
+        const uint32_t src = smem_u32(&sm.lring[pw][rslot][half][4 * l16]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 q4 = lds128(src + 256 * c);
+          v[4 * c] = q4.x; v[4 * c + 1] = q4.y; v[4 * c + 2] = q4.z; v[4 * c + 3] = q4.w;
+        }
+        float m4[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) m4[c] = fmaxf(fmaxf(v[4 * c], v[4 * c + 1]), fmaxf(v[4 * c + 2], v[4 * c + 3]));
+        float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {     // this pass's row maximum next to the previous pass's reductions
+          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+          p_sum += __shfl_xor_sync(0xffffffffu, p_sum, o);
+          if (!TAULDR) p_dot += __shfl_xor_sync(0xffffffffu, p_dot, o);
+        }
+        ml = -m * 1.4426950408889634f;
+      }
+      finish_prev();
+      if (tl != last_tl) {       // first pass of this warp in a new tile: the tile's operand stage must be free
+        mbar_wait(&sm.empty[st], (uint32_t)(((tl / STAGES) & 1) ^ 1));
+        last_tl = tl;
+      }
+      const uint32_t stage_s = smem_u32(sm.stage[st]);
+#ifdef CTDD_EXP_NOPRODUCE    // diagnostic build: producers only run the barrier protocol (isolates MMA + epilogue)
+      (void)stage_s; (void)ml; (void)r;
+      const float sum = 1.f, dot = 0.f;
+#else
+      // four independent accumulation chains of packed pairs
+      float2 sum2[4], dot2[4];
+      const float2 l2e2 = make_float2(1.4426950408889634f, 1.4426950408889634f), ml2 = make_float2(ml, ml);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        sum2[c] = make_float2(0.f, 0.f); dot2[c] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int e = 0; e < 4; e += 2) {
+          const float2 tq = e == 0 ? make_float2(t4[c].x, t4[c].y) : make_float2(t4[c].z, t4[c].w);
+          float2 ex = make_float2(v[4 * c + e], v[4 * c + e + 1]);                 // HEAD: already the numerators
+          if (!HEAD) {
+            const float2 arg = ffma2(ex, l2e2, ml2);
+            ex = make_float2(ex2_approx(arg.x), ex2_approx(arg.y));                // exp(v - max)
+          }
+          sum2[c] = fadd2(sum2[c], ex);
+          if (!TAULDR) dot2[c] = ffma2(ex, tq, dot2[c]);
+          const float2 op = TAULDR ? fmul2(ex, tq) : ex;   // tauLDR operand: e_k / (Q[k,x] + eps); 1/sum applied by the epilogue
+          v[4 * c + e] = op.x; v[4 * c + e + 1] = op.y;
+        }
+      }
+      const float2 s01 = fadd2(sum2[0], sum2[1]), s23 = fadd2(sum2[2], sum2[3]), sall = fadd2(s01, s23);
+      const float sum = sall.x + sall.y;
+      float dot = 0.f;
+      if (!TAULDR) {
+        const float2 d01 = fadd2(dot2[0], dot2[1]), d23 = fadd2(dot2[2], dot2[3]), dall = fadd2(d01, d23);
+        dot = dall.x + dall.y;
+      }
+      // the table row of the NEXT pass is requested as soon as this pass's has been consumed
+      {
+        const size_t xo = (size_t)(x_n1 < 0 ? 0 : x_n1) << 8;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) t4[c] = __ldg(reinterpret_cast<const float4*>(tabA + xo + 64 * c));
+      }
+      // k = 64c + 4*l16 .. +3 lives in K block c, 16-byte chunk l16/2 (XOR-swizzled by the row), half l16&1
+      const uint32_t off = (uint32_t)r * 128 + (uint32_t)((((l16 >> 1) ^ (r & 7)) << 4) | ((l16 & 1) << 3));
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t h0, m0, h1, m1;
+        split2(v[4 * c], v[4 * c + 1], h0, m0);
+        split2(v[4 * c + 2], v[4 * c + 3], h1, m1);
+        if (!ok) h0 = m0 = h1 = m1 = 0u;
+        sts64(stage_s + c * KBLOCK_BYTES + off, h0, h1);
+        sts64(stage_s + SPLIT_BYTES + c * KBLOCK_BYTES + off, m0, m1);
+      }
+#endif
+      // this pass's partial sums and row identity travel to the next pass (finish_prev)
+      p_sum = sum; p_dot = dot;
+      p_x = x; p_ok = ok; p_r = r; p_slot = slot; p_first = (ps == 0); p_have = true;
+      if (++rslot == LRING) { rslot = 0; ring_par ^= 1u; }
+      fence_proxy_async();
+      __syncwarp();            // every lane is done with this pass's ring slot and has written its operand rows
+      if (lane == 0) mbar_arrive(full_bar + st);
+      x_cur = x_n1;
+      if (HEAD) { mu_cur = mu_n1; ls_cur = ls_n1; }
+      x_n1 = fetch();
+      if (HEAD) { mu_n1 = f_mu; ls_n1 = f_ls; }
+    }
+    // the last pass's reductions and row scalars
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      p_sum += __shfl_xor_sync(0xffffffffu, p_sum, o);
+      if (!TAULDR) p_dot += __shfl_xor_sync(0xffffffffu, p_dot, o);
+    }
+    finish_prev();
+  } else if (warp == MMA_WARP + 1) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_LIGHT));   // idle warp of the light group
+  } else if (warp >= FIN_WARP0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_LIGHT));
+    // ======================================================================== finalizers: lane = row of this CTA
+    if constexpr (SAMPLES) {
+      const int r = (warp - FIN_WARP0) * 32 + lane;          // row of the tile's 64 that this CTA produced
+      const uint32_t cfree_remote = mapa(smem_u32(&sm.contrib_free_remote[0]), rank ^ 1u);
+      RowStats stt = {0, 0, 0, 0, 0};
+      for (int i = 0; i < my_tiles; ++i) {
+        const int tile = pair + i * npairs, slot = i % RING, cb = i % CBUF;
+        const long long g = (long long)tile * NT + (long long)rank * NH + r;
+        mbar_wait(&sm.scal_full[slot], (i / RING) & 1);
+        const uint32_t sx = sm.scal_x[slot][rank * NH + r];
+        const int x = (int)(sx & 255u);
+        const bool valid = (sx >> 24) & 1u;
+        int xb = x;
+        if (a.x_base && valid) xb = __ldg(a.x_base + g);
+        mbar_wait(&sm.contrib_full[cb], (i / CBUF) & 1);
+        int jump = 0, cnt = 0;
+        float drift = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) {
+          const int2 v = sm.contrib[cb][c][r];
+          if (KM == KM_DRIFT) drift += __int_as_float(v.x); else jump += v.x;
+          cnt += v.y;
+        }
+        if (valid) {
+          if (KM == KM_DRIFT) {
+            // sampling.py:433-453: x' = clip(x + round_half_even(h/2 * sum_s rr_s (s - x)))
+            const int ch = (int)rintf(0.5f * drift);
+            int xn = x + ch;
+            xn = xn < 0 ? 0 : (xn > S - 1 ? S - 1 : xn);
+            a.x_out[g] = xn;
+            stt.changed_base += (xn != x);
+            stt.changed_eval += (xn != x);
+            stt.nonzero += (ch != 0);
+          } else {
+            a.x_out[g] = finalize_jump(xb, x, jump, cnt, a.reject_multi, S, stt);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&sm.contrib_free_local[cb]);
+          mbar_arrive_cluster_relaxed(cfree_remote + (uint32_t)cb * 8u);
+        }
+      }
+      if (a.stats) {
+        const int v[5] = {stt.changed_base, stt.nonzero, stt.changed_eval, stt.jumped, stt.multi};
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const int tot = warp_sum_int(v[k]);
+          if (lane == 0 && tot) atomicAdd(a.stats + k, (unsigned long long)tot);
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_LIGHT));
+    // ======================================================================== MMA issue (one thread of the leader CTA)
+    if (rank == 0 && lane == 0) {
+      for (int i = 0; i < my_tiles; ++i) {
+        const int st = i % STAGES, b = i % ACC;
+        mbar_wait_cluster(&sm.full[st], (i / STAGES) & 1);
+        mbar_wait(&sm.tmem_empty[b], ((i / ACC) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + TM_ACC + b * NT;
+        // one descriptor per tile; the 48 instructions differ only by compile-time offsets (16-byte units, low word)
+        const uint64_t bd0 = make_b_desc(smem_u32(sm.stage[st]));
+        const uint32_t bd_lo = (uint32_t)bd0, bd_hi = (uint32_t)(bd0 >> 32);
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t a_tmem = tmem + (pass == 2 ? TM_QM : TM_QH);
+          const uint32_t lo = bd_lo + (pass == 1 ? (uint32_t)(SPLIT_BYTES >> 4) : 0u);
+#pragma unroll
+          for (int k16 = 0; k16 < 16; ++k16) {
+            const uint32_t boff = (uint32_t)((k16 >> 2) * KBLOCK_BYTES + (k16 & 3) * 32) >> 4;
+            umma_ts_pair(d_tmem, a_tmem + k16 * 8, lo + boff, bd_hi, IDESC, (pass | k16) ? 1u : 0u);
+          }
+        }
+        umma_commit_pair(&sm.empty[st]);
+        umma_commit_pair(&sm.tmem_full[b]);
+      }
+    } else if (rank != 0 && lane == 0) {
+      // partner CTA: relay "my producers have filled stage st" to the leader as ONE cluster-scope arrival
+      // (this thread has no memory traffic of its own, so its release costs nothing)
+      const uint32_t full_addr = mapa(smem_u32(&sm.full[0]), 0);
+      for (int i = 0; i < my_tiles; ++i) {
+        const int st = i % STAGES;
+        mbar_wait(&sm.full_local[st], (i / STAGES) & 1);
+        mbar_arrive_cluster_release(full_addr + (uint32_t)st * 8u);
+      }
+    }
+    __syncwarp();
+  } else {
+    if constexpr (REGS_EPI > REGS_LAUNCH) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
+    // ======================================================================== epilogue: lane = state
+    const int q = warp & 3;                       // TMEM quadrant -> states rank*128 + 32q + lane = one chunk of the map
+    const uint32_t h = (uint32_t)(warp >> 2);     // accumulator columns [64h, 64h+64) are the rows CTA h produced
+    const int chunk = (int)rank * 4 + q;
+    const int cs = chunk * JUMP_CHUNK;            // first state of the chunk
+    const int s_mine = cs + lane;
+    const uint32_t cbase = (uint32_t)chunk << 16; // Philox call base of this chunk
+    const uint32_t tempty_dst = mapa(smem_u32(&sm.tmem_empty[0]), 0);
+    // record slot of this chunk: shared::cta address when this CTA produced the rows, else in the partner's window
+    const uint32_t contrib_dst = (h == rank) ? smem_u32(&sm.contrib[0][chunk][0]) : mapa(smem_u32(&sm.contrib[0][chunk][0]), h);
+    const uint32_t cfull_dst = mapa(smem_u32(&sm.contrib_full[0]), h);
+    uint64_t* const cfree_wait = (h == rank) ? &sm.contrib_free_local[0] : &sm.contrib_free_remote[0];
+    const float* tabE = reinterpret_cast<const float*>(a.stat + (TAULDR ? ST_RBZT_OFF : ST_RBZ_OFF)) + s_mine;
+    const float* tabC = reinterpret_cast<const float*>(a.stat + ST_RBZ_OFF) + s_mine;   // corrector add: Rb[x][s], zero diag
+    const float* tabFull = (TAULDR ? a.RbT : a.Rb) + s_mine;                             // diagonal kept, for rr_out
+    const float hb = a.h * a.beta;
+
+    for (int i = 0; i < my_tiles; ++i) {
+      const int tile = pair + i * npairs;
+      const int slot = i % RING, b = i % ACC, cb = i % CBUF;
+      mbar_wait(&sm.scal_full[slot], (i / RING) & 1);
+      mbar_wait(&sm.tmem_full[b], (i / ACC) & 1);
+      tc_fence_after();
+      if (SAMPLES) mbar_wait(cfree_wait + cb, ((i / CBUF) & 1) ^ 1);
+#pragma unroll 1
+      for (int bb = 0; bb < 2; ++bb) {
+        const int col = (int)h * NH + 32 * bb;                         // tile column (= tile row) of this batch's row 0
+        const long long g0 = (long long)tile * NT + col;               // its global row
+        const uint32_t sx_p = smem_u32(&sm.scal_x[slot][col]);
+        const uint32_t sc_p = smem_u32(&sm.scal_c[slot][col]);
+        uint32_t acc[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + TM_ACC + b * NT + col, acc);
+        // base-rate rows of the 32 rows of the batch: 32 independent coalesced loads (chunks outside the band of
+        // non-zero rates of x are skipped: the predicate is uniform over the warp)
+        float R[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          uint32_t sx;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sx) : "r"(sx_p + 4 * j));
+          const int x = (int)(sx & 255u), lo = (int)((sx >> 8) & 255u), hi = (int)((sx >> 16) & 255u);
+          const bool inband = (hi >= cs) && (lo <= cs + JUMP_CHUNK - 1);
+          const float* src = ((KM == KM_RATES) ? tabFull : tabE) + ((size_t)x << 8);
+          R[j] = inband ? __ldg(src) : 0.f;
+        }
+        tmem_ld_wait();
+        if (bb == 1) {           // the accumulator has been read: hand the buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_relaxed(tempty_dst + (uint32_t)b * 8u);
+        }
+#ifdef CTDD_EXP_NOEPI        // diagnostic build: the epilogue only drains the accumulator (isolates producers + MMA)
+        if (SAMPLES) {
+          const uint32_t roff = (uint32_t)cb * (NCHUNK * NH * 8) + (uint32_t)(32 * bb + lane) * 8u;
+          const uint32_t z = (__float_as_uint(R[lane & 1]) ^ acc[lane & 3]) == 0x7fc12345u;
+          if (h == rank) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(contrib_dst + roff), "r"(z), "r"(0u) : "memory");
+          else st_async_cluster_v2(contrib_dst + roff, z, 0u, cfull_dst + (uint32_t)cb * 8u);
+        }
+        continue;
+#endif
+        if constexpr (KM == KM_RATES) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float c1, c0;
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(c1), "=f"(c0) : "r"(sc_p + 8 * j));
+            const float ratio = fmaf(__uint_as_float(acc[j]), c1, c0);
+            const float rfull = TAULDR ? a.beta * R[j] * ratio : ratio * (a.beta * R[j]);
+            const long long g = g0 + j;
+            if (g < a.rows) {
+              if (a.rr_out) a.rr_out[g * S + s_mine] = rfull;
+              if (a.ratio_out) a.ratio_out[g * S + s_mine] = ratio;
+            }
+          }
+        } else {
+          // lam[s, row] (zero at s == x through the zero-diagonal tables)
+          float lam[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float c1, c0;
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(c1), "=f"(c0) : "r"(sc_p + 8 * j));
+            lam[j] = fmaf(__uint_as_float(acc[j]), c1, c0) * R[j];
+          }
+          if constexpr (km_corr(KM)) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              uint32_t sx;
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sx) : "r"(sx_p + 4 * j));
+              const int x = (int)(sx & 255u), lo = (int)((sx >> 8) & 255u), hi = (int)((sx >> 16) & 255u);
+              const bool inband = (hi >= cs) && (lo <= cs + JUMP_CHUNK - 1);
+              R[j] = inband ? __ldg(tabC + ((size_t)x << 8)) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) lam[j] = fmaf(hb, R[j], lam[j]);
+          }
+          // lane = row from here: this lane's row of the batch
+          uint32_t sxl;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sxl) : "r"(sx_p + 4 * lane));
+          const int xl = (int)(sxl & 255u);
+          int2 rec = make_int2(0, 0);
+          if constexpr (KM == KM_DRIFT) {
+            // sum_s rr_s (s - x) over this chunk, for the 32 rows at once
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              uint32_t sx;
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sx) : "r"(sx_p + 4 * j));
+              R[j] = lam[j] * (float)(s_mine - (int)(sx & 255u));
+            }
+            rec.x = __float_as_int(transpose_reduce(R, lane));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) R[j] = lam[j];
+            const float tot = transpose_reduce(R, lane);           // chunk total of row `lane`
+            const Philox4 p0 = philox_rowjump((uint64_t)(a.row_offset + g0 + lane), cbase, a.offset, a.seed);
+            int K = poisson_from_unit(tot, u32_to_unit(p0.w[0]));
+            K = K > JUMP_PICK_CAP ? JUMP_PICK_CAP : K;
+            rec.y = K;
+            uint32_t todo = __ballot_sync(0xffffffffu, K > 0);
+#ifdef CTDD_EXP_NOPICK       // diagnostic build: counts are drawn, picks are not resolved
+            todo = 0;
+#endif
+            while (todo) {             // rows with picks in this chunk (warp-uniform loop)
+              const int rr = __ffs(todo) - 1;
+              todo &= todo - 1;
+              float p = select32(lam, rr);
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1) {       // inclusive prefix sums over the chunk's 32 states
+                const float n = __shfl_up_sync(0xffffffffu, p, o);
+                if (lane >= o) p += n;
+              }
+              const float ptot = __shfl_sync(0xffffffffu, p, 31);
+              const int Kr = __shfl_sync(0xffffffffu, K, rr);
+              const uint32_t w1 = __shfl_sync(0xffffffffu, p0.w[1], rr), w2 = __shfl_sync(0xffffffffu, p0.w[2], rr),
+                             w3 = __shfl_sync(0xffffffffu, p0.w[3], rr);
+              const int xr = __shfl_sync(0xffffffffu, xl, rr);
+              int jump = 0;
+              Philox4 pc = {{0u, 0u, 0u, 0u}};
+              for (int j = 0; j < Kr; ++j) {
+                uint32_t w;
+                if (j < 3) {
+                  w = j == 0 ? w1 : (j == 1 ? w2 : w3);
+                } else {
+                  const int jj = j - 3;
+                  if ((jj & 3) == 0)
+                    pc = philox_rowjump((uint64_t)(a.row_offset + g0 + rr), cbase + 1u + (uint32_t)(jj >> 2), a.offset, a.seed);
+                  w = philox_word(pc, jj & 3);
+                }
+                // first state whose prefix sum exceeds the target (the last prefix sum is the total, so one always does)
+                const float T = fminf(u32_to_unit(w), 0.99999994f) * ptot;
+                const uint32_t above = __ballot_sync(0xffffffffu, p > T);
+                const int sl = above ? __ffs(above) - 1 : 31;
+                jump += cs + sl - xr;
+              }
+              if (lane == rr) rec.x = jump;
+            }
+          }
+          // the record of (row `lane`, this chunk) goes to the CTA that produced the row
+          const uint32_t roff = (uint32_t)cb * (NCHUNK * NH * 8) + (uint32_t)(32 * bb + lane) * 8u;
+          if (h == rank) {
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(contrib_dst + roff), "r"(rec.x), "r"(rec.y) : "memory");
+          } else {
+            st_async_cluster_v2(contrib_dst + roff, (uint32_t)rec.x, (uint32_t)rec.y, cfull_dst + (uint32_t)cb * 8u);
+          }
+        }
+      }
+      if (SAMPLES && h == rank) {
+        __syncwarp();
+        if (lane == 0) {
+          // warp 0 also announces the bytes the partner's four warps will deliver for this tile
+          if (q == 0) mbar_arrive_expect_tx(&sm.contrib_full[cb], CONTRIB_TX_BYTES);
+          else mbar_arrive(&sm.contrib_full[cb]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();     // no CTA of the pair may exit (or free tensor memory) while the other can still reach it
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem);
+  }
+}
+
+}  // namespace tcq
+
+int launch_step_tcq(const ctdd_step_params* p, cudaStream_t st) {
+  using namespace tcq;
+  // per-device one-time setup (function attributes live in the device's context): a bit per device ordinal
+  static int num_sms[64] = {0};
+  static unsigned long long attr_done = 0ull;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool attr_set = dev >= 0 && dev < 64 && ((attr_done >> dev) & 1ull);
+  const size_t smem_bytes = sizeof(Smem) + 1024;
+  typedef void (*kern_t)(const tc::Args);
+#define CTDD_TCQ_ROW(T, H)                                                                                        \
+  {step_q_kernel<T, tc::KM_JUMP, H>, step_q_kernel<T, tc::KM_CORR, H>, step_q_kernel<T, tc::KM_RATES, H>,       \
+   step_q_kernel<T, tc::KM_DRIFT, H>}
+  static const kern_t kerns[4][4] = {CTDD_TCQ_ROW(false, false), CTDD_TCQ_ROW(true, false), CTDD_TCQ_ROW(false, true),
+                                     CTDD_TCQ_ROW(true, true)};
+#undef CTDD_TCQ_ROW
+  if (!attr_set) {
+    cudaDeviceGetAttribute(&num_sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j)
+        if (cudaFuncSetAttribute(kerns[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) {
+          set_error("ctdd_reverse_step: cannot reserve %zu bytes of shared memory for the tcgen05 kernel", smem_bytes);
+          cudaGetLastError();
+          return 1;
+        }
+    if (dev >= 0 && dev < 64) attr_done |= 1ull << dev;
+  }
+  tc::Args a;
+  a.branch = p->branch; a.D = p->D; a.reject_multi = p->reject_multi;
+  a.rows = (long long)p->N * p->D; a.row_offset = p->row_offset;
+  a.logits = p->logits; a.ld = p->ld_logits; a.batch_stride = p->batch_stride_logits;
+  a.x_eval = p->x_eval; a.x_base = p->x_base;
+  a.tab = reinterpret_cast<const uint8_t*>(p->tc_tables);
+  a.stat = reinterpret_cast<const uint8_t*>(p->tc_static);
+  a.RbT = p->RbT; a.Rb = p->Rb; a.beta = p->beta; a.h = p->h; a.seed = p->seed; a.offset = p->offset;
+  a.x_out = p->x_out; a.rr_out = p->rr_out; a.ratio_out = p->ratio_out;
+  a.stats = reinterpret_cast<unsigned long long*>(p->stats_out);
+  a.head_fix = p->head == CTDD_HEAD_LOGISTIC_FIX;
+  a.head_mu = p->head_mu; a.head_ls = p->head_log_scale; a.head_bs = p->head_batch_stride;
+  a.num_tiles = (int)((a.rows + NT - 1) / NT);
+  int pairs = num_sms[dev & 63] / 2;                 // one CTA pair (cluster of 2) per TPC
+  if (pairs > a.num_tiles) pairs = a.num_tiles;
+  if (pairs < 1) pairs = 1;
+  const int ki = ((p->branch == CTDD_BRANCH_TAULDR) ? 1 : 0) + (p->head != CTDD_HEAD_LOGITS ? 2 : 0);
+  int kj = 0;
+  if (p->mode == CTDD_MODE_RATES_ONLY) kj = 2;
+  else if (p->mode == CTDD_MODE_TAU_LEAP_CORR) kj = 1;
+  else if (p->mode == CTDD_MODE_MIDPOINT_DRIFT) kj = 3;
+  kerns[ki][kj]<<<2 * pairs, NUM_THREADS, smem_bytes, st>>>(a);
+  CTDD_CHECK_LAUNCH("step_q_kernel");
+  return 0;
+}
+
+}  // namespace ctdd

@@ -198,6 +198,19 @@ def reverse_rates(logits: torch.Tensor, x: torch.Tensor, Q: torch.Tensor, R: tor
 # state updates with injected uniforms
 
 
+# "map": jump counts through the shared uniform -> sample map (rng.poisson_rows; bit-comparable with the kernels);
+# "torch": through torch.poisson exactly as the reference draws them (free-running distributional checks)
+POISSON_LAW = "map"
+_TORCH_GEN = torch.Generator().manual_seed(0)
+
+
+def set_poisson_law(law: str, seed: int = 0):
+    global POISSON_LAW
+    assert law in ("map", "torch")
+    POISSON_LAW = law
+    _TORCH_GEN.manual_seed(seed)
+
+
 def _zero_at(rr: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     return rr * (1 - F.one_hot(x.long(), rr.shape[-1])).to(rr.dtype)
 
@@ -207,7 +220,10 @@ def tau_leap_update(rates_z: torch.Tensor, x_eval: torch.Tensor, x_base: torch.T
     """sampling.py:127-160 (and :481-503 for midpoint stage 2). rates_z: (N,D,S) with s==x_eval zeroed."""
     N, D, _ = rates_z.shape
     lam = (rates_z.detach() * h).numpy().reshape(N * D, S)
-    kc, _ = rng.poisson_rows(lam, row_offset, offset, seed)
+    if POISSON_LAW == "torch":     # the reference's own draw (torch.poisson, sampling.py:131): distributional checks only
+        kc = torch.poisson(torch.from_numpy(np.ascontiguousarray(lam)), generator=_TORCH_GEN).numpy().astype(np.int64)
+    else:
+        kc, _ = rng.poisson_rows(lam, row_offset, offset, seed)
     diff = np.arange(S, dtype=np.int64)[None, :] - x_eval.numpy().reshape(-1, 1).astype(np.int64)
     jump = (kc * diff).sum(axis=1)
     cnt = kc.sum(axis=1)
@@ -220,6 +236,34 @@ def tau_leap_update(rates_z: torch.Tensor, x_eval: torch.Tensor, x_base: torch.T
     stats["changed_base"] = int((xn != xb).sum())
     stats["changed_eval"] = int((xn != x_eval.numpy().reshape(-1)).sum())
     return torch.from_numpy(xn.reshape(N, D)), stats
+
+
+def tau_leap_margin(rates_z: torch.Tensor, h: float, offset: int, seed: int, row_offset: int = 0) -> np.ndarray:
+    """(N*D,) tie margin of every row of tau_leap_update on the same inputs (rng.poisson_rows_margin)."""
+    N, D, S = rates_z.shape
+    lam = (rates_z.detach() * h).numpy().reshape(N * D, S)
+    return rng.poisson_rows_margin(lam, row_offset, offset, seed)
+
+
+def euler_margin(rates_z: torch.Tensor, x: torch.Tensor, h: float, S: int, offset: int, seed: int, row_offset: int = 0):
+    """(N*D,) tie margin of every row of euler_update on the same inputs."""
+    N, D, _ = rates_z.shape
+    r = rates_z.detach().numpy().reshape(N * D, S).astype(np.float32)
+    tot = np.cumsum(r, axis=1, dtype=np.float32)[:, -1]
+    diag = np.maximum(np.float32(0.0), (np.float32(1.0) - np.float32(h) * tot).astype(np.float32))
+    P = (r * np.float32(h)).astype(np.float32)
+    P[np.arange(N * D), x.numpy().reshape(-1).astype(np.int64)] = diag
+    return rng.inv_cdf_margin(P, rng.row_units(N * D, row_offset, offset, rng.STREAM_ROW, seed))
+
+
+def midpoint_drift_margin(rates_z: torch.Tensor, x: torch.Tensor, h: float, S: int) -> np.ndarray:
+    """(N*D,) distance of 0.5*h*sum_s rr_s*(s-x) to the nearest rounding boundary (k + 1/2), relative to sum_s rr_s*|s-x|*h/2."""
+    diff = (torch.arange(S).view(1, 1, S) - x.long().unsqueeze(-1)).to(torch.float64)
+    val = (0.5 * h * torch.sum(rates_z.double() * diff, dim=-1)).numpy().reshape(-1)
+    scale = (0.5 * h * torch.sum(rates_z.double() * diff.abs(), dim=-1)).numpy().reshape(-1)
+    frac = np.abs(val - np.floor(val) - 0.5)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.where(scale > 0, frac / np.where(scale > 0, scale, 1.0), np.inf)
 
 
 def euler_update(rates_z: torch.Tensor, x: torch.Tensor, h: float, S: int, offset: int, seed: int, row_offset: int = 0):

@@ -245,3 +245,63 @@ def poisson_rows(lam: np.ndarray, row_offset: int, offset: int, seed: int):
         counts[:, c0:c1] = kc
         K += Kc
     return counts, K
+
+
+# ------------------------------------------------------------------------------------------------------
+# tie margins: how close the deciding uniforms of a row sit to a threshold of the maps above.  The tensor path
+# computes the rates with ~3e-5 relative error and sums them in a different order than this module, so it may
+# legitimately decide differently ONLY when a uniform sits within the rate tolerance of a threshold
+# (BASELINE.json north_star: "bit-exact except where the reference rate sits within ... of a Poisson threshold").
+# The parity tests assert that every mismatching row has a margin below the rate tolerance.
+
+
+def poisson_rows_margin(lam: np.ndarray, row_offset: int, offset: int, seed: int) -> np.ndarray:
+    """fp64 (rows,): smallest RELATIVE rate change that would move a decision of poisson_rows on that row.
+
+    Per chunk: (a) the count: v0 against the two neighbouring thresholds P(K > j), j in {K-1, K}; a relative change
+    d of the chunk total Lam moves P(K > j) by pmf(j) * Lam * d, so the margin is |v0 - P(K > j)| / (pmf(j) * Lam);
+    (b) every pick: |v_j * total - cum[s]| / total for the two prefix sums around the chosen state.  inf when the row
+    has no positive rate."""
+    from scipy.stats import poisson as sp
+    lam = np.ascontiguousarray(lam, dtype=np.float32)
+    rows, S = lam.shape
+    grow = np.arange(rows, dtype=np.uint64) + np.uint64(row_offset)
+    margin = np.full(rows, np.inf)
+    for ci, c0 in enumerate(range(0, S, JUMP_CHUNK)):
+        w = lam[:, c0:min(c0 + JUMP_CHUNK, S)]
+        cum = np.cumsum(w, axis=1, dtype=np.float32).astype(np.float64)
+        tot = cum[:, -1]
+        pos = tot > 0
+        v0 = u32_to_unit(rowjump_words(grow, offset, seed, ci << 16)[:, 0]).astype(np.float64)
+        K = poisson_from_unit(tot.astype(np.float32), v0.astype(np.float32))
+        t = np.where(pos, tot, 1.0)
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore", under="ignore"):
+            m = np.abs(v0 - sp.sf(K, t)) / np.maximum(sp.pmf(K, t) * t, 1e-300)
+            m1 = np.abs(v0 - sp.sf(K - 1, t)) / np.maximum(sp.pmf(np.maximum(K - 1, 0), t) * t, 1e-300)
+        m = np.where(K >= 1, np.minimum(m, m1), m)
+        margin = np.where(pos, np.minimum(margin, m), margin)
+        idx = np.flatnonzero(K > 0)
+        if idx.size == 0:
+            continue
+        Kc = np.minimum(K[idx], JUMP_PICK_CAP)
+        kmax = int(Kc.max())
+        picks = rowjump_pick_units(grow[idx], offset, seed, kmax, ci << 16).astype(np.float64)
+        c = cum[idx]
+        for j in range(kmax):
+            live = np.flatnonzero(Kc > j)
+            if live.size == 0:
+                break
+            target = np.minimum(picks[live, j], 0.99999994) * tot[idx[live]]
+            d = np.abs(c[live] - target[:, None]).min(axis=1) / tot[idx[live]]
+            margin[idx[live]] = np.minimum(margin[idx[live]], d)
+    return margin
+
+
+def inv_cdf_margin(weights: np.ndarray, v: np.ndarray) -> np.ndarray:
+    """fp64 (rows,): distance of v * total to the nearest cumulative sum, relative to the total (inv_cdf's tie margin)."""
+    w = np.asarray(weights, dtype=np.float32)
+    cum = np.cumsum(w, axis=1, dtype=np.float32).astype(np.float64)
+    tot = cum[:, -1]
+    target = np.minimum(np.asarray(v, np.float64), 0.99999994) * tot
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.where(tot > 0, np.abs(cum - target[:, None]).min(axis=1) / np.where(tot > 0, tot, 1.0), np.inf)

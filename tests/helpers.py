@@ -41,3 +41,19 @@ def mismatch_fraction(a, b):
     a, b = np.asarray(a), np.asarray(b)
     assert a.shape == b.shape, (a.shape, b.shape)
     return float((a != b).mean())
+
+
+RATE_TOL = 1e-4     # north_star: reverse rates within 1e-4 relative; a decision may differ only inside that band
+
+
+def assert_only_ties(got, want, margin, frac_tol=1e-3, rate_tol=RATE_TOL, what=""):
+    """Integer states equal to the oracle's except threshold ties: every mismatching row must have a deciding uniform
+    within `rate_tol` (relative rate change) of a threshold of the uniform -> sample map (oracle/rng.py *_margin), and
+    at most `frac_tol` of the rows (at least 2) may be such ties."""
+    got, want = np.asarray(got).reshape(-1), np.asarray(want).reshape(-1)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    bad = np.flatnonzero(got != want)
+    assert bad.size <= max(2, frac_tol * got.size), (what, bad.size, got.size)
+    if bad.size:
+        m = np.asarray(margin).reshape(-1)[bad]
+        assert np.all(m <= rate_tol), (what, "mismatch that is not a threshold tie", bad[m > rate_tol][:8], m[m > rate_tol][:8])

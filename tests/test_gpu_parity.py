@@ -5,7 +5,7 @@ import torch
 
 from oracle import cases, ctmc_oracle as oc, ref_harness as rh, rng
 from oracle.make_golden import rates_inputs
-from helpers import oracle_forward, product_model, fwd_cfg, mismatch_fraction
+from helpers import oracle_forward, product_model, fwd_cfg, mismatch_fraction, assert_only_ties
 
 pytestmark = pytest.mark.gpu
 
@@ -157,31 +157,32 @@ def test_step_modes_match_oracle(sc, impl_i):
                                reject_multi=reject, seed=seed, offset=offset, x_base=x_base, stats=stats)
         return out["x"].cpu().numpy().astype(np.int64), stats.cpu().numpy()
 
-    tol = 2e-3
+    tol = 1e-3
+    m_jump3 = oc.tau_leap_margin(rz, h, 3, seed)
     for reject in (False, True):
         got, st = run(nat.MODE_TAU_LEAP, 3, reject)
         want, ost = oc.tau_leap_update(rz, x, x, h, S, reject, 3, seed)
-        assert mismatch_fraction(got, want.numpy()) <= tol
+        assert_only_ties(got, want.numpy(), m_jump3, tol, what="tau_leap")
         assert abs(st[nat.STAT_CHANGED_BASE] - ost["changed_base"]) <= max(2, tol * N * D)
         assert abs(st[nat.STAT_ROWS_MULTI] - ost["rows_multi"]) <= max(2, tol * N * D)
     got, _ = run(nat.MODE_TAU_LEAP_CORR, 5)
     want, _ = oc.tau_leap_update(rz_corr, x, x, h, S, False, 5, seed)
-    assert mismatch_fraction(got, want.numpy()) <= tol
+    assert_only_ties(got, want.numpy(), oc.tau_leap_margin(rz_corr, h, 5, seed), tol, what="tau_leap_corr")
     got, _ = run(nat.MODE_MIDPOINT_DRIFT, 0)
     want = oc.midpoint_drift(rz, x, h, S)
-    assert mismatch_fraction(got, want.numpy()) <= tol
+    assert_only_ties(got, want.numpy(), oc.midpoint_drift_margin(rz, x, h, S), tol, what="midpoint_drift")
     g = np.random.Generator(np.random.PCG64(5))
     xb = torch.from_numpy(np.clip(x.numpy() + g.integers(-1, 2, x.shape), 0, S - 1))
     got, st = run(nat.MODE_MIDPOINT_JUMP, 7, True, xb.to(torch.int32).cuda())
     want, ost = oc.tau_leap_update(rz, x, xb, h, S, True, 7, seed)
-    assert mismatch_fraction(got, want.numpy()) <= tol
+    assert_only_ties(got, want.numpy(), oc.tau_leap_margin(rz, h, 7, seed), tol, what="midpoint_jump")
     assert abs(st[nat.STAT_NONZERO_JUMP] - ost["nonzero_jump"]) <= max(2, tol * N * D)
     got, _ = run(nat.MODE_EULER, 9)
     want, _ = oc.euler_update(rz, x, h, S, 9, seed)
-    assert mismatch_fraction(got, want.numpy()) <= tol
+    assert_only_ties(got, want.numpy(), oc.euler_margin(rz, x, h, S, 9, seed), tol, what="euler")
     got, _ = run(nat.MODE_EULER_CORR, 10)
     want, _ = oc.euler_update(rz_corr, x, h, S, 10, seed)
-    assert mismatch_fraction(got, want.numpy()) <= tol
+    assert_only_ties(got, want.numpy(), oc.euler_margin(rz_corr, x, h, S, 10, seed), tol, what="euler_corr")
 
 
 def test_row_offset_sharding_is_invariant():
@@ -265,7 +266,7 @@ def test_samplers_match_reference_fixtures(golden, case):
     res = _run_product_sampler(case, inject_oracle_q=True)
     g = golden["samplers"]
     assert res[0].dtype.kind == "i" and res[0].shape == g[f"{name}/x"].shape
-    assert mismatch_fraction(res[0], g[f"{name}/x"]) <= 5e-3
+    assert mismatch_fraction(res[0], g[f"{name}/x"]) <= 1e-3     # observed 0; a tie early in a run moves later steps
     for i, extra in enumerate(res[1:]):
         np.testing.assert_allclose(np.asarray(extra, dtype=np.float64), g[f"{name}/diag{i}"], atol=0.02, rtol=0.05,
                                    equal_nan=True)
@@ -299,21 +300,29 @@ def test_tc_path_full_tiles_and_tail_match_simt():
                 big = np.abs(b) > 1e-30
                 assert (np.abs(a - b)[big] / np.abs(b)[big]).max() <= 1e-4
                 assert np.all(np.abs(a[~big]) <= 1e-30)
+            # tie margins from the CUDA-core path's own fp32 rates (s == x zeroed, corrector: + R_t[x, :])
+            xl = x.long()
+            onehot = torch.nn.functional.one_hot(xl, S).bool()
+            rz = r_si["rr"].cpu().masked_fill(onehot, 0.0)
+            Rt = (tb["beta"] * tb["Rb"].cpu())[xl]                       # (N, D, S): row x of R_t
+            rz_corr = (rz + Rt).masked_fill(onehot, 0.0)
             for mode, reject in ((nat.MODE_TAU_LEAP, False), (nat.MODE_TAU_LEAP, True), (nat.MODE_TAU_LEAP_CORR, False)):
                 st1 = torch.zeros(8, dtype=torch.int64, device="cuda")
                 st2 = torch.zeros(8, dtype=torch.int64, device="cuda")
                 x_tc = ops.reverse_step(mode, *args, 0.01, 1e-9, impl=nat.IMPL_TC, reject_multi=reject, seed=5, offset=1, stats=st1, **kw)["x"]
                 x_si = ops.reverse_step(mode, *args, 0.01, 1e-9, impl=nat.IMPL_SIMT, reject_multi=reject, seed=5, offset=1, stats=st2, **kw)["x"]
-                assert mismatch_fraction(x_tc.cpu().numpy(), x_si.cpu().numpy()) <= 2e-3
+                margin = oc.tau_leap_margin(rz_corr if mode == nat.MODE_TAU_LEAP_CORR else rz, 0.01, 1, 5)
+                assert_only_ties(x_tc.cpu().numpy(), x_si.cpu().numpy(), margin, 1e-3, what=f"tc vs simt N={N} D={D} mode={mode}")
                 assert np.abs(st1.cpu().numpy() - st2.cpu().numpy()).max() <= max(2, 2e-3 * N * D)
 
 
-def test_free_running_histograms_tc_vs_simt():
-    """SURVEY §8c plan (4) / north_star: where bit-exactness cannot be claimed (threshold ties of the 3xBF16 tensor path)
-    the full reverse process must agree in distribution.  Two independent TauL runs (different Philox seeds) of the same
-    model, one on the tcgen05 path and one on the CUDA-core path, N = 16 384: per-dimension state histograms
-    (16 bins of 16 states) have symmetrised KL < 1e-3 on average (sampling noise of two N-samples ~ 15/N ~ 9e-4 at the
-    bound, observed well below) and < 3e-3 in every dimension."""
+def test_free_running_histograms_vs_reference_law():
+    """SURVEY §8c plan (4) / north_star: where bit-exactness cannot be claimed (threshold ties of the 3xBF16 tensor path,
+    the chunked superposition map instead of S independent draws, the Cornish-Fisher quantile above lambda = 64) the full
+    reverse process must agree in DISTRIBUTION with the reference's law.  The product TauL (tcgen05 path, Philox) against
+    the CPU oracle of TauL.sample driven by real torch.poisson draws (sampling.py:131), same stub network, independent
+    randomness, N = 16 384: per-dimension state histograms (16 bins of 16 states) have symmetrised KL < 1e-3 on average
+    (sampling noise of two N-samples ~ 15/N ~ 9e-4 at the bound, observed well below) and < 3e-3 in every dimension."""
     from ctdd_b200 import make_config
     from ctdd_b200.lib.sampling import sampling_utils
     import ctdd_b200.lib.sampling.sampling  # noqa: F401
@@ -323,12 +332,23 @@ def test_free_running_histograms_tc_vs_simt():
     cfg = cases.sampler_cfg(make_config, case)
     cfg.device = "cuda"
     m = product_model("gauss256", cfg, D, 7, 0.3, 12.0)
+    sampler = sampling_utils.get_sampler(cfg)
+    sampler.seed = 1001
+    sampler.impl = nat.IMPL_AUTO
+    x_gpu = np.asarray(sampler.sample(m, N)[0])
+    # the oracle with the reference's own Poisson law, on the CPU copy of the same network
+    fp = oracle_forward("gauss256")
+    net = rh.StubNet(S, D, 7, 0.3, 12.0)
+    oc.set_poisson_law("torch", seed=2002)
+    try:
+        x_ref, _ = oc.sample_taul(fp, lambda xx, tt: net.net(xx, tt), N, D, S, max_t=case[9],
+                                  min_t=cfg.sampler.min_t, num_steps=cfg.sampler.num_steps,
+                                  initial_dist=cfg.sampler.initial_dist, init_std=cfg.model.Q_sigma,
+                                  is_ordinal=cfg.sampler.is_ordinal, loss_name="CTElbo", seed=2002)
+    finally:
+        oc.set_poisson_law("map")
     hists = []
-    for impl, seed in ((nat.IMPL_AUTO, 1001), (nat.IMPL_SIMT, 2002)):
-        sampler = sampling_utils.get_sampler(cfg)
-        sampler.seed = seed
-        sampler.impl = impl
-        x = np.asarray(sampler.sample(m, N)[0])
+    for x in (x_gpu, np.asarray(x_ref)):
         assert x.shape == (N, D) and x.min() >= 0 and x.max() < S
         h = np.stack([np.bincount(x[:, d] // 16, minlength=16) for d in range(D)]).astype(np.float64)
         hists.append((h + 0.5) / (h + 0.5).sum(axis=1, keepdims=True))
@@ -381,5 +401,9 @@ def test_full_size_c4_properties():
     assert torch.equal(full, torch.cat([lo, hi]))
     for n0 in (0, 771):                                                            # slices vs the CUDA-core path
         sl = slice(n0, n0 + 2)                                                     # 2 samples = 6144 rows
-        ref = run(logits[sl].contiguous(), x[sl].contiguous(), 2, nat.IMPL_SIMT, row_offset=n0 * D)
-        assert mismatch_fraction(full[sl].cpu().numpy(), ref.cpu().numpy()) <= 2e-3
+        lg_s, x_s = logits[sl].contiguous(), x[sl].contiguous()
+        ref = run(lg_s, x_s, 2, nat.IMPL_SIMT, row_offset=n0 * D)
+        rr = ops.reverse_step(nat.MODE_RATES_ONLY, branch, lg_s, x_s, *tabs, N=2, D=D, S=S, impl=nat.IMPL_SIMT, want_rr=True)["rr"]
+        rz = rr.cpu().masked_fill(torch.nn.functional.one_hot(x_s.long().cpu(), S).bool(), 0.0)
+        margin = oc.tau_leap_margin(rz, h, 4, 99, row_offset=n0 * D)
+        assert_only_ties(full[sl].cpu().numpy(), ref.cpu().numpy(), margin, 1e-3, what=f"C4 slice {n0}")
