@@ -14,13 +14,13 @@
 //     128B-swizzled smem stage.  The passes of a tile are dealt round-robin to the producer warps.  The row scalars
 //     (rate scale, state, band of non-zero base rates) go to BOTH CTAs of the pair (st.async into the partner).
 //   * 3 tensor passes  Qh*ah + Qh*am + Qm*ah  accumulate in fp32 TMEM (48 tcgen05.mma of N = 128 per tile).
-//   * Epilogue, lane = state: warp (q, h) reads its 32 states x 32 rows with tcgen05.ld (two batches per tile), gathers
+//   * Epilogue: warp (q, h) reads its 32 states x 32 rows with tcgen05.ld (lane = state; two batches per tile), gathers
 //     R_b[s, x_row] for all 32 rows at once (32 independent coalesced 128-byte loads in flight; chunks outside the
-//     band of non-zero base rates of x are skipped), forms lam[s, row] and reduces over its 32 states for all 32
-//     rows with a 31-shuffle transposing butterfly, which leaves lane = row.  A warp's 32 states are one CHUNK of the
-//     chunked superposition map (ctdd_common.cuh): each chunk of a row draws its own jump count K ~ Poisson(chunk total)
-//     and its own picks, so no warp ever waits for another warp's total.  Rows with a pick in this chunk (rare per
-//     chunk) are then scanned over the 32 lanes (prefix sums, ballot = first state above the target).
+//     band of non-zero base rates of x are skipped) and forms lam[s, row].  A 4.5 KB per-warp scratch transposes the
+//     batch to lane = row.  A warp's 32 states are one CHUNK of the chunked superposition map (ctdd_common.cuh): each
+//     chunk of a row draws its own jump count K ~ Poisson(chunk total) and its own picks, so no warp ever waits for
+//     another warp's total and all 32 rows of a batch are sampled in parallel: sequential fp32 prefix sums in
+//     registers (the oracle's summation order), Philox, inverse-CDF count, picks by a register binary search.
 //   * The per-(row, chunk) results (sum of jumps, jump count / partial drift) are 8 bytes each; they go to the CTA that
 //     produced the row (plain st.shared or st.async + complete_tx), whose two finalizer warps (lane = row) add the 8
 //     chunks, apply the clamp / rejection rule and write x_out coalesced.
@@ -62,7 +62,9 @@ constexpr int SPLIT_BYTES = 4 * KBLOCK_BYTES;  // K = 256 -> 4 blocks
 constexpr int STAGE_BYTES = 2 * SPLIT_BYTES;   // hi + mid
 constexpr int TM_QH = 0, TM_QM = 128, TM_ACC = 256;  // TMEM column map (accumulator b at TM_ACC + b * NT)
 constexpr int PREFETCH_TILES = 4;      // HBM -> L2 bulk-prefetch distance (tiles of this pair's sequence)
-constexpr int LRING = 2;               // per-producer-warp ring of raw logits row pairs filled by cp.async.bulk
+constexpr int LRING = 1;               // per-producer-warp slot of raw logits row pairs filled by cp.async.bulk: refilled for the
+                                       // warp's next pass as soon as this pass has its values in registers (rows are L2 hits)
+constexpr int SCR_LD = 36;             // floats per row of an epilogue warp's transposing scratch (conflict-free 128-bit reads)
 constexpr uint32_t IDESC = make_idesc(NT);
 constexpr int NCHUNK = S / JUMP_CHUNK;                           // 8 chunks of 32 states per row
 constexpr uint32_t SCAL_TX_BYTES = NH * 12;                      // row scalars the partner sends per tile
@@ -72,9 +74,10 @@ struct Smem {
   alignas(1024) uint8_t stage[STAGES][STAGE_BYTES];
   alignas(16) float lring[NPW][LRING][2][S];   // raw fp32 logits rows, one pass ahead of their use
   alignas(16) float2 scal_c[RING][NT];         // (c1, c0) of the tile's rows: rows 0..63 from CTA 0, 64..127 from CTA 1
-  uint32_t scal_x[RING][NT];                   // x | band_lo << 8 | band_hi << 16 | valid << 24
+  uint32_t scal_x[RING][NT];                   // chunk mask of the band (bits 0-7) | valid << 8 | x << 10 (= table-row byte offset)
+  alignas(16) float scratch[NUM_EPI_WARPS][32][SCR_LD];   // per epilogue warp: lam[row][state of the chunk] (lane = state -> lane = row)
   alignas(16) int2 contrib[CBUF][NCHUNK][NH];  // per (chunk, row of THIS CTA): (sum of jumps | drift bits, jump count)
-  uint32_t band[S];                            // band of non-zero base rates per state x (this launch's branch / mode)
+  uint32_t band[S];                            // per state x: which of the 8 chunks hold a non-zero base rate (this launch's branch / mode)
   alignas(8) uint64_t full[STAGES];            // leader CTA: its 32 passes + 1 relayed arrival for the partner's 32
   uint64_t full_local[STAGES];                 // partner CTA: its 32 passes; the partner's idle MMA warp relays the phase
   uint64_t empty[STAGES];                      // multicast tcgen05.commit
@@ -90,39 +93,6 @@ struct Smem {
 
 static_assert(sizeof(Smem) + 1024 <= 232448, "shared memory budget of one CTA (227 KB) exceeded");
 static_assert(RING > STAGES + ACC + CBUF, "row-scalar ring shorter than the pipeline");
-
-// sum over the warp's 32 lanes of w[j] for all 32 j at once: afterwards w[0] of lane L is the total of index L
-// (31 shuffles instead of 32 x 5; each step halves the number of live indices per lane)
-template <int M>
-__device__ __forceinline__ void transpose_reduce_step(float (&w)[32], int lane) {
-  const bool up = (lane & M) != 0;
-#pragma unroll
-  for (int i = 0; i < M; ++i) {
-    const float keep = up ? w[i + M] : w[i];
-    const float send = up ? w[i] : w[i + M];
-    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, M);
-  }
-}
-__device__ __forceinline__ float transpose_reduce(float (&w)[32], int lane) {
-  transpose_reduce_step<16>(w, lane);
-  transpose_reduce_step<8>(w, lane);
-  transpose_reduce_step<4>(w, lane);
-  transpose_reduce_step<2>(w, lane);
-  transpose_reduce_step<1>(w, lane);
-  return w[0];
-}
-// w[r] for a warp-uniform runtime index r, without indexed register access (31 selects)
-__device__ __forceinline__ float select32(const float (&w)[32], int r) {
-  float a[16], b[8], c[4];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) a[i] = (r & 16) ? w[i + 16] : w[i];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) b[i] = (r & 8) ? a[i + 8] : a[i];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) c[i] = (r & 4) ? b[i + 4] : b[i];
-  const float d0 = (r & 2) ? c[2] : c[0], d1 = (r & 2) ? c[3] : c[1];
-  return (r & 1) ? d1 : d0;
-}
 
 // TAULDR: tauLDR rates (else SDDM reverse_prob); KM: KM_JUMP / KM_CORR / KM_RATES / KM_DRIFT;
 // HEAD: the rows' softmax numerators come from the truncated-logistic head (mu, log_scale per row) instead of logits
@@ -167,7 +137,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       lo = b & 255; hi = (b >> 8) & 255;
     }
     if (KM == KM_RATES) { lo = 0; hi = S - 1; }   // the rates output keeps the diagonal: every chunk is read
-    sm.band[x] = (uint32_t)(lo << 8) | (uint32_t)(hi << 16);
+    uint32_t mask = 0;
+    for (int c = 0; c < NCHUNK; ++c)
+      if (hi >= c * JUMP_CHUNK && lo <= c * JUMP_CHUNK + JUMP_CHUNK - 1) mask |= 1u << c;
+    sm.band[x] = mask;
   }
   if (warp == MMA_WARP) tmem_alloc(&sm.tmem_base);
   tc_fence_before();
@@ -211,7 +184,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     const float hb = (KM == KM_RATES) ? 1.0f : a.h * a.beta;   // rates-only ignores the step length
     const bool contiguous = (a.ld == S) && (a.batch_stride == (long long)a.D * S);
     uint64_t* const full_bar = rank == 0 ? &sm.full[0] : &sm.full_local[0];
-    const long long total_pass = (long long)my_tiles * PASSES_PER_TILE;   // passes of this CTA; warp pw takes pw, pw + NPW, ..
+    const int total_pass = my_tiles * PASSES_PER_TILE;   // passes of this CTA; warp pw takes pw, pw + NPW, ..
     const uint32_t scal_c_remote = mapa(smem_u32(&sm.scal_c[0][0]), rank ^ 1u);
     const uint32_t scal_x_remote = mapa(smem_u32(&sm.scal_x[0][0]), rank ^ 1u);
     const uint32_t scal_full_remote = mapa(smem_u32(&sm.scal_full[0]), rank ^ 1u);
@@ -222,23 +195,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       return a.logits + (long long)n * a.batch_stride + (long long)d * a.ld;
     };
     // first global row of pass P of this CTA
-    auto pass_row = [&](long long P) -> long long {
-      const long long tl = P / PASSES_PER_TILE;
-      return ((long long)pair + tl * npairs) * NT + (long long)rank * NH + 2 * (P - tl * PASSES_PER_TILE);
+    auto pass_row = [&](int P) -> long long {
+      const int tl = P / PASSES_PER_TILE;
+      return (long long)(pair + tl * npairs) * NT + (int)rank * NH + 2 * (P - tl * PASSES_PER_TILE);
     };
-    // Fetch stream (two passes of this warp ahead of the compute stream): lane 0 starts the bulk copy of the row pair
-    // (rows past the end are replaced by row 0: never used; adjacent rows of a contiguous logits tensor travel as one
-    // 2 KB copy); every lane fetches the state of its half's row
-    long long Pf = pw;
-    int f_slot = 0;
+    // Two fetch streams ahead of the compute stream.  States (and head parameters): two passes of this warp ahead, into
+    // registers.  Logits: lane 0 starts the bulk copy of the NEXT pass's row pair into the warp's ring slot as soon as
+    // the current pass has read its values (rows past the end are replaced by row 0: never used; adjacent rows of a
+    // contiguous logits tensor travel as one 2 KB copy; the rows were pulled into L2 some tiles earlier).
+    int Pf = pw;                         // pass whose state is fetched next
     float f_mu = 0.f, f_ls = 0.f;        // HEAD: head parameters of the row fetch() just visited
     auto fetch = [&]() -> int {
       int xv = -1;
       if (Pf < total_pass) {
-        const long long gf = pass_row(Pf);
-        if (HEAD) {
-          const long long g = gf + half;
-          if (g < a.rows) {
+        const long long g = pass_row(Pf) + half;
+        if (g < a.rows) {
+          xv = __ldg(a.x_eval + g);
+          if (HEAD) {
             long long src = g;
             if (a.head_bs != (long long)a.D) {   // (N, 2D) network output viewed as two (N, D) halves
               // 32-bit division whenever the row index fits (a 64-bit one is ~100 instructions on the warp's critical path)
@@ -248,30 +221,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
             f_mu = __ldg(a.head_mu + src);
             f_ls = __ldg(a.head_ls + src);
           }
-        } else if (lane == 0) {
-          uint64_t* bar = &sm.lring_full[pw][f_slot];
-          mbar_arrive_expect_tx(bar, 2 * S * 4);
-          if (contiguous && gf + 1 < a.rows) {
-            bulk_g2s(&sm.lring[pw][f_slot][0][0], a.logits + gf * S, 2 * S * 4, bar);
-          } else {
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-              const long long gg = (gf + hf < a.rows) ? gf + hf : 0;
-              bulk_g2s(&sm.lring[pw][f_slot][hf][0], row_ptr(gg), S * 4, bar);
-            }
-          }
-          if (contiguous) {   // pull the same two rows of a later tile from HBM into L2
-            const long long r0 = gf + (long long)PREFETCH_TILES * npairs * NT;
-            if (r0 + 2 <= a.rows) l2_prefetch_bulk(a.logits + r0 * S, 2 * S * 4);
-          }
         }
-        if (gf + half < a.rows) xv = __ldg(a.x_eval + gf + half);
         Pf += NPW;
-        f_slot = (f_slot + 1 == LRING) ? 0 : f_slot + 1;
       }
       return xv;
     };
+    auto fetch_rows = [&](int P) {     // lane 0 only
+      if (HEAD || P >= total_pass) return;
+      const long long gf = pass_row(P);
+      uint64_t* bar = &sm.lring_full[pw][0];
+      mbar_arrive_expect_tx(bar, 2 * S * 4);
+      if (contiguous && gf + 1 < a.rows) {
+        bulk_g2s(&sm.lring[pw][0][0][0], a.logits + gf * S, 2 * S * 4, bar);
+      } else {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const long long gg = (gf + hf < a.rows) ? gf + hf : 0;
+          bulk_g2s(&sm.lring[pw][0][hf][0], row_ptr(gg), S * 4, bar);
+        }
+      }
+      if (contiguous) {   // pull the same two rows of a later tile from HBM into L2
+        const long long r0 = gf + (long long)PREFETCH_TILES * npairs * NT;
+        if (r0 + 2 <= a.rows) l2_prefetch_bulk(a.logits + r0 * S, 2 * S * 4);
+      }
+    };
 
+    if (lane == 0) fetch_rows(pw);
     int x_cur = fetch();
     float mu_cur = f_mu, ls_cur = f_ls;
     int x_n1 = fetch();
@@ -302,7 +277,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         c0 = hb * 1e-35f * inv;
       }
       if (l16 == 0) {   // one lane per half-warp: the row's scalars into BOTH CTAs of the pair
-        const uint32_t sx = (uint32_t)p_x | sm.band[p_x] | (p_ok ? (1u << 24) : 0u);
+        const uint32_t sx = sm.band[p_x] | (p_ok ? (1u << 8) : 0u) | ((uint32_t)p_x << 10);
         const int idx = p_slot * NT + (int)rank * NH + p_r;
         (&sm.scal_c[0][0])[idx] = make_float2(c1, c0);
         (&sm.scal_x[0][0])[idx] = sx;
@@ -318,18 +293,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       }
       p_have = false;
     };
-    int rslot = 0;
-    uint32_t ring_par = 0;       // parity to wait for on lring_full[rslot]
-    long long last_tl = -1;
+    uint32_t ring_par = 0;       // parity to wait for on the ring slot
+    int last_tl = -1;
 #pragma unroll 1
-    for (long long P = pw; P < total_pass; P += NPW) {
-      const long long tl = P / PASSES_PER_TILE;
-      const int ps = (int)(P - tl * PASSES_PER_TILE);
-      const int st = (int)(tl % STAGES);
-      const int slot = (int)(tl % RING);
+    for (int P = pw; P < total_pass; P += NPW) {
+      const int tl = P / PASSES_PER_TILE;
+      const int ps = P - tl * PASSES_PER_TILE;
+      const int st = tl % STAGES;
+      const int slot = tl % RING;
       const bool ok = x_cur >= 0;
       const int x = ok ? x_cur : 0;
-      if (!HEAD) mbar_wait(&sm.lring_full[pw][rslot], ring_par);
+      if (!HEAD) mbar_wait(&sm.lring_full[pw][0], ring_par);
       const int r = 2 * ps + half;
       float v[16];
       float ml = 0.f;
@@ -341,12 +315,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         }
         head_numerators(mu_cur, ls_cur, a.head_fix != 0, l16, v);
       } else {
-        const uint32_t src = smem_u32(&sm.lring[pw][rslot][half][4 * l16]);
+        const uint32_t src = smem_u32(&sm.lring[pw][0][half][4 * l16]);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const float4 q4 = lds128(src + 256 * c);
           v[4 * c] = q4.x; v[4 * c + 1] = q4.y; v[4 * c + 2] = q4.z; v[4 * c + 3] = q4.w;
         }
+        ring_par ^= 1u;
+        __syncwarp();            // every lane has its values: the slot is refilled for the warp's next pass
+        if (lane == 0) fetch_rows(P + NPW);
         float m4[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) m4[c] = fmaxf(fmaxf(v[4 * c], v[4 * c + 1]), fmaxf(v[4 * c + 2], v[4 * c + 3]));
@@ -417,9 +394,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       // this pass's partial sums and row identity travel to the next pass (finish_prev)
       p_sum = sum; p_dot = dot;
       p_x = x; p_ok = ok; p_r = r; p_slot = slot; p_first = (ps == 0); p_have = true;
-      if (++rslot == LRING) { rslot = 0; ring_par ^= 1u; }
       fence_proxy_async();
-      __syncwarp();            // every lane is done with this pass's ring slot and has written its operand rows
+      __syncwarp();            // every lane has written its operand rows
       if (lane == 0) mbar_arrive(full_bar + st);
       x_cur = x_n1;
       if (HEAD) { mu_cur = mu_n1; ls_cur = ls_n1; }
@@ -447,8 +423,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         const long long g = (long long)tile * NT + (long long)rank * NH + r;
         mbar_wait(&sm.scal_full[slot], (i / RING) & 1);
         const uint32_t sx = sm.scal_x[slot][rank * NH + r];
-        const int x = (int)(sx & 255u);
-        const bool valid = (sx >> 24) & 1u;
+        const int x = (int)((sx >> 10) & 255u);
+        const bool valid = (sx >> 8) & 1u;
         int xb = x;
         if (a.x_base && valid) xb = __ldg(a.x_base + g);
         mbar_wait(&sm.contrib_full[cb], (i / CBUF) & 1);
@@ -540,9 +516,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     const uint32_t contrib_dst = (h == rank) ? smem_u32(&sm.contrib[0][chunk][0]) : mapa(smem_u32(&sm.contrib[0][chunk][0]), h);
     const uint32_t cfull_dst = mapa(smem_u32(&sm.contrib_full[0]), h);
     uint64_t* const cfree_wait = (h == rank) ? &sm.contrib_free_local[0] : &sm.contrib_free_remote[0];
-    const float* tabE = reinterpret_cast<const float*>(a.stat + (TAULDR ? ST_RBZT_OFF : ST_RBZ_OFF)) + s_mine;
-    const float* tabC = reinterpret_cast<const float*>(a.stat + ST_RBZ_OFF) + s_mine;   // corrector add: Rb[x][s], zero diag
-    const float* tabFull = (TAULDR ? a.RbT : a.Rb) + s_mine;                             // diagonal kept, for rr_out
+    // table rows are addressed as base + x * 1024 bytes (the row scalar carries x << 10): zero-diagonal R_b^T / R_b for the
+    // rates (the diagonal-keeping originals for the rates output), R_b[x][.] for the corrector add
+    const uint8_t* tabR = (KM == KM_RATES) ? reinterpret_cast<const uint8_t*>((TAULDR ? a.RbT : a.Rb) + s_mine)
+                                           : a.stat + (TAULDR ? ST_RBZT_OFF : ST_RBZ_OFF) + 4 * s_mine;
+    const uint8_t* tabCb = a.stat + ST_RBZ_OFF + 4 * s_mine;
+    const uint32_t chunkbit = 1u << chunk;
+    const uint32_t scr_p = smem_u32(&sm.scratch[warp][0][0]);
     const float hb = a.h * a.beta;
 
     for (int i = 0; i < my_tiles; ++i) {
@@ -567,11 +547,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         for (int j = 0; j < 32; ++j) {
           uint32_t sx;
           asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sx) : "r"(sx_p + 4 * j));
-          const int x = (int)(sx & 255u), lo = (int)((sx >> 8) & 255u), hi = (int)((sx >> 16) & 255u);
-          const bool inband = (hi >= cs) && (lo <= cs + JUMP_CHUNK - 1);
-          const float* src = ((KM == KM_RATES) ? tabFull : tabE) + ((size_t)x << 8);
-          R[j] = inband ? __ldg(src) : 0.f;
+          const float* src = reinterpret_cast<const float*>(tabR + (sx & 0x3FC00u));
+          R[j] = (sx & chunkbit) ? __ldg(src) : 0.f;
         }
+        // the row's Philox draw (count uniform + first three pick uniforms) does not depend on the data: computed in the
+        // shadow of the gathers.  From the transpose on this lane works on row `lane` of the batch.
+        const uint64_t grow = (uint64_t)(a.row_offset + g0 + lane);
+        Philox4 p0 = {{0u, 0u, 0u, 0u}};
+        if constexpr (KM == KM_JUMP || KM == KM_CORR) p0 = philox_rowjump(grow, cbase, a.offset, a.seed);
         tmem_ld_wait();
         if (bb == 1) {           // the accumulator has been read: hand the buffer back to the MMA warp
           tc_fence_before();
@@ -601,86 +584,128 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
             }
           }
         } else {
-          // lam[s, row] (zero at s == x through the zero-diagonal tables)
+          // lam[s, row] (zero at s == x through the zero-diagonal tables).  tauLDR without corrector: the row's scale c1
+          // is applied to the chunk total only (the picks are scale-invariant); otherwise per element.
+          constexpr bool UNSCALED = TAULDR && !km_corr(KM);
           float lam[32];
+          if constexpr (UNSCALED) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float c1, c0;
-            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(c1), "=f"(c0) : "r"(sc_p + 8 * j));
-            lam[j] = fmaf(__uint_as_float(acc[j]), c1, c0) * R[j];
+            for (int j = 0; j < 32; ++j) lam[j] = __uint_as_float(acc[j]) * R[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float c1, c0;
+              asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(c1), "=f"(c0) : "r"(sc_p + 8 * j));
+              lam[j] = fmaf(__uint_as_float(acc[j]), c1, c0) * R[j];
+            }
           }
           if constexpr (km_corr(KM)) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               uint32_t sx;
               asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sx) : "r"(sx_p + 4 * j));
-              const int x = (int)(sx & 255u), lo = (int)((sx >> 8) & 255u), hi = (int)((sx >> 16) & 255u);
-              const bool inband = (hi >= cs) && (lo <= cs + JUMP_CHUNK - 1);
-              R[j] = inband ? __ldg(tabC + ((size_t)x << 8)) : 0.f;
+              const float* src = reinterpret_cast<const float*>(tabCb + (sx & 0x3FC00u));
+              R[j] = (sx & chunkbit) ? __ldg(src) : 0.f;
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) lam[j] = fmaf(hb, R[j], lam[j]);
           }
-          // lane = row from here: this lane's row of the batch
+          // transpose through the warp's scratch: lane = state -> lane = row (row `lane` of the batch, the chunk's 32 states)
+          __syncwarp();          // the previous batch's reads of the scratch are done
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sts32(scr_p + (uint32_t)(j * SCR_LD + lane) * 4u, lam[j]);
+          __syncwarp();
+          float p[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 v4 = lds128(scr_p + (uint32_t)(lane * SCR_LD + 4 * c) * 4u);
+            p[4 * c] = v4.x; p[4 * c + 1] = v4.y; p[4 * c + 2] = v4.z; p[4 * c + 3] = v4.w;
+          }
           uint32_t sxl;
           asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sxl) : "r"(sx_p + 4 * lane));
-          const int xl = (int)(sxl & 255u);
+          const int xl = (int)((sxl >> 10) & 255u);
           int2 rec = make_int2(0, 0);
           if constexpr (KM == KM_DRIFT) {
-            // sum_s rr_s (s - x) over this chunk, for the 32 rows at once
+            // sum_s rr_s (s - x) over this chunk (sampling.py:433-453)
+            float dsum = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              uint32_t sx;
-              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sx) : "r"(sx_p + 4 * j));
-              R[j] = lam[j] * (float)(s_mine - (int)(sx & 255u));
-            }
-            rec.x = __float_as_int(transpose_reduce(R, lane));
+            for (int s2 = 0; s2 < 32; ++s2) dsum = fmaf(p[s2], (float)(cs + s2 - xl), dsum);
+            if constexpr (UNSCALED) dsum *= lds32(sc_p + 8 * lane);
+            rec.x = __float_as_int(dsum);
           } else {
+            // sequential fp32 prefix sums over the chunk's states (the oracle's summation order)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) R[j] = lam[j];
-            const float tot = transpose_reduce(R, lane);           // chunk total of row `lane`
-            const Philox4 p0 = philox_rowjump((uint64_t)(a.row_offset + g0 + lane), cbase, a.offset, a.seed);
+            for (int s2 = 1; s2 < 32; ++s2) p[s2] += p[s2 - 1];
+            float tot = p[31];
+            if constexpr (UNSCALED) tot *= lds32(sc_p + 8 * lane);
             int K = poisson_from_unit(tot, u32_to_unit(p0.w[0]));
             K = K > JUMP_PICK_CAP ? JUMP_PICK_CAP : K;
             rec.y = K;
-            uint32_t todo = __ballot_sync(0xffffffffu, K > 0);
 #ifdef CTDD_EXP_NOPICK       // diagnostic build: counts are drawn, picks are not resolved
-            todo = 0;
+            K = 0;
 #endif
-            while (todo) {             // rows with picks in this chunk (warp-uniform loop)
-              const int rr = __ffs(todo) - 1;
-              todo &= todo - 1;
-              float p = select32(lam, rr);
+            // Picks: first state whose prefix sum exceeds v * total.  The picks of the batch's 32 rows are dealt to the
+            // 32 lanes (a row with K picks would otherwise keep 31 lanes idle for K rounds): lane = row parks its prefix
+            // sums in its scratch row, a warp scan of K numbers the picks, and lane i resolves pick base + i of whatever
+            // row it belongs to (row found by a 5-shuffle search over the scan, uniforms fetched from the row's lane).
+            int jump = 0;
+            const uint32_t any = __ballot_sync(0xffffffffu, K > 0);
+            if (any) {
+              __syncwarp();
 #pragma unroll
-              for (int o = 1; o < 32; o <<= 1) {       // inclusive prefix sums over the chunk's 32 states
-                const float n = __shfl_up_sync(0xffffffffu, p, o);
-                if (lane >= o) p += n;
+              for (int c = 0; c < 8; ++c)
+                sts128(scr_p + (uint32_t)(lane * SCR_LD + 4 * c) * 4u, make_float4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]));
+              // column 32 of the scratch row: the row's jump sum (shared-memory reduction target)
+              asm volatile("st.shared.u32 [%0], %1;" ::"r"(scr_p + (uint32_t)(lane * SCR_LD + 32) * 4u), "r"(0) : "memory");
+              int incl = K;
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += n;
               }
-              const float ptot = __shfl_sync(0xffffffffu, p, 31);
-              const int Kr = __shfl_sync(0xffffffffu, K, rr);
-              const uint32_t w1 = __shfl_sync(0xffffffffu, p0.w[1], rr), w2 = __shfl_sync(0xffffffffu, p0.w[2], rr),
-                             w3 = __shfl_sync(0xffffffffu, p0.w[3], rr);
-              const int xr = __shfl_sync(0xffffffffu, xl, rr);
-              int jump = 0;
-              Philox4 pc = {{0u, 0u, 0u, 0u}};
-              for (int j = 0; j < Kr; ++j) {
-                uint32_t w;
-                if (j < 3) {
-                  w = j == 0 ? w1 : (j == 1 ? w2 : w3);
-                } else {
-                  const int jj = j - 3;
-                  if ((jj & 3) == 0)
-                    pc = philox_rowjump((uint64_t)(a.row_offset + g0 + rr), cbase + 1u + (uint32_t)(jj >> 2), a.offset, a.seed);
-                  w = philox_word(pc, jj & 3);
+              const int npick = __shfl_sync(0xffffffffu, incl, 31);
+              __syncwarp();
+              for (int base = 0; base < npick; base += 32) {
+                const int idx = base + lane;
+                // row of pick idx: the first lane whose inclusive count exceeds idx
+                int r = 0;
+#pragma unroll
+                for (int stp = 16; stp >= 1; stp >>= 1) {
+                  const int v = __shfl_sync(0xffffffffu, incl, (r + stp - 1) & 31);
+                  if (v <= idx) r += stp;
                 }
-                // first state whose prefix sum exceeds the target (the last prefix sum is the total, so one always does)
-                const float T = fminf(u32_to_unit(w), 0.99999994f) * ptot;
-                const uint32_t above = __ballot_sync(0xffffffffu, p > T);
-                const int sl = above ? __ffs(above) - 1 : 31;
-                jump += cs + sl - xr;
+                r &= 31;                                  // lanes beyond the last pick (idx >= npick) walk a valid row
+                const int j = idx - (__shfl_sync(0xffffffffu, incl, r) - __shfl_sync(0xffffffffu, K, r));
+                const uint32_t w1 = __shfl_sync(0xffffffffu, p0.w[1], r), w2 = __shfl_sync(0xffffffffu, p0.w[2], r),
+                               w3 = __shfl_sync(0xffffffffu, p0.w[3], r);
+                if (idx < npick) {
+                  uint32_t w = j == 0 ? w1 : (j == 1 ? w2 : w3);
+                  if (j >= 3) {
+                    const int jj = j - 3;
+                    const Philox4 pc = philox_rowjump((uint64_t)(a.row_offset + g0 + r), cbase + 1u + (uint32_t)(jj >> 2), a.offset, a.seed);
+                    w = philox_word(pc, jj & 3);
+                  }
+                  const uint32_t prow = scr_p + (uint32_t)(r * SCR_LD) * 4u;
+                  const float ptot = lds32(prow + 31 * 4);
+                  float T = fminf(u32_to_unit(w), 0.99999994f) * ptot;
+                  // the product can round up to the total itself: then the pick is the last state with a positive rate
+                  if (T >= ptot) T = __uint_as_float(__float_as_uint(ptot) - 1u);
+                  // two rounds of independent loads: 7 splitters of stride 4, then the 3 entries below the next one
+                  int c1 = 0;
+#pragma unroll
+                  for (int m = 0; m < 7; ++m) c1 += (lds32(prow + 4 * (4 * m + 3)) <= T) ? 1 : 0;
+                  const uint32_t p2 = prow + 16 * c1;
+                  const int c2 = ((lds32(p2) <= T) ? 1 : 0) + ((lds32(p2 + 4) <= T) ? 1 : 0) + ((lds32(p2 + 8) <= T) ? 1 : 0);
+                  uint32_t sxr;
+                  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sxr) : "r"(sx_p + 4 * r));
+                  const int dj = cs + 4 * c1 + c2 - (int)((sxr >> 10) & 255u);
+                  asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(prow + 32 * 4), "r"(dj) : "memory");
+                }
               }
-              if (lane == rr) rec.x = jump;
+              __syncwarp();
+              asm volatile("ld.shared.s32 %0, [%1];" : "=r"(jump) : "r"(scr_p + (uint32_t)(lane * SCR_LD + 32) * 4u));
             }
+            rec.x = jump;
           }
           // the record of (row `lane`, this chunk) goes to the CTA that produced the row
           const uint32_t roff = (uint32_t)cb * (NCHUNK * NH * 8) + (uint32_t)(32 * bb + lane) * 8u;

@@ -6,13 +6,14 @@ executed warp-instructions / stall samples of the tcgen05 kernel per source line
 """
 import csv, re, subprocess, sys, os, collections, tempfile
 
+SRC = os.environ.get("CTDD_SRC", "ctdd_step_tcq")   # source file (without .cu) whose kernel is analysed
 LIB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                    "continuous-time-diffusion-models-for-discrete-data_b200", "libctdd_b200.so")
 
 
 def line_map(kernel):
     d = tempfile.mkdtemp()
-    subprocess.run(["cuobjdump", "-xelf", "ctdd_step_tc.sm_100a.cubin", LIB], cwd=d, check=True, capture_output=True)
+    subprocess.run(["cuobjdump", "-xelf", SRC + ".sm_100a.cubin", LIB], cwd=d, check=True, capture_output=True)
     cub = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
     txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, cub)], capture_output=True, text=True).stdout
     m, cur, infn = {}, None, False
@@ -24,11 +25,11 @@ def line_map(kernel):
         f = re.search(r'//## File "([^"]+)", line (\d+)(.*)', ln)
         if f:
             # keep the OUTERMOST location in ctdd_step_tc.cu (inlined helpers report their own line first)
-            if f.group(1).endswith("ctdd_step_tc.cu") and "inlined at" not in f.group(3):
+            if f.group(1).endswith(SRC + ".cu") and "inlined at" not in f.group(3):
                 cur = int(f.group(2))
             elif "inlined at" in f.group(3):
                 g = re.findall(r'inlined at "([^"]+)", line (\d+)', f.group(3))
-                g = [int(b) for a, b in g if a.endswith("ctdd_step_tc.cu")]
+                g = [int(b) for a, b in g if a.endswith(SRC + ".cu")]
                 if g:
                     cur = g[-1]
             continue
