@@ -91,6 +91,8 @@ def lib() -> ctypes.CDLL:
     L.ctdd_tc_tables_bytes.restype = c_int64
     L.ctdd_tc_static_bytes.argtypes = [c_int]
     L.ctdd_tc_static_bytes.restype = c_int64
+    L.ctdd_tc_static_align.argtypes = []
+    L.ctdd_tc_static_align.restype = c_int64
     L.ctdd_prep_tc_static.argtypes = [c_void_p, c_int, c_void_p, c_void_p]
     L.ctdd_prep_tc_static.restype = c_int
     L.ctdd_prep_tc_tables.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_void_p]
@@ -138,11 +140,55 @@ def ptr(t) -> int:
         raise RuntimeError("ctdd_b200 kernels need CUDA tensors; got a host tensor (there is no CPU fallback)")
     if not t.is_contiguous():
         raise RuntimeError("ctdd_b200 kernels need contiguous tensors")
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"ctdd_b200: tensor on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                           "the kernels launch on the current device's stream (wrap the call in torch.cuda.device(...))")
     return t.data_ptr()
 
 
 def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def _first_cuda_tensor(objs):
+    for o in objs:
+        if isinstance(o, torch.Tensor):
+            if o.is_cuda:
+                return o
+        elif isinstance(o, (list, tuple)):
+            t = _first_cuda_tensor(o)
+            if t is not None:
+                return t
+        elif hasattr(o, "mu") and isinstance(getattr(o, "mu"), torch.Tensor) and o.mu.is_cuda:   # ops.LogisticHead
+            return o.mu
+    return None
+
+
+def on_tensor_device(fn):
+    """Run `fn` with the CUDA device of its first CUDA tensor argument current: the library launches on the current
+    device's stream and keeps per-device state (cudaGetDevice), so a tensor on cuda:1 while cuda:0 is current would
+    otherwise be an illegal access.  ptr() refuses such a mismatch outright."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        t = _first_cuda_tensor(args)
+        if t is None:
+            t = _first_cuda_tensor(tuple(kw.values()))
+        if t is None or t.device.index == torch.cuda.current_device():
+            return fn(*args, **kw)
+        with torch.cuda.device(t.device):
+            return fn(*args, **kw)
+    return wrapper
+
+
+def on_device(device):
+    """Context manager: make `device` (a torch.device / str / model.device) current if it is a CUDA device."""
+    import contextlib
+    dev = torch.device(device) if device is not None else None
+    if dev is None or dev.type != "cuda":
+        return contextlib.nullcontext()
+    return torch.cuda.device(dev)
 
 
 def launch_count() -> int:

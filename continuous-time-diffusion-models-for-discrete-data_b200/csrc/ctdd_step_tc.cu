@@ -906,10 +906,17 @@ __global__ void prep_static_kernel(const float* __restrict__ Rb, uint8_t* __rest
   float* rbzt = reinterpret_cast<float*>(out + ST_RBZT_OFF);
   float* rbz = reinterpret_cast<float*>(out + ST_RBZ_OFF);
   float* rowsum = reinterpret_cast<float*>(out + ST_ROWSUM_OFF);
+  float* rbt = reinterpret_cast<float*>(out + ST_RBT_OFF);
+  float* rbf = reinterpret_cast<float*>(out + ST_RB_OFF);
+  float* zero = reinterpret_cast<float*>(out + ST_ZERO_OFF);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S * S; i += gridDim.x * blockDim.x) {
     const int x = i / S, s = i % S;
-    rbzt[i] = (s == x) ? 0.f : Rb[(size_t)s * S + x];
-    rbz[i] = (s == x) ? 0.f : Rb[i];
+    const float t = Rb[(size_t)s * S + x], r = Rb[i];
+    rbzt[i] = (s == x) ? 0.f : t;
+    rbz[i] = (s == x) ? 0.f : r;
+    rbt[i] = t;
+    rbf[i] = r;
+    if (i < S) zero[i] = 0.f;
   }
   int* bandT = reinterpret_cast<int*>(out + ST_BANDT_OFF);
   int* bandR = reinterpret_cast<int*>(out + ST_BANDR_OFF);
@@ -1010,6 +1017,7 @@ int launch_step_tc(const ctdd_step_params* p, cudaStream_t st) {
 
 extern "C" int64_t ctdd_tc_tables_bytes(int S) { return S == ctdd::tc::S ? (int64_t)ctdd::tc::TAB_BYTES : 0; }
 extern "C" int64_t ctdd_tc_static_bytes(int S) { return S == ctdd::tc::S ? (int64_t)ctdd::tc::ST_BYTES : 0; }
+extern "C" int64_t ctdd_tc_static_align(void) { return (int64_t)ctdd::tc::ST_ALIGN; }
 
 extern "C" int ctdd_prep_tc_tables(const float* Q, const float* QT, const float* Rb, int T, int S, float eps,
                                    int branch, void* tables_out, void* stream) {
@@ -1034,6 +1042,10 @@ extern "C" int ctdd_prep_tc_static(const float* Rb, int S, void* static_out, voi
   using namespace ctdd;
   if (S != tc::S) { set_error("ctdd_prep_tc_static: the tcgen05 path needs S == 256 (got %d)", S); return 2; }
   if (!Rb || !static_out) { set_error("ctdd_prep_tc_static: null pointer"); return 2; }
+  if (reinterpret_cast<uintptr_t>(static_out) % tc::ST_ALIGN) {
+    set_error("ctdd_prep_tc_static: static_out must be aligned to ctdd_tc_static_align() = %zu bytes", tc::ST_ALIGN);
+    return 2;
+  }
   tc::prep_static_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(Rb, reinterpret_cast<uint8_t*>(static_out));
   CTDD_CHECK_LAUNCH("prep_static_kernel");
   return 0;

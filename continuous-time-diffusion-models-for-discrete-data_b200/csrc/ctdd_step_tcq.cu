@@ -78,10 +78,10 @@ struct Smem {
   alignas(16) float scratch[NUM_EPI_WARPS][32][SCR_LD];   // per epilogue warp: lam[row][state of the chunk] (lane = state -> lane = row)
   alignas(16) int2 contrib[CBUF][NCHUNK][NH];  // per (chunk, row of THIS CTA): (sum of jumps | drift bits, jump count)
   uint32_t band[S];                            // per state x: which of the 8 chunks hold a non-zero base rate (this launch's branch / mode)
-  alignas(8) uint64_t full[STAGES];            // leader CTA: its 32 passes + 1 relayed arrival for the partner's 32
-  uint64_t full_local[STAGES];                 // partner CTA: its 32 passes; the partner's idle MMA warp relays the phase
+  alignas(8) uint64_t full[STAGES];            // leader CTA: its NPW producer warps + 1 relayed arrival for the partner's
+  uint64_t full_local[STAGES];                 // partner CTA: its NPW producer warps; the partner's idle MMA warp relays the phase
   uint64_t empty[STAGES];                      // multicast tcgen05.commit
-  uint64_t scal_full[RING];                    // 32 local passes + the partner's bytes (st.async complete_tx)
+  uint64_t scal_full[RING];                    // NPW local producer warps + the partner's bytes (st.async complete_tx)
   uint64_t lring_full[NPW][LRING];             // cp.async.bulk complete_tx of one row pair
   uint64_t tmem_full[ACC];                     // multicast tcgen05.commit
   uint64_t tmem_empty[ACC];                    // used in the leader CTA: 8 local + 8 remote epilogue warps
@@ -92,6 +92,7 @@ struct Smem {
 };
 
 static_assert(sizeof(Smem) + 1024 <= 232448, "shared memory budget of one CTA (227 KB) exceeded");
+static_assert(NPW <= PASSES_PER_TILE, "every producer warp must own a pass in every tile");
 static_assert(RING > STAGES + ACC + CBUF, "row-scalar ring shorter than the pipeline");
 
 // TAULDR: tauLDR rates (else SDDM reverse_prob); KM: KM_JUMP / KM_CORR / KM_RATES / KM_DRIFT;
@@ -109,11 +110,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&sm.full[i], PASSES_PER_TILE + 1);
-      mbar_init(&sm.full_local[i], PASSES_PER_TILE);
+      mbar_init(&sm.full[i], NPW + 1);
+      mbar_init(&sm.full_local[i], NPW);
       mbar_init(&sm.empty[i], 1);
     }
-    for (int i = 0; i < RING; ++i) mbar_init(&sm.scal_full[i], PASSES_PER_TILE);
+    for (int i = 0; i < RING; ++i) mbar_init(&sm.scal_full[i], NPW);
     for (int w = 0; w < NPW; ++w)
       for (int i = 0; i < LRING; ++i) mbar_init(&sm.lring_full[w][i], 1);
     for (int i = 0; i < ACC; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], 2 * NUM_EPI_WARPS); }
@@ -184,9 +185,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     const float hb = (KM == KM_RATES) ? 1.0f : a.h * a.beta;   // rates-only ignores the step length
     const bool contiguous = (a.ld == S) && (a.batch_stride == (long long)a.D * S);
     uint64_t* const full_bar = rank == 0 ? &sm.full[0] : &sm.full_local[0];
-    const int total_pass = my_tiles * PASSES_PER_TILE;   // passes of this CTA; warp pw takes pw, pw + NPW, ..
-    const uint32_t scal_c_remote = mapa(smem_u32(&sm.scal_c[0][0]), rank ^ 1u);
-    const uint32_t scal_x_remote = mapa(smem_u32(&sm.scal_x[0][0]), rank ^ 1u);
+    // passes of this CTA: pass P = 32 * tl + ps builds rows 2 ps, 2 ps + 1 of the CTA's 64 rows of its tl-th tile; warp pw
+    // takes P = pw, pw + NPW, ..  Three cursors run over that sequence (compute, logits fetch one pass ahead, state fetch
+    // two passes ahead); they advance by additions only.
+    struct Cursor {
+      int tl, ps;
+      __device__ __forceinline__ void advance() { ps += NPW; if (ps >= PASSES_PER_TILE) { ps -= PASSES_PER_TILE; ++tl; } }
+    };
+    auto cursor_row = [&](const Cursor& c) -> long long {        // first global row of the pass
+      return (long long)(pair + c.tl * npairs) * NT + (int)rank * NH + 2 * c.ps;
+    };
+    const uint32_t scal_c_p = smem_u32(&sm.scal_c[0][0]), scal_x_p = smem_u32(&sm.scal_x[0][0]), band_p = smem_u32(&sm.band[0]);
+    const uint32_t scal_c_remote = mapa(scal_c_p, rank ^ 1u);
+    const uint32_t scal_x_remote = mapa(scal_x_p, rank ^ 1u);
     const uint32_t scal_full_remote = mapa(smem_u32(&sm.scal_full[0]), rank ^ 1u);
 
     auto row_ptr = [&](long long g) -> const float* {
@@ -194,21 +205,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       const uint32_t n = (uint32_t)g / (uint32_t)a.D, d = (uint32_t)g - n * (uint32_t)a.D;
       return a.logits + (long long)n * a.batch_stride + (long long)d * a.ld;
     };
-    // first global row of pass P of this CTA
-    auto pass_row = [&](int P) -> long long {
-      const int tl = P / PASSES_PER_TILE;
-      return (long long)(pair + tl * npairs) * NT + (int)rank * NH + 2 * (P - tl * PASSES_PER_TILE);
-    };
-    // Two fetch streams ahead of the compute stream.  States (and head parameters): two passes of this warp ahead, into
-    // registers.  Logits: lane 0 starts the bulk copy of the NEXT pass's row pair into the warp's ring slot as soon as
-    // the current pass has read its values (rows past the end are replaced by row 0: never used; adjacent rows of a
-    // contiguous logits tensor travel as one 2 KB copy; the rows were pulled into L2 some tiles earlier).
-    int Pf = pw;                         // pass whose state is fetched next
+    // States (and head parameters): two passes of this warp ahead, into registers.
+    Cursor cx = {0, pw};
     float f_mu = 0.f, f_ls = 0.f;        // HEAD: head parameters of the row fetch() just visited
     auto fetch = [&]() -> int {
       int xv = -1;
-      if (Pf < total_pass) {
-        const long long g = pass_row(Pf) + half;
+      if (cx.tl < my_tiles) {
+        const long long g = cursor_row(cx) + half;
         if (g < a.rows) {
           xv = __ldg(a.x_eval + g);
           if (HEAD) {
@@ -222,13 +225,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
             f_ls = __ldg(a.head_ls + src);
           }
         }
-        Pf += NPW;
+        cx.advance();
       }
       return xv;
     };
-    auto fetch_rows = [&](int P) {     // lane 0 only
-      if (HEAD || P >= total_pass) return;
-      const long long gf = pass_row(P);
+    // Logits: lane 0 starts the bulk copy of the NEXT pass's row pair into the warp's ring slot as soon as the current
+    // pass has read its values (rows past the end are replaced by row 0: never used; adjacent rows of a contiguous
+    // logits tensor travel as one 2 KB copy; the rows were pulled from HBM into L2 some tiles earlier).
+    Cursor cf = {0, pw};
+    auto fetch_rows = [&]() {            // lane 0 only
+      if (HEAD || cf.tl >= my_tiles) return;
+      const long long gf = cursor_row(cf);
       uint64_t* bar = &sm.lring_full[pw][0];
       mbar_arrive_expect_tx(bar, 2 * S * 4);
       if (contiguous && gf + 1 < a.rows) {
@@ -244,9 +251,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         const long long r0 = gf + (long long)PREFETCH_TILES * npairs * NT;
         if (r0 + 2 <= a.rows) l2_prefetch_bulk(a.logits + r0 * S, 2 * S * 4);
       }
+      cf.advance();
     };
 
-    if (lane == 0) fetch_rows(pw);
+    if (lane == 0) fetch_rows();
     int x_cur = fetch();
     float mu_cur = f_mu, ls_cur = f_ls;
     int x_n1 = fetch();
@@ -259,11 +267,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     }
     // The row reductions (sum e, sum e*Q[.,x]) and the row scalars of a pass are FINISHED IN THE NEXT PASS: its per-lane
     // partial sums are carried over, their butterflies run next to the next pass's row-maximum butterfly, and the
-    // scalar records / scal_full arrival follow there.  Only the operand rows (what the MMA waits for) are completed
-    // inside the pass itself.
+    // scalar records follow there.  Only the operand rows (what the MMA waits for) are completed inside the pass itself.
+    // Barrier arrivals (operands: full, scalars: scal_full) happen once per warp and tile, after the warp's last pass in it.
     float p_sum = 1.f, p_dot = 0.f;
-    int p_x = 0, p_r = 0, p_slot = 0;
-    bool p_ok = false, p_have = false, p_first = false;
+    int p_x = 0, p_idx = 0, p_slot = 0;
+    bool p_ok = false, p_have = false, p_last = false;
     auto finish_prev = [&]() {          // p_sum / p_dot hold the reduced values
       if (!p_have) return;
       const float rs = __frcp_rn(p_sum);
@@ -277,32 +285,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         c0 = hb * 1e-35f * inv;
       }
       if (l16 == 0) {   // one lane per half-warp: the row's scalars into BOTH CTAs of the pair
-        const uint32_t sx = sm.band[p_x] | (p_ok ? (1u << 8) : 0u) | ((uint32_t)p_x << 10);
-        const int idx = p_slot * NT + (int)rank * NH + p_r;
-        (&sm.scal_c[0][0])[idx] = make_float2(c1, c0);
-        (&sm.scal_x[0][0])[idx] = sx;
+        uint32_t bandx;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(bandx) : "r"(band_p + 4u * (uint32_t)p_x));
+        const uint32_t sx = bandx | (p_ok ? (1u << 8) : 0u) | ((uint32_t)p_x << 10);
+        sts64(scal_c_p + (uint32_t)p_idx * 8u, __float_as_uint(c1), __float_as_uint(c0));
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(scal_x_p + (uint32_t)p_idx * 4u), "r"(sx) : "memory");
         const uint32_t bar = scal_full_remote + (uint32_t)p_slot * 8u;
-        st_async_cluster_v2(scal_c_remote + (uint32_t)idx * 8u, __float_as_uint(c1), __float_as_uint(c0), bar);
-        st_async_cluster_b32(scal_x_remote + (uint32_t)idx * 4u, sx, bar);
+        st_async_cluster_v2(scal_c_remote + (uint32_t)p_idx * 8u, __float_as_uint(c1), __float_as_uint(c0), bar);
+        st_async_cluster_b32(scal_x_remote + (uint32_t)p_idx * 4u, sx, bar);
       }
-      __syncwarp();
-      if (lane == 0) {
-        // the first pass of a tile also announces the bytes the partner's producers deliver for this tile
-        if (p_first) mbar_arrive_expect_tx(&sm.scal_full[p_slot], SCAL_TX_BYTES);
-        else mbar_arrive(&sm.scal_full[p_slot]);
+      if (p_last) {
+        __syncwarp();
+        if (lane == 0) {
+          // warp 0 also announces the bytes the partner's producers deliver for this tile
+          if (pw == 0) mbar_arrive_expect_tx(&sm.scal_full[p_slot], SCAL_TX_BYTES);
+          else mbar_arrive(&sm.scal_full[p_slot]);
+        }
       }
       p_have = false;
     };
     uint32_t ring_par = 0;       // parity to wait for on the ring slot
     int last_tl = -1;
+    Cursor cc = {0, pw};
 #pragma unroll 1
-    for (int P = pw; P < total_pass; P += NPW) {
-      const int tl = P / PASSES_PER_TILE;
-      const int ps = P - tl * PASSES_PER_TILE;
+    while (cc.tl < my_tiles) {
+      const int tl = cc.tl, ps = cc.ps;
       const int st = tl % STAGES;
       const int slot = tl % RING;
       const bool ok = x_cur >= 0;
       const int x = ok ? x_cur : 0;
+      const bool last_in_tile = ps + NPW >= PASSES_PER_TILE;     // this warp's next pass belongs to another tile
       if (!HEAD) mbar_wait(&sm.lring_full[pw][0], ring_par);
       const int r = 2 * ps + half;
       float v[16];
@@ -323,7 +335,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         }
         ring_par ^= 1u;
         __syncwarp();            // every lane has its values: the slot is refilled for the warp's next pass
-        if (lane == 0) fetch_rows(P + NPW);
+        if (lane == 0) fetch_rows();
         float m4[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) m4[c] = fmaxf(fmaxf(v[4 * c], v[4 * c + 1]), fmaxf(v[4 * c + 2], v[4 * c + 3]));
@@ -379,6 +391,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
 #pragma unroll
         for (int c = 0; c < 4; ++c) t4[c] = __ldg(reinterpret_cast<const float4*>(tabA + xo + 64 * c));
       }
+      // rows past the end (the last tile only) contribute zero operand rows
+      if (__any_sync(0xffffffffu, !ok)) {
+        if (!ok) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] = 0.f;
+        }
+      }
       // k = 64c + 4*l16 .. +3 lives in K block c, 16-byte chunk l16/2 (XOR-swizzled by the row), half l16&1
       const uint32_t off = (uint32_t)r * 128 + (uint32_t)((((l16 >> 1) ^ (r & 7)) << 4) | ((l16 & 1) << 3));
 #pragma unroll
@@ -386,21 +405,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         uint32_t h0, m0, h1, m1;
         split2(v[4 * c], v[4 * c + 1], h0, m0);
         split2(v[4 * c + 2], v[4 * c + 3], h1, m1);
-        if (!ok) h0 = m0 = h1 = m1 = 0u;
         sts64(stage_s + c * KBLOCK_BYTES + off, h0, h1);
         sts64(stage_s + SPLIT_BYTES + c * KBLOCK_BYTES + off, m0, m1);
       }
 #endif
       // this pass's partial sums and row identity travel to the next pass (finish_prev)
       p_sum = sum; p_dot = dot;
-      p_x = x; p_ok = ok; p_r = r; p_slot = slot; p_first = (ps == 0); p_have = true;
-      fence_proxy_async();
-      __syncwarp();            // every lane has written its operand rows
-      if (lane == 0) mbar_arrive(full_bar + st);
+      p_x = x; p_ok = ok; p_idx = slot * NT + (int)rank * NH + r; p_slot = slot; p_last = last_in_tile; p_have = true;
+      if (last_in_tile) {      // the warp's operand rows of this tile are in place
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar + st);
+      }
       x_cur = x_n1;
       if (HEAD) { mu_cur = mu_n1; ls_cur = ls_n1; }
       x_n1 = fetch();
       if (HEAD) { mu_n1 = f_mu; ls_n1 = f_ls; }
+      cc.advance();
     }
     // the last pass's reductions and row scalars
 #pragma unroll
@@ -516,11 +537,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     const uint32_t contrib_dst = (h == rank) ? smem_u32(&sm.contrib[0][chunk][0]) : mapa(smem_u32(&sm.contrib[0][chunk][0]), h);
     const uint32_t cfull_dst = mapa(smem_u32(&sm.contrib_full[0]), h);
     uint64_t* const cfree_wait = (h == rank) ? &sm.contrib_free_local[0] : &sm.contrib_free_remote[0];
-    // table rows are addressed as base + x * 1024 bytes (the row scalar carries x << 10): zero-diagonal R_b^T / R_b for the
-    // rates (the diagonal-keeping originals for the rates output), R_b[x][.] for the corrector add
-    const uint8_t* tabR = (KM == KM_RATES) ? reinterpret_cast<const uint8_t*>((TAULDR ? a.RbT : a.Rb) + s_mine)
-                                           : a.stat + (TAULDR ? ST_RBZT_OFF : ST_RBZ_OFF) + 4 * s_mine;
-    const uint8_t* tabCb = a.stat + ST_RBZ_OFF + 4 * s_mine;
+    // Table rows are addressed as static blob + 32-bit offset: the blob is 2 MiB aligned, so the upper address word is
+    // a constant and the lower word is one add.  Offset of a row = table + x * 1024 (the row scalar carries x << 10):
+    // zero-diagonal R_b^T / R_b for the rates (the diagonal-keeping copies for the rates output), R_b[x][.] for the
+    // corrector add, the zero row for chunks outside the band of x.
+    const uint32_t stat_hi = (uint32_t)(reinterpret_cast<uintptr_t>(a.stat) >> 32);
+    const uint32_t lane_lo = (uint32_t)reinterpret_cast<uintptr_t>(a.stat) + 4u * (uint32_t)s_mine;
+    constexpr uint32_t TAB_R = (uint32_t)((KM == KM_RATES) ? (TAULDR ? ST_RBT_OFF : ST_RB_OFF) : (TAULDR ? ST_RBZT_OFF : ST_RBZ_OFF));
+    auto stat_ptr = [&](uint32_t off) -> const float* {
+      return reinterpret_cast<const float*>(((unsigned long long)stat_hi << 32) | (unsigned long long)(lane_lo + off));
+    };
     const uint32_t chunkbit = 1u << chunk;
     const uint32_t scr_p = smem_u32(&sm.scratch[warp][0][0]);
     const float hb = a.h * a.beta;
@@ -540,16 +566,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         const uint32_t sc_p = smem_u32(&sm.scal_c[slot][col]);
         uint32_t acc[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + TM_ACC + b * NT + col, acc);
-        // base-rate rows of the 32 rows of the batch: 32 independent coalesced loads (chunks outside the band of
-        // non-zero rates of x are skipped: the predicate is uniform over the warp)
+        // base-rate rows of the 32 rows of the batch: 32 independent coalesced loads.  Lane L prepares the table offset of
+        // row L (the zero row when this chunk lies outside the band of non-zero rates of its x); a shuffle hands it to all.
+        uint32_t sxl;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sxl) : "r"(sx_p + 4 * lane));
+        const uint32_t offl = (sxl & chunkbit) ? TAB_R + (sxl & 0x3FC00u) : (uint32_t)ST_ZERO_OFF;
         float R[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          uint32_t sx;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sx) : "r"(sx_p + 4 * j));
-          const float* src = reinterpret_cast<const float*>(tabR + (sx & 0x3FC00u));
-          R[j] = (sx & chunkbit) ? __ldg(src) : 0.f;
-        }
+        for (int j = 0; j < 32; ++j) R[j] = __ldg(stat_ptr(__shfl_sync(0xffffffffu, offl, j)));
         // the row's Philox draw (count uniform + first three pick uniforms) does not depend on the data: computed in the
         // shadow of the gathers.  From the transpose on this lane works on row `lane` of the batch.
         const uint64_t grow = (uint64_t)(a.row_offset + g0 + lane);
@@ -600,13 +624,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
             }
           }
           if constexpr (km_corr(KM)) {
+            const uint32_t offc = (sxl & chunkbit) ? (uint32_t)ST_RBZ_OFF + (sxl & 0x3FC00u) : (uint32_t)ST_ZERO_OFF;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              uint32_t sx;
-              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sx) : "r"(sx_p + 4 * j));
-              const float* src = reinterpret_cast<const float*>(tabCb + (sx & 0x3FC00u));
-              R[j] = (sx & chunkbit) ? __ldg(src) : 0.f;
-            }
+            for (int j = 0; j < 32; ++j) R[j] = __ldg(stat_ptr(__shfl_sync(0xffffffffu, offc, j)));
 #pragma unroll
             for (int j = 0; j < 32; ++j) lam[j] = fmaf(hb, R[j], lam[j]);
           }
@@ -621,8 +641,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
             const float4 v4 = lds128(scr_p + (uint32_t)(lane * SCR_LD + 4 * c) * 4u);
             p[4 * c] = v4.x; p[4 * c + 1] = v4.y; p[4 * c + 2] = v4.z; p[4 * c + 3] = v4.w;
           }
-          uint32_t sxl;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sxl) : "r"(sx_p + 4 * lane));
           const int xl = (int)((sxl >> 10) & 255u);
           int2 rec = make_int2(0, 0);
           if constexpr (KM == KM_DRIFT) {
@@ -762,6 +780,10 @@ int launch_step_tcq(const ctdd_step_params* p, cudaStream_t st) {
           return 1;
         }
     if (dev >= 0 && dev < 64) attr_done |= 1ull << dev;
+  }
+  if (reinterpret_cast<uintptr_t>(p->tc_static) % tc::ST_ALIGN) {
+    set_error("ctdd_reverse_step: tc_static must be aligned to ctdd_tc_static_align() = %zu bytes", tc::ST_ALIGN);
+    return 2;
   }
   tc::Args a;
   a.branch = p->branch; a.D = p->D; a.reject_multi = p->reject_multi;

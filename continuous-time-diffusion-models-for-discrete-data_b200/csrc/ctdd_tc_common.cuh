@@ -17,13 +17,19 @@ constexpr size_t TAB_QM_OFF = TAB_QH_OFF + (size_t)S * 128 * 4;  // uint32 [256]
 constexpr size_t TAB_A_OFF = TAB_QM_OFF + (size_t)S * 128 * 4;   // float [x][k]  tauLDR: 1/(Q[k,x]+eps); SDDM: Q[k,x]
 constexpr size_t TAB_G_OFF = TAB_A_OFF + (size_t)S * S * 4;      // float [x][k]  total-rate table (see prep_g_kernel)
 constexpr size_t TAB_BYTES = TAB_G_OFF + (size_t)S * S * 4;
-// static blob (ctdd_prep_tc_static)
+// static blob (ctdd_prep_tc_static); the caller places it on a ST_ALIGN boundary, so that "blob + offset" never carries
+// into the upper address word (the epilogue adds 32-bit offsets to a constant upper word)
+constexpr size_t ST_ALIGN = (size_t)2 << 20;
 constexpr size_t ST_RBZT_OFF = 0;                                // float [x][s] = Rb[s][x], zero at s == x
 constexpr size_t ST_RBZ_OFF = (size_t)S * S * 4;                 // float [x][s] = Rb[x][s], zero at s == x
-constexpr size_t ST_ROWSUM_OFF = 2 * (size_t)S * S * 4;          // float [x] = sum_s Rbz[x][s]
+constexpr size_t ST_RBT_OFF = 2 * (size_t)S * S * 4;             // float [x][s] = Rb[s][x], diagonal kept (rates output)
+constexpr size_t ST_RB_OFF = 3 * (size_t)S * S * 4;              // float [x][s] = Rb[x][s], diagonal kept
+constexpr size_t ST_ZERO_OFF = 4 * (size_t)S * S * 4;            // float [S] zeros: the "row" read for chunks outside the band
+constexpr size_t ST_ROWSUM_OFF = ST_ZERO_OFF + (size_t)S * 4;    // float [x] = sum_s Rbz[x][s]
 constexpr size_t ST_BANDT_OFF = ST_ROWSUM_OFF + (size_t)S * 4;   // int [x] = lo | hi << 8: first / last s with Rbzt[x][s] != 0
 constexpr size_t ST_BANDR_OFF = ST_BANDT_OFF + (size_t)S * 4;    // int [x], same for Rbz[x][s]   (empty: lo = 255, hi = 0)
 constexpr size_t ST_BYTES = ST_BANDR_OFF + (size_t)S * 4;
+static_assert(ST_BYTES <= ST_ALIGN, "static blob larger than its alignment");
 
 enum { KM_JUMP = 0, KM_CORR = 1, KM_RATES = 2, KM_DRIFT = 3, KM_EULER = 4, KM_EULER_CORR = 5 };
 // the corrector variants add h * R_t[x,:] to the rates; the Euler variants draw ONE categorical per row over

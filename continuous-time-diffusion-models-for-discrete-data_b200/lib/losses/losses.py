@@ -46,6 +46,21 @@ class _LossBase:
     seed = None
     noise_offset = 0
 
+    def __init_subclass__(cls, **kw):
+        # calc_loss runs with the model's device current (the kernels launch on the current device's stream)
+        super().__init_subclass__(**kw)
+        fn = cls.__dict__.get("calc_loss")
+        if fn is not None:
+            import functools
+
+            @functools.wraps(fn)
+            def calc_loss(self, a, b, *args, **kwargs):
+                state = a if isinstance(a, dict) else b
+                model = state.get("model") if isinstance(state, dict) else None
+                with nat.on_device(getattr(model, "device", None)):
+                    return fn(self, a, b, *args, **kwargs)
+            cls.calc_loss = calc_loss
+
     def _prepare(self, model, minibatch, t_hi, clamp_max=None, want_tilde=True):
         if len(minibatch.shape) == 4:
             B, C, H, W = minibatch.shape

@@ -77,9 +77,10 @@ class _EigenForward:
         Q = torch.empty((B, S, S), dtype=torch.float32, device=d_int.device)
         QT = torch.empty_like(Q) if want_transpose else None
         right = self._Uinv if inverse else self._U_T()
-        nat.check(nat.lib().ctdd_build_qt0(nat.ptr(self._U), nat.ptr(right), nat.ptr(self._lam), nat.ptr(d_int), B, S,
-                                           1 if self._normalize else 0, self._clamp_below, nat.ptr(Q), nat.ptr(QT),
-                                           nat.stream()), "ctdd_build_qt0")
+        with nat.on_device(d_int.device):
+            nat.check(nat.lib().ctdd_build_qt0(nat.ptr(self._U), nat.ptr(right), nat.ptr(self._lam), nat.ptr(d_int), B, S,
+                                               1 if self._normalize else 0, self._clamp_below, nat.ptr(Q), nat.ptr(QT),
+                                               nat.stream()), "ctdd_build_qt0")
         return (Q, QT) if want_transpose else Q
 
     def _U_T(self):
@@ -131,8 +132,9 @@ class _EigenForward:
             self._move_to(beta.device)
         B, S = beta.shape[0], self.S
         out = torch.empty((B, S, S), dtype=torch.float32, device=beta.device)
-        nat.check(nat.lib().ctdd_build_rate(nat.ptr(self._Rb), nat.ptr(beta), B, S, nat.ptr(out), nat.stream()),
-                  "ctdd_build_rate")
+        with nat.on_device(beta.device):
+            nat.check(nat.lib().ctdd_build_rate(nat.ptr(self._Rb), nat.ptr(beta), B, S, nat.ptr(out), nat.stream()),
+                      "ctdd_build_rate")
         return out
 
 

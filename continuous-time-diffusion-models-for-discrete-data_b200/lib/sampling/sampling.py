@@ -153,6 +153,20 @@ class _SamplerBase:
     row_offset = 0
     impl = nat.IMPL_AUTO
 
+    def __init_subclass__(cls, **kw):
+        # every sampler runs with model.device current (the kernels launch on the current device's stream); a model on
+        # cuda:1 while cuda:0 is current is legal in the reference and must be legal here
+        super().__init_subclass__(**kw)
+        fn = cls.__dict__.get("sample")
+        if fn is not None:
+            import functools
+
+            @functools.wraps(fn)
+            def sample(self, model, *args, **kwargs):
+                with nat.on_device(getattr(model, "device", None)):
+                    return fn(self, model, *args, **kwargs)
+            cls.sample = sample
+
 
 @sampling_utils.register_sampler
 class TauL(_SamplerBase):

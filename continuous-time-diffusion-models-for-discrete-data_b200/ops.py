@@ -9,6 +9,7 @@ import torch
 from . import _native as nat
 
 
+@nat.on_tensor_device
 def build_qt0(U, Uinv, lam, d_int, normalize=True, clamp_below=1e-8, want_transpose=False):
     """Q_b = U diag(exp(lam*d_int[b])) Uinv -> (B,S,S) [and Q^T]."""
     B, S = d_int.shape[0], U.shape[0]
@@ -20,6 +21,7 @@ def build_qt0(U, Uinv, lam, d_int, normalize=True, clamp_below=1e-8, want_transp
     return (Q, QT) if want_transpose else Q
 
 
+@nat.on_tensor_device
 def prep_tc_tables(Q, QT, Rb, eps, branch):
     """Per-time-point tables of the tcgen05 path; Q/QT are (T,S,S). Returns a (T, bytes) uint8 tensor or None."""
     T, S = Q.shape[0], Q.shape[-1]
@@ -32,17 +34,24 @@ def prep_tc_tables(Q, QT, Rb, eps, branch):
     return out
 
 
+@nat.on_tensor_device
 def prep_tc_static(Rb):
     """Time-independent tables of the tcgen05 path (uint8 blob) or None when the path is unavailable for this S."""
     S = Rb.shape[-1]
     nbytes = int(nat.lib().ctdd_tc_static_bytes(S))
     if nbytes <= 0:
         return None
-    out = torch.empty((nbytes,), dtype=torch.uint8, device=Rb.device)
+    # the blob must sit on a ctdd_tc_static_align() boundary: over-allocate and take the aligned window (a view, so the
+    # storage stays alive with it)
+    align = int(nat.lib().ctdd_tc_static_align())
+    buf = torch.empty((nbytes + align,), dtype=torch.uint8, device=Rb.device)
+    skip = (-buf.data_ptr()) % align
+    out = buf[skip:skip + nbytes]
     nat.check(nat.lib().ctdd_prep_tc_static(nat.ptr(Rb), S, nat.ptr(out), nat.stream()), "ctdd_prep_tc_static")
     return out
 
 
+@nat.on_tensor_device
 def reverse_step(mode, branch, logits, x_eval, Q, QT, Rb, RbT, beta, h, eps, *, N, D, S, x_base=None,
                  reject_multi=False, seed=0, offset=0, row_offset=0, impl=nat.IMPL_AUTO, tc_tables=None, tc_static=None,
                  workspace=None, stats=None, want_rr=False, want_ratio=False, logits_offset_elems=0,
@@ -106,6 +115,7 @@ class _LogisticLogitsFn(torch.autograd.Function):
         return logistic_logits(mu_c, ls_c, S, fix_logistic)
 
     @staticmethod
+    @nat.on_tensor_device
     def backward(ctx, grad_logits):
         mu_c, ls_c = ctx.saved_tensors
         S, fix, shape, dt_mu, dt_ls = ctx.meta
@@ -118,6 +128,7 @@ class _LogisticLogitsFn(torch.autograd.Function):
         return dmu.view(shape).to(dt_mu), dls.view(shape).to(dt_ls), None, None
 
 
+@nat.on_tensor_device
 def logistic_logits_autograd(mu, log_scale, S, fix_logistic=False):
     """(N, D, S) logits of the head, differentiable w.r.t. mu and log_scale (training path)."""
     return _LogisticLogitsFn.apply(mu, log_scale, S, fix_logistic)
@@ -177,6 +188,7 @@ def _head_views(mu, ls, N, D):
     return mu, ls, bs_mu
 
 
+@nat.on_tensor_device
 def logistic_logits(mu, log_scale, S, fix_logistic=False, out=None):
     """Truncated-logistic head -> (N, D, S) fp32 logits in one pass (replaces sample_logistic, models.py:28-74)."""
     N = mu.shape[0]
@@ -197,6 +209,7 @@ def _as_f32_rows(x):
     return x.to(torch.float32).contiguous()
 
 
+@nat.on_tensor_device
 def pair_similarity(x, y, bd=0.1, hamming=False):
     """(N, M) matrix exp(-bd * sum_d |x_d - y_d|) (or D - sum_d |.| with hamming=True), metrics.py:6-22."""
     x, y = _as_f32_rows(x), _as_f32_rows(y)
@@ -209,6 +222,7 @@ def pair_similarity(x, y, bd=0.1, hamming=False):
     return K
 
 
+@nat.on_tensor_device
 def pair_similarity_sums(x, y, bd=0.1, hamming=False):
     """float64 tensor (3,): sum_{i != j} k(x_i, x_j), sum_{i != j} k(y_i, y_j), sum_{i, j} k(x_i, y_j) — the three sums
     of binary_mmd (metrics.py:25-48), no (N, M) or (N, M, D) tensor."""
@@ -227,6 +241,7 @@ def pair_similarity_sums(x, y, bd=0.1, hamming=False):
     return out
 
 
+@nat.on_tensor_device
 def state_histogram(x, S, counts=None):
     """Per-dimension state counts of samples x (N, D) -> int32 (D, S); pass `counts` (from an earlier call) to accumulate.
     Raises if any state lies outside [0, S)."""
@@ -285,10 +300,12 @@ class EmaTable:
     def update(self, one_minus_decay):
         """shadow <- shadow - one_minus_decay * (shadow - param), in place, on the current stream."""
         if self.n_chunks:
-            nat.check(nat.lib().ctdd_ema_update(self.table.data_ptr(), self.n_chunks, float(one_minus_decay), nat.stream()),
-                      "ctdd_ema_update")
+            with nat.on_device(self.table.device):
+                nat.check(nat.lib().ctdd_ema_update(self.table.data_ptr(), self.n_chunks, float(one_minus_decay), nat.stream()),
+                          "ctdd_ema_update")
 
 
+@nat.on_tensor_device
 def sample_categorical_shared(probs, rows, seed, offset=0, row_offset=0):
     x = torch.empty((rows,), dtype=torch.int32, device=probs.device)
     nat.check(nat.lib().ctdd_sample_categorical_shared(nat.ptr(probs.contiguous()), probs.shape[0], rows, row_offset,
@@ -297,6 +314,7 @@ def sample_categorical_shared(probs, rows, seed, offset=0, row_offset=0):
     return x
 
 
+@nat.on_tensor_device
 def noise_xt(Q, Rb, beta, x0, seed, offset=0, batch_offset=0, want_tilde=True):
     """x_t ~ Cat(Q[b, x0, :]) and the one-jump proposal x~ (lib/losses/losses.py:46-101). x0: (B,D) int32."""
     B, D = x0.shape
@@ -333,6 +351,11 @@ class _LossTerms(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, ga, gb, gc, gd, gn):
+        with nat.on_device(ctx.saved_tensors[0].device):
+            return _LossTerms._backward(ctx, ga, gb, gc, gd, gn)
+
+    @staticmethod
+    def _backward(ctx, ga, gb, gc, gd, gn):
         logits, Q, QT, Rb, beta, x0, xt, x_tilde, ws = ctx.saved_tensors
         kind, logit_branch, crm_type, eps, has_tilde = ctx.meta
         B, D, S = logits.shape
@@ -348,6 +371,7 @@ class _LossTerms(torch.autograd.Function):
         return (grad,) + (None,) * 11
 
 
+@nat.on_tensor_device
 def loss_terms(logits, kind, Q, QT, Rb, beta, x0, xt, x_tilde=None, eps=1e-9, logit_branch=nat.BRANCH_SDDM_REVERSE_PROB,
                crm_type=0):
     """(out_a, out_b, out_c, out_d, out_nll) per sample — see ctdd_loss_params in include/ctdd.h."""

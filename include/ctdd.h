@@ -167,8 +167,11 @@ int ctdd_reverse_step(const ctdd_step_params* p, void* stream);
  * (tauLDR; Q[k,x] for the SDDM branch) and the total-rate table G (sum_s lam_s of a row is one dot
  * product with G[x][.]).  T time points at once. */
 int64_t ctdd_tc_tables_bytes(int S);
-/* time-independent tables of the tcgen05 path: Rb^T and Rb with zeroed diagonals (sampler gathers), row sums */
+/* time-independent tables of the tcgen05 path: Rb^T and Rb with zeroed and with kept diagonals (epilogue gathers), a zero
+ * row, row sums, the band of non-zero base rates per state.  static_out must be aligned to ctdd_tc_static_align() bytes
+ * (the epilogue addresses the blob with 32-bit offsets under a constant upper address word). */
 int64_t ctdd_tc_static_bytes(int S);
+int64_t ctdd_tc_static_align(void);
 int ctdd_prep_tc_static(const float* Rb, int S, void* static_out, void* stream);
 int ctdd_prep_tc_tables(const float* Q, const float* QT, const float* Rb, int T, int S, float eps,
                         int branch, void* tables_out, void* stream);
