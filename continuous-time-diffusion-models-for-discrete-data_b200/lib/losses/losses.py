@@ -174,10 +174,12 @@ class CondCTElbo(_LossBase):
             logits = sliced(c["x_tilde"])
             reg, outer, norm, _, ce = ops.loss_terms(logits, nat.LOSS_CTELBO, xt=c["x_tilde"], x_tilde=c["x_tilde"], **kw)
         else:
+            # the reference's second pass overwrites x_logits (losses.py:660-666), so its cross-entropy term (:777-779)
+            # is taken at the logits of x~, not of x_t
             logits = sliced(c["xt"])
-            reg, _, _, _, ce = ops.loss_terms(logits, nat.LOSS_CTELBO, xt=c["xt"], x_tilde=c["x_tilde"], **kw)
-            _, outer, norm, _, _ = ops.loss_terms(sliced(c["x_tilde"]), nat.LOSS_CTELBO, xt=c["x_tilde"],
-                                                  x_tilde=c["x_tilde"], **kw)
+            reg, _, _, _, _ = ops.loss_terms(logits, nat.LOSS_CTELBO, xt=c["xt"], x_tilde=c["x_tilde"], **kw)
+            _, outer, norm, _, ce = ops.loss_terms(sliced(c["x_tilde"]), nat.LOSS_CTELBO, xt=c["x_tilde"],
+                                                   x_tilde=c["x_tilde"], **kw)
         neg_elbo = torch.mean(-outer / norm) + torch.mean(reg)
         return neg_elbo + self.nll_weight * torch.sum(ce) / (c["B"] * c["D"])
 

@@ -100,6 +100,7 @@ LOSSES = [
     ("nll_univar3", "NLL", "univar3_logsqr", 8, 9, dict(), 1.0, 204, 0),
     ("ctelbolambda_uni2", "CTElboLambda", "univar2_sqrtcos", 8, 16, dict(), 0.99999, 205, 300),
     ("condctelbo_gauss32", "CondCTElbo", "gauss32", 6, 10, dict(condition_dim=4), 1.0, 206, 0),
+    ("condctelbo_gauss32_2pass", "CondCTElbo", "gauss32", 6, 10, dict(condition_dim=4, one_forward_pass=False), 1.0, 217, 0),
     ("catrm_gauss32_rm", "CatRM", "gauss32", 6, 10, dict(logit_type="reverse_prob", loss_type="rm"), 1.0, 207, 0),
     ("catrm_gauss32_mle_direct", "CatRM", "gauss32", 6, 10, dict(logit_type="direct", loss_type="mle"), 1.0, 208, 0),
     ("catrm_univar3_elbo", "CatRM", "univar3_logsqr", 8, 9, dict(logit_type="reverse_prob", loss_type="elbo", ce_coeff=0.25), 1.0, 209, 0),

@@ -137,8 +137,10 @@ def loss_value(name, fp, model, x0, ts, *, seed, offset=0, eps=1e-9, nll_weight=
             p = F.softmax(logits, dim=2)
             reg, outer, norm = ctelbo_terms(p, p, Q, R, x0, xtil, xtil, eps)
         else:
-            logits = sl(xt)
-            reg, outer, norm = ctelbo_terms(F.softmax(logits, dim=2), F.softmax(sl(xtil), dim=2), Q, R, x0, xt, xtil, eps)
+            # losses.py:660-666: the second pass OVERWRITES x_logits, so the cross-entropy (:777-779) sees the logits of x~
+            logits_reg = sl(xt)
+            logits = sl(xtil)
+            reg, outer, norm = ctelbo_terms(F.softmax(logits_reg, dim=2), F.softmax(logits, dim=2), Q, R, x0, xt, xtil, eps)
         return torch.mean(-outer / norm) + torch.mean(reg) + nll_weight * ce(logits)
     if name in ("ScoreElbo", "SDDMElbo"):
         logits = model(xtil, ts)
