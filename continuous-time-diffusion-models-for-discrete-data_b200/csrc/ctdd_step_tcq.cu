@@ -61,11 +61,21 @@ constexpr int KBLOCK_BYTES = NH * 128;         // one 64-wide K block of one spl
 constexpr int SPLIT_BYTES = 4 * KBLOCK_BYTES;  // K = 256 -> 4 blocks
 constexpr int STAGE_BYTES = 2 * SPLIT_BYTES;   // hi + mid
 constexpr int TM_QH = 0, TM_QM = 128, TM_ACC = 256;  // TMEM column map (accumulator b at TM_ACC + b * NT)
-constexpr int PREFETCH_TILES = 4;      // HBM -> L2 bulk-prefetch distance (tiles of this pair's sequence)
+#ifndef CTDD_PREFETCH_TILES
+#define CTDD_PREFETCH_TILES 0
+#endif
+constexpr int PREFETCH_TILES = CTDD_PREFETCH_TILES;      // HBM -> L2 bulk-prefetch distance (tiles of this pair's sequence)
 constexpr int LRING = 1;               // per-producer-warp slot of raw logits row pairs filled by cp.async.bulk: refilled for the
                                        // warp's next pass as soon as this pass has its values in registers (rows are L2 hits)
 constexpr int SCR_LD = 36;             // floats per row of an epilogue warp's transposing scratch (conflict-free 128-bit reads)
 constexpr uint32_t IDESC = make_idesc(NT);
+#ifndef CTDD_POLL_LONG
+#define CTDD_POLL_LONG 512
+#endif
+constexpr uint32_t POLL_LONG = CTDD_POLL_LONG;   // ns between polls of the roles that wait for a whole tile (producers on a free stage, finalizers)
+#ifndef CTDD_EXP_PMASK
+#define CTDD_EXP_PMASK 0     // diagnostic builds: producer stages switched off (wrong numerics, timing only)
+#endif
 constexpr int NCHUNK = S / JUMP_CHUNK;                           // 8 chunks of 32 states per row
 constexpr uint32_t SCAL_TX_BYTES = NH * 12;                      // row scalars the partner sends per tile
 constexpr uint32_t CONTRIB_TX_BYTES = (NUM_EPI_WARPS / 2) * 2 * 32 * 8;   // records the partner's 4 warps send per tile
@@ -188,13 +198,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     // passes of this CTA: pass P = 32 * tl + ps builds rows 2 ps, 2 ps + 1 of the CTA's 64 rows of its tl-th tile; warp pw
     // takes P = pw, pw + NPW, ..  Three cursors run over that sequence (compute, logits fetch one pass ahead, state fetch
     // two passes ahead); they advance by additions only.
+    const int tile_step = npairs * NT - 2 * PASSES_PER_TILE;     // rows from the wrap of ps to the same ps of the next tile
     struct Cursor {
       int tl, ps;
-      __device__ __forceinline__ void advance() { ps += NPW; if (ps >= PASSES_PER_TILE) { ps -= PASSES_PER_TILE; ++tl; } }
+      long long row;       // first global row of the pass
+      __device__ __forceinline__ void advance(int step) {
+        ps += NPW; row += 2 * NPW;
+        if (ps >= PASSES_PER_TILE) { ps -= PASSES_PER_TILE; ++tl; row += step; }
+      }
     };
-    auto cursor_row = [&](const Cursor& c) -> long long {        // first global row of the pass
-      return (long long)(pair + c.tl * npairs) * NT + (int)rank * NH + 2 * c.ps;
-    };
+    const long long row0 = (long long)pair * NT + (int)rank * NH + 2 * pw;   // pass pw of this CTA's first tile
     const uint32_t scal_c_p = smem_u32(&sm.scal_c[0][0]), scal_x_p = smem_u32(&sm.scal_x[0][0]), band_p = smem_u32(&sm.band[0]);
     const uint32_t scal_c_remote = mapa(scal_c_p, rank ^ 1u);
     const uint32_t scal_x_remote = mapa(scal_x_p, rank ^ 1u);
@@ -206,12 +219,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       return a.logits + (long long)n * a.batch_stride + (long long)d * a.ld;
     };
     // States (and head parameters): two passes of this warp ahead, into registers.
-    Cursor cx = {0, pw};
+    Cursor cx = {0, pw, row0};
     float f_mu = 0.f, f_ls = 0.f;        // HEAD: head parameters of the row fetch() just visited
     auto fetch = [&]() -> int {
       int xv = -1;
       if (cx.tl < my_tiles) {
-        const long long g = cursor_row(cx) + half;
+        const long long g = cx.row + half;
         if (g < a.rows) {
           xv = __ldg(a.x_eval + g);
           if (HEAD) {
@@ -225,36 +238,46 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
             f_ls = __ldg(a.head_ls + src);
           }
         }
-        cx.advance();
+        cx.advance(tile_step);
       }
       return xv;
     };
     // Logits: lane 0 starts the bulk copy of the NEXT pass's row pair into the warp's ring slot as soon as the current
     // pass has read its values (rows past the end are replaced by row 0: never used; adjacent rows of a contiguous
     // logits tensor travel as one 2 KB copy; the rows were pulled from HBM into L2 some tiles earlier).
-    Cursor cf = {0, pw};
-    auto fetch_rows = [&]() {            // lane 0 only
+    Cursor cf = {0, pw, row0};
+    // (every lane runs the warp-uniform bookkeeping, lane 0 alone issues: the addresses then live in uniform registers)
+    auto fetch_rows = [&]() {
       if (HEAD || cf.tl >= my_tiles) return;
-      const long long gf = cursor_row(cf);
-      uint64_t* bar = &sm.lring_full[pw][0];
-      mbar_arrive_expect_tx(bar, 2 * S * 4);
-      if (contiguous && gf + 1 < a.rows) {
-        bulk_g2s(&sm.lring[pw][0][0][0], a.logits + gf * S, 2 * S * 4, bar);
-      } else {
+      const long long gf = cf.row;
+      if (lane == 0) {
+        uint64_t* bar = &sm.lring_full[pw][0];
+        mbar_arrive_expect_tx(bar, 2 * S * 4);
+        if (contiguous && gf + 1 < a.rows) {
+          bulk_g2s(&sm.lring[pw][0][0][0], a.logits + gf * S, 2 * S * 4, bar);
+        } else {
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          const long long gg = (gf + hf < a.rows) ? gf + hf : 0;
-          bulk_g2s(&sm.lring[pw][0][hf][0], row_ptr(gg), S * 4, bar);
+          for (int hf = 0; hf < 2; ++hf) {
+            const long long gg = (gf + hf < a.rows) ? gf + hf : 0;
+            bulk_g2s(&sm.lring[pw][0][hf][0], row_ptr(gg), S * 4, bar);
+          }
+        }
+        if (contiguous && PREFETCH_TILES > 0) {   // pull the same two rows of a later tile from HBM into L2
+          const long long r0 = gf + (long long)PREFETCH_TILES * npairs * NT;
+#ifdef CTDD_EXP_PFBIG      // diagnostic build: one 16 KB prefetch per 8 passes instead of 2 KB per pass
+          if ((cf.ps & 7) == 0 && r0 + 16 <= a.rows) l2_prefetch_bulk(a.logits + r0 * S, 16 * S * 4);
+#else
+          if (r0 + 2 <= a.rows) l2_prefetch_bulk(a.logits + r0 * S, 2 * S * 4);
+#endif
+          // and the states of that tile (read two passes ahead, straight into registers): one 128-byte line serves
+          // 16 passes; the pass that starts a line pulls it
+          if ((cf.ps & 15) == 0 && r0 < a.rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.x_eval + r0));
         }
       }
-      if (contiguous) {   // pull the same two rows of a later tile from HBM into L2
-        const long long r0 = gf + (long long)PREFETCH_TILES * npairs * NT;
-        if (r0 + 2 <= a.rows) l2_prefetch_bulk(a.logits + r0 * S, 2 * S * 4);
-      }
-      cf.advance();
+      cf.advance(tile_step);
     };
 
-    if (lane == 0) fetch_rows();
+    if (!(CTDD_EXP_PMASK & 8)) fetch_rows();
     int x_cur = fetch();
     float mu_cur = f_mu, ls_cur = f_ls;
     int x_n1 = fetch();
@@ -284,7 +307,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         c1 = hb * rs * inv;                                      // lam_s = (D_s * c1 + c0) * Rb[x,s]
         c0 = hb * 1e-35f * inv;
       }
-      if (l16 == 0) {   // one lane per half-warp: the row's scalars into BOTH CTAs of the pair
+      if (l16 == 0 && !(CTDD_EXP_PMASK & 2)) {   // one lane per half-warp: the row's scalars into BOTH CTAs of the pair
         uint32_t bandx;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(bandx) : "r"(band_p + 4u * (uint32_t)p_x));
         const uint32_t sx = bandx | (p_ok ? (1u << 8) : 0u) | ((uint32_t)p_x << 10);
@@ -298,7 +321,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         __syncwarp();
         if (lane == 0) {
           // warp 0 also announces the bytes the partner's producers deliver for this tile
-          if (pw == 0) mbar_arrive_expect_tx(&sm.scal_full[p_slot], SCAL_TX_BYTES);
+          if (pw == 0) mbar_arrive_expect_tx(&sm.scal_full[p_slot], (CTDD_EXP_PMASK & 2) ? 0u : SCAL_TX_BYTES);
           else mbar_arrive(&sm.scal_full[p_slot]);
         }
       }
@@ -306,7 +329,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     };
     uint32_t ring_par = 0;       // parity to wait for on the ring slot
     int last_tl = -1;
-    Cursor cc = {0, pw};
+    Cursor cc = {0, pw, row0};
 #pragma unroll 1
     while (cc.tl < my_tiles) {
       const int tl = cc.tl, ps = cc.ps;
@@ -315,7 +338,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       const bool ok = x_cur >= 0;
       const int x = ok ? x_cur : 0;
       const bool last_in_tile = ps + NPW >= PASSES_PER_TILE;     // this warp's next pass belongs to another tile
-      if (!HEAD) mbar_wait(&sm.lring_full[pw][0], ring_par);
+      if (!HEAD && !(CTDD_EXP_PMASK & (8 | 32))) mbar_wait(&sm.lring_full[pw][0], ring_par);   // 32: copies run, nobody waits
       const int r = 2 * ps + half;
       float v[16];
       float ml = 0.f;
@@ -335,13 +358,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         }
         ring_par ^= 1u;
         __syncwarp();            // every lane has its values: the slot is refilled for the warp's next pass
-        if (lane == 0) fetch_rows();
+        if (!(CTDD_EXP_PMASK & 8)) fetch_rows();
         float m4[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) m4[c] = fmaxf(fmaxf(v[4 * c], v[4 * c + 1]), fmaxf(v[4 * c + 2], v[4 * c + 3]));
         float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {     // this pass's row maximum next to the previous pass's reductions
+        for (int o = (CTDD_EXP_PMASK & 4) ? 0 : 8; o > 0; o >>= 1) {     // this pass's row maximum next to the previous pass's reductions
           m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
           p_sum += __shfl_xor_sync(0xffffffffu, p_sum, o);
           if (!TAULDR) p_dot += __shfl_xor_sync(0xffffffffu, p_dot, o);
@@ -350,7 +373,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       }
       finish_prev();
       if (tl != last_tl) {       // first pass of this warp in a new tile: the tile's operand stage must be free
-        mbar_wait(&sm.empty[st], (uint32_t)(((tl / STAGES) & 1) ^ 1));
+        mbar_wait<POLL_LONG>(&sm.empty[st], (uint32_t)(((tl / STAGES) & 1) ^ 1));
         last_tl = tl;
       }
       const uint32_t stage_s = smem_u32(sm.stage[st]);
@@ -386,7 +409,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         dot = dall.x + dall.y;
       }
       // the table row of the NEXT pass is requested as soon as this pass's has been consumed
-      {
+      if (!(CTDD_EXP_PMASK & 1)) {
         const size_t xo = (size_t)(x_n1 < 0 ? 0 : x_n1) << 8;
 #pragma unroll
         for (int c = 0; c < 4; ++c) t4[c] = __ldg(reinterpret_cast<const float4*>(tabA + xo + 64 * c));
@@ -405,8 +428,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         uint32_t h0, m0, h1, m1;
         split2(v[4 * c], v[4 * c + 1], h0, m0);
         split2(v[4 * c + 2], v[4 * c + 3], h1, m1);
-        sts64(stage_s + c * KBLOCK_BYTES + off, h0, h1);
-        sts64(stage_s + SPLIT_BYTES + c * KBLOCK_BYTES + off, m0, m1);
+        if (!(CTDD_EXP_PMASK & 16) || h0 == 0x12345u) {
+          sts64(stage_s + c * KBLOCK_BYTES + off, h0, h1);
+          sts64(stage_s + SPLIT_BYTES + c * KBLOCK_BYTES + off, m0, m1);
+        }
       }
 #endif
       // this pass's partial sums and row identity travel to the next pass (finish_prev)
@@ -421,7 +446,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       if (HEAD) { mu_cur = mu_n1; ls_cur = ls_n1; }
       x_n1 = fetch();
       if (HEAD) { mu_n1 = f_mu; ls_n1 = f_ls; }
-      cc.advance();
+      cc.advance(tile_step);
     }
     // the last pass's reductions and row scalars
 #pragma unroll
@@ -442,13 +467,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       for (int i = 0; i < my_tiles; ++i) {
         const int tile = pair + i * npairs, slot = i % RING, cb = i % CBUF;
         const long long g = (long long)tile * NT + (long long)rank * NH + r;
-        mbar_wait(&sm.scal_full[slot], (i / RING) & 1);
+        mbar_wait<POLL_LONG>(&sm.scal_full[slot], (i / RING) & 1);
         const uint32_t sx = sm.scal_x[slot][rank * NH + r];
         const int x = (int)((sx >> 10) & 255u);
         const bool valid = (sx >> 8) & 1u;
         int xb = x;
         if (a.x_base && valid) xb = __ldg(a.x_base + g);
-        mbar_wait(&sm.contrib_full[cb], (i / CBUF) & 1);
+        mbar_wait<POLL_LONG>(&sm.contrib_full[cb], (i / CBUF) & 1);
         int jump = 0, cnt = 0;
         float drift = 0.f;
 #pragma unroll
@@ -518,7 +543,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       const uint32_t full_addr = mapa(smem_u32(&sm.full[0]), 0);
       for (int i = 0; i < my_tiles; ++i) {
         const int st = i % STAGES;
-        mbar_wait(&sm.full_local[st], (i / STAGES) & 1);
+        mbar_wait<POLL_LONG>(&sm.full_local[st], (i / STAGES) & 1);
         mbar_arrive_cluster_release(full_addr + (uint32_t)st * 8u);
       }
     }
@@ -541,12 +566,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     // a constant and the lower word is one add.  Offset of a row = table + x * 1024 (the row scalar carries x << 10):
     // zero-diagonal R_b^T / R_b for the rates (the diagonal-keeping copies for the rates output), R_b[x][.] for the
     // corrector add, the zero row for chunks outside the band of x.
-    const uint32_t stat_hi = (uint32_t)(reinterpret_cast<uintptr_t>(a.stat) >> 32);
-    const uint32_t lane_lo = (uint32_t)reinterpret_cast<uintptr_t>(a.stat) + 4u * (uint32_t)s_mine;
+    const float* stat_lane = reinterpret_cast<const float*>(a.stat) + s_mine;
     constexpr uint32_t TAB_R = (uint32_t)((KM == KM_RATES) ? (TAULDR ? ST_RBT_OFF : ST_RB_OFF) : (TAULDR ? ST_RBZT_OFF : ST_RBZ_OFF));
-    auto stat_ptr = [&](uint32_t off) -> const float* {
-      return reinterpret_cast<const float*>(((unsigned long long)stat_hi << 32) | (unsigned long long)(lane_lo + off));
-    };
+    auto stat_ptr = [&](uint32_t off) -> const float* { return stat_lane + (off >> 2); };   // one widening multiply-add
     const uint32_t chunkbit = 1u << chunk;
     const uint32_t scr_p = smem_u32(&sm.scratch[warp][0][0]);
     const float hb = a.h * a.beta;

@@ -94,7 +94,13 @@ __device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_add
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // wait for a phase: one try_wait (which suspends in hardware for a short, implementation-defined time), then a
-// sleep / try_wait loop - a warp that has to wait longer must not eat issue slots of the warps it is waiting for
+// sleep / try_wait loop - a warp that has to wait longer must not eat issue slots of the warps it is waiting for.
+// SLEEP_NS: pause between polls; roles whose waits are long (a whole tile) and whose wake-up is not on the critical path
+// use a longer one.
+#ifndef CTDD_POLL_NS
+#define CTDD_POLL_NS 96
+#endif
+template <uint32_t SLEEP_NS = CTDD_POLL_NS>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -106,7 +112,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@!p bra WAIT_%=;\n"
       "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u), "r"(96u)
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u), "r"(SLEEP_NS)
       : "memory");
 }
 // same, for phases completed by arrivals from the partner CTA: acquire at cluster scope once the phase has flipped
