@@ -52,8 +52,8 @@ constexpr int NUM_THREADS = (FIRST_PROD_WARP + NPW + 4) * 32;
 // 8 * EPI + NPW * PROD + 4 * LIGHT must not exceed (12 + NPW) * (launch allocation), or the .inc never returns.
 constexpr int REGS_LAUNCH = (65536 / NUM_THREADS) & ~7;          // what __launch_bounds__ gives every thread
 constexpr int REGS_LIGHT = 48;
-constexpr int REGS_PROD = NPW == 12 ? 80 : 96;
-constexpr int REGS_EPI = NPW == 12 ? 96 : 112;
+constexpr int REGS_PROD = NPW == 16 ? 64 : (NPW == 12 ? 80 : 96);
+constexpr int REGS_EPI = NPW == 8 ? 112 : 96;
 static_assert(NUM_EPI_WARPS * REGS_EPI + NPW * REGS_PROD + 4 * REGS_LIGHT <= (NUM_EPI_WARPS + NPW + 4) * REGS_LAUNCH,
               "setmaxnreg budget exceeds the launch allocation");
 constexpr int PASSES_PER_TILE = NH / 2;                          // 32 two-row passes per tile and CTA

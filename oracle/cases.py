@@ -72,6 +72,19 @@ SAMPLERS = [
 ]
 
 
+# Whole-sampler cases at S = 256 for the classes whose reference implementation cannot run there (MidPointTauL has no
+# state_change table for DiscreteCIFAR10) or was fixture-tested at small S only (LBJF): checked against
+# the oracle samplers, which are pinned to the reference at S = 2 / 3 / 32 by the fixtures above.  BASELINE config C5.
+SAMPLERS_S256 = [
+    ("midpoint_gauss256_sddm", "MidPointTauL", "gauss256", 16, 24, "SDDMElbo", "reverse_prob", (0.3, 12.0),
+     dict(num_steps=6, min_t=0.01), 1.0, 131),
+    ("midpoint_gauss256_tauldr", "MidPointTauL", "gauss256", 16, 24, "CTElbo", None, (0.3, 12.0),
+     dict(num_steps=6, min_t=0.01), 1.0, 132),
+    ("lbjf_gauss256", "LBJF", "gauss256", 16, 24, "CTElbo", None, (0.3, 12.0),
+     dict(num_steps=6, min_t=0.01, corrector_entry_time=0.3, num_corrector_steps=1), 1.0, 133),
+]
+
+
 def sampler_cfg(make_cfg, case):
     """Build the config object (same keys as the reference's ml_collections configs) for a SAMPLERS case."""
     name, cls, fwd, N, D, loss_name, logit_type, stub, over, max_t, seed = case

@@ -136,11 +136,13 @@ def test_loss_accepts_both_argument_orders_and_4d_minibatch(golden):
         losses_utils.get_loss(cfg)
 
 
-@pytest.mark.parametrize("cls,over", [("CatRMNLL", dict(logit_type="reverse_prob", loss_type="rm", nll_weight=0.01)),
-                                      ("CTElbo", dict(nll_weight=0.001)),
-                                      ("SDDMElbo", dict(logit_type="reverse_prob", nll_weight=0.01))],
-                         ids=["CatRMNLL", "CTElbo", "SDDMElbo"])
-def test_losses_at_c3_size_match_the_oracle(cls, over):
+@pytest.mark.parametrize("cls,over,B,D", [("CatRMNLL", dict(logit_type="reverse_prob", loss_type="rm", nll_weight=0.01), 64, 784),
+                                          ("CTElbo", dict(nll_weight=0.001), 64, 784),
+                                          ("SDDMElbo", dict(logit_type="reverse_prob", nll_weight=0.01), 64, 784),
+                                          ("SDDMElbo", dict(logit_type="reverse_prob", nll_weight=0.01), 16, 3072),
+                                          ("CTElbo", dict(nll_weight=0.001), 16, 3072)],
+                         ids=["CatRMNLL", "CTElbo", "SDDMElbo", "SDDMElbo-C5", "CTElbo-C5"])
+def test_losses_at_c3_size_match_the_oracle(cls, over, B, D):
     """BASELINE.json config C3 (S=256, D=784, B=64): loss value vs the CPU oracle on the same time draw and injected
     noising uniforms (1e-4 relative), d loss / d w vs the oracle's autograd (2e-3 of the largest entry: fp32 sums over
     50 k rows in different orders), and the shift invariance every softmax-composed loss has: the logit gradient of each
@@ -150,7 +152,7 @@ def test_losses_at_c3_size_match_the_oracle(cls, over):
     from ctdd_b200.lib.losses import losses_utils
     import ctdd_b200.lib.losses.losses  # noqa: F401
     from oracle import loss_oracle as lo
-    B, D, S, seed = 64, 784, 256, 321
+    S, seed = 256, 321      # (B, D): C3 = (64, 784); C5 = CIFAR10 shape D = 3072 at the per-GPU batch of the smallest sweep point
     case = ("c3", cls, "gauss256", B, D, over, 1.0, seed, 0)
     cfg = cases.loss_cfg(make_config, case, device="cuda")
     g = np.random.Generator(np.random.PCG64(seed))

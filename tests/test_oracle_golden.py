@@ -5,7 +5,7 @@ import torch
 
 from oracle import cases, ctmc_oracle as oc, ref_harness as rh, rng
 from oracle.make_golden import rates_inputs
-from helpers import oracle_forward
+from helpers import oracle_forward, run_oracle_sampler
 
 
 @pytest.mark.parametrize("name", list(cases.FORWARD))
@@ -53,55 +53,11 @@ def test_reverse_rates_match_reference(golden, case):
     np.testing.assert_allclose(ratio.numpy(), g[f"{name}/ratio"], rtol=2e-5, atol=1e-30)
 
 
-def _run_oracle_sampler(case, head=False):
-    name, cls, fwd, N, D, loss_name, logit_type, stub, over, max_t, seed = case
-    cfg = cases.sampler_cfg(rh.make_cfg, case)
-    S, sc = cfg.data.S, cfg.sampler
-    fp = oracle_forward(fwd)
-    if head:        # stub network emitting (mu, log_scale) + the oracle's truncated-logistic head; `stub` = fix_logistic
-        from oracle import head_oracle as ho
-        hnet = rh.HeadStubNet(S, D, seed)
-        model = lambda x, t: ho.truncated_logistic_logits(*hnet.head_params(x, t), S, stub)
-    else:
-        net = rh.StubNet(S, D, seed, stub[0], stub[1])
-        model = lambda x, t: net.net(x, t)
-    lt = logit_type or "reverse_prob"
-    common = dict(min_t=sc.min_t, num_steps=sc.num_steps, initial_dist=sc.initial_dist, seed=seed)
-    if cls == "TauL":
-        return oc.sample_taul(fp, model, N, D, S, max_t=max_t, init_std=cfg.model.Q_sigma, is_ordinal=sc.is_ordinal,
-                              loss_name=loss_name, logit_type=lt, corrector_entry_time=sc.corrector_entry_time,
-                              num_corrector_steps=sc.num_corrector_steps, **common)
-    if cls == "LBJF":
-        return oc.sample_lbjf(fp, model, N, D, S, max_t=max_t, init_std=cfg.model.Q_sigma, loss_name=loss_name,
-                              logit_type=lt, corrector_entry_time=sc.corrector_entry_time,
-                              num_corrector_steps=sc.num_corrector_steps, **common)
-    if cls == "MidPointTauL":
-        return oc.sample_midpoint(fp, model, N, D, S, max_t=max_t, init_std=cfg.model.Q_sigma, is_ordinal=sc.is_ordinal,
-                                  loss_name=loss_name, logit_type=lt, **common)
-    if cls == "ExactSampling":
-        return oc.sample_exact(fp, model, N, D, S, max_t=max_t, min_t=sc.min_t, num_steps=sc.num_steps,
-                               initial_dist=sc.initial_dist, init_std=cfg.model.Q_sigma, seed=seed)
-    if cls == "PCTauL":
-        return (oc.sample_pctaul(fp, model, N, D, S, corrector_entry_time=sc.corrector_entry_time,
-                                 num_corrector_steps=sc.num_corrector_steps,
-                                 corrector_step_size_multiplier=sc.corrector_step_size_multiplier, **common),)
-    g = np.random.Generator(np.random.PCG64(seed))
-    conditioner = torch.from_numpy(g.integers(0, S, (N, sc.condition_dim)))
-    if cls == "ConditionalTauLeaping":
-        return (oc.sample_conditional_taul(fp, model, N, D, S, conditioner, condition_dim=sc.condition_dim,
-                                           init_std=cfg.model.Q_sigma, **common),)
-    return (oc.sample_conditional_pctaul(fp, model, N, D, S, conditioner, condition_dim=sc.condition_dim,
-                                         init_std=cfg.model.Q_sigma, reject=bool(sc.reject_multiple_jumps),
-                                         corrector_entry_time=sc.corrector_entry_time,
-                                         num_corrector_steps=sc.num_corrector_steps,
-                                         corrector_step_size_multiplier=sc.corrector_step_size_multiplier, **common),)
-
-
 @pytest.mark.parametrize("case", cases.SAMPLERS, ids=[c[0] for c in cases.SAMPLERS])
 def test_sampler_matches_reference_with_injected_uniforms(golden, case):
     """Final integer states and diagnostics of the oracle samplers equal the reference's, bit for bit."""
     name = case[0]
-    res = _run_oracle_sampler(case)
+    res = run_oracle_sampler(case)
     g = golden["samplers"]
     np.testing.assert_array_equal(np.asarray(res[0]), g[f"{name}/x"])
     for i, extra in enumerate(res[1:]):

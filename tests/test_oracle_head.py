@@ -68,7 +68,7 @@ def test_head_identity_used_by_the_kernels():
 def test_oracle_samplers_with_head_match_reference(golden, case):
     """Whole samplers whose model ends in the truncated-logistic head: the oracle (oracle head + oracle sampler) lands on
     the states the reference (its sample_logistic + its sampler) produced under the same injected uniforms."""
-    from test_oracle_golden import _run_oracle_sampler
+    from helpers import run_oracle_sampler as _run_oracle_sampler
     with torch.no_grad():
         res = _run_oracle_sampler(case, head=True)
     want = golden["head"][f"{case[0]}/x"]
