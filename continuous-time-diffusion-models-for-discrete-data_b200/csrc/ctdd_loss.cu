@@ -206,6 +206,10 @@ __global__ void __launch_bounds__(256, ROWS == 32 ? 2 : 1) loss_kernel(const Arg
   const float beta = a.beta[b];
   const bool ctelbo = a.kind == CTDD_LOSS_CTELBO;
   const bool direct = !ctelbo && a.logit_type == CTDD_BRANCH_SDDM_DIRECT;
+  // reverse_prob: ll = log(u + 1e-35) (model_utils.py:41-46).  reverse_logscale (model_utils.py:49-54) is the log-sum-exp
+  // form of the same contraction without the guard: ll = log(u), and -1e9 where no term survives (log q = -1e9 there)
+  const float lle = (!ctelbo && a.logit_type == CTDD_BRANCH_SDDM_REVERSE_LOGSCALE) ? 0.f : 1e-35f;
+  auto ll_of = [&](float u) { const float v = u + lle; return v > 0.f ? __logf(v) : -1e9f; };
   if (tid < ROWS) {
     const size_t r = (size_t)b * a.D + d0 + (tid < nr ? tid : 0);
     s_x0[tid] = a.x0[r];
@@ -252,7 +256,7 @@ __global__ void __launch_bounds__(256, ROWS == 32 ? 2 : 1) loss_kernel(const Arg
   if (!ctelbo) {
     if (tid < ROWS) {
       const float ux = sU[tid * S + s_xr[tid]];
-      s_llx[tid] = direct ? ux : logf(ux + 1e-35f);
+      s_llx[tid] = direct ? ux : (ux + lle > 0.f ? logf(ux + lle) : -1e9f);
     }
     __syncthreads();
   }
@@ -284,11 +288,11 @@ __global__ void __launch_bounds__(256, ROWS == 32 ? 2 : 1) loss_kernel(const Arg
       const float* rcol = a.RbT ? a.RbT + (size_t)xr * S : nullptr;      // Rb[., xr] (SDDM only)
       for (int s = lane; s < S; s += 32) {
         const float uraw = sU[r * S + s];
-        const float ll = direct ? uraw : __logf(uraw + 1e-35f);
+        const float ll = direct ? uraw : ll_of(uraw);
         float dll = 0.f;
         if (a.kind == CTDD_LOSS_SDDM) {
           const float rs = (s == xr) ? 0.f : beta * rcol[s];
-          const float e = direct ? __expf(ll - llx) : (uraw + 1e-35f) * inv_ex;
+          const float e = direct ? __expf(ll - llx) : (uraw + lle) * inv_ex;
           const float w = (s == xr) ? 0.f : rs * Q[(size_t)x0 * S + s] * inv_den;
           const float Z = baseZ - zt + (-beta * a.RbD[s]);
           ra += e * rs;
@@ -311,7 +315,7 @@ __global__ void __launch_bounds__(256, ROWS == 32 ? 2 : 1) loss_kernel(const Arg
             }
           }
         }
-        if (BWD) sU[r * S + s] = direct ? dll : __fdividef(dll, uraw + 1e-35f);   // cotangent of u (or of ll for direct)
+        if (BWD) sU[r * S + s] = direct ? dll : (uraw + lle > 0.f ? __fdividef(dll, uraw + lle) : 0.f);   // cotangent of u (or of ll for direct)
       }
     }
     ra = warp_sum(ra); rb = warp_sum(rb); rc = warp_sum(rc); wsum = warp_sum(wsum);
@@ -397,8 +401,9 @@ int run_loss(const ctdd_loss_params* p, void* stream, bool bwd) {
   if (p->B <= 0 || p->D <= 0 || p->S < 2) { set_error("ctdd_loss: bad sizes"); return 2; }
   if (p->kind < CTDD_LOSS_CTELBO || p->kind > CTDD_LOSS_SDDM) { set_error("ctdd_loss: unknown kind %d", p->kind); return 2; }
   if (!p->logits || !p->Q || !p->QT || !p->Rb || !p->beta || !p->x0 || !p->xt) { set_error("ctdd_loss: null input"); return 2; }
-  if (p->kind != CTDD_LOSS_CTELBO && !(p->logit_type == CTDD_BRANCH_SDDM_DIRECT || p->logit_type == CTDD_BRANCH_SDDM_REVERSE_PROB)) {
-    set_error("ctdd_loss: logit_type %d not supported by the fused kernels (direct / reverse_prob)", p->logit_type);
+  if (p->kind != CTDD_LOSS_CTELBO && !(p->logit_type == CTDD_BRANCH_SDDM_DIRECT || p->logit_type == CTDD_BRANCH_SDDM_REVERSE_PROB ||
+                                       p->logit_type == CTDD_BRANCH_SDDM_REVERSE_LOGSCALE)) {
+    set_error("ctdd_loss: unknown logit_type %d", p->logit_type);
     return 3;
   }
   if (p->kind == CTDD_LOSS_CTELBO && !p->x_tilde) { set_error("ctdd_loss: x_tilde required"); return 2; }

@@ -8,8 +8,9 @@ Same registered names, config keys and `calc_loss` signatures (BOTH argument ord
   * every (B,D,S)-sized term of CT-ELBO / SDDM-ELBO / ratio matching, forward and backward w.r.t. the logits:
     `ctdd_loss_forward` / `ctdd_loss_backward` behind one autograd.Function (ops.loss_terms);
   * the final O(B) combination (means, nll weights, lambda mixing) is torch arithmetic on (B,) vectors.
-`reverse_logscale` materialises (B,D,S,S) in the reference (infeasible at S=256); it is served by the differentiable
-torch composition `model_utils.get_logprob_with_logits` on top of the kernel-built q_{t|0} and is documented as such.
+`reverse_logscale` materialises (B,D,S,S) in the reference (infeasible at S=256); here it is the same fused kernel as
+`reverse_prob`: the log-sum-exp over k of log p_k + log q[k,s] IS log(sum_k p_k q[k,s]) without the 1e-35 guard, and
+-1e9 where no term survives (csrc/ctdd_loss.cu), so no (B,D,S,S) tensor and no PyTorch loss body exists.
 EBMAux / BinEBMAux / d3pm_loss are out of scope.
 """
 from __future__ import annotations
@@ -19,7 +20,6 @@ import torch.nn.functional as F
 
 from ... import _native as nat
 from ... import ops
-from ..models import model_utils
 from . import losses_utils
 
 _CRM_TYPES = {"rm": 0, "mle": 1, "elbo": 2}
@@ -201,33 +201,10 @@ class _SDDMFamily(_LossBase):
         c = self._prepare(model, minibatch, 1.0, clamp_max=0.99999)
         logits = _dense(model(c["x_tilde"].long(), c["ts"]), model.S)
         branch = nat.branch_for(self.cfg.loss.name, self.cfg.loss.logit_type)
-        if branch == nat.BRANCH_SDDM_REVERSE_LOGSCALE:
-            return _sddm_terms_torch(self.cfg, model, c, logits, self.ratio_eps)
         reg, outer, norm, rm, ce = ops.loss_terms(logits, nat.LOSS_SDDM, Q=c["Q"], QT=c["QT"], Rb=c["Rb"], beta=c["beta"],
                                                   x0=c["x0"], xt=c["x_tilde"], eps=self.ratio_eps, logit_branch=branch)
         neg_elbo = torch.mean(-outer / norm) + torch.mean(reg)
         return neg_elbo, torch.sum(rm) / c["B"], torch.sum(ce) / (c["B"] * c["D"])
-
-
-def _sddm_terms_torch(cfg, model, c, logits, eps):
-    """reverse_logscale only: torch composition on kernel-built q (documented in the module docstring)."""
-    B, D, S = logits.shape
-    ll_all, ll_xt = model_utils.get_logprob_with_logits(cfg, model, c["x_tilde"], c["ts"], logits)
-    Q, Rb, beta = c["Q"], c["Rb"], c["beta"]
-    R = Rb.unsqueeze(0) * beta.view(B, 1, 1)
-    bi = torch.arange(B, device=logits.device).view(B, 1)
-    xt, x0 = c["x_tilde"].long(), c["x0"].long()
-    mask = 1.0 - F.one_hot(xt, S).float()
-    rate_col = R.transpose(1, 2)[bi, xt]                     # R[b, :, x~]
-    L = ll_all - ll_xt.unsqueeze(-1)
-    reg = torch.sum(torch.exp(L) * mask * rate_col, dim=(1, 2))
-    w = mask * rate_col * Q[bi, x0] / (Q[bi, x0, xt] + eps).unsqueeze(-1)
-    z = -torch.diagonal(R, dim1=1, dim2=2)
-    zx = z[bi, xt]
-    Z = zx.sum(1).view(B, 1, 1) - zx.unsqueeze(-1) + z.view(B, 1, S)
-    neg_elbo = torch.mean(-torch.sum(w * L, dim=(1, 2)) / torch.sum(w / Z, dim=(1, 2))) + torch.mean(reg)
-    ce = F.cross_entropy(logits.permute(0, 2, 1), x0)
-    return neg_elbo, torch.sum(-ll_xt) / B, ce
 
 
 @losses_utils.register_loss
@@ -266,31 +243,10 @@ class _CatRMFamily(_LossBase):
         c = self._prepare(model, minibatch, t_hi, clamp_max=clamp_max, want_tilde=False)
         logits = _dense(model(c["xt"].long(), c["ts"]), model.S)
         branch = nat.branch_for(self.cfg.loss.name, self.cfg.loss.logit_type)
-        if branch == nat.BRANCH_SDDM_REVERSE_LOGSCALE:
-            ll_all, ll_xt = model_utils.get_logprob_with_logits(self.cfg, model, c["xt"], c["ts"], logits)
-            loss = _crm_loss_torch(self.cfg.loss.loss_type, ll_all, ll_xt, c, self.S)
-            ce = F.cross_entropy(logits.permute(0, 2, 1), c["x0"].long())
-            return torch.sum(loss) * (1 - self.cfg.loss.ce_coeff) / c["B"], ce
         crm, _, _, _, ce = ops.loss_terms(logits, nat.LOSS_CRM, Q=c["Q"], QT=c["QT"], Rb=c["Rb"], beta=c["beta"], x0=c["x0"],
                                           xt=c["xt"], eps=self.ratio_eps, logit_branch=branch,
                                           crm_type=_CRM_TYPES[self.cfg.loss.loss_type])
         return torch.sum(crm) * (1 - self.cfg.loss.ce_coeff) / c["B"], torch.sum(ce) / (c["B"] * c["D"])
-
-
-def _crm_loss_torch(loss_type, ll_all, ll_xt, c, S):
-    from ..utils import utils
-    if loss_type == "rm":
-        return -ll_xt
-    if loss_type == "mle":
-        return -((S - 1) * ll_xt + torch.sum(utils.log1mexp(ll_all), dim=-1) - utils.log1mexp(ll_xt))
-    B = ll_all.shape[0]
-    bi = torch.arange(B, device=ll_all.device).view(B, 1)
-    xt = c["xt"].long()
-    oh = F.one_hot(xt, S).float()
-    e = torch.exp(ll_all - ll_xt.unsqueeze(-1))
-    first = torch.sum(e * c["QT"][bi, xt] * (1 - oh), dim=-1)
-    second = torch.sum((ll_xt.unsqueeze(-1) - ll_all) * c["Q"][bi, xt] * (1 - oh), dim=-1)
-    return first - second
 
 
 @losses_utils.register_loss

@@ -4,19 +4,18 @@ Only the head lives here — the score networks (U-Net, DiT, ...) stay the refer
 reference turns the two numbers per dimension the U-Net emits (`model_output == 'logistic_pars'`,
 lib/networks/unet.py:450-452) into an (B, D, S) logits tensor with ~20 elementwise passes; here
 
-* under `torch.no_grad()` (every sampler) `TruncatedLogisticHead.head_forward` returns an `ops.LogisticHead`, which the
-  samplers pass straight into the fused reverse-step kernel: the logits never exist in memory;
+* inside this package's samplers (`ops.fused_head()` context, no gradients) `TruncatedLogisticHead.head_forward` returns
+  an `ops.LogisticHead`, which the samplers pass straight into the fused reverse-step kernel: the logits never exist in
+  memory.  Any other caller of `model(x, t)` gets the (B, D, S) logits tensor, as from the reference;
 * `sample_logistic(...)` is the reference's function with the same signature, backed by one CUDA pass
   (`ctdd_logistic_logits`) when no gradient is required;
 * with gradients enabled (training) the head is one `autograd.Function`: the same forward kernel, and a backward kernel
   (`ctdd_logistic_logits_backward`) that recomputes the head from (mu, log_scale) and reads the incoming (B, D, S) gradient
-  once — instead of autograd through ~20 saved (B, D, S) tensors.  `_logistic_logits_torch` keeps the same closed form in
-  differentiable torch ops for host tensors / double precision checks.
+  once — instead of autograd through ~20 saved (B, D, S) tensors.  Host or non-fp32 inputs are refused (no fallback).
 """
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
 
 from ... import ops
 
@@ -27,25 +26,14 @@ def log_minus_exp(a, b, eps=1e-6):
 
 
 def _logistic_logits_autograd(mu, log_scale, S, fix_logistic):
-    """Differentiable head on the training path: CUDA forward + backward kernels for fp32 CUDA tensors."""
-    if mu.is_cuda and mu.dtype == torch.float32 and log_scale.dtype == torch.float32:
-        return ops.logistic_logits_autograd(mu, log_scale, S, fix_logistic).view(*mu.shape, S)
-    return _logistic_logits_torch(mu, log_scale, S, fix_logistic)
-
-
-def _logistic_logits_torch(mu, log_scale, S, fix_logistic):
-    """The head in differentiable torch ops: log(u_{s+1} (kappa v_s + 1e-6)) with u = sigmoid(z), v = sigmoid(-z) at the
-    bin edges (identical in exact arithmetic to the reference's logsigmoid / log_minus_exp chain; see csrc/ctdd_head.cu)."""
-    mu = mu.unsqueeze(-1)
-    inv = torch.exp(2.0 - log_scale).unsqueeze(-1)
-    edges = torch.linspace(-1.0, 1.0, S + 1, device=mu.device, dtype=mu.dtype)
-    z = (edges - mu) * inv
-    log_u, log_v = F.logsigmoid(z), F.logsigmoid(-z)
-    kappa = -torch.expm1(-inv * (2.0 / S))
-    logits = log_u[..., 1:] + torch.log(kappa * torch.exp(log_v[..., :-1]) + 1e-6)
-    if fix_logistic:
-        logits = torch.minimum(logits, log_v[..., :-1] + torch.log(kappa * torch.exp(log_u[..., 1:]) + 1e-6))
-    return logits
+    """Differentiable head on the training path: CUDA forward + backward kernels (fp32 CUDA tensors; like the rest of the
+    package there is no CPU / PyTorch fallback)."""
+    if not (mu.is_cuda and log_scale.is_cuda):
+        raise RuntimeError("ctdd_b200: the truncated-logistic head runs on CUDA tensors only (no CPU fallback)")
+    if mu.dtype != torch.float32 or log_scale.dtype != torch.float32:
+        raise RuntimeError(f"ctdd_b200: the truncated-logistic head takes float32 (mu, log_scale); got {mu.dtype}, "
+                           f"{log_scale.dtype} - run the head outside autocast or cast the network output")
+    return ops.logistic_logits_autograd(mu, log_scale, S, fix_logistic).view(*mu.shape, S)
 
 
 def sample_logistic(net_out, B, C, D, S, fix_logistic, device):
@@ -65,7 +53,9 @@ class TruncatedLogisticHead:
         mu, log_scale = net_out[0], net_out[1]
         if torch.is_grad_enabled() and (mu.requires_grad or log_scale.requires_grad):
             return _logistic_logits_autograd(mu, log_scale, self.S, self.fix_logistic).view(B, D, self.S)
-        return ops.LogisticHead(mu, log_scale, self.fix_logistic)
+        if ops.fused_head_enabled():      # this package's samplers: the head is evaluated inside the reverse-step kernel
+            return ops.LogisticHead(mu, log_scale, self.fix_logistic)
+        return ops.logistic_logits(mu, log_scale, self.S, self.fix_logistic).view(B, D, self.S)
 
 
 class EMA:

@@ -163,7 +163,8 @@ class _SamplerBase:
 
             @functools.wraps(fn)
             def sample(self, model, *args, **kwargs):
-                with nat.on_device(getattr(model, "device", None)):
+                # ... and with the un-materialised output head switched on: StepEngine fuses it into the step kernel
+                with nat.on_device(getattr(model, "device", None)), ops.fused_head():
                     return fn(self, model, *args, **kwargs)
             cls.sample = sample
 

@@ -134,6 +134,31 @@ def logistic_logits_autograd(mu, log_scale, S, fix_logistic=False):
     return _LogisticLogitsFn.apply(mu, log_scale, S, fix_logistic)
 
 
+# Opt-in for the un-materialised head: only code that knows how to consume an ops.LogisticHead (this package's samplers,
+# which fuse it into the reverse-step kernel) switches it on; every other caller of model(x, t) gets the (B, D, S) logits
+# tensor the reference returns.
+import contextlib
+import threading
+
+_head_mode = threading.local()
+
+
+def fused_head_enabled() -> bool:
+    return bool(getattr(_head_mode, "on", False))
+
+
+@contextlib.contextmanager
+def fused_head(on: bool = True):
+    """Inside this context a TruncatedLogisticHead model evaluated without gradients returns an ops.LogisticHead (the two
+    numbers per dimension) instead of the (B, D, S) logits."""
+    prev = fused_head_enabled()
+    _head_mode.on = bool(on)
+    try:
+        yield
+    finally:
+        _head_mode.on = prev
+
+
 class LogisticHead:
     """What a model's forward may return instead of (N, D, S) logits when its output layer is the truncated-logistic
     head (reference lib/models/models.py:248-282, cfg.model.model_output == 'logistic_pars'): the two numbers per

@@ -227,7 +227,13 @@ def test_samplers_with_fused_head_match_reference_fixtures(golden, case):
     S = cfg.data.S
     m = _head_product_model(cfg, S, D, seed, fix)
     with torch.no_grad():
-        assert isinstance(m(torch.zeros((2, D), dtype=torch.long, device="cuda"), torch.ones(2, device="cuda")), ops.LogisticHead)
+        xz, tz = torch.zeros((2, D), dtype=torch.long, device="cuda"), torch.ones(2, device="cuda")
+        dense = m(xz, tz)                               # a foreign caller gets the reference's (B, D, S) logits tensor
+        assert isinstance(dense, torch.Tensor) and dense.shape == (2, D, S)
+        with ops.fused_head():                          # the samplers switch the un-materialised head on
+            head = m(xz, tz)
+            assert isinstance(head, ops.LogisticHead)
+            assert torch.equal(head.logits(S), dense)
     fp = oracle_forward(fwd)
 
     def tables(ts, device):
