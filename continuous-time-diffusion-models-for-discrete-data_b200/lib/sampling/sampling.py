@@ -76,9 +76,53 @@ class StepEngine:
         self.workspace = torch.empty((max(ws, 1),), dtype=torch.uint8, device=self.device) if ws > 0 else None
         ncalls = max_calls if max_calls is not None else 4 * len(self.times) + 8
         self.stats = torch.zeros((ncalls, nat.STAT_COUNT), dtype=torch.int64, device=self.device)
+        # Per-step host work is kept to pointer arithmetic: the time vectors of the whole schedule are built once, the
+        # state ping-pongs between three resident buffers, and ONE ctdd_step_params struct is reused - only the fields
+        # that change from step to step are rewritten (the reference allocates ~25 tensors and syncs once per step).
+        self._t_all = torch.tensor(self.times, dtype=torch.float32, device=self.device).view(-1, 1).expand(-1, N).contiguous()
+        self._xbuf = [torch.empty((N, D), dtype=torch.int32, device=self.device) for _ in range(3)]
+        self._xptr = [b.data_ptr() for b in self._xbuf]
+        self._q0, self._qt0 = self.Q.data_ptr(), self.QT.data_ptr()
+        self._tc0 = self.tc_tables.data_ptr() if self.tc_tables is not None else 0
+        self._stats0 = self.stats.data_ptr()
+        self._fn = nat.lib().ctdd_reverse_step
+        self._p = nat.StepParams(
+            mode=0, branch=branch, impl=impl, N=N, D=D, S=S, row_offset=self.row_offset, ld_logits=S,
+            batch_stride_logits=D * S, Rb=self.Rb.data_ptr(), RbT=self.RbT.data_ptr(),
+            tc_static=(self.tc_static.data_ptr() if self.tc_static is not None else None), eps=self.eps, seed=self.seed,
+            workspace=(self.workspace.data_ptr() if self.workspace is not None else None))
 
     def t_ones(self, tidx):
-        return self.times[tidx] * torch.ones((self.N,), device=self.device)
+        return self._t_all[tidx]
+
+    def _fast_step(self, mode, logits, x_eval, tidx, h, reject_multi, x_base, row):
+        """The common case of step(): dense contiguous fp32 logits or an un-materialised head, state update only."""
+        N, D, S = self.N, self.D, self.S
+        p = self._p
+        if isinstance(logits, ops.LogisticHead):
+            mu, ls, fix = logits.as_tuple()
+            mu, ls, head_bs = ops._head_views(mu, ls, N, D)
+            p.head = nat.HEAD_LOGISTIC_FIX if fix else nat.HEAD_LOGISTIC
+            p.head_mu, p.head_log_scale, p.head_batch_stride, p.logits = mu.data_ptr(), ls.data_ptr(), int(head_bs), None
+        else:
+            p.head, p.head_mu, p.head_log_scale, p.head_batch_stride = nat.HEAD_LOGITS, None, None, 0
+            p.logits = logits.data_ptr()
+        xe = x_eval.data_ptr()
+        xb = x_base.data_ptr() if x_base is not None else 0
+        k = 0
+        while self._xptr[k] == xe or self._xptr[k] == xb:      # an output buffer that is neither input
+            k += 1
+        ss = S * S * 4
+        p.mode, p.x_eval, p.x_base, p.x_out = mode, xe, (xb or None), self._xptr[k]
+        p.Q, p.QT = self._q0 + tidx * ss, self._qt0 + tidx * ss
+        p.tc_tables = (self._tc0 + tidx * self.tc_bytes) if self._tc0 else None
+        p.beta, p.h, p.reject_multi, p.offset = float(self.beta[tidx]), float(h), (1 if reject_multi else 0), self.call
+        p.stats_out = self._stats0 + row * nat.STAT_COUNT * 8
+        p.rr_out = p.ratio_out = None
+        rc = self._fn(p, torch.cuda.current_stream().cuda_stream)
+        if rc != 0:
+            nat.check(rc, "ctdd_reverse_step")
+        return self._xbuf[k]
 
     def step(self, mode, logits, x_eval, tidx, h, reject_multi=False, x_base=None, draws=True,
              want_rr=False, want_ratio=False, logits_view=None, stats=None):
@@ -97,6 +141,18 @@ class StepEngine:
         if isinstance(logits, ops.LogisticHead):   # truncated-logistic output head: fused into the step kernel
             head, logits = logits.as_tuple(), None
         row = self.call if self.call < self.stats.shape[0] else self.stats.shape[0] - 1
+        fast = (logits_view is None and stats is None and not want_rr and not want_ratio and mode != nat.MODE_EXACT
+                and x_eval.dtype == torch.int32 and x_eval.is_contiguous() and x_eval.device == self.device
+                and (x_base is None or (x_base.dtype == torch.int32 and x_base.is_contiguous()))
+                and torch.cuda.current_device() == (self.device.index or 0)
+                and ((head is not None and self.tc_tables is not None)
+                     or (head is None and logits.dtype == torch.float32 and logits.is_contiguous() and logits.is_cuda)))
+        if fast:
+            x_out = self._fast_step(mode, ops.LogisticHead(*head) if head is not None else logits, x_eval, tidx, h,
+                                    reject_multi, x_base, row)
+            if draws:
+                self.call += 1
+            return x_out, row
         out = ops.reverse_step(
             mode, self.branch, logits, x_eval, self.Q[tidx], self.QT[tidx], self.Rb, self.RbT, self.beta[tidx], h,
             self.eps, N=N, D=D, S=S, x_base=x_base, reject_multi=reject_multi, seed=self.seed, offset=self.call,

@@ -190,8 +190,19 @@ def test_losses_at_c3_size_match_the_oracle(cls, over, B, D):
                          one_forward_pass=L.one_forward_pass)
     want.backward()
     np.testing.assert_allclose(loss.item(), want.item(), rtol=1e-4)
-    gw, ow = m.w.grad.cpu().numpy(), net.w.grad.numpy()
-    assert np.abs(gw - ow).max() <= 2e-3 * np.abs(ow).max() + 1e-12
+    # yardstick: the same oracle evaluated in fp64.  The fp32 oracle (= the reference's arithmetic) carries its own
+    # summation noise in d loss / d w (49 k rows, per-sample weights 1 / sig_norm spanning decades: ~1e-2 relative at the
+    # C5 shape), so the kernel is held to max(2e-3 of the largest entry, 2 x the reference's own fp32 error).
+    import types
+    net64 = rh.StubNet(S, D, seed, 1.0, 3.0).double()
+    fp64 = types.SimpleNamespace(S=S, transition=lambda t: fp.transition(t).double(), rate=lambda t: fp.rate(t).double())
+    want64 = lo.loss_value(cls, fp64, lambda x, t, label=None: net64.net(x, t.double()), x0, ts, seed=seed, eps=L.eps_ratio,
+                           nll_weight=L.nll_weight, logit_type=L.logit_type, loss_type=L.loss_type, ce_coeff=L.ce_coeff,
+                           one_forward_pass=L.one_forward_pass)
+    want64.backward()
+    gw, ow, o64 = m.w.grad.cpu().numpy().astype(np.float64), net.w.grad.numpy().astype(np.float64), net64.w.grad.numpy()
+    ref_noise = np.abs(ow - o64).max()
+    assert np.abs(gw - o64).max() <= max(2e-3 * np.abs(o64).max(), 2.0 * ref_noise) + 1e-12, (np.abs(gw - o64).max(), ref_noise)
     gl = seen[0].grad
     rowsum = gl.sum(-1).abs().max().item()
     assert rowsum <= 2e-5 * gl.abs().max().item() * S ** 0.5 + 1e-12, rowsum
