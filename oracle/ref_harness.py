@@ -24,7 +24,17 @@ import torch.nn as nn
 from . import rng
 from . import ctmc_oracle as oc
 
+import os
+
+# the read-only reference in the build container; on the GPU box (no /root/reference) the copy that
+# tools/stage_reference.py placed under the git-ignored baseline/_ref/ (bench.py --impl reference only)
 REF_ROOT = "/root/reference/TAUnSDDM"
+if not os.path.isdir(REF_ROOT):
+    REF_ROOT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "TAUnSDDM")
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REF_ROOT, "lib", "sampling"))
 
 
 class Cfg(dict):
