@@ -45,6 +45,9 @@ class _LossBase:
     ts_override = None
     seed = None
     noise_offset = 0
+    #: global index of this rank's first sample (data-parallel training: the noising draws are keyed on the GLOBAL sample,
+    #: so N ranks with batch slices reproduce the single-process run of the concatenated batch)
+    batch_offset = 0
 
     def __init_subclass__(cls, **kw):
         # calc_loss runs with the model's device current (the kernels launch on the current device's stream)
@@ -80,7 +83,7 @@ class _LossBase:
         Rb, _ = model.base_rate_tables(Q.device)
         x0 = minibatch.to(device=Q.device, dtype=torch.int32).contiguous()
         seed = self.seed if self.seed is not None else _seed_from_torch()
-        xt, xtil = ops.noise_xt(Q, Rb, beta, x0, seed, self.noise_offset, want_tilde=want_tilde)
+        xt, xtil = ops.noise_xt(Q, Rb, beta, x0, seed, self.noise_offset, batch_offset=self.batch_offset, want_tilde=want_tilde)
         return dict(B=B, D=D, ts=ts, Q=Q, QT=QT, beta=beta, Rb=Rb, x0=x0, xt=xt, x_tilde=xtil, minibatch=minibatch)
 
 
