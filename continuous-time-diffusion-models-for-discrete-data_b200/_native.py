@@ -62,7 +62,7 @@ class LossParams(ctypes.Structure):
         ("eps", c_float),
         ("out_a", c_void_p), ("out_b", c_void_p), ("out_c", c_void_p), ("out_d", c_void_p), ("out_nll", c_void_p),
         ("ga", c_void_p), ("gb", c_void_p), ("gd", c_void_p), ("gn", c_void_p),
-        ("grad_logits", c_void_p), ("workspace", c_void_p),
+        ("grad_logits", c_void_p), ("workspace", c_void_p), ("tc_scratch", c_void_p),
     ]
 
 
@@ -118,6 +118,10 @@ def lib() -> ctypes.CDLL:
     L.ctdd_loss_workspace_bytes.restype = c_int64
     L.ctdd_loss_forward.argtypes = [ctypes.POINTER(LossParams), c_void_p]
     L.ctdd_loss_backward.argtypes = [ctypes.POINTER(LossParams), c_void_p]
+    L.ctdd_loss_tc_scratch_bytes.argtypes = [c_int, c_int, c_int]
+    L.ctdd_loss_tc_scratch_bytes.restype = c_int64
+    L.ctdd_bgemm256_tc.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]
+    L.ctdd_bgemm256_tc.restype = c_int
     for name in ("ctdd_build_qt0", "ctdd_build_rate", "ctdd_reverse_step", "ctdd_prep_tc_tables",
                  "ctdd_sample_categorical_shared", "ctdd_noise_xt", "ctdd_loss_forward", "ctdd_loss_backward"):
         getattr(L, name).restype = c_int

@@ -34,6 +34,10 @@ struct Args {
   float* out_a; float* out_b; float* out_c; float* out_d; float* out_nll;
   const float* ga; const float* gb; const float* gd; const float* gn;
   float* grad;
+  float* bufA;         // tensor-core path (S == 256): [B][D][S] GEMM operand p, later the cotangent V
+  float* bufU;         // tensor-core path: [B][D][S] u = p Q (kept from forward to backward), later dp = V Q^T
+  float* lse;          // tensor-core path: [B][D] log-sum-exp of every logits row (kept from forward to backward)
+  float* fix;          // tensor-core path: [B][D] cotangent of u at the evaluation state that comes through ll_x (backward)
 };
 
 __device__ __forceinline__ float log1mexp_ref(float v) {  // lib/utils/utils.py:86-91
@@ -390,6 +394,200 @@ __global__ void __launch_bounds__(256, ROWS == 32 ? 2 : 1) loss_kernel(const Arg
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Tensor-core path (S == 256, SDDM / CRM kinds, reverse_prob / reverse_logscale): the two contractions run on tcgen05
+// (ctdd_bgemm256_tc); what is left of loss_kernel are three streaming passes, one warp per row, lane l owns the states
+// 4l..4l+3 and 128+4l..+3 (two coalesced 128-bit accesses per array), no shared-memory staging:
+//   tc_pre_kernel   softmax p -> bufA, lse -> a.lse, cross-entropy sum                       (forward)
+//   tc_terms_kernel u from bufU: the per-(row, s) terms and their per-sample sums            (forward)
+//                   or the cotangent V = dL/du -> bufA                                        (backward)
+//   tc_post_kernel  dp = V Q^T from bufU: softmax Jacobian + cross-entropy gradient -> grad   (backward)
+// The arithmetic per element is loss_kernel's (phases 1, 3 and 5).
+constexpr int TC_S = 256;
+constexpr int TC_ROWS = 32;      // rows of ONE sample per CTA (8 warps x 4 rows): one atomicAdd per CTA and output
+
+struct Row8 { float v[8]; };
+__device__ __forceinline__ Row8 load_row8(const float* p, int lane) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p) + lane), b = __ldg(reinterpret_cast<const float4*>(p + 128) + lane);
+  return Row8{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+}
+__device__ __forceinline__ void store_row8(float* p, int lane, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[lane] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p + 128)[lane] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ int state_of(int lane, int e) { return (e < 4 ? 0 : 128) + 4 * lane + (e & 3); }
+// value of element `s` of a row held as Row8 across the warp
+__device__ __forceinline__ float row_elem(const float (&v)[8], int s, int lane) {
+  const int e = ((s >> 7) << 2) | (s & 3), src = (s & 127) >> 2;
+  float x = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) x = (k == e) ? v[k] : x;
+  return __shfl_sync(0xffffffffu, x, src);
+}
+// sum over the CTA's warps of up to 5 per-warp values, then one atomicAdd each (thread 0)
+__device__ __forceinline__ void block_accumulate(float (&acc)[5], float* const (&dst)[5], int n) {
+  __shared__ float s_part[8][5];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0)
+    for (int k = 0; k < n; ++k) s_part[warp][k] = acc[k];
+  __syncthreads();
+  if (threadIdx.x < n) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += s_part[w][threadIdx.x];
+    atomicAdd(dst[threadIdx.x], t);
+  }
+}
+
+__global__ void __launch_bounds__(256) tc_pre_kernel(const Args a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.y;
+  float nll = 0.f;
+  for (int r = warp; r < TC_ROWS; r += 8) {
+    const int d = blockIdx.x * TC_ROWS + r;
+    if (d >= a.D) break;
+    const size_t row = (size_t)b * a.D + d;
+    const Row8 l = load_row8(a.logits + row * TC_S, lane);
+    float m = l.v[0];
+#pragma unroll
+    for (int e = 1; e < 8; ++e) m = fmaxf(m, l.v[e]);
+    m = warp_max(m);
+    float ex[8], sum = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { ex[e] = expf(l.v[e] - m); sum += ex[e]; }
+    sum = warp_sum(sum);
+    const float lse = m + logf(sum), rsum = 1.f / sum;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ex[e] *= rsum;
+    store_row8(a.bufA + row * TC_S, lane, ex);
+    const float lx0 = row_elem(l.v, a.x0[row], lane);
+    if (lane == 0) { a.lse[row] = lse; nll += lse - lx0; }
+  }
+  float acc[5] = {nll, 0.f, 0.f, 0.f, 0.f};
+  float* const dst[5] = {a.out_nll + b, nullptr, nullptr, nullptr, nullptr};
+  block_accumulate(acc, dst, 1);
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(256) tc_terms_kernel(const Args a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.y;
+  const float* Q = a.Q + (size_t)b * TC_S * TC_S;
+  const float* QT = a.QT + (size_t)b * TC_S * TC_S;
+  const float beta = a.beta[b];
+  const float lle = (a.logit_type == CTDD_BRANCH_SDDM_REVERSE_LOGSCALE) ? 0.f : 1e-35f;   // see loss_kernel
+  const float baseZ = (a.kind != CTDD_LOSS_CRM) ? a.baseZ[b] : 0.f;
+  const float ga = BWD ? a.ga[b] : 0.f, gb = BWD ? a.gb[b] : 0.f, gd = BWD ? a.gd[b] : 0.f;
+  float sa = 0.f, sb = 0.f, sc = 0.f, sd = 0.f;      // per-warp sums over its rows (forward)
+  for (int r = warp; r < TC_ROWS; r += 8) {
+    const int d = blockIdx.x * TC_ROWS + r;
+    if (d >= a.D) break;
+    const size_t row = (size_t)b * a.D + d;
+    const int x0 = a.x0[row], xr = a.xt[row];
+    const Row8 u = load_row8(a.bufU + row * TC_S, lane);
+    const float ux = row_elem(u.v, xr, lane);
+    const float llx = ux + lle > 0.f ? logf(ux + lle) : -1e9f;
+    float ra = 0.f, rb = 0.f, rc = 0.f, wsum = 0.f;
+    float V[8];
+    if (a.kind == CTDD_LOSS_SDDM) {
+      const Row8 rcol = load_row8(a.RbT + (size_t)xr * TC_S, lane);       // Rb[., xr]
+      const Row8 qx0 = load_row8(Q + (size_t)x0 * TC_S, lane);            // Q[x0, .]
+      const Row8 zd = load_row8(a.RbD, lane);                             // Rb[s, s]
+      const float inv_den = 1.f / (Q[(size_t)x0 * TC_S + xr] + a.eps);
+      const float inv_ex = expf(-llx);
+      const float zt = -beta * a.Rb[(size_t)xr * TC_S + xr];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int s = state_of(lane, e);
+        const float uraw = u.v[e];
+        const float ll = uraw + lle > 0.f ? __logf(uraw + lle) : -1e9f;
+        const float rs = (s == xr) ? 0.f : beta * rcol.v[e];
+        const float ev = (uraw + lle) * inv_ex;
+        const float w = (s == xr) ? 0.f : rs * qx0.v[e] * inv_den;
+        const float Z = baseZ - zt + (-beta * zd.v[e]);
+        ra += ev * rs;
+        rb += w * (ll - llx);
+        rc += __fdividef(w, Z);
+        wsum += w;
+        const float dll = ga * ev * rs + gb * w;
+        V[e] = (uraw + lle > 0.f) ? __fdividef(dll, uraw + lle) : 0.f;
+      }
+    } else {      // CRM
+      Row8 qsx, qxs;
+      if (a.crm_type == 2) { qsx = load_row8(QT + (size_t)xr * TC_S, lane); qxs = load_row8(Q + (size_t)xr * TC_S, lane); }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int s = state_of(lane, e);
+        const float uraw = u.v[e];
+        const float ll = uraw + lle > 0.f ? __logf(uraw + lle) : -1e9f;
+        float dll = 0.f;
+        if (a.crm_type == 1) {          // mle
+          ra += -log1mexp_ref(ll);
+          const float el = expf(ll);
+          dll = (s == xr) ? 0.f : ga * el / (1.f - el);
+        } else if (a.crm_type == 2) {   // elbo
+          if (s != xr) {
+            const float ev = expf(ll - llx);
+            ra += ev * qsx.v[e] - (llx - ll) * qxs.v[e];
+            wsum += ev * qsx.v[e] + qxs.v[e];
+            dll = ga * (ev * qsx.v[e] + qxs.v[e]);
+          }
+        }
+        V[e] = (uraw + lle > 0.f) ? __fdividef(dll, uraw + lle) : 0.f;
+      }
+    }
+    ra = warp_sum(ra); rb = warp_sum(rb); rc = warp_sum(rc); wsum = warp_sum(wsum);
+    float dllx;
+    if (a.kind == CTDD_LOSS_SDDM) {
+      dllx = -ga * ra - gb * wsum;
+    } else {
+      if (a.crm_type == 0) { ra = -llx; dllx = -ga; }
+      else if (a.crm_type == 1) { ra = -((float)(TC_S - 1) * llx) + ra + log1mexp_ref(llx); dllx = -ga * (float)(TC_S - 1); }
+      else { dllx = -ga * wsum; }
+    }
+    dllx -= gd;
+    if (BWD) {
+      // The cotangent at the evaluation state also receives d/d ll_x (u_x + lle = exp(ll_x)).  That one-hot part is kept
+      // OUT of the tensor-core product: it is the large, cancelling term of the softmax Jacobian, and its contribution
+      // dp[k] += fix * Q[k][x] is one exact fp32 row gather in tc_post_kernel instead of a 3 x BF16 product.
+      if (lane == 0) a.fix[row] = dllx / expf(llx);
+      store_row8(a.bufA + row * TC_S, lane, V);
+    } else {
+      sa += ra; sb += rb; sc += rc; sd += -llx;
+    }
+  }
+  if (!BWD) {
+    float acc[5] = {sa, sb, sc, sd, 0.f};
+    float* const dst[5] = {a.out_a + b, a.out_b + b, a.out_c + b, a.out_d + b, nullptr};
+    block_accumulate(acc, dst, 4);
+  }
+}
+
+__global__ void __launch_bounds__(256) tc_post_kernel(const Args a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = blockIdx.y;
+  const float gn = a.gn[b];
+  for (int r = warp; r < TC_ROWS; r += 8) {
+    const int d = blockIdx.x * TC_ROWS + r;
+    if (d >= a.D) break;
+    const size_t row = (size_t)b * a.D + d;
+    const Row8 l = load_row8(a.logits + row * TC_S, lane);
+    Row8 dp = load_row8(a.bufU + row * TC_S, lane);
+    const float lse = a.lse[row], fix = a.fix[row];
+    const int x0 = a.x0[row];
+    const Row8 qx = load_row8(a.QT + ((size_t)b * TC_S + a.xt[row]) * TC_S, lane);     // Q[k][x] over k
+    float p[8], dot = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      dp.v[e] = fmaf(fix, qx.v[e], dp.v[e]);
+      p[e] = expf(l.v[e] - lse);
+      dot += p[e] * dp.v[e];
+    }
+    dot = warp_sum(dot);
+    float g[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g[e] = p[e] * (dp.v[e] - dot) + gn * (p[e] - (state_of(lane, e) == x0 ? 1.f : 0.f));
+    store_row8(a.grad + row * TC_S, lane, g);
+  }
+}
+
 }  // namespace loss
 }  // namespace ctdd
 
@@ -428,10 +626,10 @@ int run_loss(const ctdd_loss_params* p, void* stream, bool bwd) {
   a.kind = p->kind; a.logit_type = p->logit_type; a.crm_type = p->crm_type; a.B = p->B; a.D = p->D; a.S = S;
   a.logits = p->logits; a.Q = p->Q; a.QT = p->QT; a.Rb = p->Rb; a.beta = p->beta;
   a.x0 = p->x0; a.xt = p->xt; a.x_tilde = p->x_tilde; a.eps = p->eps;
-  // workspace: [G: B*S*S, CTELBO only][baseZ: B][RbT: S*S][RbD: S]
+  // workspace: [G: B*S*S, CTELBO only][baseZ: B, padded to a multiple of 4][RbT: S*S][RbD: S]
   a.G = reinterpret_cast<const float*>(p->workspace);
   a.baseZ = p->workspace ? reinterpret_cast<const float*>(p->workspace) + (p->kind == CTDD_LOSS_CTELBO ? (size_t)p->B * S * S : 0) : nullptr;
-  a.RbT = (a.baseZ && p->kind != CTDD_LOSS_CRM) ? a.baseZ + p->B : nullptr;
+  a.RbT = (a.baseZ && p->kind != CTDD_LOSS_CRM) ? a.baseZ + ((p->B + 3) & ~3) : nullptr;   // 16-byte aligned rows
   a.RbD = a.RbT ? a.RbT + (size_t)S * S : nullptr;
   a.out_a = p->out_a; a.out_b = p->out_b; a.out_c = p->out_c; a.out_d = p->out_d; a.out_nll = p->out_nll;
   a.ga = p->ga; a.gb = p->gb; a.gd = p->gd; a.gn = p->gn; a.grad = p->grad_logits;
@@ -451,6 +649,39 @@ int run_loss(const ctdd_loss_params* p, void* stream, bool bwd) {
       CTDD_CHECK_LAUNCH("basez_kernel");
     }
   }
+  // S == 256, SDDM / CRM kinds with a scratch buffer: the two contractions run on tcgen05 (ctdd_bgemm256_tc) between three
+  // streaming kernels.  u = p Q and the rows' log-sum-exp are kept in the scratch from the forward to the backward call.
+  // (CT-ELBO stays on the fp32 CUDA-core contraction: its operand p / (Q[k,x~] + eps) spans 9 decades and the softmax
+  // Jacobian cancels to ~1e-4 of its terms, which takes the 3 x BF16 product error past the gradient parity bar.)
+  const bool direct_branch = p->logit_type == CTDD_BRANCH_SDDM_DIRECT;
+  if (S == 256 && p->tc_scratch && p->kind != CTDD_LOSS_CTELBO && !direct_branch) {
+    if (reinterpret_cast<uintptr_t>(p->tc_scratch) & 15) { set_error("ctdd_loss: tc_scratch must be 16-byte aligned"); return 2; }
+    const size_t n = (size_t)p->B * p->D * S;
+    a.bufA = reinterpret_cast<float*>(p->tc_scratch);
+    a.bufU = a.bufA + n;
+    a.lse = a.bufU + n;
+    a.fix = a.lse + (size_t)p->B * p->D;
+    dim3 tgrid((p->D + TC_ROWS - 1) / TC_ROWS, p->B);
+    if (!bwd) {
+      tc_pre_kernel<<<tgrid, 256, 0, st>>>(a);
+      CTDD_CHECK_LAUNCH("tc_pre_kernel");
+      if (int rc = ctdd_bgemm256_tc(a.bufA, p->QT, p->B, p->D, a.bufU, stream)) return rc;      // u[s] = sum_k p[k] Q[k][s]
+      tc_terms_kernel<false><<<tgrid, 256, 0, st>>>(a);
+      CTDD_CHECK_LAUNCH("tc_terms_kernel");
+    } else {
+      tc_terms_kernel<true><<<tgrid, 256, 0, st>>>(a);
+      CTDD_CHECK_LAUNCH("tc_terms_kernel<bwd>");
+      if (p->kind == CTDD_LOSS_CRM && p->crm_type == 0) {      // ratio matching 'rm': the cotangent is the one-hot part only
+        cudaMemsetAsync(a.bufU, 0, n * sizeof(float), st);
+      } else {
+        if (int rc = ctdd_bgemm256_tc(a.bufA, p->Q, p->B, p->D, a.bufU, stream)) return rc;     // dp[k] = sum_s V[s] Q[k][s]
+      }
+      tc_post_kernel<<<tgrid, 256, 0, st>>>(a);
+      CTDD_CHECK_LAUNCH("tc_post_kernel");
+    }
+    return 0;
+  }
+  a.bufA = a.bufU = a.lse = a.fix = nullptr;
   int threads = ((S + 31) / 32) * 32;
   if (threads > 256) threads = 256;
   if (threads < 64) threads = 64;
@@ -468,9 +699,13 @@ int run_loss(const ctdd_loss_params* p, void* stream, bool bwd) {
 }  // namespace
 
 extern "C" int64_t ctdd_loss_workspace_bytes(int kind, int B, int S) {
-  if (kind == CTDD_LOSS_CTELBO) return ((int64_t)B * S * S + B + (int64_t)S * S + S) * 4;
-  if (kind == CTDD_LOSS_SDDM) return ((int64_t)B + (int64_t)S * S + S) * 4;
+  const int64_t Bp = (B + 3) & ~3;
+  if (kind == CTDD_LOSS_CTELBO) return ((int64_t)B * S * S + Bp + (int64_t)S * S + S) * 4;
+  if (kind == CTDD_LOSS_SDDM) return (Bp + (int64_t)S * S + S) * 4;
   return 0;
+}
+extern "C" int64_t ctdd_loss_tc_scratch_bytes(int B, int D, int S) {
+  return S == 256 ? ((int64_t)2 * B * D * S + (int64_t)2 * B * D + 4) * 4 : 0;
 }
 extern "C" int ctdd_loss_forward(const ctdd_loss_params* p, void* stream) { return run_loss(p, stream, false); }
 extern "C" int ctdd_loss_backward(const ctdd_loss_params* p, void* stream) { return run_loss(p, stream, true); }

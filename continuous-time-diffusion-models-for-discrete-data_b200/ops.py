@@ -352,9 +352,25 @@ def noise_xt(Q, Rb, beta, x0, seed, offset=0, batch_offset=0, want_tilde=True):
     return xt, xtilde
 
 
+@nat.on_tensor_device
+def bgemm256(X, M, out=None):
+    """out[b,d,n] = sum_k X[b,d,k] * M[b,n,k] on tcgen05 (S = 256; 3 x BF16 split precision).  X: (B,D,256), M: (B,256,256)."""
+    B, D, S = X.shape
+    if S != 256 or tuple(M.shape) != (B, 256, 256):
+        raise ValueError(f"bgemm256 needs X (B,D,256) and M (B,256,256); got {tuple(X.shape)}, {tuple(M.shape)}")
+    X = X.contiguous().float()
+    M = M.contiguous().float()
+    if out is None:
+        out = torch.empty((B, D, S), dtype=torch.float32, device=X.device)
+    nat.check(nat.lib().ctdd_bgemm256_tc(nat.ptr(X), nat.ptr(M), B, D, nat.ptr(out), nat.stream()), "ctdd_bgemm256_tc")
+    return out
+
+
 class _LossTerms(torch.autograd.Function):
     """Per-sample loss terms (out_a, out_b, out_c, out_d, out_nll), each (B,), differentiable w.r.t. `logits`
     through the fused backward kernel (include/ctdd.h: ctdd_loss_forward / ctdd_loss_backward)."""
+    #: S == 256: run the two contractions on tcgen05 (set False to force the CUDA-core kernel, e.g. as a cross-check)
+    use_tc = True
 
     @staticmethod
     def forward(ctx, logits, kind, logit_branch, crm_type, Q, QT, Rb, beta, x0, xt, x_tilde, eps):
@@ -364,12 +380,18 @@ class _LossTerms(torch.autograd.Function):
         outs = torch.zeros((5, B), dtype=torch.float32, device=dev)
         nbytes = int(nat.lib().ctdd_loss_workspace_bytes(kind, B, S))
         ws = torch.empty((max(nbytes, 4),), dtype=torch.uint8, device=dev)
+        # S == 256: scratch of the tensor-core contractions (u = A Q is kept in it for the backward call)
+        wants_tc = _LossTerms.use_tc and kind != nat.LOSS_CTELBO and logit_branch != nat.BRANCH_SDDM_DIRECT
+        nscr = int(nat.lib().ctdd_loss_tc_scratch_bytes(B, D, S)) if wants_tc else 0
+        scr = torch.empty((nscr,), dtype=torch.uint8, device=dev) if nscr > 0 else None
         p = nat.LossParams(kind=kind, logit_type=logit_branch, crm_type=crm_type, B=B, D=D, S=S,
                            logits=nat.ptr(logits), Q=nat.ptr(Q), QT=nat.ptr(QT), Rb=nat.ptr(Rb), beta=nat.ptr(beta),
                            x0=nat.ptr(x0), xt=nat.ptr(xt), x_tilde=nat.ptr(x_tilde), eps=float(eps),
                            out_a=outs[0].data_ptr(), out_b=outs[1].data_ptr(), out_c=outs[2].data_ptr(),
-                           out_d=outs[3].data_ptr(), out_nll=outs[4].data_ptr(), workspace=nat.ptr(ws))
+                           out_d=outs[3].data_ptr(), out_nll=outs[4].data_ptr(), workspace=nat.ptr(ws),
+                           tc_scratch=nat.ptr(scr))
         nat.check(nat.lib().ctdd_loss_forward(p, nat.stream()), "ctdd_loss_forward")
+        ctx.scr = scr
         ctx.save_for_backward(logits, Q, QT, Rb, beta, x0, xt, x_tilde if x_tilde is not None else xt, ws)
         ctx.meta = (kind, logit_branch, crm_type, float(eps), x_tilde is not None)
         return outs[0], outs[1], outs[2], outs[3], outs[4]
@@ -391,7 +413,7 @@ class _LossTerms(torch.autograd.Function):
                            logits=nat.ptr(logits), Q=nat.ptr(Q), QT=nat.ptr(QT), Rb=nat.ptr(Rb), beta=nat.ptr(beta),
                            x0=nat.ptr(x0), xt=nat.ptr(xt), x_tilde=(nat.ptr(x_tilde) if has_tilde else None), eps=eps,
                            ga=nat.ptr(ga), gb=nat.ptr(gb), gd=nat.ptr(gd), gn=nat.ptr(gn), grad_logits=nat.ptr(grad),
-                           workspace=nat.ptr(ws))
+                           workspace=nat.ptr(ws), tc_scratch=nat.ptr(ctx.scr))
         nat.check(nat.lib().ctdd_loss_backward(p, nat.stream()), "ctdd_loss_backward")
         return (grad,) + (None,) * 11
 

@@ -246,6 +246,11 @@ typedef struct ctdd_loss_params {
   const float* ga; const float* gb; const float* gd; const float* gn;
   float* grad_logits;    /* [B,D,S] */
   void* workspace;       /* >= ctdd_loss_workspace_bytes(kind, B, S); written by forward, read by backward */
+  /* appended field (zero-initialised = CUDA-core contractions).  S == 256, kinds SDDM and CRM with reverse_prob /
+   * reverse_logscale: >= ctdd_loss_tc_scratch_bytes(B, D, S) bytes, 16-byte aligned; the two (B*D x S)(S x S) contractions
+   * then run on tcgen05 (ctdd_bgemm256_tc).  Written by forward, read AND overwritten by backward: pass the same buffer to
+   * both calls, untouched in between.  Ignored for CT-ELBO and the `direct` logit type. */
+  void* tc_scratch;
 } ctdd_loss_params;
 
 enum {
@@ -254,7 +259,14 @@ enum {
   CTDD_LOSS_SDDM = 2     /* losses.py:1345-1500 (ScoreElbo), :389-544 (SDDMElbo) */
 };
 
+/* Per-sample contraction of the loss terms on tcgen05 (S == 256 only): out[b,d,n] = sum_k X[b,d,k] * M[b,n,k], fp32 in / out,
+ * 3 x BF16 split precision (relative error ~3e-5).  Replaces the batched matmuls with a per-sample q_{t|0} of
+ * lib/losses/losses.py:148-150, :179-181 and lib/models/model_utils.py:44-46 (forward: M = QT, backward: M = Q).
+ * X, out: [B, D, 256]; M: [B, 256, 256]; all 16-byte aligned. */
+int ctdd_bgemm256_tc(const float* X, const float* M, int B, int D, float* out, void* stream);
+
 int64_t ctdd_loss_workspace_bytes(int kind, int B, int S);
+int64_t ctdd_loss_tc_scratch_bytes(int B, int D, int S);
 int ctdd_loss_forward(const ctdd_loss_params* p, void* stream);
 int ctdd_loss_backward(const ctdd_loss_params* p, void* stream);
 
