@@ -206,3 +206,59 @@ def test_losses_at_c3_size_match_the_oracle(cls, over, B, D):
     gl = seen[0].grad
     rowsum = gl.sum(-1).abs().max().item()
     assert rowsum <= 2e-5 * gl.abs().max().item() * S ** 0.5 + 1e-12, rowsum
+
+
+def _nat():
+    from ctdd_b200 import _native as nat
+    return nat
+
+
+def test_bgemm256_matches_fp64_einsum():
+    """ctdd_bgemm256_tc (per-sample contraction on tcgen05, 3 x BF16): out[b,d,n] = sum_k X[b,d,k] M[b,n,k] within 1e-4
+    relative of an fp64 einsum for non-negative operands spanning several decades, ragged row counts (tile tails, a sample
+    boundary inside a CTA pair's tile range, fewer tiles than CTA pairs)."""
+    from ctdd_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for B, D in ((1, 1), (2, 130), (3, 784), (5, 3072), (80, 300)):
+        X = torch.rand((B, D, 256), device="cuda", generator=g) * torch.exp(4 * torch.randn((B, D, 1), device="cuda", generator=g))
+        M = torch.rand((B, 256, 256), device="cuda", generator=g)
+        out = ops.bgemm256(X, M)
+        ref = torch.einsum("bdk,bnk->bdn", X.double(), M.double())
+        rel = ((out.double() - ref).abs() / ref.abs().clamp_min(1e-30)).max().item()
+        assert rel <= 1e-4, (B, D, rel)
+    with pytest.raises(ValueError):
+        ops.bgemm256(torch.zeros((1, 2, 32), device="cuda"), torch.zeros((1, 32, 32), device="cuda"))
+
+
+def test_tensor_core_loss_path_matches_cuda_core_path():
+    """SDDM / CRM loss terms at S = 256 with the contractions on tcgen05 against the fp32 CUDA-core kernel of the same
+    library: per-sample terms within 1e-4, logit gradient within 1e-4 of its largest entry."""
+    from ctdd_b200 import make_config, ops
+    from ctdd_b200.lib.models import forward_model as fm
+    nat = _nat()
+    B, D, S = 5, 200, 256
+    cfg = make_config(data=dict(S=S), model=dict(rate_sigma=6.0, Q_sigma=512.0, time_exp=100.0, time_base=3.0), device="cuda")
+    model = fm.GaussianTargetRate(cfg, "cuda")
+    g = torch.Generator(device="cuda").manual_seed(1)
+    ts = torch.rand(B, device="cuda", generator=g) * 0.9 + 0.05
+    Q, QT = model._build_qt0(model._transition_delta(ts), inverse=True, want_transpose=True)
+    beta = model._rate_scalar(ts).float().contiguous()
+    Rb, _ = model.base_rate_tables(Q.device)
+    x0 = torch.randint(0, S, (B, D), device="cuda", generator=g, dtype=torch.int32)
+    xt, xtil = ops.noise_xt(Q, Rb, beta, x0, 5, 0)
+    logits = torch.randn((B, D, S), device="cuda", generator=g) - (torch.arange(S, device="cuda").view(1, 1, S) - x0.unsqueeze(-1)).float() ** 2 / 128.0
+    for kind, kw in ((nat.LOSS_SDDM, dict(xt=xtil)), (nat.LOSS_SDDM, dict(xt=xtil, logit_branch=nat.BRANCH_SDDM_REVERSE_LOGSCALE)),
+                     (nat.LOSS_CRM, dict(xt=xt, crm_type=0)), (nat.LOSS_CRM, dict(xt=xt, crm_type=1)), (nat.LOSS_CRM, dict(xt=xt, crm_type=2))):
+        res = []
+        for tc in (False, True):
+            ops._LossTerms.use_tc = tc
+            try:
+                lg = logits.clone().requires_grad_(True)
+                o = ops.loss_terms(lg, kind, Q=Q, QT=QT, Rb=Rb, beta=beta, x0=x0, eps=1e-9, **kw)
+                (o[0].sum() + 0.3 * o[1].sum() + 0.1 * o[3].sum() + 0.01 * o[4].sum()).backward()
+                res.append(([t.detach().cpu().double() for t in o], lg.grad.detach().cpu().double()))
+            finally:
+                ops._LossTerms.use_tc = True
+        for a, b in zip(res[0][0], res[1][0]):
+            assert ((a - b).abs() <= 1e-4 * a.abs().clamp_min(1e-6)).all(), (kind, kw)
+        assert (res[0][1] - res[1][1]).abs().max() <= 1e-4 * res[0][1].abs().max(), (kind, kw)
