@@ -420,27 +420,51 @@ def run_ours(args, w, rank, world, local_rank):
         f1.record()
         torch.cuda.synchronize(dev)
         head_ms = f0.elapsed_time(f1) / 3
-        # end to end from HOST buffers: 2 floats + 1 state per dimension in, 1 state out
+        # end to end from HOST buffers: 2 floats + 1 state per dimension in, 1 state out, EVERY step.  Three streams and two
+        # buffer sets: the H2D copy of step j + 1, the kernel of step j and the D2H read-back of step j - 1 overlap, so a
+        # step costs the slowest of the three instead of their sum (and the host link is shared more evenly when 8 ranks
+        # feed their GPUs at once).
         host_head = torch.empty((B, 2 * D), dtype=torch.float32, pin_memory=True)
         host_head.copy_(heads[W])
-        dev_head = torch.empty((B, 2 * D), dtype=torch.float32, device=dev)
-        dev_x = torch.empty((B, D), dtype=torch.int32, device=dev)
+        NBUF = 2
+        dev_head = [torch.empty((B, 2 * D), dtype=torch.float32, device=dev) for _ in range(NBUF)]
+        dev_x = [torch.empty((B, D), dtype=torch.int32, device=dev) for _ in range(NBUF)]
+        host_outs = [torch.empty((B, D), dtype=torch.int32, pin_memory=True) for _ in range(NBUF)]
+        s_in, s_run, s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
+        ev_in = [torch.cuda.Event() for _ in range(NBUF)]
+        ev_run = [torch.cuda.Event() for _ in range(NBUF)]
+        hws = [torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev) for _ in range(NBUF)]
 
-        def head_e2e(i):
-            dev_head.copy_(host_head, non_blocking=True)
-            dev_x.copy_(host_x, non_blocking=True)
-            mu_h, ls_h = torch.chunk(dev_head, 2, dim=1)
-            out = ops.reverse_step(mode, branch, None, dev_x, Q[i], QT[i], Rb, RbT, beta[i], h, 1e-9, N=B, D=D, S=S,
-                                   reject_multi=not w["ordinal"], seed=0xC7DD, offset=i, row_offset=row_offset, impl=impl,
-                                   tc_tables=tc[i], tc_static=tcs, workspace=workspace, head=(mu_h, ls_h, False))["x"]
-            host_out.copy_(out, non_blocking=True)
-            torch.cuda.synchronize(dev)
+        def head_e2e(i, k):
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(ev_run[k])                 # the kernel that last read this buffer set has finished
+                dev_head[k].copy_(host_head, non_blocking=True)
+                dev_x[k].copy_(host_x, non_blocking=True)
+                ev_in[k].record(s_in)
+            with torch.cuda.stream(s_run):
+                s_run.wait_event(ev_in[k])
+                mu_h, ls_h = torch.chunk(dev_head[k], 2, dim=1)
+                out = ops.reverse_step(mode, branch, None, dev_x[k], Q[i], QT[i], Rb, RbT, beta[i], h, 1e-9, N=B, D=D, S=S,
+                                       reject_multi=not w["ordinal"], seed=0xC7DD, offset=i, row_offset=row_offset, impl=impl,
+                                       tc_tables=tc[i], tc_static=tcs, workspace=hws[k], head=(mu_h, ls_h, False))["x"]
+                ev_run[k].record(s_run)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_run[k])
+                out.record_stream(s_out)
+                host_outs[k].copy_(out, non_blocking=True)
 
-        head_e2e(0)
+        def drain():
+            for st_ in (s_in, s_run, s_out):
+                st_.synchronize()
+
+        for j in range(2):
+            head_e2e(j, j % NBUF)
+        drain()
         barrier()
         t0 = time.perf_counter()
         for j in range(K):
-            head_e2e(W + j)
+            head_e2e(W + j, j % NBUF)
+        drain()
         barrier()
         fe_ms = (time.perf_counter() - t0) * 1e3 / K
         t_f = torch.tensor([fused_ms, fe_ms], dtype=torch.float64, device=dev)
@@ -453,7 +477,8 @@ def run_ours(args, w, rank, world, local_rank):
                  "standalone_head_kernel_ms": head_ms,
                  "e2e": {"ms_per_step": fe_ms, "tflops": world * fl_ / (fe_ms * 1e-3) / 1e12,
                          "h2d_bytes_per_step": int(B * 2 * D * 4 + B * D * 4), "d2h_bytes_per_step": int(B * D * 4),
-                         "note": "C-ABI step fed from pinned HOST head parameters + state, result read back to host"}}
+                         "note": "C-ABI step fed from pinned HOST head parameters + state every step, new state read back every "
+                                 "step; H2D / kernel / D2H of consecutive steps overlap on three streams"}}
         del heads, noise
 
     # ---- the sampler CLASS end to end (the reference-facing API): TauL.sample(model, B) with a stub network that returns
