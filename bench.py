@@ -434,6 +434,8 @@ def run_ours(args, w, rank, world, local_rank):
         ev_in = [torch.cuda.Event() for _ in range(NBUF)]
         ev_run = [torch.cuda.Event() for _ in range(NBUF)]
         hws = [torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev) for _ in range(NBUF)]
+        dev_out = [torch.empty((B, D), dtype=torch.int32, device=dev) for _ in range(NBUF)]
+        ev_out = [torch.cuda.Event() for _ in range(NBUF)]
 
         def head_e2e(i, k):
             with torch.cuda.stream(s_in):
@@ -443,15 +445,17 @@ def run_ours(args, w, rank, world, local_rank):
                 ev_in[k].record(s_in)
             with torch.cuda.stream(s_run):
                 s_run.wait_event(ev_in[k])
+                s_run.wait_event(ev_out[k])                # the read-back that last used this output buffer has finished
                 mu_h, ls_h = torch.chunk(dev_head[k], 2, dim=1)
                 out = ops.reverse_step(mode, branch, None, dev_x[k], Q[i], QT[i], Rb, RbT, beta[i], h, 1e-9, N=B, D=D, S=S,
                                        reject_multi=not w["ordinal"], seed=0xC7DD, offset=i, row_offset=row_offset, impl=impl,
-                                       tc_tables=tc[i], tc_static=tcs, workspace=hws[k], head=(mu_h, ls_h, False))["x"]
+                                       tc_tables=tc[i], tc_static=tcs, workspace=hws[k], head=(mu_h, ls_h, False),
+                                       x_out=dev_out[k])["x"]
                 ev_run[k].record(s_run)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_run[k])
-                out.record_stream(s_out)
                 host_outs[k].copy_(out, non_blocking=True)
+                ev_out[k].record(s_out)
 
         def drain():
             for st_ in (s_in, s_run, s_out):

@@ -55,7 +55,7 @@ def prep_tc_static(Rb):
 def reverse_step(mode, branch, logits, x_eval, Q, QT, Rb, RbT, beta, h, eps, *, N, D, S, x_base=None,
                  reject_multi=False, seed=0, offset=0, row_offset=0, impl=nat.IMPL_AUTO, tc_tables=None, tc_static=None,
                  workspace=None, stats=None, want_rr=False, want_ratio=False, logits_offset_elems=0,
-                 batch_stride=None, head=None):
+                 batch_stride=None, head=None, x_out=None):
     """One fused reverse-rate evaluation (+ state update). Returns dict(x=..., rr=..., ratio=...).
 
     `head=(mu, log_scale, fix_logistic)` replaces `logits` (pass None) by the parameters of the truncated-logistic
@@ -78,7 +78,12 @@ def reverse_step(mode, branch, logits, x_eval, Q, QT, Rb, RbT, beta, h, eps, *, 
         if logits.dtype != torch.float32:
             logits = logits.float()
         logits = logits.contiguous()
-    x_out = torch.empty((N, D), dtype=torch.int32, device=dev) if mode != nat.MODE_RATES_ONLY else None
+    if mode == nat.MODE_RATES_ONLY:
+        x_out = None
+    elif x_out is None:
+        x_out = torch.empty((N, D), dtype=torch.int32, device=dev)
+    elif x_out.dtype != torch.int32 or tuple(x_out.shape) != (N, D) or not x_out.is_contiguous():
+        raise ValueError("x_out must be a contiguous (N, D) int32 tensor")
     rr = torch.empty((N, D, S), dtype=torch.float32, device=dev) if want_rr else None
     ratio = torch.empty((N, D, S), dtype=torch.float32, device=dev) if want_ratio else None
     if workspace is None:
