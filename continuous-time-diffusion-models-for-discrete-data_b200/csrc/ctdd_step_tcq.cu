@@ -39,15 +39,29 @@ constexpr int STAGES = 2;              // smem operand stages (64 KB each)
 constexpr int ACC = 2;                 // TMEM accumulator buffers (NT columns each)
 constexpr int CBUF = 2;                // contribution buffers (epilogue -> finalizer)
 constexpr int RING = 8;                // per-tile row-scalar ring (> STAGES + ACC + CBUF)
-constexpr int NUM_EPI_WARPS = 8;       // warps 0-7: TMEM quadrant w&3, column half w>>2 (= CTA that owns those rows)
-constexpr int FIRST_PROD_WARP = 8;
+constexpr int NUM_EPI_WARPS = 8;       // epilogue warp e: TMEM quadrant e&3, column half e>>2 (= CTA that owns those rows)
+#ifndef CTDD_EPI_HIGH
+#define CTDD_EPI_HIGH 0
+#endif
+#ifndef CTDD_GATHER
+#define CTDD_GATHER 1
+#endif
+// Warp numbering: the scheduler of an SM sub-partition favours its higher-numbered warps.  CTDD_EPI_HIGH = 1 puts the
+// epilogue warps above the producers (producers 0.., epilogue NPW.., light group last).
+constexpr bool EPI_HIGH = CTDD_EPI_HIGH != 0;
+// base-rate gather of the tauLDR sampling modes: 1 = lane = row, four 256-bit loads of the row's own table piece (few
+// instructions, 32 LSU wavefronts per load); 2 = lane = state, one coalesced predicated load per in-band row (one wavefront
+// per load, ~5 instructions per row)
+constexpr int GATHER = CTDD_GATHER;
 #ifndef CTDD_TCQ_NPW
 #define CTDD_TCQ_NPW 12
 #endif
 constexpr int NPW = CTDD_TCQ_NPW;      // producer warps (a multiple of 4: register budgets are per 4-warp group)
-constexpr int MMA_WARP = FIRST_PROD_WARP + NPW;   // light group: MMA issue / relay, idle, 2 finalizer warps
+constexpr int FIRST_PROD_WARP = EPI_HIGH ? 0 : NUM_EPI_WARPS;
+constexpr int FIRST_EPI_WARP = EPI_HIGH ? NPW : 0;
+constexpr int MMA_WARP = NUM_EPI_WARPS + NPW;   // light group: MMA issue / relay, idle, 2 finalizer warps
 constexpr int FIN_WARP0 = MMA_WARP + 2;
-constexpr int NUM_THREADS = (FIRST_PROD_WARP + NPW + 4) * 32;
+constexpr int NUM_THREADS = (NUM_EPI_WARPS + NPW + 4) * 32;
 // setmaxnreg targets.  The registers handed out by .inc are the ones the CTA's own warps released with .dec:
 // 8 * EPI + NPW * PROD + 4 * LIGHT must not exceed (12 + NPW) * (launch allocation), or the .inc never returns.
 constexpr int REGS_LAUNCH = (65536 / NUM_THREADS) & ~7;          // what __launch_bounds__ gives every thread
@@ -91,8 +105,10 @@ struct Smem {
   alignas(8) uint64_t full[STAGES];            // leader CTA: its NPW producer warps + 1 relayed arrival for the partner's
   uint64_t full_local[STAGES];                 // partner CTA: its NPW producer warps; the partner's idle MMA warp relays the phase
   uint64_t empty[STAGES];                      // multicast tcgen05.commit
-  uint64_t scal_full[RING];                    // NPW local producer warps + the partner's bytes (st.async complete_tx)
+  uint64_t scal_local[RING];                   // NPW local producer warps: this CTA's 64 rows of the tile have their scalars
+  uint64_t scal_full[RING];                    // the local loader's arrival (scal_local seen) + the partner's bytes (DSMEM bulk copy)
   uint64_t lring_full[NPW][LRING];             // cp.async.bulk complete_tx of one row pair
+  uint64_t lring_free[NPW];                    // the producer warp has its values in registers: the loader may refill the slot
   uint64_t tmem_full[ACC];                     // multicast tcgen05.commit
   uint64_t tmem_empty[ACC];                    // used in the leader CTA: 8 local + 8 remote epilogue warps
   uint64_t contrib_full[CBUF];                 // 4 local epilogue warps + the bytes of the partner's 4 warps
@@ -100,6 +116,35 @@ struct Smem {
   uint64_t contrib_free_remote[CBUF];          // the 2 finalizer warps of the PARTNER are done with the partner's buffer
   uint32_t tmem_base;
 };
+
+#ifdef CTDD_TC_TRACE
+// diagnostic build only (CTDD_TRACE=1 python build.py): per-tile clock stamps of the first CTA pair's roles, read back with
+// ctdd_debug_trace_read_q; never compiled into the product library
+constexpr int TRACE_TILES = 512, TRACE_EVENTS = 8, TRACE_ROLES = 7;   // 5: epilogue detail (q = 0, h = 0, batch 0), 6: producer pass detail
+__device__ long long g_trace[2][TRACE_ROLES][TRACE_TILES][TRACE_EVENTS];
+#define TRACEQ(role, tile, ev)                                                                      \
+  do {                                                                                              \
+    if (blockIdx.x < 2 && (tile) < TRACE_TILES) g_trace[blockIdx.x][role][tile][ev] = clock64();    \
+  } while (0)
+// stamp taken once `dep` (a register) is available: the and.b32 consumes it, zero is a run-time 0 the compiler cannot fold
+#define TRACEQ_DEP(role, tile, ev, dep, zero)                                                       \
+  do {                                                                                              \
+    if (blockIdx.x < 2 && (tile) < TRACE_TILES) {                                                   \
+      long long c_;                                                                                 \
+      asm volatile("{ .reg .b32 t; .reg .b64 t2, c; and.b32 t, %1, %2; cvt.u64.u32 t2, t; mov.u64 c, %%clock64; add.u64 %0, c, t2; }" \
+                   : "=l"(c_) : "r"(dep), "r"(zero));                                               \
+      g_trace[blockIdx.x][role][tile][ev] = c_;                                                     \
+    }                                                                                               \
+  } while (0)
+#define TRACEQ_ADD(role, tile, ev, val)                                                             \
+  do {                                                                                              \
+    if (blockIdx.x < 2 && (tile) < TRACE_TILES) g_trace[blockIdx.x][role][tile][ev] += (val);       \
+  } while (0)
+#else
+#define TRACEQ(role, tile, ev) do { } while (0)
+#define TRACEQ_ADD(role, tile, ev, val) do { } while (0)
+#define TRACEQ_DEP(role, tile, ev, dep, zero) do { } while (0)
+#endif
 
 static_assert(sizeof(Smem) + 1024 <= 232448, "shared memory budget of one CTA (227 KB) exceeded");
 static_assert(NPW <= PASSES_PER_TILE, "every producer warp must own a pass in every tile");
@@ -124,9 +169,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       mbar_init(&sm.full_local[i], NPW);
       mbar_init(&sm.empty[i], 1);
     }
-    for (int i = 0; i < RING; ++i) mbar_init(&sm.scal_full[i], NPW);
-    for (int w = 0; w < NPW; ++w)
+    for (int i = 0; i < RING; ++i) { mbar_init(&sm.scal_local[i], NPW); mbar_init(&sm.scal_full[i], 1); }
+    for (int w = 0; w < NPW; ++w) {
       for (int i = 0; i < LRING; ++i) mbar_init(&sm.lring_full[w][i], 1);
+      mbar_init(&sm.lring_free[w], 1);
+    }
     for (int i = 0; i < ACC; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], 2 * NUM_EPI_WARPS); }
     for (int i = 0; i < CBUF; ++i) {
       mbar_init(&sm.contrib_full[i], NUM_EPI_WARPS / 2);
@@ -182,7 +229,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
   cluster_sync_all();    // barriers initialised and both A halves resident before any cross-CTA traffic
   tc_fence_after();
 
-  if (warp >= FIRST_PROD_WARP && warp < MMA_WARP) {
+  if (warp >= FIRST_PROD_WARP && warp < FIRST_PROD_WARP + NPW) {
     if constexpr (REGS_PROD > REGS_LAUNCH) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
     else if constexpr (REGS_PROD < REGS_LAUNCH) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
     // ======================================================================== producers: 16 lanes per row, 2 rows per pass
@@ -193,7 +240,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     // cp.async.bulk fills two passes ahead, so no global-memory latency sits on the warp's critical path.
     const float* tabA = reinterpret_cast<const float*>(a.tab + TAB_A_OFF) + 4 * l16;
     const float hb = (KM == KM_RATES) ? 1.0f : a.h * a.beta;   // rates-only ignores the step length
-    const bool contiguous = (a.ld == S) && (a.batch_stride == (long long)a.D * S);
     uint64_t* const full_bar = rank == 0 ? &sm.full[0] : &sm.full_local[0];
     // passes of this CTA: pass P = 32 * tl + ps builds rows 2 ps, 2 ps + 1 of the CTA's 64 rows of its tl-th tile; warp pw
     // takes P = pw, pw + NPW, ..  Three cursors run over that sequence (compute, logits fetch one pass ahead, state fetch
@@ -209,15 +255,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     };
     const long long row0 = (long long)pair * NT + (int)rank * NH + 2 * pw;   // pass pw of this CTA's first tile
     const uint32_t scal_c_p = smem_u32(&sm.scal_c[0][0]), scal_x_p = smem_u32(&sm.scal_x[0][0]), band_p = smem_u32(&sm.band[0]);
-    const uint32_t scal_c_remote = mapa(scal_c_p, rank ^ 1u);
-    const uint32_t scal_x_remote = mapa(scal_x_p, rank ^ 1u);
-    const uint32_t scal_full_remote = mapa(smem_u32(&sm.scal_full[0]), rank ^ 1u);
 
-    auto row_ptr = [&](long long g) -> const float* {
-      if (contiguous) return a.logits + g * S;
-      const uint32_t n = (uint32_t)g / (uint32_t)a.D, d = (uint32_t)g - n * (uint32_t)a.D;
-      return a.logits + (long long)n * a.batch_stride + (long long)d * a.ld;
-    };
     // States (and head parameters): two passes of this warp ahead, into registers.
     Cursor cx = {0, pw, row0};
     float f_mu = 0.f, f_ls = 0.f;        // HEAD: head parameters of the row fetch() just visited
@@ -242,42 +280,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       }
       return xv;
     };
-    // Logits: lane 0 starts the bulk copy of the NEXT pass's row pair into the warp's ring slot as soon as the current
-    // pass has read its values (rows past the end are replaced by row 0: never used; adjacent rows of a contiguous
-    // logits tensor travel as one 2 KB copy; the rows were pulled from HBM into L2 some tiles earlier).
-    Cursor cf = {0, pw, row0};
-    // (every lane runs the warp-uniform bookkeeping, lane 0 alone issues: the addresses then live in uniform registers)
-    auto fetch_rows = [&]() {
-      if (HEAD || cf.tl >= my_tiles) return;
-      const long long gf = cf.row;
-      if (lane == 0) {
-        uint64_t* bar = &sm.lring_full[pw][0];
-        mbar_arrive_expect_tx(bar, 2 * S * 4);
-        if (contiguous && gf + 1 < a.rows) {
-          bulk_g2s(&sm.lring[pw][0][0][0], a.logits + gf * S, 2 * S * 4, bar);
-        } else {
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            const long long gg = (gf + hf < a.rows) ? gf + hf : 0;
-            bulk_g2s(&sm.lring[pw][0][hf][0], row_ptr(gg), S * 4, bar);
-          }
-        }
-        if (contiguous && PREFETCH_TILES > 0) {   // pull the same two rows of a later tile from HBM into L2
-          const long long r0 = gf + (long long)PREFETCH_TILES * npairs * NT;
-#ifdef CTDD_EXP_PFBIG      // diagnostic build: one 16 KB prefetch per 8 passes instead of 2 KB per pass
-          if ((cf.ps & 7) == 0 && r0 + 16 <= a.rows) l2_prefetch_bulk(a.logits + r0 * S, 16 * S * 4);
-#else
-          if (r0 + 2 <= a.rows) l2_prefetch_bulk(a.logits + r0 * S, 2 * S * 4);
-#endif
-          // and the states of that tile (read two passes ahead, straight into registers): one 128-byte line serves
-          // 16 passes; the pass that starts a line pulls it
-          if ((cf.ps & 15) == 0 && r0 < a.rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.x_eval + r0));
-        }
-      }
-      cf.advance(tile_step);
-    };
-
-    if (!(CTDD_EXP_PMASK & 8)) fetch_rows();
+    // Logits: the loader warp (light group) refills this warp's ring slot as soon as the warp reports that the current
+    // pass has its values in registers (lring_free); the rows were pulled from HBM into L2 some tiles earlier.
     int x_cur = fetch();
     float mu_cur = f_mu, ls_cur = f_ls;
     int x_n1 = fetch();
@@ -307,23 +311,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         c1 = hb * rs * inv;                                      // lam_s = (D_s * c1 + c0) * Rb[x,s]
         c0 = hb * 1e-35f * inv;
       }
-      if (l16 == 0 && !(CTDD_EXP_PMASK & 2)) {   // one lane per half-warp: the row's scalars into BOTH CTAs of the pair
+      if (l16 == 0) {   // one lane per half-warp: the row's scalars (the loader forwards the tile's 64 records to the partner CTA)
         uint32_t bandx;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(bandx) : "r"(band_p + 4u * (uint32_t)p_x));
         const uint32_t sx = bandx | (p_ok ? (1u << 8) : 0u) | ((uint32_t)p_x << 10);
         sts64(scal_c_p + (uint32_t)p_idx * 8u, __float_as_uint(c1), __float_as_uint(c0));
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(scal_x_p + (uint32_t)p_idx * 4u), "r"(sx) : "memory");
-        const uint32_t bar = scal_full_remote + (uint32_t)p_slot * 8u;
-        st_async_cluster_v2(scal_c_remote + (uint32_t)p_idx * 8u, __float_as_uint(c1), __float_as_uint(c0), bar);
-        st_async_cluster_b32(scal_x_remote + (uint32_t)p_idx * 4u, sx, bar);
       }
       if (p_last) {
+        fence_proxy_async();     // the records are read by a bulk copy (async proxy)
         __syncwarp();
-        if (lane == 0) {
-          // warp 0 also announces the bytes the partner's producers deliver for this tile
-          if (pw == 0) mbar_arrive_expect_tx(&sm.scal_full[p_slot], (CTDD_EXP_PMASK & 2) ? 0u : SCAL_TX_BYTES);
-          else mbar_arrive(&sm.scal_full[p_slot]);
-        }
+        if (lane == 0) mbar_arrive(&sm.scal_local[p_slot]);
       }
       p_have = false;
     };
@@ -338,7 +336,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       const bool ok = x_cur >= 0;
       const int x = ok ? x_cur : 0;
       const bool last_in_tile = ps + NPW >= PASSES_PER_TILE;     // this warp's next pass belongs to another tile
-      if (!HEAD && !(CTDD_EXP_PMASK & (8 | 32))) mbar_wait(&sm.lring_full[pw][0], ring_par);   // 32: copies run, nobody waits
+#ifdef CTDD_TC_TRACE
+      const long long tq0 = clock64();
+      const bool ptr_on = (pw == 0 && lane == 0 && tl != last_tl);
+      const uint32_t pzero = (uint32_t)a.head_fix >> 8;
+      if (ptr_on) TRACEQ(6, tl, 0);
+#endif
+      if (!HEAD) mbar_wait(&sm.lring_full[pw][0], ring_par);
+#ifdef CTDD_TC_TRACE
+      if (pw == 0 && lane == 0) TRACEQ_ADD(0, tl, 3, clock64() - tq0);
+      if (ptr_on) TRACEQ(6, tl, 1);
+#endif
       const int r = 2 * ps + half;
       float v[16];
       float ml = 0.f;
@@ -357,8 +365,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
           v[4 * c] = q4.x; v[4 * c + 1] = q4.y; v[4 * c + 2] = q4.z; v[4 * c + 3] = q4.w;
         }
         ring_par ^= 1u;
-        __syncwarp();            // every lane has its values: the slot is refilled for the warp's next pass
-        if (!(CTDD_EXP_PMASK & 8)) fetch_rows();
+#ifdef CTDD_TC_TRACE
+        if (ptr_on) TRACEQ_DEP(6, tl, 2, __float_as_uint(v[15]), pzero);
+#endif
+        __syncwarp();            // every lane has its values: the slot may be refilled for the warp's next pass
+        if (lane == 0) mbar_arrive(&sm.lring_free[pw]);
+#ifdef CTDD_TC_TRACE
+        if (ptr_on) TRACEQ(6, tl, 3);
+#endif
         float m4[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) m4[c] = fmaxf(fmaxf(v[4 * c], v[4 * c + 1]), fmaxf(v[4 * c + 2], v[4 * c + 3]));
@@ -371,9 +385,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         }
         ml = -m * 1.4426950408889634f;
       }
+#ifdef CTDD_TC_TRACE
+      if (ptr_on) TRACEQ_DEP(6, tl, 4, __float_as_uint(ml), pzero);
+#endif
       finish_prev();
+#ifdef CTDD_TC_TRACE
+      if (ptr_on) TRACEQ(6, tl, 5);
+#endif
       if (tl != last_tl) {       // first pass of this warp in a new tile: the tile's operand stage must be free
+        if (pw == 0 && lane == 0) TRACEQ(0, tl, 0);
         mbar_wait<POLL_LONG>(&sm.empty[st], (uint32_t)(((tl / STAGES) & 1) ^ 1));
+        if (pw == 0 && lane == 0) TRACEQ(0, tl, 1);
         last_tl = tl;
       }
       const uint32_t stage_s = smem_u32(sm.stage[st]);
@@ -408,6 +430,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         const float2 d01 = fadd2(dot2[0], dot2[1]), d23 = fadd2(dot2[2], dot2[3]), dall = fadd2(d01, d23);
         dot = dall.x + dall.y;
       }
+#ifdef CTDD_TC_TRACE
+      if (ptr_on) TRACEQ_DEP(6, tl, 6, __float_as_uint(sum), pzero);
+#endif
       // the table row of the NEXT pass is requested as soon as this pass's has been consumed
       if (!(CTDD_EXP_PMASK & 1)) {
         const size_t xo = (size_t)(x_n1 < 0 ? 0 : x_n1) << 8;
@@ -434,6 +459,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         }
       }
 #endif
+#ifdef CTDD_TC_TRACE
+      if (ptr_on) TRACEQ(6, tl, 7);
+#endif
       // this pass's partial sums and row identity travel to the next pass (finish_prev)
       p_sum = sum; p_dot = dot;
       p_x = x; p_ok = ok; p_idx = slot * NT + (int)rank * NH + r; p_slot = slot; p_last = last_in_tile; p_have = true;
@@ -441,6 +469,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(full_bar + st);
+        if (pw == 0 && lane == 0) TRACEQ(0, tl, 2);
       }
       x_cur = x_n1;
       if (HEAD) { mu_cur = mu_n1; ls_cur = ls_n1; }
@@ -456,7 +485,72 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     }
     finish_prev();
   } else if (warp == MMA_WARP + 1) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_LIGHT));   // idle warp of the light group
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_LIGHT));
+    // ======================================================================== loader: everything the producers would otherwise
+    // issue themselves.  Lane w < NPW serves producer warp w: the bulk copy of each of that warp's passes' row pair into
+    // its ring slot as soon as the warp has released the slot (a bulk-copy issue costs the issuing thread a few hundred
+    // cycles: off the producers' critical path, and spread over NPW lanes here), plus the HBM -> L2 prefetch of rows some
+    // tiles ahead.  Lane 31 forwards each finished tile's 64 row-scalar records to the partner CTA as two DSMEM bulk
+    // copies.  Nobody blocks: the warp polls, every lane acts on what is ready.
+    {
+      const bool contiguous = (a.ld == S) && (a.batch_stride == (long long)a.D * S);
+      auto row_ptr = [&](long long g) -> const float* {
+        if (contiguous) return a.logits + g * S;
+        const uint32_t n = (uint32_t)g / (uint32_t)a.D, d = (uint32_t)g - n * (uint32_t)a.D;
+        return a.logits + (long long)n * a.batch_stride + (long long)d * a.ld;
+      };
+      const uint32_t scal_c_p = smem_u32(&sm.scal_c[0][rank * NH]), scal_x_p = smem_u32(&sm.scal_x[0][rank * NH]);
+      const uint32_t scal_c_remote = mapa(scal_c_p, rank ^ 1u), scal_x_remote = mapa(scal_x_p, rank ^ 1u);
+      const uint32_t scal_full_remote = mapa(smem_u32(&sm.scal_full[0]), rank ^ 1u);
+      const long long tile_rows = (long long)npairs * NT;
+      const long long row00 = (long long)pair * NT + (int)rank * NH;      // first row of this CTA's half of its first tile
+      const int total = my_tiles * PASSES_PER_TILE;
+      const bool refill_lane = !HEAD && lane < NPW;
+      const int w = refill_lane ? lane : 0;
+      int P = lane;              // next pass of warp w in the CTA's pass sequence (P = 32 * tile + pass in the tile)
+      int n = 0;                 // how many of the warp's passes have been issued
+      int fwd = 0;               // (lane 31) next tile whose scalars go to the partner
+      while (true) {
+        const bool more_r = refill_lane && P < total;
+        const bool more_f = lane == 31 && fwd < my_tiles;
+        if (!__any_sync(0xffffffffu, more_r || more_f)) break;
+        bool did = false;
+        if (more_r && (n == 0 || mbar_test(&sm.lring_free[w], (uint32_t)((n - 1) & 1)))) {
+          const long long gf = row00 + (long long)(P >> 5) * tile_rows + 2 * (P & 31);
+          uint64_t* bar = &sm.lring_full[w][0];
+          mbar_arrive_expect_tx(bar, 2 * S * 4);
+          if (contiguous && gf + 1 < a.rows) {
+            bulk_g2s(&sm.lring[w][0][0][0], a.logits + gf * S, 2 * S * 4, bar);
+          } else {               // rows past the end are replaced by row 0 (never used)
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              const long long gg = (gf + hf < a.rows) ? gf + hf : 0;
+              bulk_g2s(&sm.lring[w][0][hf][0], row_ptr(gg), S * 4, bar);
+            }
+          }
+          if (contiguous && PREFETCH_TILES > 0) {   // the same two rows of a later tile from HBM into L2
+            const long long r0 = gf + (long long)PREFETCH_TILES * tile_rows;
+            if (r0 + 2 <= a.rows) l2_prefetch_bulk(a.logits + r0 * S, 2 * S * 4);
+          }
+          P += NPW; ++n;
+          did = true;
+        }
+        if (more_f) {
+          const int slot = fwd % RING;
+          if (mbar_test(&sm.scal_local[slot], (uint32_t)((fwd / RING) & 1))) {
+            // local consumers: this arrival + the partner's 768 bytes complete the phase
+            mbar_arrive_expect_tx(&sm.scal_full[slot], SCAL_TX_BYTES);
+            const uint32_t bar = scal_full_remote + (uint32_t)slot * 8u;
+            bulk_s2cluster(scal_c_remote + (uint32_t)slot * (NT * 8u), scal_c_p + (uint32_t)slot * (NT * 8u), NH * 8u, bar);
+            bulk_s2cluster(scal_x_remote + (uint32_t)slot * (NT * 4u), scal_x_p + (uint32_t)slot * (NT * 4u), NH * 4u, bar);
+            ++fwd;
+            did = true;
+          }
+        }
+        if (!__any_sync(0xffffffffu, did)) asm volatile("nanosleep.u32 32;");
+      }
+    }
+    __syncwarp();
   } else if (warp >= FIN_WARP0) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_LIGHT));
     // ======================================================================== finalizers: lane = row of this CTA
@@ -467,13 +561,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       for (int i = 0; i < my_tiles; ++i) {
         const int tile = pair + i * npairs, slot = i % RING, cb = i % CBUF;
         const long long g = (long long)tile * NT + (long long)rank * NH + r;
+        if (r == 0) TRACEQ(4, i, 0);
         mbar_wait<POLL_LONG>(&sm.scal_full[slot], (i / RING) & 1);
+        if (r == 0) TRACEQ(4, i, 1);
         const uint32_t sx = sm.scal_x[slot][rank * NH + r];
         const int x = (int)((sx >> 10) & 255u);
         const bool valid = (sx >> 8) & 1u;
         int xb = x;
         if (a.x_base && valid) xb = __ldg(a.x_base + g);
         mbar_wait<POLL_LONG>(&sm.contrib_full[cb], (i / CBUF) & 1);
+        if (r == 0) TRACEQ(4, i, 2);
         int jump = 0, cnt = 0;
         float drift = 0.f;
 #pragma unroll
@@ -501,6 +598,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
           mbar_arrive(&sm.contrib_free_local[cb]);
           mbar_arrive_cluster_relaxed(cfree_remote + (uint32_t)cb * 8u);
         }
+        if (r == 0) TRACEQ(4, i, 3);
       }
       if (a.stats) {
         const int v[5] = {stt.changed_base, stt.nonzero, stt.changed_eval, stt.jumped, stt.multi};
@@ -517,8 +615,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     if (rank == 0 && lane == 0) {
       for (int i = 0; i < my_tiles; ++i) {
         const int st = i % STAGES, b = i % ACC;
+        TRACEQ(1, i, 0);
         mbar_wait_cluster(&sm.full[st], (i / STAGES) & 1);
+        TRACEQ(1, i, 1);
         mbar_wait(&sm.tmem_empty[b], ((i / ACC) & 1) ^ 1);
+        TRACEQ(1, i, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem + TM_ACC + b * NT;
         // one descriptor per tile; the 48 instructions differ only by compile-time offsets (16-byte units, low word)
@@ -536,6 +637,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         }
         umma_commit_pair(&sm.empty[st]);
         umma_commit_pair(&sm.tmem_full[b]);
+        TRACEQ(1, i, 3);
       }
     } else if (rank != 0 && lane == 0) {
       // partner CTA: relay "my producers have filled stage st" to the leader as ONE cluster-scope arrival
@@ -551,8 +653,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
   } else {
     if constexpr (REGS_EPI > REGS_LAUNCH) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
     // ======================================================================== epilogue: lane = state
-    const int q = warp & 3;                       // TMEM quadrant -> states rank*128 + 32q + lane = one chunk of the map
-    const uint32_t h = (uint32_t)(warp >> 2);     // accumulator columns [64h, 64h+64) are the rows CTA h produced
+    const int ew = warp - FIRST_EPI_WARP;         // (FIRST_EPI_WARP is a multiple of 4: ew & 3 is the warp's TMEM quadrant)
+    const int q = ew & 3;                         // TMEM quadrant -> states rank*128 + 32q + lane = one chunk of the map
+    const uint32_t h = (uint32_t)(ew >> 2);       // accumulator columns [64h, 64h+64) are the rows CTA h produced
     const int chunk = (int)rank * 4 + q;
     const int cs = chunk * JUMP_CHUNK;            // first state of the chunk
     const int s_mine = cs + lane;
@@ -570,16 +673,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     constexpr uint32_t TAB_R = (uint32_t)((KM == KM_RATES) ? (TAULDR ? ST_RBT_OFF : ST_RB_OFF) : (TAULDR ? ST_RBZT_OFF : ST_RBZ_OFF));
     auto stat_ptr = [&](uint32_t off) -> const float* { return stat_lane + (off >> 2); };   // one widening multiply-add
     const uint32_t chunkbit = 1u << chunk;
-    const uint32_t scr_p = smem_u32(&sm.scratch[warp][0][0]);
+    const uint32_t scr_p = smem_u32(&sm.scratch[ew][0][0]);
     const float hb = a.h * a.beta;
 
     for (int i = 0; i < my_tiles; ++i) {
       const int tile = pair + i * npairs;
       const int slot = i % RING, b = i % ACC, cb = i % CBUF;
+      const int trole = 2 + (ew >> 2);
+      const bool tr_on = (q == 0 && lane == 0);
+      if (tr_on) TRACEQ(trole, i, 0);
       mbar_wait(&sm.scal_full[slot], (i / RING) & 1);
+      if (tr_on) TRACEQ(trole, i, 1);
       mbar_wait(&sm.tmem_full[b], (i / ACC) & 1);
       tc_fence_after();
+      if (tr_on) TRACEQ(trole, i, 2);
       if (SAMPLES) mbar_wait(cfree_wait + cb, ((i / CBUF) & 1) ^ 1);
+      if (tr_on) TRACEQ(trole, i, 3);
 #pragma unroll 1
       for (int bb = 0; bb < 2; ++bb) {
         const int col = (int)h * NH + 32 * bb;                         // tile column (= tile row) of this batch's row 0
@@ -588,35 +697,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         const uint32_t sc_p = smem_u32(&sm.scal_c[slot][col]);
         uint32_t acc[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + TM_ACC + b * NT + col, acc);
-        // base-rate rows of the 32 rows of the batch: 32 independent coalesced loads.  Lane L prepares the table offset of
-        // row L (the zero row when this chunk lies outside the band of non-zero rates of its x); a shuffle hands it to all.
-        uint32_t sxl;
+        uint32_t sxl;            // row scalar of row `lane` of the batch
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sxl) : "r"(sx_p + 4 * lane));
-        const uint32_t offl = (sxl & chunkbit) ? TAB_R + (sxl & 0x3FC00u) : (uint32_t)ST_ZERO_OFF;
-        float R[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) R[j] = __ldg(stat_ptr(__shfl_sync(0xffffffffu, offl, j)));
-        // the row's Philox draw (count uniform + first three pick uniforms) does not depend on the data: computed in the
-        // shadow of the gathers.  From the transpose on this lane works on row `lane` of the batch.
-        const uint64_t grow = (uint64_t)(a.row_offset + g0 + lane);
-        Philox4 p0 = {{0u, 0u, 0u, 0u}};
-        if constexpr (KM == KM_JUMP || KM == KM_CORR) p0 = philox_rowjump(grow, cbase, a.offset, a.seed);
-        tmem_ld_wait();
-        if (bb == 1) {           // the accumulator has been read: hand the buffer back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster_relaxed(tempty_dst + (uint32_t)b * 8u);
-        }
-#ifdef CTDD_EXP_NOEPI        // diagnostic build: the epilogue only drains the accumulator (isolates producers + MMA)
-        if (SAMPLES) {
-          const uint32_t roff = (uint32_t)cb * (NCHUNK * NH * 8) + (uint32_t)(32 * bb + lane) * 8u;
-          const uint32_t z = (__float_as_uint(R[lane & 1]) ^ acc[lane & 3]) == 0x7fc12345u;
-          if (h == rank) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(contrib_dst + roff), "r"(z), "r"(0u) : "memory");
-          else st_async_cluster_v2(contrib_dst + roff, z, 0u, cfull_dst + (uint32_t)cb * 8u);
-        }
-        continue;
-#endif
         if constexpr (KM == KM_RATES) {
+          // rates output: lane = state.  Base-rate entries R[s_mine, x_row] of the 32 rows: 32 coalesced 128-byte loads
+          // (lane L prepares the table offset of row L, a shuffle hands it to all).
+          const uint32_t offl = TAB_R + (sxl & 0x3FC00u);
+          float R[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) R[j] = __ldg(stat_ptr(__shfl_sync(0xffffffffu, offl, j)));
+          tmem_ld_wait();
+          if (bb == 1) {           // the accumulator has been read: hand the buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster_relaxed(tempty_dst + (uint32_t)b * 8u);
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float c1, c0;
@@ -630,38 +725,90 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
             }
           }
         } else {
-          // lam[s, row] (zero at s == x through the zero-diagonal tables).  tauLDR without corrector: the row's scale c1
-          // is applied to the chunk total only (the picks are scale-invariant); otherwise per element.
+          // Sampling modes work with lane = ROW: lane L reads the 32 base-rate entries of ITS row's state for this chunk
+          // (one 128-byte piece of the zero-diagonal table row x, four 256-bit loads; the zero row when the chunk lies
+          // outside the band of non-zero rates of x), the accumulator is transposed through the warp's scratch, and
+          // lam[row, s] = D[s, row] * R[x_row][s] is formed where the prefix sums need it.
           constexpr bool UNSCALED = TAULDR && !km_corr(KM);
-          float lam[32];
-          if constexpr (UNSCALED) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) lam[j] = __uint_as_float(acc[j]) * R[j];
+          constexpr bool COALESCED = UNSCALED && GATHER == 2;
+          const bool inband = (sxl & chunkbit) != 0u;
+          const uint32_t inmask = __ballot_sync(0xffffffffu, inband);   // bit j: row j of the batch has non-zero rates in this chunk
+          float R[32];
+          if constexpr (COALESCED) {
+            // tauLDR without corrector: lane = state.  R[s_mine, x_j] for the in-band rows j of the batch: one coalesced
+            // 128-byte load per row (the LSU data pipe is the kernel's busiest unit: a load whose lanes touch 32 different
+            // lines costs 32 wavefronts, a coalesced one costs one).  The rows' table offsets are read four at a time
+            // as broadcast 128-bit shared loads; rows outside the band are neither loaded nor transposed.
+            const float* rbase = stat_ptr(TAB_R);
+            GatherRows<0>::run(R, rbase, sx_p, inmask, (uint32_t)a.head_fix >> 8);
           } else {
+            // other sampling modes: lane = ROW reads the 32 base-rate entries of ITS row's state for this chunk (one
+            // 128-byte piece of the zero-diagonal table row x, four 256-bit loads; the zero row outside the band)
+            const uint8_t* rrow = a.stat + (inband ? TAB_R + (sxl & 0x3FC00u) : (uint32_t)ST_ZERO_OFF) + cs * 4;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float c1, c0;
-              asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(c1), "=f"(c0) : "r"(sc_p + 8 * j));
-              lam[j] = fmaf(__uint_as_float(acc[j]), c1, c0) * R[j];
-            }
+            for (int c = 0; c < 4; ++c) ldg256(rrow + 32 * c, &R[8 * c]);
           }
-          if constexpr (km_corr(KM)) {
-            const uint32_t offc = (sxl & chunkbit) ? (uint32_t)ST_RBZ_OFF + (sxl & 0x3FC00u) : (uint32_t)ST_ZERO_OFF;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) R[j] = __ldg(stat_ptr(__shfl_sync(0xffffffffu, offc, j)));
-#pragma unroll
-            for (int j = 0; j < 32; ++j) lam[j] = fmaf(hb, R[j], lam[j]);
+          // the row's Philox draw (count uniform + first three pick uniforms) does not depend on the data: computed in the
+          // shadow of the loads
+          const uint64_t grow = (uint64_t)(a.row_offset + g0 + lane);
+          Philox4 p0 = {{0u, 0u, 0u, 0u}};
+          if constexpr (KM == KM_JUMP || KM == KM_CORR) p0 = philox_rowjump(grow, cbase, a.offset, a.seed);
+          tmem_ld_wait();
+          if (tr_on) TRACEQ(trole, i, 4 + 2 * bb);
+          if (bb == 1) {           // the accumulator has been read: hand the buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster_relaxed(tempty_dst + (uint32_t)b * 8u);
           }
+#ifdef CTDD_EXP_NOEPI        // diagnostic build: the epilogue only drains the accumulator (isolates producers + MMA)
+          {
+            const uint32_t roff = (uint32_t)cb * (NCHUNK * NH * 8) + (uint32_t)(32 * bb + lane) * 8u;
+            const uint32_t z = (__float_as_uint(R[lane & 1]) ^ acc[lane & 3]) == 0x7fc12345u;
+            if (h == rank) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(contrib_dst + roff), "r"(z), "r"(0u) : "memory");
+            else st_async_cluster_v2(contrib_dst + roff, z, 0u, cfull_dst + (uint32_t)cb * 8u);
+          }
+          continue;
+#endif
           // transpose through the warp's scratch: lane = state -> lane = row (row `lane` of the batch, the chunk's 32 states)
           __syncwarp();          // the previous batch's reads of the scratch are done
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sts32(scr_p + (uint32_t)(j * SCR_LD + lane) * 4u, lam[j]);
+          for (int j = 0; j < 32; ++j) {
+            if constexpr (COALESCED) {     // lam[s, row j] = D * R; rows outside the band stay out of the scratch
+              if (inmask & (1u << j)) sts32(scr_p + (uint32_t)(j * SCR_LD + lane) * 4u, __uint_as_float(acc[j]) * R[j]);
+            } else {
+              sts32(scr_p + (uint32_t)(j * SCR_LD + lane) * 4u, __uint_as_float(acc[j]));
+            }
+          }
           __syncwarp();
           float p[32];
+          // (a row outside the band reads stale scratch contents: its total is forced to zero below)
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const float4 v4 = lds128(scr_p + (uint32_t)(lane * SCR_LD + 4 * c) * 4u);
             p[4 * c] = v4.x; p[4 * c + 1] = v4.y; p[4 * c + 2] = v4.z; p[4 * c + 3] = v4.w;
+          }
+#ifdef CTDD_TC_TRACE
+          const uint32_t tzero = (uint32_t)a.head_fix >> 8;
+          if (tr_on && h == 0 && bb == 0) {
+            TRACEQ(5, i, 0);
+            TRACEQ_DEP(5, i, 1, __float_as_uint(p[31]), tzero);    // transposed values have arrived
+            TRACEQ_DEP(5, i, 2, __float_as_uint(p[0]), tzero);
+          }
+#endif
+          // lam[s, row] (zero at s == x through the zero-diagonal tables).  tauLDR without corrector: the row's scale c1
+          // is applied to the chunk total only (the picks are scale-invariant); otherwise per element.
+          float sc1 = 0.f, sc0 = 0.f;
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(sc1), "=f"(sc0) : "r"(sc_p + 8 * lane));
+          if constexpr (!UNSCALED) {
+#pragma unroll
+            for (int s2 = 0; s2 < 32; ++s2) p[s2] = fmaf(p[s2], sc1, sc0) * R[s2];
+            if constexpr (km_corr(KM)) {
+              const uint8_t* crow = a.stat + (inband ? (uint32_t)ST_RBZ_OFF + (sxl & 0x3FC00u) : (uint32_t)ST_ZERO_OFF) + cs * 4;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) ldg256(crow + 32 * c, &R[8 * c]);
+#pragma unroll
+              for (int s2 = 0; s2 < 32; ++s2) p[s2] = fmaf(hb, R[s2], p[s2]);
+            }
           }
           const int xl = (int)((sxl >> 10) & 255u);
           int2 rec = make_int2(0, 0);
@@ -669,15 +816,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
             // sum_s rr_s (s - x) over this chunk (sampling.py:433-453)
             float dsum = 0.f;
 #pragma unroll
-            for (int s2 = 0; s2 < 32; ++s2) dsum = fmaf(p[s2], (float)(cs + s2 - xl), dsum);
-            if constexpr (UNSCALED) dsum *= lds32(sc_p + 8 * lane);
+            for (int s2 = 0; s2 < 32; ++s2) {
+              const float lam = (UNSCALED && !COALESCED) ? p[s2] * R[s2] : p[s2];
+              dsum = fmaf(lam, (float)(cs + s2 - xl), dsum);
+            }
+            if constexpr (UNSCALED) dsum = inband ? dsum * sc1 : 0.f;
             rec.x = __float_as_int(dsum);
           } else {
             // sequential fp32 prefix sums over the chunk's states (the oracle's summation order)
+            if constexpr (UNSCALED && !COALESCED) {     // product and running sum in one fused multiply-add per state
+              p[0] *= R[0];
 #pragma unroll
-            for (int s2 = 1; s2 < 32; ++s2) p[s2] += p[s2 - 1];
+              for (int s2 = 1; s2 < 32; ++s2) p[s2] = fmaf(p[s2], R[s2], p[s2 - 1]);
+            } else {
+#pragma unroll
+              for (int s2 = 1; s2 < 32; ++s2) p[s2] += p[s2 - 1];
+            }
             float tot = p[31];
-            if constexpr (UNSCALED) tot *= lds32(sc_p + 8 * lane);
+            if constexpr (UNSCALED) tot = inband ? tot * sc1 : 0.f;
+#ifdef CTDD_TC_TRACE
+            if (tr_on && h == 0 && bb == 0) TRACEQ_DEP(5, i, 3, __float_as_uint(tot), tzero);   // prefix chain done
+#endif
             int K = poisson_from_unit(tot, u32_to_unit(p0.w[0]));
             K = K > JUMP_PICK_CAP ? JUMP_PICK_CAP : K;
             rec.y = K;
@@ -690,7 +849,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
             // row it belongs to (row found by a 5-shuffle search over the scan, uniforms fetched from the row's lane).
             int jump = 0;
             const uint32_t any = __ballot_sync(0xffffffffu, K > 0);
-            if (any) {
+#ifdef CTDD_TC_TRACE
+            if (tr_on && h == 0 && bb == 0) { TRACEQ_DEP(5, i, 4, any, tzero); TRACEQ_ADD(5, i, 6, (long long)__popc(any)); }   // counts drawn
+#endif
+            // Few picks per row (the common case once the schedule has left its first tenth): every lane resolves the
+            // picks of ITS row from the prefix sums it holds in registers - the pick is the number of prefix sums <= the
+            // target, 31 independent compares, no shared memory, no shuffles; one round per pick, uniforms of call 0.
+            int maxK = 0;
+            if (any) maxK = __reduce_max_sync(0xffffffffu, K);
+            if (any && maxK <= 3) {
+              const float ptot = p[31];
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {
+                if (j < maxK) {
+                  const uint32_t w = j == 0 ? p0.w[1] : (j == 1 ? p0.w[2] : p0.w[3]);
+                  float T = fminf(u32_to_unit(w), 0.99999994f) * ptot;
+                  // the product can round up to the total itself: then the pick is the last state with a positive rate
+                  if (T >= ptot) T = __uint_as_float(__float_as_uint(ptot) - 1u);
+                  int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+                  for (int s2 = 0; s2 < 28; s2 += 4) {
+                    c0 += (p[s2] <= T) ? 1 : 0; c1 += (p[s2 + 1] <= T) ? 1 : 0;
+                    c2 += (p[s2 + 2] <= T) ? 1 : 0; c3 += (p[s2 + 3] <= T) ? 1 : 0;
+                  }
+                  c0 += (p[28] <= T) ? 1 : 0; c1 += (p[29] <= T) ? 1 : 0; c2 += (p[30] <= T) ? 1 : 0;
+                  if (K > j) jump += cs + (c0 + c1) + (c2 + c3) - xl;
+                }
+              }
+            } else if (any) {
               __syncwarp();
 #pragma unroll
               for (int c = 0; c < 8; ++c)
@@ -746,6 +932,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
               asm volatile("ld.shared.s32 %0, [%1];" : "=r"(jump) : "r"(scr_p + (uint32_t)(lane * SCR_LD + 32) * 4u));
             }
             rec.x = jump;
+#ifdef CTDD_TC_TRACE
+            if (tr_on && h == 0 && bb == 0) TRACEQ_DEP(5, i, 5, (uint32_t)jump, tzero);   // picks resolved
+#endif
           }
           // the record of (row `lane`, this chunk) goes to the CTA that produced the row
           const uint32_t roff = (uint32_t)cb * (NCHUNK * NH * 8) + (uint32_t)(32 * bb + lane) * 8u;
@@ -754,6 +943,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
           } else {
             st_async_cluster_v2(contrib_dst + roff, (uint32_t)rec.x, (uint32_t)rec.y, cfull_dst + (uint32_t)cb * 8u);
           }
+          if (tr_on) TRACEQ(trole, i, 5 + 2 * bb);
         }
       }
       if (SAMPLES && h == rank) {
@@ -832,5 +1022,17 @@ int launch_step_tcq(const ctdd_step_params* p, cudaStream_t st) {
   CTDD_CHECK_LAUNCH("step_q_kernel");
   return 0;
 }
+
+
+#ifdef CTDD_TC_TRACE
+extern "C" int ctdd_debug_trace_read_q(void* host, long long bytes) {
+  return (int)cudaMemcpyFromSymbol(host, ctdd::tcq::g_trace, (size_t)bytes);
+}
+extern "C" int ctdd_debug_trace_clear_q() {
+  void* p = nullptr;
+  cudaGetSymbolAddress(&p, ctdd::tcq::g_trace);
+  return (int)cudaMemset(p, 0, sizeof(ctdd::tcq::g_trace));
+}
+#endif
 
 }  // namespace ctdd

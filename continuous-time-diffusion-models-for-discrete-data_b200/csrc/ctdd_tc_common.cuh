@@ -204,6 +204,44 @@ __device__ __forceinline__ float4 ld_stream(const float* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
+// 32 bytes of read-only table data per lane in one request (one sector; the address must be 32-byte aligned)
+__device__ __forceinline__ void ldg256(const uint8_t* p, float* v) {
+  asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+      : "l"(p));
+}
+// read-only load of base[(sx & 0x3FC00) / 4] when bit BIT of mask is set (one widening multiply-add forms the address);
+// zero otherwise (a destination left undefined would stay live across the caller's whole loop body)
+template <int BIT>
+__device__ __forceinline__ float ldg_row(const float* base, uint32_t sx, uint32_t mask) {
+  float v = 0.f;
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 a;\n.reg .b32 t, o;\nand.b32 t, %3, %4;\nsetp.ne.u32 p, t, 0;\nand.b32 o, %1, 0x3FC00;\n"
+      "mad.wide.u32 a, o, 1, %2;\n@p ld.global.nc.f32 %0, [a];\n}\n"
+      : "+f"(v)
+      : "r"(sx), "l"(base), "r"(mask), "n"(1u << BIT));
+  return v;
+}
+// rows 4C .. 31 of a batch: the rows' scalars (table offset in bits 10..17) are read four at a time as broadcast 128-bit
+// shared loads, then one predicated coalesced load per row.  Each group's shared address is made to depend on the
+// previous group's data (`chain` is a run-time zero): without that the assembler hoists all 32 address computations
+// (64 registers) above the first load and spills.
+template <int C>
+struct GatherRows {
+  static __device__ __forceinline__ void run(float (&R)[32], const float* rbase, uint32_t sx_p, uint32_t inmask, uint32_t chain) {
+    uint32_t s0, s1, s2, s3;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(s3) : "r"(sx_p + 16 * C));
+    R[4 * C] = ldg_row<4 * C>(rbase, s0, inmask);
+    R[4 * C + 1] = ldg_row<4 * C + 1>(rbase, s1, inmask);
+    R[4 * C + 2] = ldg_row<4 * C + 2>(rbase, s2, inmask);
+    R[4 * C + 3] = ldg_row<4 * C + 3>(rbase, s3, inmask);
+    GatherRows<C + 1>::run(R, rbase, sx_p + (s3 & chain), inmask, chain);
+  }
+};
+template <>
+struct GatherRows<8> {
+  static __device__ __forceinline__ void run(float (&)[32], const float*, uint32_t, uint32_t, uint32_t) {}
+};
 // explicit shared-space accesses (the compiler emits generic LD/ST for pointers it cannot prove to be shared)
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
@@ -256,6 +294,22 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+
+// bulk copy this CTA's shared memory -> shared memory of a CTA of the cluster; bytes reported to an mbarrier there
+__device__ __forceinline__ void bulk_s2cluster(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t mbar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
+               "r"(src_cta), "r"(bytes), "r"(mbar_cluster)
+               : "memory");
+}
+// non-blocking phase test
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+               : "=r"(ok)
+               : "r"(smem_u32(bar)), "r"(parity)
+               : "memory");
+  return ok != 0;
 }
 
 // packed fp32 pairs (Blackwell: one issue slot for two lanes of an FMA / ADD / MUL / SUB)
