@@ -46,6 +46,12 @@ constexpr int NUM_EPI_WARPS = 8;       // epilogue warp e: TMEM quadrant e&3, co
 #ifndef CTDD_GATHER
 #define CTDD_GATHER 1
 #endif
+#ifndef CTDD_LOGITS_DIRECT
+#define CTDD_LOGITS_DIRECT 0
+#endif
+// 1: the producers read the raw logits rows straight into registers, one pass ahead (128-bit streaming loads);
+// 0: through the per-warp shared-memory ring that the loader warp fills with bulk copies
+constexpr bool LOGITS_DIRECT = CTDD_LOGITS_DIRECT != 0;
 // Warp numbering: the scheduler of an SM sub-partition favours its higher-numbered warps.  CTDD_EPI_HIGH = 1 puts the
 // epilogue warps above the producers (producers 0.., epilogue NPW.., light group last).
 constexpr bool EPI_HIGH = CTDD_EPI_HIGH != 0;
@@ -242,49 +248,58 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     const float hb = (KM == KM_RATES) ? 1.0f : a.h * a.beta;   // rates-only ignores the step length
     uint64_t* const full_bar = rank == 0 ? &sm.full[0] : &sm.full_local[0];
     // passes of this CTA: pass P = 32 * tl + ps builds rows 2 ps, 2 ps + 1 of the CTA's 64 rows of its tl-th tile; warp pw
-    // takes P = pw, pw + NPW, ..  Three cursors run over that sequence (compute, logits fetch one pass ahead, state fetch
-    // two passes ahead); they advance by additions only.
-    const int tile_step = npairs * NT - 2 * PASSES_PER_TILE;     // rows from the wrap of ps to the same ps of the next tile
-    struct Cursor {
-      int tl, ps;
-      long long row;       // first global row of the pass
-      __device__ __forceinline__ void advance(int step) {
-        ps += NPW; row += 2 * NPW;
-        if (ps >= PASSES_PER_TILE) { ps -= PASSES_PER_TILE; ++tl; row += step; }
-      }
-    };
-    const long long row0 = (long long)pair * NT + (int)rank * NH + 2 * pw;   // pass pw of this CTA's first tile
+    // takes P = pw, pw + NPW, ..  The states are fetched two passes of the warp ahead, the logits (LOGITS_DIRECT) one;
+    // every position is derived from the one pass counter (row indices fit 32 bits: a row is 1 KB of logits).
+    const int total_passes = my_tiles * PASSES_PER_TILE;
+    const uint32_t tile_rows = (uint32_t)npairs * NT;
+    const uint32_t row00 = (uint32_t)pair * NT + rank * NH;      // first row of this CTA's half of its first tile
+    const uint32_t rows32 = (uint32_t)a.rows;
+    auto row_of = [&](int Pq) -> uint32_t { return row00 + (uint32_t)(Pq >> 5) * tile_rows + 2u * (uint32_t)(Pq & 31); };
     const uint32_t scal_c_p = smem_u32(&sm.scal_c[0][0]), scal_x_p = smem_u32(&sm.scal_x[0][0]), band_p = smem_u32(&sm.band[0]);
 
     // States (and head parameters): two passes of this warp ahead, into registers.
-    Cursor cx = {0, pw, row0};
     float f_mu = 0.f, f_ls = 0.f;        // HEAD: head parameters of the row fetch() just visited
-    auto fetch = [&]() -> int {
+    auto fetch = [&](int Pq) -> int {
       int xv = -1;
-      if (cx.tl < my_tiles) {
-        const long long g = cx.row + half;
-        if (g < a.rows) {
+      if (Pq < total_passes) {
+        const uint32_t g = row_of(Pq) + half;
+        if (g < rows32) {
           xv = __ldg(a.x_eval + g);
           if (HEAD) {
             long long src = g;
             if (a.head_bs != (long long)a.D) {   // (N, 2D) network output viewed as two (N, D) halves
-              // 32-bit division whenever the row index fits (a 64-bit one is ~100 instructions on the warp's critical path)
-              const long long n = (a.rows <= 0xFFFFFFFFLL) ? (long long)((uint32_t)g / (uint32_t)a.D) : g / a.D;
-              src = n * a.head_bs + (g - n * a.D);
+              const uint32_t n = g / (uint32_t)a.D;
+              src = (long long)n * a.head_bs + (g - n * (uint32_t)a.D);
             }
             f_mu = __ldg(a.head_mu + src);
             f_ls = __ldg(a.head_ls + src);
           }
         }
-        cx.advance(tile_step);
       }
       return xv;
     };
     // Logits: the loader warp (light group) refills this warp's ring slot as soon as the warp reports that the current
     // pass has its values in registers (lring_free); the rows were pulled from HBM into L2 some tiles earlier.
-    int x_cur = fetch();
+    float4 vn[4];                // LOGITS_DIRECT: the next pass's 16 logits of this lane
+    auto load_next = [&](int Pq) {
+      if (HEAD || !LOGITS_DIRECT || Pq >= total_passes) return;
+      const uint32_t g = row_of(Pq) + half;
+      const long long gg = g < rows32 ? g : 0;     // rows past the end read row 0 (never used)
+      const float* src;
+      if ((a.ld == S) && (a.batch_stride == (long long)a.D * S)) {
+        src = a.logits + gg * S;
+      } else {
+        const uint32_t n = (uint32_t)gg / (uint32_t)a.D, d = (uint32_t)gg - n * (uint32_t)a.D;
+        src = a.logits + (long long)n * a.batch_stride + (long long)d * a.ld;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) vn[c] = ld_stream(src + 4 * l16 + 64 * c);
+    };
+    int P = pw;
+    load_next(P);
+    int x_cur = fetch(P);
     float mu_cur = f_mu, ls_cur = f_ls;
-    int x_n1 = fetch();
+    int x_n1 = fetch(P + NPW);
     float mu_n1 = f_mu, ls_n1 = f_ls;
     float4 t4[4];
     {
@@ -327,10 +342,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     };
     uint32_t ring_par = 0;       // parity to wait for on the ring slot
     int last_tl = -1;
-    Cursor cc = {0, pw, row0};
 #pragma unroll 1
-    while (cc.tl < my_tiles) {
-      const int tl = cc.tl, ps = cc.ps;
+    while (P < total_passes) {
+      const int tl = P >> 5, ps = P & 31;
       const int st = tl % STAGES;
       const int slot = tl % RING;
       const bool ok = x_cur >= 0;
@@ -342,7 +356,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       const uint32_t pzero = (uint32_t)a.head_fix >> 8;
       if (ptr_on) TRACEQ(6, tl, 0);
 #endif
-      if (!HEAD) mbar_wait(&sm.lring_full[pw][0], ring_par);
+      if (!HEAD && !LOGITS_DIRECT) mbar_wait(&sm.lring_full[pw][0], ring_par);
 #ifdef CTDD_TC_TRACE
       if (pw == 0 && lane == 0) TRACEQ_ADD(0, tl, 3, clock64() - tq0);
       if (ptr_on) TRACEQ(6, tl, 1);
@@ -358,18 +372,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         }
         head_numerators(mu_cur, ls_cur, a.head_fix != 0, l16, v);
       } else {
-        const uint32_t src = smem_u32(&sm.lring[pw][0][half][4 * l16]);
+        if constexpr (LOGITS_DIRECT) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float4 q4 = lds128(src + 256 * c);
-          v[4 * c] = q4.x; v[4 * c + 1] = q4.y; v[4 * c + 2] = q4.z; v[4 * c + 3] = q4.w;
+          for (int c = 0; c < 4; ++c) { v[4 * c] = vn[c].x; v[4 * c + 1] = vn[c].y; v[4 * c + 2] = vn[c].z; v[4 * c + 3] = vn[c].w; }
+          load_next(P + NPW);    // the next pass's rows are in flight for the whole of this pass
+        } else {
+          const uint32_t src = smem_u32(&sm.lring[pw][0][half][4 * l16]);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float4 q4 = lds128(src + 256 * c);
+            v[4 * c] = q4.x; v[4 * c + 1] = q4.y; v[4 * c + 2] = q4.z; v[4 * c + 3] = q4.w;
+          }
+          ring_par ^= 1u;
         }
-        ring_par ^= 1u;
 #ifdef CTDD_TC_TRACE
         if (ptr_on) TRACEQ_DEP(6, tl, 2, __float_as_uint(v[15]), pzero);
 #endif
-        __syncwarp();            // every lane has its values: the slot may be refilled for the warp's next pass
-        if (lane == 0) mbar_arrive(&sm.lring_free[pw]);
+        if constexpr (!LOGITS_DIRECT) {
+          __syncwarp();          // every lane has its values: the slot may be refilled for the warp's next pass
+          if (lane == 0) mbar_arrive(&sm.lring_free[pw]);
+        }
 #ifdef CTDD_TC_TRACE
         if (ptr_on) TRACEQ(6, tl, 3);
 #endif
@@ -473,9 +495,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       }
       x_cur = x_n1;
       if (HEAD) { mu_cur = mu_n1; ls_cur = ls_n1; }
-      x_n1 = fetch();
+      x_n1 = fetch(P + 2 * NPW);
       if (HEAD) { mu_n1 = f_mu; ls_n1 = f_ls; }
-      cc.advance(tile_step);
+      P += NPW;
     }
     // the last pass's reductions and row scalars
 #pragma unroll
@@ -505,7 +527,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       const long long tile_rows = (long long)npairs * NT;
       const long long row00 = (long long)pair * NT + (int)rank * NH;      // first row of this CTA's half of its first tile
       const int total = my_tiles * PASSES_PER_TILE;
-      const bool refill_lane = !HEAD && lane < NPW;
+      const bool refill_lane = !HEAD && !LOGITS_DIRECT && lane < NPW;
       const int w = refill_lane ? lane : 0;
       int P = lane;              // next pass of warp w in the CTA's pass sequence (P = 32 * tile + pass in the tile)
       int n = 0;                 // how many of the warp's passes have been issued
@@ -820,7 +842,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
               const float lam = (UNSCALED && !COALESCED) ? p[s2] * R[s2] : p[s2];
               dsum = fmaf(lam, (float)(cs + s2 - xl), dsum);
             }
-            if constexpr (UNSCALED) dsum = inband ? dsum * sc1 : 0.f;
+            dsum = inband ? (UNSCALED ? dsum * sc1 : dsum) : 0.f;      // (outside the band the scratch row is stale)
             rec.x = __float_as_int(dsum);
           } else {
             // sequential fp32 prefix sums over the chunk's states (the oracle's summation order)
@@ -833,7 +855,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
               for (int s2 = 1; s2 < 32; ++s2) p[s2] += p[s2 - 1];
             }
             float tot = p[31];
-            if constexpr (UNSCALED) tot = inband ? tot * sc1 : 0.f;
+            tot = inband ? (UNSCALED ? tot * sc1 : tot) : 0.f;          // (outside the band the scratch row is stale)
 #ifdef CTDD_TC_TRACE
             if (tr_on && h == 0 && bb == 0) TRACEQ_DEP(5, i, 3, __float_as_uint(tot), tzero);   // prefix chain done
 #endif

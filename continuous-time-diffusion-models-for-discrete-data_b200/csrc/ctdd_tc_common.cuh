@@ -210,6 +210,14 @@ __device__ __forceinline__ void ldg256(const uint8_t* p, float* v) {
       : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
       : "l"(p));
 }
+// the same when `on`, eight zeros otherwise
+__device__ __forceinline__ void ldg256_pred(const uint8_t* p, float* v, bool on) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = 0.f;
+  asm("{\n.reg .pred q;\nsetp.ne.u32 q, %9, 0;\n@q ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n}\n"
+      : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7])
+      : "l"(p), "r"((uint32_t)on));
+}
 // read-only load of base[(sx & 0x3FC00) / 4] when bit BIT of mask is set (one widening multiply-add forms the address);
 // zero otherwise (a destination left undefined would stay live across the caller's whole loop body)
 template <int BIT>
