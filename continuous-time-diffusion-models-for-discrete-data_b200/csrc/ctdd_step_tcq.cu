@@ -212,22 +212,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
 
-  // Q^T half of this CTA -> tensor memory (A operand). Warp q < 4 owns TMEM lanes [32q, 32q+32).
-  if (warp < 4) {
-    const int srow = (int)rank * 128 + warp * 32 + lane;
-#pragma unroll 1
-    for (int split = 0; split < 2; ++split) {
+  // Q^T half of this CTA -> tensor memory (A operand).  A warp reaches the TMEM lanes [32q, 32q+32) of its quadrant
+  // q = warp & 3; the quadrant's 8 pieces of 32 columns (4 per bf16 split) are dealt to all the warps of that quadrant, so
+  // that the whole 128 KB is requested at once instead of in eight dependent round trips of four warps.
+  {
+    const int q = warp & 3;
+    const int srow = (int)rank * 128 + q * 32 + lane;
+    constexpr int WPQ = NUM_THREADS / 128;           // warps per quadrant
+    for (int piece = warp >> 2; piece < 8; piece += WPQ) {
+      const int split = piece >> 2, c = (piece & 3) * 32;
       const uint4* src = reinterpret_cast<const uint4*>(a.tab + (split ? TAB_QM_OFF : TAB_QH_OFF)) + (size_t)srow * 32;
-#pragma unroll 1
-      for (int c = 0; c < 128; c += 32) {
-        uint32_t r[32];
+      uint32_t r[32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint4 v = __ldg(src + (c >> 2) + i);
-          r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
-        }
-        tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + (split ? TM_QM : TM_QH) + c, r);
+      for (int i = 0; i < 8; ++i) {
+        const uint4 v = __ldg(src + (c >> 2) + i);
+        r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
       }
+      tmem_st32(tmem + ((uint32_t)(q * 32) << 16) + (split ? TM_QM : TM_QH) + c, r);
     }
     tmem_st_wait();
   }

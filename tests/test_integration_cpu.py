@@ -74,3 +74,19 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["metric"] == "reverse_step_tflops" and d["unit"] == "TFLOP/s"
     assert d["higher_is_better"] is True and d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["value"] > 0
+
+
+def test_staged_reference_imports_without_the_reference_checkout():
+    """bench.py --impl reference runs on the GPU box, where only baseline/_ref/ (staged by tools/stage_reference.py) exists:
+    the staged files must be importable on their own (lib/losses/losses.py pulls lib.d3pm at module level)."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    staged = os.path.join(root, "baseline", "_ref", "TAUnSDDM")
+    if not os.path.isdir(os.path.join(staged, "lib", "sampling")):
+        import pytest
+        pytest.skip("no staged reference (baseline/_ref is created by __graft_entry__.build() where /root/reference exists)")
+    code = ("import sys; sys.path.insert(0, %r); from oracle import ref_harness as rh; rh.REF_ROOT = %r; "
+            "ref = rh.import_reference(); assert ref.ss.__file__.startswith(%r) and ref.ll.__file__.startswith(%r); print('ok')"
+            % (root, staged, staged, staged))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]

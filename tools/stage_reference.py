@@ -17,6 +17,7 @@ FILES = [
     "lib/models/forward_model.py", "lib/models/model_utils.py", "lib/models/__init__.py",
     "lib/losses/losses.py", "lib/losses/losses_utils.py", "lib/losses/__init__.py",
     "lib/utils/utils.py", "lib/utils/__init__.py",
+    "lib/d3pm.py", "lib/d3pm_utils.py", "lib/__init__.py",      # lib/losses/losses.py imports lib.d3pm at module level
 ]
 
 
