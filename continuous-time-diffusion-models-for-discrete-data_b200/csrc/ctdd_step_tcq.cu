@@ -85,7 +85,20 @@ constexpr int TM_QH = 0, TM_QM = 128, TM_ACC = 256;  // TMEM column map (accumul
 #define CTDD_PREFETCH_TILES 0
 #endif
 constexpr int PREFETCH_TILES = CTDD_PREFETCH_TILES;      // HBM -> L2 bulk-prefetch distance (tiles of this pair's sequence)
-constexpr int LRING = 1;               // per-producer-warp slot of raw logits row pairs filled by cp.async.bulk: refilled for the
+#ifndef CTDD_LRING
+#define CTDD_LRING 1
+#endif
+#ifndef CTDD_GROUP_REFILL
+#define CTDD_GROUP_REFILL 0
+#endif
+// 1: the ring slots of all producer warps (NPW consecutive passes = 2 * NPW consecutive rows, contiguous in a dense logits
+// tensor) are refilled by ONE bulk copy per round; 0: one copy per warp and pass
+constexpr bool GROUP_REFILL = CTDD_GROUP_REFILL != 0 && CTDD_LRING == 1;
+#ifndef CTDD_PREFETCH_ROUNDS
+#define CTDD_PREFETCH_ROUNDS 0
+#endif
+constexpr int PREFETCH_ROUNDS = CTDD_PREFETCH_ROUNDS;   // GROUP_REFILL: HBM -> L2 prefetch of the round that many rounds ahead
+constexpr int LRING = CTDD_LRING;      // per-producer-warp slots of raw logits row pairs filled by cp.async.bulk: refilled for the
                                        // warp's next pass as soon as this pass has its values in registers (rows are L2 hits)
 constexpr int SCR_LD = 36;             // floats per row of an epilogue warp's transposing scratch (conflict-free 128-bit reads)
 constexpr uint32_t IDESC = make_idesc(NT);
@@ -105,7 +118,11 @@ struct Smem {
   alignas(16) float lring[NPW][LRING][2][S];   // raw fp32 logits rows, one pass ahead of their use
   alignas(16) float2 scal_c[RING][NT];         // (c1, c0) of the tile's rows: rows 0..63 from CTA 0, 64..127 from CTA 1
   uint32_t scal_x[RING][NT];                   // chunk mask of the band (bits 0-7) | valid << 8 | x << 10 (= table-row byte offset)
-  alignas(16) float scratch[NUM_EPI_WARPS][32][SCR_LD];   // per epilogue warp: lam[row][state of the chunk] (lane = state -> lane = row)
+#ifdef CTDD_EXP_NOEPI
+  alignas(16) float scratch[NUM_EPI_WARPS][2][SCR_LD];    // (diagnostic build: the epilogue does not transpose)
+#else
+  alignas(16) float scratch[NUM_EPI_WARPS][32][SCR_LD];
+#endif   // per epilogue warp: lam[row][state of the chunk] (lane = state -> lane = row)
   alignas(16) int2 contrib[CBUF][NCHUNK][NH];  // per (chunk, row of THIS CTA): (sum of jumps | drift bits, jump count)
   uint32_t band[S];                            // per state x: which of the 8 chunks hold a non-zero base rate (this launch's branch / mode)
   alignas(8) uint64_t full[STAGES];            // leader CTA: its NPW producer warps + 1 relayed arrival for the partner's
@@ -114,7 +131,8 @@ struct Smem {
   uint64_t scal_local[RING];                   // NPW local producer warps: this CTA's 64 rows of the tile have their scalars
   uint64_t scal_full[RING];                    // the local loader's arrival (scal_local seen) + the partner's bytes (DSMEM bulk copy)
   uint64_t lring_full[NPW][LRING];             // cp.async.bulk complete_tx of one row pair
-  uint64_t lring_free[NPW];                    // the producer warp has its values in registers: the loader may refill the slot
+  uint64_t lring_free[NPW][LRING];             // the producer warp has its values in registers: the loader may refill the slot
+  uint64_t lring_full_g, lring_free_g;         // GROUP_REFILL: one round of all NPW slots (bytes of the round's copies / NPW warps)
   uint64_t tmem_full[ACC];                     // multicast tcgen05.commit
   uint64_t tmem_empty[ACC];                    // used in the leader CTA: 8 local + 8 remote epilogue warps
   uint64_t contrib_full[CBUF];                 // 4 local epilogue warps + the bytes of the partner's 4 warps
@@ -178,8 +196,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     for (int i = 0; i < RING; ++i) { mbar_init(&sm.scal_local[i], NPW); mbar_init(&sm.scal_full[i], 1); }
     for (int w = 0; w < NPW; ++w) {
       for (int i = 0; i < LRING; ++i) mbar_init(&sm.lring_full[w][i], 1);
-      mbar_init(&sm.lring_free[w], 1);
+      for (int i = 0; i < LRING; ++i) mbar_init(&sm.lring_free[w][i], 1);
     }
+    mbar_init(&sm.lring_full_g, 1);
+    mbar_init(&sm.lring_free_g, NPW);
     for (int i = 0; i < ACC; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], 2 * NUM_EPI_WARPS); }
     for (int i = 0; i < CBUF; ++i) {
       mbar_init(&sm.contrib_full[i], NUM_EPI_WARPS / 2);
@@ -341,7 +361,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       }
       p_have = false;
     };
-    uint32_t ring_par = 0;       // parity to wait for on the ring slot
+    int ring_n = 0;              // passes of this warp so far: slot ring_n % LRING, phase ring_n / LRING
     int last_tl = -1;
 #pragma unroll 1
     while (P < total_passes) {
@@ -357,7 +377,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       const uint32_t pzero = (uint32_t)a.head_fix >> 8;
       if (ptr_on) TRACEQ(6, tl, 0);
 #endif
-      if (!HEAD && !LOGITS_DIRECT) mbar_wait(&sm.lring_full[pw][0], ring_par);
+      const int rslot = ring_n % LRING;
+      if (!HEAD && !LOGITS_DIRECT) {
+        if (GROUP_REFILL) mbar_wait(&sm.lring_full_g, (uint32_t)(ring_n & 1));
+        else mbar_wait(&sm.lring_full[pw][rslot], (uint32_t)((ring_n / LRING) & 1));
+      }
 #ifdef CTDD_TC_TRACE
       if (pw == 0 && lane == 0) TRACEQ_ADD(0, tl, 3, clock64() - tq0);
       if (ptr_on) TRACEQ(6, tl, 1);
@@ -378,20 +402,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
           for (int c = 0; c < 4; ++c) { v[4 * c] = vn[c].x; v[4 * c + 1] = vn[c].y; v[4 * c + 2] = vn[c].z; v[4 * c + 3] = vn[c].w; }
           load_next(P + NPW);    // the next pass's rows are in flight for the whole of this pass
         } else {
-          const uint32_t src = smem_u32(&sm.lring[pw][0][half][4 * l16]);
+          const uint32_t src = smem_u32(&sm.lring[pw][rslot][half][4 * l16]);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const float4 q4 = lds128(src + 256 * c);
             v[4 * c] = q4.x; v[4 * c + 1] = q4.y; v[4 * c + 2] = q4.z; v[4 * c + 3] = q4.w;
           }
-          ring_par ^= 1u;
+          ++ring_n;
         }
 #ifdef CTDD_TC_TRACE
         if (ptr_on) TRACEQ_DEP(6, tl, 2, __float_as_uint(v[15]), pzero);
 #endif
         if constexpr (!LOGITS_DIRECT) {
           __syncwarp();          // every lane has its values: the slot may be refilled for the warp's next pass
-          if (lane == 0) mbar_arrive(&sm.lring_free[pw]);
+          if (lane == 0) {
+            if (GROUP_REFILL) {
+              mbar_arrive(&sm.lring_free_g);
+            } else {             // release the slot and arm its next fill (the loader only issues the copy)
+              mbar_arrive_expect_tx(&sm.lring_full[pw][rslot], 2 * S * 4);
+              mbar_arrive(&sm.lring_free[pw][rslot]);
+            }
+          }
         }
 #ifdef CTDD_TC_TRACE
         if (ptr_on) TRACEQ(6, tl, 3);
@@ -528,7 +559,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       const long long tile_rows = (long long)npairs * NT;
       const long long row00 = (long long)pair * NT + (int)rank * NH;      // first row of this CTA's half of its first tile
       const int total = my_tiles * PASSES_PER_TILE;
-      const bool refill_lane = !HEAD && !LOGITS_DIRECT && lane < NPW;
+      const bool refill_lane = !HEAD && !LOGITS_DIRECT && !GROUP_REFILL && lane < NPW;
+      const bool group_lane = !HEAD && !LOGITS_DIRECT && GROUP_REFILL && lane == 0;
+      int grp = 0;               // (lane 0, GROUP_REFILL) next round: passes NPW * grp .. + NPW - 1 of the CTA's sequence
       const int w = refill_lane ? lane : 0;
       int P = lane;              // next pass of warp w in the CTA's pass sequence (P = 32 * tile + pass in the tile)
       int n = 0;                 // how many of the warp's passes have been issued
@@ -536,19 +569,59 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       while (true) {
         const bool more_r = refill_lane && P < total;
         const bool more_f = lane == 31 && fwd < my_tiles;
-        if (!__any_sync(0xffffffffu, more_r || more_f)) break;
+        const bool more_g = group_lane && grp * NPW < total;
+        if (!__any_sync(0xffffffffu, more_r || more_f || more_g)) break;
         bool did = false;
-        if (more_r && (n == 0 || mbar_test(&sm.lring_free[w], (uint32_t)((n - 1) & 1)))) {
+        if (more_g && (grp == 0 || mbar_test(&sm.lring_free_g, (uint32_t)((grp - 1) & 1)))) {
+          // rows of the round: passes P0 .. P1 - 1; they are contiguous within a tile (2 rows per pass), a round crosses at
+          // most one tile boundary -> one or two copies into the contiguous slot array; rows past the end are not copied
+          const int P0 = grp * NPW, P1 = (P0 + NPW < total) ? P0 + NPW : total;
+          const int tlA = P0 >> 5;
+          const int PeA = (P1 < ((tlA + 1) << 5)) ? P1 : ((tlA + 1) << 5);     // end of the first tile's part of the round
+          auto seg_rows = [&](long long r0, int npass) -> long long {
+            long long nrows = 2LL * npass;
+            if (r0 + nrows > a.rows) nrows = a.rows > r0 ? a.rows - r0 : 0;
+            return nrows;
+          };
+          const long long rA = row00 + (long long)tlA * tile_rows + 2 * (P0 & 31);
+          const long long rB = row00 + (long long)(tlA + 1) * tile_rows;       // (pass 0 of the next tile)
+          const long long nA = seg_rows(rA, PeA - P0), nB = (PeA < P1) ? seg_rows(rB, P1 - PeA) : 0;
+          mbar_arrive_expect_tx(&sm.lring_full_g, (uint32_t)(nA + nB) * S * 4);
+          float* dA = &sm.lring[0][0][0][0];
+          float* dB = &sm.lring[0][0][0][0] + (size_t)(PeA - P0) * 2 * S;
+          if (contiguous) {
+            if (nA > 0) bulk_g2s(dA, a.logits + rA * S, (uint32_t)nA * S * 4, &sm.lring_full_g);
+            if (nB > 0) bulk_g2s(dB, a.logits + rB * S, (uint32_t)nB * S * 4, &sm.lring_full_g);
+          } else {               // strided logits: one copy per row
+            for (long long rr = 0; rr < nA; ++rr) bulk_g2s(dA + rr * S, row_ptr(rA + rr), S * 4, &sm.lring_full_g);
+            for (long long rr = 0; rr < nB; ++rr) bulk_g2s(dB + rr * S, row_ptr(rB + rr), S * 4, &sm.lring_full_g);
+          }
+          if (contiguous && PREFETCH_ROUNDS > 0) {      // the rows of a later round from HBM into L2
+            const int Q0 = (grp + PREFETCH_ROUNDS) * NPW;
+            if (Q0 + NPW <= total) {
+              const int tq = Q0 >> 5;
+              const int Qe = (Q0 + NPW < ((tq + 1) << 5)) ? Q0 + NPW : ((tq + 1) << 5);
+              const long long qA = row00 + (long long)tq * tile_rows + 2 * (Q0 & 31), qB = row00 + (long long)(tq + 1) * tile_rows;
+              const long long mA = seg_rows(qA, Qe - Q0), mB = (Qe < Q0 + NPW) ? seg_rows(qB, Q0 + NPW - Qe) : 0;
+              if (mA > 0) l2_prefetch_bulk(a.logits + qA * S, (uint32_t)mA * S * 4);
+              if (mB > 0) l2_prefetch_bulk(a.logits + qB * S, (uint32_t)mB * S * 4);
+            }
+          }
+          ++grp;
+          did = true;
+        }
+        const int lslot = n % LRING;
+        if (more_r && (n < LRING || mbar_test(&sm.lring_free[w][lslot], (uint32_t)((n / LRING - 1) & 1)))) {
           const long long gf = row00 + (long long)(P >> 5) * tile_rows + 2 * (P & 31);
-          uint64_t* bar = &sm.lring_full[w][0];
-          mbar_arrive_expect_tx(bar, 2 * S * 4);
+          uint64_t* bar = &sm.lring_full[w][lslot];
+          if (n < LRING) mbar_arrive_expect_tx(bar, 2 * S * 4);   // later fills are armed by the producer warp when it releases the slot
           if (contiguous && gf + 1 < a.rows) {
-            bulk_g2s(&sm.lring[w][0][0][0], a.logits + gf * S, 2 * S * 4, bar);
+            bulk_g2s(&sm.lring[w][lslot][0][0], a.logits + gf * S, 2 * S * 4, bar);
           } else {               // rows past the end are replaced by row 0 (never used)
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
               const long long gg = (gf + hf < a.rows) ? gf + hf : 0;
-              bulk_g2s(&sm.lring[w][0][hf][0], row_ptr(gg), S * 4, bar);
+              bulk_g2s(&sm.lring[w][lslot][hf][0], row_ptr(gg), S * 4, bar);
             }
           }
           if (contiguous && PREFETCH_TILES > 0) {   // the same two rows of a later tile from HBM into L2
