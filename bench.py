@@ -536,12 +536,27 @@ def run_ours(args, w, rank, world, local_rank):
         # what the schedule's tables cost (q_{t|0} for 1000 time points + the tensor-path tables), amortised per step
         torch.cuda.synchronize(dev)
         t1 = time.perf_counter()
-        tq, tqt, _ = stub.qt0_tables(list(np.linspace(w["max_t"], w["min_t"], loop_steps)), dev)
-        if S == 256:
-            ops.prep_tc_tables(tq, tqt, Rb, 1e-9, branch)
+        tq, tqt, tbeta = stub.qt0_tables(list(np.linspace(w["max_t"], w["min_t"], loop_steps)), dev)
+        ttc = ops.prep_tc_tables(tq, tqt, Rb, 1e-9, branch) if S == 256 else None
         torch.cuda.synchronize(dev)
         tables_ms = (time.perf_counter() - t1) * 1e3 / loop_steps
-        del tq, tqt
+        # the step kernel alone over THIS schedule (40 time points spread over all of it, stub logits of the final states):
+        # the bench's own K steps skip the first W / (K + W) of the schedule, where a step costs up to 3x the average
+        xs_d = torch.from_numpy(np.asarray(xs)).to(dev).to(torch.int32)
+        lg_s = stub(xs_d, None)
+        sched_ms = []
+        hs = (w["max_t"] - w["min_t"]) / loop_steps
+        for i in np.linspace(0, loop_steps - 1, 40).astype(int):
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            ops.reverse_step(mode, branch, lg_s, xs_d, tq[i], tqt[i], Rb, RbT, tbeta[i], hs, 1e-9, N=B, D=D, S=S,
+                             reject_multi=not w["ordinal"], seed=0xC7DD, offset=int(i), row_offset=row_offset, impl=impl,
+                             tc_tables=(ttc[i] if ttc is not None else None), tc_static=tcs, workspace=workspace)
+            eb.record()
+            torch.cuda.synchronize(dev)
+            sched_ms.append(ea.elapsed_time(eb))
+        sched_kernel_ms = float(np.mean(sched_ms))
+        del tq, tqt, ttc
         t_l = torch.tensor([loop_ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t_l, op=dist.ReduceOp.MAX)
@@ -560,7 +575,10 @@ def run_ours(args, w, rank, world, local_rank):
                        "q_{t|0} / table build for every time point and the final read-back", "steps": loop_steps,
                 "ms_per_step": loop_ms, "stub_network_ms": stub_ms, "table_build_ms_per_step": tables_ms,
                 "sampler_ms_per_step": loop_ms - stub_ms,
-                "host_overhead_ms_per_step": loop_ms - stub_ms - tables_ms - ms,
+                "step_kernel_ms_over_this_schedule": sched_kernel_ms,
+                "host_overhead_ms_per_step": loop_ms - stub_ms - tables_ms - sched_kernel_ms,
+                "overhead_note": "loop - stub network - tables - step kernel over the same schedule; +-0.1 ms (the stub's "
+                                 "stand-alone time is not exactly its in-loop time)",
                 "includes_final_gather": world > 1,
                 "samples_per_s": world * B / (loop_steps * loop_ms * 1e-3)}
 

@@ -98,6 +98,10 @@ constexpr bool GROUP_REFILL = CTDD_GROUP_REFILL != 0 && CTDD_LRING == 1;
 #define CTDD_PREFETCH_ROUNDS 0
 #endif
 constexpr int PREFETCH_ROUNDS = CTDD_PREFETCH_ROUNDS;   // GROUP_REFILL: HBM -> L2 prefetch of the round that many rounds ahead
+#ifndef CTDD_REGPICK_MAX
+#define CTDD_REGPICK_MAX 3
+#endif
+constexpr int REGPICK_MAX = CTDD_REGPICK_MAX;   // largest per-(row, chunk) jump count of a batch that is resolved from registers (3, 7 or 11)
 constexpr int LRING = CTDD_LRING;      // per-producer-warp slots of raw logits row pairs filled by cp.async.bulk: refilled for the
                                        // warp's next pass as soon as this pass has its values in registers (rows are L2 hits)
 constexpr int SCR_LD = 36;             // floats per row of an epilogue warp's transposing scratch (conflict-free 128-bit reads)
@@ -953,12 +957,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
             // target, 31 independent compares, no shared memory, no shuffles; one round per pick, uniforms of call 0.
             int maxK = 0;
             if (any) maxK = __reduce_max_sync(0xffffffffu, K);
-            if (any && maxK <= 3) {
+            if (any && maxK <= REGPICK_MAX) {
               const float ptot = p[31];
+              Philox4 pc1 = {{0u, 0u, 0u, 0u}}, pc2 = {{0u, 0u, 0u, 0u}};
+              if (REGPICK_MAX > 3 && maxK > 3) pc1 = philox_rowjump(grow, cbase + 1u, a.offset, a.seed);     // picks 3..6
+              if (REGPICK_MAX > 7 && maxK > 7) pc2 = philox_rowjump(grow, cbase + 2u, a.offset, a.seed);     // picks 7..10
 #pragma unroll
-              for (int j = 0; j < 3; ++j) {
+              for (int j = 0; j < REGPICK_MAX; ++j) {
                 if (j < maxK) {
-                  const uint32_t w = j == 0 ? p0.w[1] : (j == 1 ? p0.w[2] : p0.w[3]);
+                  const uint32_t w = j < 3 ? p0.w[1 + j] : (j < 7 ? pc1.w[j - 3] : pc2.w[j - 7]);
                   float T = fminf(u32_to_unit(w), 0.99999994f) * ptot;
                   // the product can round up to the total itself: then the pick is the last state with a positive rate
                   if (T >= ptot) T = __uint_as_float(__float_as_uint(ptot) - 1u);
