@@ -38,7 +38,7 @@ constexpr int NT = 2 * NH;             // rows per pair tile (= UMMA N)
 constexpr int STAGES = 2;              // smem operand stages (64 KB each)
 constexpr int ACC = 2;                 // TMEM accumulator buffers (NT columns each)
 constexpr int CBUF = 2;                // contribution buffers (epilogue -> finalizer)
-constexpr int RING = 8;                // per-tile row-scalar ring (> STAGES + ACC + CBUF)
+constexpr int RING = 7;                // per-tile row-scalar ring (> STAGES + ACC + CBUF)
 constexpr int NUM_EPI_WARPS = 8;       // epilogue warp e: TMEM quadrant e&3, column half e>>2 (= CTA that owns those rows)
 #ifndef CTDD_EPI_HIGH
 #define CTDD_EPI_HIGH 0
@@ -104,7 +104,7 @@ constexpr int PREFETCH_ROUNDS = CTDD_PREFETCH_ROUNDS;   // GROUP_REFILL: HBM -> 
 constexpr int REGPICK_MAX = CTDD_REGPICK_MAX;   // largest per-(row, chunk) jump count of a batch that is resolved from registers (3, 7 or 11)
 constexpr int LRING = CTDD_LRING;      // per-producer-warp slots of raw logits row pairs filled by cp.async.bulk: refilled for the
                                        // warp's next pass as soon as this pass has its values in registers (rows are L2 hits)
-constexpr int SCR_LD = 36;             // floats per row of an epilogue warp's transposing scratch (conflict-free 128-bit reads)
+constexpr int SCR_LD = 34;             // floats per row of an epilogue warp's transposing scratch (conflict-free 64-bit reads; 32 states + the jump-sum column)
 constexpr uint32_t IDESC = make_idesc(NT);
 #ifndef CTDD_POLL_LONG
 #define CTDD_POLL_LONG 512
@@ -115,7 +115,7 @@ constexpr uint32_t POLL_LONG = CTDD_POLL_LONG;   // ns between polls of the role
 #endif
 constexpr int NCHUNK = S / JUMP_CHUNK;                           // 8 chunks of 32 states per row
 constexpr uint32_t SCAL_TX_BYTES = NH * 12;                      // row scalars the partner sends per tile
-constexpr uint32_t CONTRIB_TX_BYTES = (NUM_EPI_WARPS / 2) * 2 * 32 * 8;   // records the partner's 4 warps send per tile
+constexpr uint32_t CONTRIB_TX_BYTES = (NUM_EPI_WARPS / 2) * 2 * 32 * 4;   // records the partner's 4 warps send per tile
 
 struct Smem {
   alignas(1024) uint8_t stage[STAGES][STAGE_BYTES];
@@ -127,8 +127,8 @@ struct Smem {
 #else
   alignas(16) float scratch[NUM_EPI_WARPS][32][SCR_LD];
 #endif   // per epilogue warp: lam[row][state of the chunk] (lane = state -> lane = row)
-  alignas(16) int2 contrib[CBUF][NCHUNK][NH];  // per (chunk, row of THIS CTA): (sum of jumps | drift bits, jump count)
-  uint32_t band[S];                            // per state x: which of the 8 chunks hold a non-zero base rate (this launch's branch / mode)
+  alignas(16) int contrib[CBUF][NCHUNK][NH];   // per (chunk, row of THIS CTA): sum of jumps << 2 | min(jump count, 3), or the drift's float bits
+  uint8_t band[S];                             // per state x: which of the 8 chunks hold a non-zero base rate (this launch's branch / mode)
   alignas(8) uint64_t full[STAGES];            // leader CTA: its NPW producer warps + 1 relayed arrival for the partner's
   uint64_t full_local[STAGES];                 // partner CTA: its NPW producer warps; the partner's idle MMA warp relays the phase
   uint64_t empty[STAGES];                      // multicast tcgen05.commit
@@ -228,7 +228,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     uint32_t mask = 0;
     for (int c = 0; c < NCHUNK; ++c)
       if (hi >= c * JUMP_CHUNK && lo <= c * JUMP_CHUNK + JUMP_CHUNK - 1) mask |= 1u << c;
-    sm.band[x] = mask;
+    sm.band[x] = (uint8_t)mask;
   }
   if (warp == MMA_WARP) tmem_alloc(&sm.tmem_base);
   tc_fence_before();
@@ -353,7 +353,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       }
       if (l16 == 0) {   // one lane per half-warp: the row's scalars (the loader forwards the tile's 64 records to the partner CTA)
         uint32_t bandx;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(bandx) : "r"(band_p + 4u * (uint32_t)p_x));
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(bandx) : "r"(band_p + (uint32_t)p_x));
         const uint32_t sx = bandx | (p_ok ? (1u << 8) : 0u) | ((uint32_t)p_x << 10);
         sts64(scal_c_p + (uint32_t)p_idx * 8u, __float_as_uint(c1), __float_as_uint(c0));
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(scal_x_p + (uint32_t)p_idx * 4u), "r"(sx) : "memory");
@@ -675,9 +675,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         float drift = 0.f;
 #pragma unroll
         for (int c = 0; c < NCHUNK; ++c) {
-          const int2 v = sm.contrib[cb][c][r];
-          if (KM == KM_DRIFT) drift += __int_as_float(v.x); else jump += v.x;
-          cnt += v.y;
+          const int v = sm.contrib[cb][c][r];
+          // (the count of a chunk is saturated at 3: only "none / one / several" of the row's total matters downstream)
+          if (KM == KM_DRIFT) drift += __int_as_float(v); else { jump += v >> 2; cnt += v & 3; }
         }
         if (valid) {
           if (KM == KM_DRIFT) {
@@ -862,10 +862,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
           }
 #ifdef CTDD_EXP_NOEPI        // diagnostic build: the epilogue only drains the accumulator (isolates producers + MMA)
           {
-            const uint32_t roff = (uint32_t)cb * (NCHUNK * NH * 8) + (uint32_t)(32 * bb + lane) * 8u;
+            const uint32_t roff = (uint32_t)cb * (NCHUNK * NH * 4) + (uint32_t)(32 * bb + lane) * 4u;
             const uint32_t z = (__float_as_uint(R[lane & 1]) ^ acc[lane & 3]) == 0x7fc12345u;
-            if (h == rank) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(contrib_dst + roff), "r"(z), "r"(0u) : "memory");
-            else st_async_cluster_v2(contrib_dst + roff, z, 0u, cfull_dst + (uint32_t)cb * 8u);
+            if (h == rank) asm volatile("st.shared.b32 [%0], %1;" ::"r"(contrib_dst + roff), "r"(z) : "memory");
+            else st_async_cluster_b32(contrib_dst + roff, z, cfull_dst + (uint32_t)cb * 8u);
           }
           continue;
 #endif
@@ -883,9 +883,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
           float p[32];
           // (a row outside the band reads stale scratch contents: its total is forced to zero below)
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 v4 = lds128(scr_p + (uint32_t)(lane * SCR_LD + 4 * c) * 4u);
-            p[4 * c] = v4.x; p[4 * c + 1] = v4.y; p[4 * c + 2] = v4.z; p[4 * c + 3] = v4.w;
+          for (int c = 0; c < 16; ++c) {
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(p[2 * c]), "=f"(p[2 * c + 1]) : "r"(scr_p + (uint32_t)(lane * SCR_LD + 2 * c) * 4u));
           }
 #ifdef CTDD_TC_TRACE
           const uint32_t tzero = (uint32_t)a.head_fix >> 8;
@@ -982,8 +981,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
             } else if (any) {
               __syncwarp();
 #pragma unroll
-              for (int c = 0; c < 8; ++c)
-                sts128(scr_p + (uint32_t)(lane * SCR_LD + 4 * c) * 4u, make_float4(p[4 * c], p[4 * c + 1], p[4 * c + 2], p[4 * c + 3]));
+              for (int c = 0; c < 16; ++c)
+                sts64(scr_p + (uint32_t)(lane * SCR_LD + 2 * c) * 4u, __float_as_uint(p[2 * c]), __float_as_uint(p[2 * c + 1]));
               // column 32 of the scratch row: the row's jump sum (shared-memory reduction target)
               asm volatile("st.shared.u32 [%0], %1;" ::"r"(scr_p + (uint32_t)(lane * SCR_LD + 32) * 4u), "r"(0) : "memory");
               int incl = K;
@@ -1040,11 +1039,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
 #endif
           }
           // the record of (row `lane`, this chunk) goes to the CTA that produced the row
-          const uint32_t roff = (uint32_t)cb * (NCHUNK * NH * 8) + (uint32_t)(32 * bb + lane) * 8u;
+          const uint32_t roff = (uint32_t)cb * (NCHUNK * NH * 4) + (uint32_t)(32 * bb + lane) * 4u;
+          const uint32_t word = (KM == KM_DRIFT) ? (uint32_t)rec.x : (((uint32_t)rec.x << 2) | (uint32_t)(rec.y > 3 ? 3 : rec.y));
           if (h == rank) {
-            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(contrib_dst + roff), "r"(rec.x), "r"(rec.y) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(contrib_dst + roff), "r"(word) : "memory");
           } else {
-            st_async_cluster_v2(contrib_dst + roff, (uint32_t)rec.x, (uint32_t)rec.y, cfull_dst + (uint32_t)cb * 8u);
+            st_async_cluster_b32(contrib_dst + roff, word, cfull_dst + (uint32_t)cb * 8u);
           }
           if (tr_on) TRACEQ(trole, i, 5 + 2 * bb);
         }
