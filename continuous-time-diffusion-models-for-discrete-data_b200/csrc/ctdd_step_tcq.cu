@@ -86,14 +86,17 @@ constexpr int TM_QH = 0, TM_QM = 128, TM_ACC = 256;  // TMEM column map (accumul
 #endif
 constexpr int PREFETCH_TILES = CTDD_PREFETCH_TILES;      // HBM -> L2 bulk-prefetch distance (tiles of this pair's sequence)
 #ifndef CTDD_LRING
-#define CTDD_LRING 1
+#define CTDD_LRING 2
 #endif
 #ifndef CTDD_GROUP_REFILL
-#define CTDD_GROUP_REFILL 0
+#define CTDD_GROUP_REFILL 1
 #endif
 // 1: the ring slots of all producer warps (NPW consecutive passes = 2 * NPW consecutive rows, contiguous in a dense logits
 // tensor) are refilled by ONE bulk copy per round; 0: one copy per warp and pass
-constexpr bool GROUP_REFILL = CTDD_GROUP_REFILL != 0 && CTDD_LRING == 1;
+constexpr bool GROUP_REFILL = CTDD_GROUP_REFILL != 0;
+// GROUP_REFILL: producer warps 4g .. 4g+3 (one per SM sub-partition, the same rank in each scheduler's priority order, so they
+// advance together) share one fill per round: their 4 consecutive passes are 8 consecutive rows of one tile = one 8 KB copy
+constexpr int GSZ = 4, NSUB = CTDD_TCQ_NPW / GSZ;
 #ifndef CTDD_PREFETCH_ROUNDS
 #define CTDD_PREFETCH_ROUNDS 0
 #endif
@@ -119,7 +122,7 @@ constexpr uint32_t CONTRIB_TX_BYTES = (NUM_EPI_WARPS / 2) * 2 * 32 * 4;   // rec
 
 struct Smem {
   alignas(1024) uint8_t stage[STAGES][STAGE_BYTES];
-  alignas(16) float lring[NPW][LRING][2][S];   // raw fp32 logits rows, one pass ahead of their use
+  alignas(16) float lring[LRING][NPW][2][S];   // raw fp32 logits rows, LRING passes of every producer warp ahead of their use
   alignas(16) float2 scal_c[RING][NT];         // (c1, c0) of the tile's rows: rows 0..63 from CTA 0, 64..127 from CTA 1
   uint32_t scal_x[RING][NT];                   // chunk mask of the band (bits 0-7) | valid << 8 | x << 10 (= table-row byte offset)
 #ifdef CTDD_EXP_NOEPI
@@ -136,7 +139,7 @@ struct Smem {
   uint64_t scal_full[RING];                    // the local loader's arrival (scal_local seen) + the partner's bytes (DSMEM bulk copy)
   uint64_t lring_full[NPW][LRING];             // cp.async.bulk complete_tx of one row pair
   uint64_t lring_free[NPW][LRING];             // the producer warp has its values in registers: the loader may refill the slot
-  uint64_t lring_full_g, lring_free_g;         // GROUP_REFILL: one round of all NPW slots (bytes of the round's copies / NPW warps)
+  uint64_t lring_full_g[LRING][NSUB], lring_free_g[LRING][NSUB];   // GROUP_REFILL: one round of a 4-warp group (bytes of the copy / its 4 warps)
   uint64_t tmem_full[ACC];                     // multicast tcgen05.commit
   uint64_t tmem_empty[ACC];                    // used in the leader CTA: 8 local + 8 remote epilogue warps
   uint64_t contrib_full[CBUF];                 // 4 local epilogue warps + the bytes of the partner's 4 warps
@@ -202,8 +205,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       for (int i = 0; i < LRING; ++i) mbar_init(&sm.lring_full[w][i], 1);
       for (int i = 0; i < LRING; ++i) mbar_init(&sm.lring_free[w][i], 1);
     }
-    mbar_init(&sm.lring_full_g, 1);
-    mbar_init(&sm.lring_free_g, NPW);
+    for (int i = 0; i < LRING; ++i)
+      for (int g = 0; g < NSUB; ++g) { mbar_init(&sm.lring_full_g[i][g], 1); mbar_init(&sm.lring_free_g[i][g], GSZ); }
     for (int i = 0; i < ACC; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], 2 * NUM_EPI_WARPS); }
     for (int i = 0; i < CBUF; ++i) {
       mbar_init(&sm.contrib_full[i], NUM_EPI_WARPS / 2);
@@ -383,7 +386,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
 #endif
       const int rslot = ring_n % LRING;
       if (!HEAD && !LOGITS_DIRECT) {
-        if (GROUP_REFILL) mbar_wait(&sm.lring_full_g, (uint32_t)(ring_n & 1));
+        if (GROUP_REFILL) mbar_wait(&sm.lring_full_g[rslot][pw / GSZ], (uint32_t)((ring_n / LRING) & 1));
         else mbar_wait(&sm.lring_full[pw][rslot], (uint32_t)((ring_n / LRING) & 1));
       }
 #ifdef CTDD_TC_TRACE
@@ -406,7 +409,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
           for (int c = 0; c < 4; ++c) { v[4 * c] = vn[c].x; v[4 * c + 1] = vn[c].y; v[4 * c + 2] = vn[c].z; v[4 * c + 3] = vn[c].w; }
           load_next(P + NPW);    // the next pass's rows are in flight for the whole of this pass
         } else {
-          const uint32_t src = smem_u32(&sm.lring[pw][rslot][half][4 * l16]);
+          const uint32_t src = smem_u32(&sm.lring[rslot][pw][half][4 * l16]);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const float4 q4 = lds128(src + 256 * c);
@@ -421,7 +424,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
           __syncwarp();          // every lane has its values: the slot may be refilled for the warp's next pass
           if (lane == 0) {
             if (GROUP_REFILL) {
-              mbar_arrive(&sm.lring_free_g);
+              mbar_arrive(&sm.lring_free_g[rslot][pw / GSZ]);
             } else {             // release the slot and arm its next fill (the loader only issues the copy)
               mbar_arrive_expect_tx(&sm.lring_full[pw][rslot], 2 * S * 4);
               mbar_arrive(&sm.lring_free[pw][rslot]);
@@ -564,8 +567,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       const long long row00 = (long long)pair * NT + (int)rank * NH;      // first row of this CTA's half of its first tile
       const int total = my_tiles * PASSES_PER_TILE;
       const bool refill_lane = !HEAD && !LOGITS_DIRECT && !GROUP_REFILL && lane < NPW;
-      const bool group_lane = !HEAD && !LOGITS_DIRECT && GROUP_REFILL && lane == 0;
-      int grp = 0;               // (lane 0, GROUP_REFILL) next round: passes NPW * grp .. + NPW - 1 of the CTA's sequence
+      const bool group_lane = !HEAD && !LOGITS_DIRECT && GROUP_REFILL && lane < NSUB;
+      int grp = 0;               // (lanes < NSUB, GROUP_REFILL) next round of the lane's group: passes NPW * grp + 4 * lane .. + 3
       const int w = refill_lane ? lane : 0;
       int P = lane;              // next pass of warp w in the CTA's pass sequence (P = 32 * tile + pass in the tile)
       int n = 0;                 // how many of the warp's passes have been issued
@@ -573,42 +576,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       while (true) {
         const bool more_r = refill_lane && P < total;
         const bool more_f = lane == 31 && fwd < my_tiles;
-        const bool more_g = group_lane && grp * NPW < total;
+        const bool more_g = group_lane && grp * NPW + GSZ * lane < total;
         if (!__any_sync(0xffffffffu, more_r || more_f || more_g)) break;
         bool did = false;
-        if (more_g && (grp == 0 || mbar_test(&sm.lring_free_g, (uint32_t)((grp - 1) & 1)))) {
-          // rows of the round: passes P0 .. P1 - 1; they are contiguous within a tile (2 rows per pass), a round crosses at
-          // most one tile boundary -> one or two copies into the contiguous slot array; rows past the end are not copied
-          const int P0 = grp * NPW, P1 = (P0 + NPW < total) ? P0 + NPW : total;
-          const int tlA = P0 >> 5;
-          const int PeA = (P1 < ((tlA + 1) << 5)) ? P1 : ((tlA + 1) << 5);     // end of the first tile's part of the round
-          auto seg_rows = [&](long long r0, int npass) -> long long {
-            long long nrows = 2LL * npass;
+        const int gslot = grp % LRING;
+        if (more_g && (grp < LRING || mbar_test(&sm.lring_free_g[gslot][lane], (uint32_t)((grp / LRING - 1) & 1)))) {
+          // round grp of group `lane`: passes P0 .. P0 + 3 (4-aligned: never across a tile boundary) = 8 consecutive rows;
+          // rows past the end of the batch are not copied
+          const int P0 = grp * NPW + GSZ * lane;
+          auto seg_rows = [&](long long r0) -> long long {
+            long long nrows = 2LL * GSZ;
             if (r0 + nrows > a.rows) nrows = a.rows > r0 ? a.rows - r0 : 0;
             return nrows;
           };
-          const long long rA = row00 + (long long)tlA * tile_rows + 2 * (P0 & 31);
-          const long long rB = row00 + (long long)(tlA + 1) * tile_rows;       // (pass 0 of the next tile)
-          const long long nA = seg_rows(rA, PeA - P0), nB = (PeA < P1) ? seg_rows(rB, P1 - PeA) : 0;
-          mbar_arrive_expect_tx(&sm.lring_full_g, (uint32_t)(nA + nB) * S * 4);
-          float* dA = &sm.lring[0][0][0][0];
-          float* dB = &sm.lring[0][0][0][0] + (size_t)(PeA - P0) * 2 * S;
+          const long long rA = row00 + (long long)(P0 >> 5) * tile_rows + 2 * (P0 & 31);
+          const long long nA = seg_rows(rA);
+          uint64_t* gbar = &sm.lring_full_g[gslot][lane];
+          mbar_arrive_expect_tx(gbar, (uint32_t)nA * S * 4);
+          float* dA = &sm.lring[gslot][GSZ * lane][0][0];
           if (contiguous) {
-            if (nA > 0) bulk_g2s(dA, a.logits + rA * S, (uint32_t)nA * S * 4, &sm.lring_full_g);
-            if (nB > 0) bulk_g2s(dB, a.logits + rB * S, (uint32_t)nB * S * 4, &sm.lring_full_g);
+            if (nA > 0) bulk_g2s(dA, a.logits + rA * S, (uint32_t)nA * S * 4, gbar);
           } else {               // strided logits: one copy per row
-            for (long long rr = 0; rr < nA; ++rr) bulk_g2s(dA + rr * S, row_ptr(rA + rr), S * 4, &sm.lring_full_g);
-            for (long long rr = 0; rr < nB; ++rr) bulk_g2s(dB + rr * S, row_ptr(rB + rr), S * 4, &sm.lring_full_g);
+            for (long long rr = 0; rr < nA; ++rr) bulk_g2s(dA + rr * S, row_ptr(rA + rr), S * 4, gbar);
           }
           if (contiguous && PREFETCH_ROUNDS > 0) {      // the rows of a later round from HBM into L2
-            const int Q0 = (grp + PREFETCH_ROUNDS) * NPW;
-            if (Q0 + NPW <= total) {
-              const int tq = Q0 >> 5;
-              const int Qe = (Q0 + NPW < ((tq + 1) << 5)) ? Q0 + NPW : ((tq + 1) << 5);
-              const long long qA = row00 + (long long)tq * tile_rows + 2 * (Q0 & 31), qB = row00 + (long long)(tq + 1) * tile_rows;
-              const long long mA = seg_rows(qA, Qe - Q0), mB = (Qe < Q0 + NPW) ? seg_rows(qB, Q0 + NPW - Qe) : 0;
+            const int Q0 = P0 + PREFETCH_ROUNDS * NPW;
+            if (Q0 < total) {
+              const long long qA = row00 + (long long)(Q0 >> 5) * tile_rows + 2 * (Q0 & 31);
+              const long long mA = seg_rows(qA);
               if (mA > 0) l2_prefetch_bulk(a.logits + qA * S, (uint32_t)mA * S * 4);
-              if (mB > 0) l2_prefetch_bulk(a.logits + qB * S, (uint32_t)mB * S * 4);
             }
           }
           ++grp;
@@ -620,12 +616,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
           uint64_t* bar = &sm.lring_full[w][lslot];
           if (n < LRING) mbar_arrive_expect_tx(bar, 2 * S * 4);   // later fills are armed by the producer warp when it releases the slot
           if (contiguous && gf + 1 < a.rows) {
-            bulk_g2s(&sm.lring[w][lslot][0][0], a.logits + gf * S, 2 * S * 4, bar);
+            bulk_g2s(&sm.lring[lslot][w][0][0], a.logits + gf * S, 2 * S * 4, bar);
           } else {               // rows past the end are replaced by row 0 (never used)
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
               const long long gg = (gf + hf < a.rows) ? gf + hf : 0;
-              bulk_g2s(&sm.lring[w][lslot][hf][0], row_ptr(gg), S * 4, bar);
+              bulk_g2s(&sm.lring[lslot][w][hf][0], row_ptr(gg), S * 4, bar);
             }
           }
           if (contiguous && PREFETCH_TILES > 0) {   // the same two rows of a later tile from HBM into L2
