@@ -97,6 +97,10 @@ constexpr bool GROUP_REFILL = CTDD_GROUP_REFILL != 0;
 // GROUP_REFILL: producer warps 4g .. 4g+3 (one per SM sub-partition, the same rank in each scheduler's priority order, so they
 // advance together) share one fill per round: their 4 consecutive passes are 8 consecutive rows of one tile = one 8 KB copy
 constexpr int GSZ = 4, NSUB = CTDD_TCQ_NPW / GSZ;
+#ifndef CTDD_LOADER_SLEEP_NS
+#define CTDD_LOADER_SLEEP_NS 32
+#endif
+constexpr int LOADER_SLEEP_NS = CTDD_LOADER_SLEEP_NS;   // pause of the loader warp when a poll found nothing to do
 #ifndef CTDD_PREFETCH_ROUNDS
 #define CTDD_PREFETCH_ROUNDS 0
 #endif
@@ -643,7 +647,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
             did = true;
           }
         }
-        if (!__any_sync(0xffffffffu, did)) asm volatile("nanosleep.u32 32;");
+        if (!__any_sync(0xffffffffu, did)) asm volatile("nanosleep.u32 %0;" ::"n"(LOADER_SLEEP_NS));   // (a poll costs ~30 issue slots of this warp's scheduler)
       }
     }
     __syncwarp();
