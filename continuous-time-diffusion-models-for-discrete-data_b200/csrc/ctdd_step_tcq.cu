@@ -40,31 +40,12 @@ constexpr int ACC = 2;                 // TMEM accumulator buffers (NT columns e
 constexpr int CBUF = 2;                // contribution buffers (epilogue -> finalizer)
 constexpr int RING = 7;                // per-tile row-scalar ring (> STAGES + ACC + CBUF)
 constexpr int NUM_EPI_WARPS = 8;       // epilogue warp e: TMEM quadrant e&3, column half e>>2 (= CTA that owns those rows)
-#ifndef CTDD_EPI_HIGH
-#define CTDD_EPI_HIGH 0
-#endif
-#ifndef CTDD_GATHER
-#define CTDD_GATHER 1
-#endif
-#ifndef CTDD_LOGITS_DIRECT
-#define CTDD_LOGITS_DIRECT 0
-#endif
-// 1: the producers read the raw logits rows straight into registers, one pass ahead (128-bit streaming loads);
-// 0: through the per-warp shared-memory ring that the loader warp fills with bulk copies
-constexpr bool LOGITS_DIRECT = CTDD_LOGITS_DIRECT != 0;
-// Warp numbering: the scheduler of an SM sub-partition favours its higher-numbered warps.  CTDD_EPI_HIGH = 1 puts the
-// epilogue warps above the producers (producers 0.., epilogue NPW.., light group last).
-constexpr bool EPI_HIGH = CTDD_EPI_HIGH != 0;
-// base-rate gather of the tauLDR sampling modes: 1 = lane = row, four 256-bit loads of the row's own table piece (few
-// instructions, 32 LSU wavefronts per load); 2 = lane = state, one coalesced predicated load per in-band row (one wavefront
-// per load, ~5 instructions per row)
-constexpr int GATHER = CTDD_GATHER;
 #ifndef CTDD_TCQ_NPW
 #define CTDD_TCQ_NPW 12
 #endif
 constexpr int NPW = CTDD_TCQ_NPW;      // producer warps (a multiple of 4: register budgets are per 4-warp group)
-constexpr int FIRST_PROD_WARP = EPI_HIGH ? 0 : NUM_EPI_WARPS;
-constexpr int FIRST_EPI_WARP = EPI_HIGH ? NPW : 0;
+constexpr int FIRST_PROD_WARP = NUM_EPI_WARPS;
+constexpr int FIRST_EPI_WARP = 0;
 constexpr int MMA_WARP = NUM_EPI_WARPS + NPW;   // light group: MMA issue / relay, idle, 2 finalizer warps
 constexpr int FIN_WARP0 = MMA_WARP + 2;
 constexpr int NUM_THREADS = (NUM_EPI_WARPS + NPW + 4) * 32;
@@ -81,30 +62,17 @@ constexpr int KBLOCK_BYTES = NH * 128;         // one 64-wide K block of one spl
 constexpr int SPLIT_BYTES = 4 * KBLOCK_BYTES;  // K = 256 -> 4 blocks
 constexpr int STAGE_BYTES = 2 * SPLIT_BYTES;   // hi + mid
 constexpr int TM_QH = 0, TM_QM = 128, TM_ACC = 256;  // TMEM column map (accumulator b at TM_ACC + b * NT)
-#ifndef CTDD_PREFETCH_TILES
-#define CTDD_PREFETCH_TILES 0
-#endif
-constexpr int PREFETCH_TILES = CTDD_PREFETCH_TILES;      // HBM -> L2 bulk-prefetch distance (tiles of this pair's sequence)
 #ifndef CTDD_LRING
 #define CTDD_LRING 2
 #endif
-#ifndef CTDD_GROUP_REFILL
-#define CTDD_GROUP_REFILL 1
-#endif
-// 1: the ring slots of all producer warps (NPW consecutive passes = 2 * NPW consecutive rows, contiguous in a dense logits
-// tensor) are refilled by ONE bulk copy per round; 0: one copy per warp and pass
-constexpr bool GROUP_REFILL = CTDD_GROUP_REFILL != 0;
-// GROUP_REFILL: producer warps 4g .. 4g+3 (one per SM sub-partition, the same rank in each scheduler's priority order, so they
-// advance together) share one fill per round: their 4 consecutive passes are 8 consecutive rows of one tile = one 8 KB copy
+// The logits ring is refilled per GROUP of 4 producer warps 4g .. 4g+3 (one per SM sub-partition, the same rank in each
+// scheduler's priority order, so they advance together): their 4 consecutive passes are 8 consecutive rows of one tile = one
+// 8 KB bulk copy per group and round.
 constexpr int GSZ = 4, NSUB = CTDD_TCQ_NPW / GSZ;
-#ifndef CTDD_LOADER_SLEEP_NS
-#define CTDD_LOADER_SLEEP_NS 32
-#endif
-constexpr int LOADER_SLEEP_NS = CTDD_LOADER_SLEEP_NS;   // pause of the loader warp when a poll found nothing to do
 #ifndef CTDD_PREFETCH_ROUNDS
 #define CTDD_PREFETCH_ROUNDS 0
 #endif
-constexpr int PREFETCH_ROUNDS = CTDD_PREFETCH_ROUNDS;   // GROUP_REFILL: HBM -> L2 prefetch of the round that many rounds ahead
+constexpr int PREFETCH_ROUNDS = CTDD_PREFETCH_ROUNDS;   // HBM -> L2 prefetch of the round that many rounds ahead (measured: no gain)
 #ifndef CTDD_REGPICK_MAX
 #define CTDD_REGPICK_MAX 3
 #endif
@@ -117,9 +85,6 @@ constexpr uint32_t IDESC = make_idesc(NT);
 #define CTDD_POLL_LONG 512
 #endif
 constexpr uint32_t POLL_LONG = CTDD_POLL_LONG;   // ns between polls of the roles that wait for a whole tile (producers on a free stage, finalizers)
-#ifndef CTDD_EXP_PMASK
-#define CTDD_EXP_PMASK 0     // diagnostic builds: producer stages switched off (wrong numerics, timing only)
-#endif
 constexpr int NCHUNK = S / JUMP_CHUNK;                           // 8 chunks of 32 states per row
 constexpr uint32_t SCAL_TX_BYTES = NH * 12;                      // row scalars the partner sends per tile
 constexpr uint32_t CONTRIB_TX_BYTES = (NUM_EPI_WARPS / 2) * 2 * 32 * 4;   // records the partner's 4 warps send per tile
@@ -141,9 +106,8 @@ struct Smem {
   uint64_t empty[STAGES];                      // multicast tcgen05.commit
   uint64_t scal_local[RING];                   // NPW local producer warps: this CTA's 64 rows of the tile have their scalars
   uint64_t scal_full[RING];                    // the local loader's arrival (scal_local seen) + the partner's bytes (DSMEM bulk copy)
-  uint64_t lring_full[NPW][LRING];             // cp.async.bulk complete_tx of one row pair
-  uint64_t lring_free[NPW][LRING];             // the producer warp has its values in registers: the loader may refill the slot
-  uint64_t lring_full_g[LRING][NSUB], lring_free_g[LRING][NSUB];   // GROUP_REFILL: one round of a 4-warp group (bytes of the copy / its 4 warps)
+  uint64_t lring_full_g[LRING][NSUB];          // one round of a 4-warp group: the bytes of its bulk copy
+  uint64_t lring_free_g[LRING][NSUB];          // its 4 warps have their values in registers: the loader may refill the slots
   uint64_t tmem_full[ACC];                     // multicast tcgen05.commit
   uint64_t tmem_empty[ACC];                    // used in the leader CTA: 8 local + 8 remote epilogue warps
   uint64_t contrib_full[CBUF];                 // 4 local epilogue warps + the bytes of the partner's 4 warps
@@ -205,10 +169,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       mbar_init(&sm.empty[i], 1);
     }
     for (int i = 0; i < RING; ++i) { mbar_init(&sm.scal_local[i], NPW); mbar_init(&sm.scal_full[i], 1); }
-    for (int w = 0; w < NPW; ++w) {
-      for (int i = 0; i < LRING; ++i) mbar_init(&sm.lring_full[w][i], 1);
-      for (int i = 0; i < LRING; ++i) mbar_init(&sm.lring_free[w][i], 1);
-    }
     for (int i = 0; i < LRING; ++i)
       for (int g = 0; g < NSUB; ++g) { mbar_init(&sm.lring_full_g[i][g], 1); mbar_init(&sm.lring_free_g[i][g], GSZ); }
     for (int i = 0; i < ACC; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], 2 * NUM_EPI_WARPS); }
@@ -280,7 +240,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     const float hb = (KM == KM_RATES) ? 1.0f : a.h * a.beta;   // rates-only ignores the step length
     uint64_t* const full_bar = rank == 0 ? &sm.full[0] : &sm.full_local[0];
     // passes of this CTA: pass P = 32 * tl + ps builds rows 2 ps, 2 ps + 1 of the CTA's 64 rows of its tl-th tile; warp pw
-    // takes P = pw, pw + NPW, ..  The states are fetched two passes of the warp ahead, the logits (LOGITS_DIRECT) one;
+    // takes P = pw, pw + NPW, ..  The states are fetched two passes of the warp ahead;
     // every position is derived from the one pass counter (row indices fit 32 bits: a row is 1 KB of logits).
     const int total_passes = my_tiles * PASSES_PER_TILE;
     const uint32_t tile_rows = (uint32_t)npairs * NT;
@@ -312,23 +272,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     };
     // Logits: the loader warp (light group) refills this warp's ring slot as soon as the warp reports that the current
     // pass has its values in registers (lring_free); the rows were pulled from HBM into L2 some tiles earlier.
-    float4 vn[4];                // LOGITS_DIRECT: the next pass's 16 logits of this lane
-    auto load_next = [&](int Pq) {
-      if (HEAD || !LOGITS_DIRECT || Pq >= total_passes) return;
-      const uint32_t g = row_of(Pq) + half;
-      const long long gg = g < rows32 ? g : 0;     // rows past the end read row 0 (never used)
-      const float* src;
-      if ((a.ld == S) && (a.batch_stride == (long long)a.D * S)) {
-        src = a.logits + gg * S;
-      } else {
-        const uint32_t n = (uint32_t)gg / (uint32_t)a.D, d = (uint32_t)gg - n * (uint32_t)a.D;
-        src = a.logits + (long long)n * a.batch_stride + (long long)d * a.ld;
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) vn[c] = ld_stream(src + 4 * l16 + 64 * c);
-    };
     int P = pw;
-    load_next(P);
     int x_cur = fetch(P);
     float mu_cur = f_mu, ls_cur = f_ls;
     int x_n1 = fetch(P + NPW);
@@ -389,10 +333,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       if (ptr_on) TRACEQ(6, tl, 0);
 #endif
       const int rslot = ring_n % LRING;
-      if (!HEAD && !LOGITS_DIRECT) {
-        if (GROUP_REFILL) mbar_wait(&sm.lring_full_g[rslot][pw / GSZ], (uint32_t)((ring_n / LRING) & 1));
-        else mbar_wait(&sm.lring_full[pw][rslot], (uint32_t)((ring_n / LRING) & 1));
-      }
+      if (!HEAD) mbar_wait(&sm.lring_full_g[rslot][pw / GSZ], (uint32_t)((ring_n / LRING) & 1));
 #ifdef CTDD_TC_TRACE
       if (pw == 0 && lane == 0) TRACEQ_ADD(0, tl, 3, clock64() - tq0);
       if (ptr_on) TRACEQ(6, tl, 1);
@@ -408,33 +349,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         }
         head_numerators(mu_cur, ls_cur, a.head_fix != 0, l16, v);
       } else {
-        if constexpr (LOGITS_DIRECT) {
+        const uint32_t src = smem_u32(&sm.lring[rslot][pw][half][4 * l16]);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) { v[4 * c] = vn[c].x; v[4 * c + 1] = vn[c].y; v[4 * c + 2] = vn[c].z; v[4 * c + 3] = vn[c].w; }
-          load_next(P + NPW);    // the next pass's rows are in flight for the whole of this pass
-        } else {
-          const uint32_t src = smem_u32(&sm.lring[rslot][pw][half][4 * l16]);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float4 q4 = lds128(src + 256 * c);
-            v[4 * c] = q4.x; v[4 * c + 1] = q4.y; v[4 * c + 2] = q4.z; v[4 * c + 3] = q4.w;
-          }
-          ++ring_n;
+        for (int c = 0; c < 4; ++c) {
+          const float4 q4 = lds128(src + 256 * c);
+          v[4 * c] = q4.x; v[4 * c + 1] = q4.y; v[4 * c + 2] = q4.z; v[4 * c + 3] = q4.w;
         }
+        ++ring_n;
 #ifdef CTDD_TC_TRACE
         if (ptr_on) TRACEQ_DEP(6, tl, 2, __float_as_uint(v[15]), pzero);
 #endif
-        if constexpr (!LOGITS_DIRECT) {
-          __syncwarp();          // every lane has its values: the slot may be refilled for the warp's next pass
-          if (lane == 0) {
-            if (GROUP_REFILL) {
-              mbar_arrive(&sm.lring_free_g[rslot][pw / GSZ]);
-            } else {             // release the slot and arm its next fill (the loader only issues the copy)
-              mbar_arrive_expect_tx(&sm.lring_full[pw][rslot], 2 * S * 4);
-              mbar_arrive(&sm.lring_free[pw][rslot]);
-            }
-          }
-        }
+        __syncwarp();            // every lane has its values: the group's slots may be refilled once its 4 warps say so
+        if (lane == 0) mbar_arrive(&sm.lring_free_g[rslot][pw / GSZ]);
 #ifdef CTDD_TC_TRACE
         if (ptr_on) TRACEQ(6, tl, 3);
 #endif
@@ -443,7 +369,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         for (int c = 0; c < 4; ++c) m4[c] = fmaxf(fmaxf(v[4 * c], v[4 * c + 1]), fmaxf(v[4 * c + 2], v[4 * c + 3]));
         float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
 #pragma unroll
-        for (int o = (CTDD_EXP_PMASK & 4) ? 0 : 8; o > 0; o >>= 1) {     // this pass's row maximum next to the previous pass's reductions
+        for (int o = 8; o > 0; o >>= 1) {     // this pass's row maximum next to the previous pass's reductions
           m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
           p_sum += __shfl_xor_sync(0xffffffffu, p_sum, o);
           if (!TAULDR) p_dot += __shfl_xor_sync(0xffffffffu, p_dot, o);
@@ -499,7 +425,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       if (ptr_on) TRACEQ_DEP(6, tl, 6, __float_as_uint(sum), pzero);
 #endif
       // the table row of the NEXT pass is requested as soon as this pass's has been consumed
-      if (!(CTDD_EXP_PMASK & 1)) {
+      {
         const size_t xo = (size_t)(x_n1 < 0 ? 0 : x_n1) << 8;
 #pragma unroll
         for (int c = 0; c < 4; ++c) t4[c] = __ldg(reinterpret_cast<const float4*>(tabA + xo + 64 * c));
@@ -518,7 +444,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         uint32_t h0, m0, h1, m1;
         split2(v[4 * c], v[4 * c + 1], h0, m0);
         split2(v[4 * c + 2], v[4 * c + 3], h1, m1);
-        if (!(CTDD_EXP_PMASK & 16) || h0 == 0x12345u) {
+        {
           sts64(stage_s + c * KBLOCK_BYTES + off, h0, h1);
           sts64(stage_s + SPLIT_BYTES + c * KBLOCK_BYTES + off, m0, m1);
         }
@@ -552,11 +478,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
   } else if (warp == MMA_WARP + 1) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_LIGHT));
     // ======================================================================== loader: everything the producers would otherwise
-    // issue themselves.  Lane w < NPW serves producer warp w: the bulk copy of each of that warp's passes' row pair into
-    // its ring slot as soon as the warp has released the slot (a bulk-copy issue costs the issuing thread a few hundred
-    // cycles: off the producers' critical path, and spread over NPW lanes here), plus the HBM -> L2 prefetch of rows some
-    // tiles ahead.  Lane 31 forwards each finished tile's 64 row-scalar records to the partner CTA as two DSMEM bulk
-    // copies.  Nobody blocks: the warp polls, every lane acts on what is ready.
+    // issue themselves.  Lane g < NSUB serves producer warps 4g .. 4g+3: ONE 8 KB bulk copy per round into their four ring
+    // slots as soon as all four have released them (a bulk-copy issue costs the issuing thread a few hundred cycles: off
+    // the producers' critical path).  Lane 31 forwards each finished tile's 64 row-scalar records to the partner CTA as
+    // two DSMEM bulk copies.  Nobody blocks: the warp polls, every lane acts on what is ready.
     {
       const bool contiguous = (a.ld == S) && (a.batch_stride == (long long)a.D * S);
       auto row_ptr = [&](long long g) -> const float* {
@@ -570,18 +495,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       const long long tile_rows = (long long)npairs * NT;
       const long long row00 = (long long)pair * NT + (int)rank * NH;      // first row of this CTA's half of its first tile
       const int total = my_tiles * PASSES_PER_TILE;
-      const bool refill_lane = !HEAD && !LOGITS_DIRECT && !GROUP_REFILL && lane < NPW;
-      const bool group_lane = !HEAD && !LOGITS_DIRECT && GROUP_REFILL && lane < NSUB;
-      int grp = 0;               // (lanes < NSUB, GROUP_REFILL) next round of the lane's group: passes NPW * grp + 4 * lane .. + 3
-      const int w = refill_lane ? lane : 0;
-      int P = lane;              // next pass of warp w in the CTA's pass sequence (P = 32 * tile + pass in the tile)
-      int n = 0;                 // how many of the warp's passes have been issued
+      const bool group_lane = !HEAD && lane < NSUB;
+      int grp = 0;               // (lanes < NSUB) next round of the lane's group: passes NPW * grp + 4 * lane .. + 3
       int fwd = 0;               // (lane 31) next tile whose scalars go to the partner
       while (true) {
-        const bool more_r = refill_lane && P < total;
         const bool more_f = lane == 31 && fwd < my_tiles;
         const bool more_g = group_lane && grp * NPW + GSZ * lane < total;
-        if (!__any_sync(0xffffffffu, more_r || more_f || more_g)) break;
+        if (!__any_sync(0xffffffffu, more_f || more_g)) break;
         bool did = false;
         const int gslot = grp % LRING;
         if (more_g && (grp < LRING || mbar_test(&sm.lring_free_g[gslot][lane], (uint32_t)((grp / LRING - 1) & 1)))) {
@@ -614,27 +534,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
           ++grp;
           did = true;
         }
-        const int lslot = n % LRING;
-        if (more_r && (n < LRING || mbar_test(&sm.lring_free[w][lslot], (uint32_t)((n / LRING - 1) & 1)))) {
-          const long long gf = row00 + (long long)(P >> 5) * tile_rows + 2 * (P & 31);
-          uint64_t* bar = &sm.lring_full[w][lslot];
-          if (n < LRING) mbar_arrive_expect_tx(bar, 2 * S * 4);   // later fills are armed by the producer warp when it releases the slot
-          if (contiguous && gf + 1 < a.rows) {
-            bulk_g2s(&sm.lring[lslot][w][0][0], a.logits + gf * S, 2 * S * 4, bar);
-          } else {               // rows past the end are replaced by row 0 (never used)
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-              const long long gg = (gf + hf < a.rows) ? gf + hf : 0;
-              bulk_g2s(&sm.lring[lslot][w][hf][0], row_ptr(gg), S * 4, bar);
-            }
-          }
-          if (contiguous && PREFETCH_TILES > 0) {   // the same two rows of a later tile from HBM into L2
-            const long long r0 = gf + (long long)PREFETCH_TILES * tile_rows;
-            if (r0 + 2 <= a.rows) l2_prefetch_bulk(a.logits + r0 * S, 2 * S * 4);
-          }
-          P += NPW; ++n;
-          did = true;
-        }
         if (more_f) {
           const int slot = fwd % RING;
           if (mbar_test(&sm.scal_local[slot], (uint32_t)((fwd / RING) & 1))) {
@@ -647,7 +546,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
             did = true;
           }
         }
-        if (!__any_sync(0xffffffffu, did)) asm volatile("nanosleep.u32 %0;" ::"n"(LOADER_SLEEP_NS));   // (a poll costs ~30 issue slots of this warp's scheduler)
+        if (!__any_sync(0xffffffffu, did)) asm volatile("nanosleep.u32 32;");
       }
     }
     __syncwarp();
@@ -830,20 +729,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
           // outside the band of non-zero rates of x), the accumulator is transposed through the warp's scratch, and
           // lam[row, s] = D[s, row] * R[x_row][s] is formed where the prefix sums need it.
           constexpr bool UNSCALED = TAULDR && !km_corr(KM);
-          constexpr bool COALESCED = UNSCALED && GATHER == 2;
           const bool inband = (sxl & chunkbit) != 0u;
-          const uint32_t inmask = __ballot_sync(0xffffffffu, inband);   // bit j: row j of the batch has non-zero rates in this chunk
           float R[32];
-          if constexpr (COALESCED) {
-            // tauLDR without corrector: lane = state.  R[s_mine, x_j] for the in-band rows j of the batch: one coalesced
-            // 128-byte load per row (the LSU data pipe is the kernel's busiest unit: a load whose lanes touch 32 different
-            // lines costs 32 wavefronts, a coalesced one costs one).  The rows' table offsets are read four at a time
-            // as broadcast 128-bit shared loads; rows outside the band are neither loaded nor transposed.
-            const float* rbase = stat_ptr(TAB_R);
-            GatherRows<0>::run(R, rbase, sx_p, inmask, (uint32_t)a.head_fix >> 8);
-          } else {
-            // other sampling modes: lane = ROW reads the 32 base-rate entries of ITS row's state for this chunk (one
-            // 128-byte piece of the zero-diagonal table row x, four 256-bit loads; the zero row outside the band)
+          {
             const uint8_t* rrow = a.stat + (inband ? TAB_R + (sxl & 0x3FC00u) : (uint32_t)ST_ZERO_OFF) + cs * 4;
 #pragma unroll
             for (int c = 0; c < 4; ++c) ldg256(rrow + 32 * c, &R[8 * c]);
@@ -872,16 +760,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
           // transpose through the warp's scratch: lane = state -> lane = row (row `lane` of the batch, the chunk's 32 states)
           __syncwarp();          // the previous batch's reads of the scratch are done
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if constexpr (COALESCED) {     // lam[s, row j] = D * R; rows outside the band stay out of the scratch
-              if (inmask & (1u << j)) sts32(scr_p + (uint32_t)(j * SCR_LD + lane) * 4u, __uint_as_float(acc[j]) * R[j]);
-            } else {
-              sts32(scr_p + (uint32_t)(j * SCR_LD + lane) * 4u, __uint_as_float(acc[j]));
-            }
-          }
+          for (int j = 0; j < 32; ++j) sts32(scr_p + (uint32_t)(j * SCR_LD + lane) * 4u, __uint_as_float(acc[j]));
           __syncwarp();
           float p[32];
-          // (a row outside the band reads stale scratch contents: its total is forced to zero below)
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
             asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(p[2 * c]), "=f"(p[2 * c + 1]) : "r"(scr_p + (uint32_t)(lane * SCR_LD + 2 * c) * 4u));
@@ -916,14 +797,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
             float dsum = 0.f;
 #pragma unroll
             for (int s2 = 0; s2 < 32; ++s2) {
-              const float lam = (UNSCALED && !COALESCED) ? p[s2] * R[s2] : p[s2];
+              const float lam = UNSCALED ? p[s2] * R[s2] : p[s2];
               dsum = fmaf(lam, (float)(cs + s2 - xl), dsum);
             }
-            dsum = inband ? (UNSCALED ? dsum * sc1 : dsum) : 0.f;      // (outside the band the scratch row is stale)
+            if constexpr (UNSCALED) dsum *= sc1;
             rec.x = __float_as_int(dsum);
           } else {
             // sequential fp32 prefix sums over the chunk's states (the oracle's summation order)
-            if constexpr (UNSCALED && !COALESCED) {     // product and running sum in one fused multiply-add per state
+            if constexpr (UNSCALED) {     // product and running sum in one fused multiply-add per state
               p[0] *= R[0];
 #pragma unroll
               for (int s2 = 1; s2 < 32; ++s2) p[s2] = fmaf(p[s2], R[s2], p[s2 - 1]);
@@ -932,7 +813,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
               for (int s2 = 1; s2 < 32; ++s2) p[s2] += p[s2 - 1];
             }
             float tot = p[31];
-            tot = inband ? (UNSCALED ? tot * sc1 : tot) : 0.f;          // (outside the band the scratch row is stale)
+            if constexpr (UNSCALED) tot *= sc1;
 #ifdef CTDD_TC_TRACE
             if (tr_on && h == 0 && bb == 0) TRACEQ_DEP(5, i, 3, __float_as_uint(tot), tzero);   // prefix chain done
 #endif

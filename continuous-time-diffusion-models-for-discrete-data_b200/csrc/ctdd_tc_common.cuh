@@ -218,38 +218,6 @@ __device__ __forceinline__ void ldg256_pred(const uint8_t* p, float* v, bool on)
       : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7])
       : "l"(p), "r"((uint32_t)on));
 }
-// read-only load of base[(sx & 0x3FC00) / 4] when bit BIT of mask is set (one widening multiply-add forms the address);
-// zero otherwise (a destination left undefined would stay live across the caller's whole loop body)
-template <int BIT>
-__device__ __forceinline__ float ldg_row(const float* base, uint32_t sx, uint32_t mask) {
-  float v = 0.f;
-  asm volatile(
-      "{\n.reg .pred p;\n.reg .b64 a;\n.reg .b32 t, o;\nand.b32 t, %3, %4;\nsetp.ne.u32 p, t, 0;\nand.b32 o, %1, 0x3FC00;\n"
-      "mad.wide.u32 a, o, 1, %2;\n@p ld.global.nc.f32 %0, [a];\n}\n"
-      : "+f"(v)
-      : "r"(sx), "l"(base), "r"(mask), "n"(1u << BIT));
-  return v;
-}
-// rows 4C .. 31 of a batch: the rows' scalars (table offset in bits 10..17) are read four at a time as broadcast 128-bit
-// shared loads, then one predicated coalesced load per row.  Each group's shared address is made to depend on the
-// previous group's data (`chain` is a run-time zero): without that the assembler hoists all 32 address computations
-// (64 registers) above the first load and spills.
-template <int C>
-struct GatherRows {
-  static __device__ __forceinline__ void run(float (&R)[32], const float* rbase, uint32_t sx_p, uint32_t inmask, uint32_t chain) {
-    uint32_t s0, s1, s2, s3;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(s0), "=r"(s1), "=r"(s2), "=r"(s3) : "r"(sx_p + 16 * C));
-    R[4 * C] = ldg_row<4 * C>(rbase, s0, inmask);
-    R[4 * C + 1] = ldg_row<4 * C + 1>(rbase, s1, inmask);
-    R[4 * C + 2] = ldg_row<4 * C + 2>(rbase, s2, inmask);
-    R[4 * C + 3] = ldg_row<4 * C + 3>(rbase, s3, inmask);
-    GatherRows<C + 1>::run(R, rbase, sx_p + (s3 & chain), inmask, chain);
-  }
-};
-template <>
-struct GatherRows<8> {
-  static __device__ __forceinline__ void run(float (&)[32], const float*, uint32_t, uint32_t, uint32_t) {}
-};
 // explicit shared-space accesses (the compiler emits generic LD/ST for pointers it cannot prove to be shared)
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
