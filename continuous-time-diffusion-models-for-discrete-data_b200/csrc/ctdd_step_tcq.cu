@@ -9,24 +9,31 @@
 //     in tensor memory as the A operand (TS form) for the whole kernel; 2 accumulators of 128 columns.  With N = 128
 //     an instruction sits on the 64-cycle floor of the TS form (the A slice is read from tensor memory at 64 B/cycle).
 //   * N side = data rows; each CTA produces 64 rows of a tile.  Producer warps work on two rows per pass, 16 lanes per
-//     row: raw fp32 logits through a per-warp smem ring filled by cp.async.bulk (HBM -> L2 prefetch some tiles ahead),
-//     row softmax by half-warp butterflies, gathered reciprocal denominators 1/(Q[k,x]+eps), bf16 hi/mid split, K-major
-//     128B-swizzled smem stage.  The passes of a tile are dealt round-robin to the producer warps.  The row scalars
-//     (rate scale, state, band of non-zero base rates) go to BOTH CTAs of the pair (st.async into the partner).
+//     row: raw fp32 logits from a per-warp ring of two 2 KB slots, row softmax by half-warp butterflies, gathered reciprocal
+//     denominators 1/(Q[k,x]+eps), bf16 hi/mid split, K-major 128B-swizzled smem stage.  The passes of a tile are dealt
+//     round-robin to the producer warps; one pass counter per warp, every position derives from it.
+//   * A loader warp issues what the producers would otherwise stall on: per GROUP of 4 producer warps (one per SM
+//     sub-partition; their 4 consecutive passes are 8 consecutive rows) ONE 8 KB cp.async.bulk per round into the group's
+//     ring slots, and per tile two DSMEM bulk copies that forward the 64 row-scalar records (rate scale, state, band of
+//     non-zero base rates) to the partner CTA.
 //   * 3 tensor passes  Qh*ah + Qh*am + Qm*ah  accumulate in fp32 TMEM (48 tcgen05.mma of N = 128 per tile).
-//   * Epilogue: warp (q, h) reads its 32 states x 32 rows with tcgen05.ld (lane = state; two batches per tile), gathers
-//     R_b[s, x_row] for all 32 rows at once (32 independent coalesced 128-byte loads in flight; chunks outside the
-//     band of non-zero base rates of x are skipped) and forms lam[s, row].  A 4.5 KB per-warp scratch transposes the
-//     batch to lane = row.  A warp's 32 states are one CHUNK of the chunked superposition map (ctdd_common.cuh): each
-//     chunk of a row draws its own jump count K ~ Poisson(chunk total) and its own picks, so no warp ever waits for
-//     another warp's total and all 32 rows of a batch are sampled in parallel: sequential fp32 prefix sums in
-//     registers (the oracle's summation order), Philox, inverse-CDF count, picks by a register binary search.
-//   * The per-(row, chunk) results (sum of jumps, jump count / partial drift) are 8 bytes each; they go to the CTA that
-//     produced the row (plain st.shared or st.async + complete_tx), whose two finalizer warps (lane = row) add the 8
-//     chunks, apply the clamp / rejection rule and write x_out coalesced.
-// Nothing but those 8-byte records and the row scalars crosses between the CTAs of a pair.
+//   * Epilogue: warp (q, h) reads its 32 states x 32 rows with tcgen05.ld (lane = state; two batches per tile).  In the
+//     load's shadow lane = ROW fetches the 32 base-rate entries R_b[chunk states, x_row] of its own row (128 bytes of the
+//     zero-diagonal [x][s] table; the zero row when the chunk lies outside the band of x) and the row's Philox call.  A
+//     4.3 KB per-warp scratch transposes the accumulator to lane = row.  A warp's 32 states are one CHUNK of the chunked
+//     superposition map (ctdd_common.cuh): each chunk of a row draws its own jump count K ~ Poisson(chunk total) and its
+//     own picks, so no warp ever waits for another warp's total and all 32 rows of a batch are sampled in parallel:
+//     sequential fp32 prefix sums in registers (the oracle's summation order, one FMA per state), inverse-CDF count,
+//     picks by 31 register compares per pick when the batch's largest K is <= 3, else dealt to the 32 lanes over the prefix
+//     sums parked in the scratch.
+//   * The per-(row, chunk) result is one 32-bit record (sum of jumps << 2 | min(K, 3), or the partial drift); it goes to
+//     the CTA that produced the row (plain st.shared or st.async + complete_tx), whose two finalizer warps (lane = row) add
+//     the 8 chunks, apply the clamp / rejection rule and write x_out coalesced.
+// Nothing but those records and the row scalars crosses between the CTAs of a pair.
 // Warp roles per CTA: 8 epilogue warps, NPW producer warps, and a light group with the MMA-issue warp (leader CTA
-// issues; the partner's relays its producers' arrivals), one idle warp and the 2 finalizer warps.
+// issues; the partner's relays its producers' arrivals), the loader warp and the 2 finalizer warps.
+// Measurements, the hardware ceiling of the MMA stream and the variants that were tried and dropped:
+// profiles/r2_step_tcq_summary.md.
 #include "ctdd_tc_common.cuh"
 
 namespace ctdd {
