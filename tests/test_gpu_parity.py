@@ -332,6 +332,32 @@ def test_tc_path_full_tiles_and_tail_match_simt():
                 assert np.abs(st1.cpu().numpy() - st2.cpu().numpy()).max() <= max(2, 2e-3 * N * D)
 
 
+def test_tc_path_strided_logits_view_equals_contiguous_copy():
+    """The conditional samplers hand the kernel the view logits[:, c:, :] of the network's output (pointer offset + batch
+    stride, reference sampling.py:369-426) - on the tensor path those rows are not contiguous across samples, so the loader
+    warp copies them row by row.  The result must be bit-equal to the same call on a contiguous copy, in every sampling
+    mode, for row counts with tile tails."""
+    from ctdd_b200 import ops
+    nat = _nat()
+    for (N, Dfull, c) in ((3, 29, 8), (6, 200, 72), (40, 340, 40)):
+        D = Dfull - c
+        fp, logits_full, x_full, S = _random_problem("gauss256", N, Dfull, 0.35, 41 + N, 12.0)
+        tb = _tables(fp, 0.35)
+        for loss_name, lt in (("CTElbo", None), ("CatRM", "reverse_prob")):
+            branch = nat.branch_for(loss_name, lt)
+            _, tct, tcs = _tc(tb, branch, S, nat.IMPL_AUTO)
+            lg = logits_full.cuda()
+            x = x_full[:, c:].contiguous().to(torch.int32).cuda()
+            lg_copy = lg[:, c:, :].contiguous()
+            common = dict(N=N, D=D, S=S, tc_tables=tct, tc_static=tcs, impl=nat.IMPL_TC, seed=11, offset=3)
+            for mode in (nat.MODE_TAU_LEAP, nat.MODE_TAU_LEAP_CORR, nat.MODE_MIDPOINT_DRIFT, nat.MODE_EULER):
+                a = ops.reverse_step(mode, branch, lg, x, tb["Q"], tb["QT"], tb["Rb"], tb["RbT"], tb["beta"], 0.01, 1e-9,
+                                     logits_offset_elems=c * S, batch_stride=Dfull * S, **common)["x"]
+                b = ops.reverse_step(mode, branch, lg_copy, x, tb["Q"], tb["QT"], tb["Rb"], tb["RbT"], tb["beta"], 0.01, 1e-9,
+                                     **common)["x"]
+                assert torch.equal(a, b), (N, Dfull, c, loss_name, mode)
+
+
 def test_free_running_histograms_vs_reference_law():
     """SURVEY §8c plan (4) / north_star: where bit-exactness cannot be claimed (threshold ties of the 3xBF16 tensor path,
     the chunked superposition map instead of S independent draws, the Cornish-Fisher quantile above lambda = 64) the full
