@@ -50,8 +50,13 @@ __device__ __forceinline__ void flush_stats(const RowStats& st, unsigned long lo
 
 // ------------------------------------------------------------------------------------------------
 // small S: thread per 8 rows
-template <int S>
-__global__ void __launch_bounds__(128) step_small_kernel(StepArgs a) {
+// MODE / BRANCH >= 0: the launch's mode and branch as compile-time constants (the two BASELINE configurations: every other
+// mode's code drops out of the instruction stream); -1: read from the arguments at run time.
+template <int S, int MODE = -1, int BRANCH = -1>
+__global__ void __launch_bounds__(128) step_small_kernel(StepArgs a_in) {
+  StepArgs a = a_in;
+  if (MODE >= 0) a.mode = MODE;
+  if (BRANCH >= 0) a.branch = BRANCH;
   __shared__ float sQ[S * S], sRb[S * S];
   for (int i = threadIdx.x; i < S * S; i += blockDim.x) { sQ[i] = a.Q[i]; sRb[i] = a.Rb[i]; }
   __syncthreads();
@@ -434,8 +439,18 @@ int launch_step_simt(const ctdd_step_params* p, cudaStream_t st) {
     const int threads = 128;
     const unsigned blocks = (unsigned)((groups + threads - 1) / threads);
     switch (S) {
-      case 2: step_small_kernel<2><<<blocks, threads, 0, st>>>(a); break;
-      case 3: step_small_kernel<3><<<blocks, threads, 0, st>>>(a); break;
+      case 2:   // C1: S = 2, tau-leaping on the tauLDR branch
+        if (a.mode == CTDD_MODE_TAU_LEAP && a.branch == CTDD_BRANCH_TAULDR)
+          step_small_kernel<2, CTDD_MODE_TAU_LEAP, CTDD_BRANCH_TAULDR><<<blocks, threads, 0, st>>>(a);
+        else
+          step_small_kernel<2><<<blocks, threads, 0, st>>>(a);
+        break;
+      case 3:   // C2: S = 3, Euler (LBJF) on the tauLDR branch
+        if (a.mode == CTDD_MODE_EULER && a.branch == CTDD_BRANCH_TAULDR)
+          step_small_kernel<3, CTDD_MODE_EULER, CTDD_BRANCH_TAULDR><<<blocks, threads, 0, st>>>(a);
+        else
+          step_small_kernel<3><<<blocks, threads, 0, st>>>(a);
+        break;
       case 4: step_small_kernel<4><<<blocks, threads, 0, st>>>(a); break;
       case 5: step_small_kernel<5><<<blocks, threads, 0, st>>>(a); break;
       case 6: step_small_kernel<6><<<blocks, threads, 0, st>>>(a); break;
