@@ -1000,6 +1000,10 @@ int launch_step_tcq(const ctdd_step_params* p, cudaStream_t st) {
   a.stats = reinterpret_cast<unsigned long long*>(p->stats_out);
   a.head_fix = p->head == CTDD_HEAD_LOGISTIC_FIX;
   a.head_mu = p->head_mu; a.head_ls = p->head_log_scale; a.head_bs = p->head_batch_stride;
+  if (a.rows >= (1LL << 31)) {      // the producers index rows with 32 bits (2^31 rows would be 2 TB of logits)
+    set_error("ctdd_reverse_step: N * D = %lld rows exceed the tensor path's 2^31 - 1", a.rows);
+    return 2;
+  }
   a.num_tiles = (int)((a.rows + NT - 1) / NT);
   int pairs = num_sms[dev & 63] / 2;                 // one CTA pair (cluster of 2) per TPC
   if (pairs > a.num_tiles) pairs = a.num_tiles;
