@@ -1,5 +1,8 @@
+"""Diagnostic (not part of the product): accuracy (vs an fp64 einsum) and time of ops.bgemm256 - the per-sample tcgen05
+GEMM of the loss path - at a few (B, D) shapes."""
+import os
 import sys,torch,time
-sys.path.insert(0,'/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ctdd_b200 import ops
 torch.manual_seed(0)
 for (B,D) in ((1,1),(2,130),(3,784),(5,3072),(64,3072),(80,300)):
