@@ -75,7 +75,10 @@ constexpr int TM_QH = 0, TM_QM = 128, TM_ACC = 256;  // TMEM column map (accumul
 // The logits ring is refilled per GROUP of 4 producer warps 4g .. 4g+3 (one per SM sub-partition, the same rank in each
 // scheduler's priority order, so they advance together): their 4 consecutive passes are 8 consecutive rows of one tile = one
 // 8 KB bulk copy per group and round.
-constexpr int GSZ = 4, NSUB = CTDD_TCQ_NPW / GSZ;
+#ifndef CTDD_GSZ
+#define CTDD_GSZ 4
+#endif
+constexpr int GSZ = CTDD_GSZ, NSUB = CTDD_TCQ_NPW / GSZ;   // (GSZ = 1, 2, 4: passes of a group never cross a tile boundary)
 #ifndef CTDD_PREFETCH_ROUNDS
 #define CTDD_PREFETCH_ROUNDS 0
 #endif
