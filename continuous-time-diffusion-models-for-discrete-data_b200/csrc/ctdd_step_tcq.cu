@@ -259,34 +259,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     auto row_of = [&](int Pq) -> uint32_t { return row00 + (uint32_t)(Pq >> 5) * tile_rows + 2u * (uint32_t)(Pq & 31); };
     const uint32_t scal_c_p = smem_u32(&sm.scal_c[0][0]), scal_x_p = smem_u32(&sm.scal_x[0][0]), band_p = smem_u32(&sm.band[0]);
 
-    // States (and head parameters): two passes of this warp ahead, into registers.
-    float f_mu = 0.f, f_ls = 0.f;        // HEAD: head parameters of the row fetch() just visited
+    // States: two passes of this warp ahead, into registers.
     auto fetch = [&](int Pq) -> int {
       int xv = -1;
       if (Pq < total_passes) {
         const uint32_t g = row_of(Pq) + half;
-        if (g < rows32) {
-          xv = __ldg(a.x_eval + g);
-          if (HEAD) {
-            long long src = g;
-            if (a.head_bs != (long long)a.D) {   // (N, 2D) network output viewed as two (N, D) halves
-              const uint32_t n = g / (uint32_t)a.D;
-              src = (long long)n * a.head_bs + (g - n * (uint32_t)a.D);
-            }
-            f_mu = __ldg(a.head_mu + src);
-            f_ls = __ldg(a.head_ls + src);
-          }
-        }
+        if (g < rows32) xv = __ldg(a.x_eval + g);
       }
       return xv;
     };
-    // Logits: the loader warp (light group) refills this warp's ring slot as soon as the warp reports that the current
-    // pass has its values in registers (lring_free); the rows were pulled from HBM into L2 some tiles earlier.
+    // Logits (HEAD: the rows' head records): the loader warp (light group) refills the ring slots of this warp's group as
+    // soon as its 4 warps report that the current pass has its values in registers (lring_free_g).
     int P = pw;
     int x_cur = fetch(P);
-    float mu_cur = f_mu, ls_cur = f_ls;
     int x_n1 = fetch(P + NPW);
-    float mu_n1 = f_mu, ls_n1 = f_ls;
     float4 t4[4];
     {
       const size_t xo = (size_t)(x_cur < 0 ? 0 : x_cur) << 8;
@@ -343,7 +329,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       if (ptr_on) TRACEQ(6, tl, 0);
 #endif
       const int rslot = ring_n % LRING;
-      if (!HEAD) mbar_wait(&sm.lring_full_g[rslot][pw / GSZ], (uint32_t)((ring_n / LRING) & 1));
+      mbar_wait(&sm.lring_full_g[rslot][pw / GSZ], (uint32_t)((ring_n / LRING) & 1));
 #ifdef CTDD_TC_TRACE
       if (pw == 0 && lane == 0) TRACEQ_ADD(0, tl, 3, clock64() - tq0);
       if (ptr_on) TRACEQ(6, tl, 1);
@@ -357,7 +343,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
           p_sum += __shfl_xor_sync(0xffffffffu, p_sum, o);
           if (!TAULDR) p_dot += __shfl_xor_sync(0xffffffffu, p_dot, o);
         }
-        head_numerators(mu_cur, ls_cur, a.head_fix != 0, l16, v);
+        // the row's head record (8 floats made by the loader warp): two broadcast 128-bit loads per half-warp
+        const uint32_t hsrc = smem_u32(&sm.lring[rslot][pw][half][0]);
+        const float4 h0 = lds128(hsrc), h1 = lds128(hsrc + 16);
+        ++ring_n;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.lring_free_g[rslot][pw / GSZ]);
+        const HeadRec hr = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        head_numerators_rec(hr, a.head_fix != 0, l16, v);
       } else {
         const uint32_t src = smem_u32(&sm.lring[rslot][pw][half][4 * l16]);
 #pragma unroll
@@ -473,9 +466,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         if (pw == 0 && lane == 0) TRACEQ(0, tl, 2);
       }
       x_cur = x_n1;
-      if (HEAD) { mu_cur = mu_n1; ls_cur = ls_n1; }
       x_n1 = fetch(P + 2 * NPW);
-      if (HEAD) { mu_n1 = f_mu; ls_n1 = f_ls; }
       P += NPW;
     }
     // the last pass's reductions and row scalars
@@ -506,13 +497,52 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
       const long long row00 = (long long)pair * NT + (int)rank * NH;      // first row of this CTA's half of its first tile
       const int total = my_tiles * PASSES_PER_TILE;
       const bool group_lane = !HEAD && lane < NSUB;
+      // HEAD: lanes 8g .. 8g+7 make the head records of the 8 rows of group g's round (lane & 7 = row of the round); the
+      // (mu, log_scale) of the next round are loaded one round ahead
+      const bool head_lane = HEAD && lane < 2 * GSZ * NSUB;
+      const int hg = lane / (2 * GSZ), hi = lane % (2 * GSZ);
+      float h_mu = 0.f, h_ls = 0.f;
+      auto head_load = [&](int round) {
+        h_mu = 0.f; h_ls = 0.f;
+        const int Pq = round * NPW + GSZ * hg + (hi >> 1);
+        if (!head_lane || Pq >= total) return;
+        const long long g = row00 + (long long)(Pq >> 5) * tile_rows + 2 * (Pq & 31) + (hi & 1);
+        if (g >= a.rows) return;
+        long long src = g;
+        if (a.head_bs != (long long)a.D) {   // (N, 2D) network output viewed as two (N, D) halves
+          const uint32_t n = (uint32_t)g / (uint32_t)a.D;
+          src = (long long)n * a.head_bs + ((uint32_t)g - n * (uint32_t)a.D);
+        }
+        h_mu = __ldg(a.head_mu + src);
+        h_ls = __ldg(a.head_ls + src);
+      };
+      if (HEAD) head_load(0);
       int grp = 0;               // (lanes < NSUB) next round of the lane's group: passes NPW * grp + 4 * lane .. + 3
       int fwd = 0;               // (lane 31) next tile whose scalars go to the partner
       while (true) {
         const bool more_f = lane == 31 && fwd < my_tiles;
         const bool more_g = group_lane && grp * NPW + GSZ * lane < total;
-        if (!__any_sync(0xffffffffu, more_f || more_g)) break;
+        const bool more_h = head_lane && grp * NPW + GSZ * hg < total;
+        if (!__any_sync(0xffffffffu, more_f || more_g || more_h)) break;
         bool did = false;
+        if (HEAD) {
+          // every group's slot of this round must be free (the three groups advance in lockstep here: one test each)
+          const int hslot = grp % LRING;
+          const bool free_ok = !more_h || grp < LRING || mbar_test(&sm.lring_free_g[hslot][hg], (uint32_t)((grp / LRING - 1) & 1));
+          if (__any_sync(0xffffffffu, more_h) && __all_sync(0xffffffffu, free_ok)) {
+            if (more_h) {
+              const HeadRec hr = head_row_record(h_mu, h_ls, a.head_fix != 0);
+              const uint32_t dst = smem_u32(&sm.lring[hslot][GSZ * hg + (hi >> 1)][hi & 1][0]);
+              sts128(dst, make_float4(hr.mu, hr.sc, hr.off0, hr.kap));
+              sts128(dst + 16, make_float4(hr.A, hr.B, hr.c, 0.f));
+            }
+            head_load(grp + 1);
+            __syncwarp();
+            if (more_h && hi == 0) mbar_arrive(&sm.lring_full_g[hslot][hg]);
+            ++grp;
+            did = true;
+          }
+        }
         const int gslot = grp % LRING;
         if (more_g && (grp < LRING || mbar_test(&sm.lring_free_g[gslot][lane], (uint32_t)((grp / LRING - 1) & 1)))) {
           // round grp of group `lane`: passes P0 .. P0 + 3 (4-aligned: never across a tile boundary) = 8 consecutive rows;

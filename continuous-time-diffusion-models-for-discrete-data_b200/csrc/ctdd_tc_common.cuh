@@ -352,25 +352,38 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void head_numerators(float mu, float ls, bool fix, int l16, float (&P)[16]) {
-  constexpr float L2E = 1.4426950408889634f, BW = 2.0f / S, EPS = 1e-6f;
+// The part of it that depends on the row only (8 floats): made once per row - by the loader warp in ctdd_step_tcq.cu, by
+// every lane in ctdd_step_tc.cu.
+struct HeadRec { float mu, sc, off0, kap, A, B, c, pad; };
+__device__ __forceinline__ HeadRec head_row_record(float mu, float ls, bool fix) {
+  constexpr float L2E = 1.4426950408889634f, BW = 2.0f / S;
   const float inv = expf(2.0f - ls);
-  const float kap = -expm1f(-inv * BW);
+  HeadRec h;
+  h.mu = mu;
+  h.kap = -expm1f(-inv * BW);
   const float z_first = (-1.0f - mu) * inv, z_last = (1.0f - mu) * inv;
   float c = 0.f;
   if (z_last < 0.f) c = -z_last; else if (fix && z_first > 0.f) c = -z_first;
-  const float A = c > 0.f ? expf(-c) : 1.0f, B = c < 0.f ? expf(c) : 1.0f;
-  // exponent (base 2) of e_j = exp(-z_j - c) for edge j = 64c + 4*l16 + k:  t_c * sc + off[k]
-  const float sc = -inv * L2E;
+  h.c = c;
+  h.A = c > 0.f ? expf(-c) : 1.0f;
+  h.B = c < 0.f ? expf(c) : 1.0f;
+  h.sc = -inv * L2E;             // exponent (base 2) of e_j = exp(-z_j - c) for edge j = 64c + 4*l16 + k:  t_c * sc + off[k]
+  h.off0 = -c * L2E;
+  h.pad = 0.f;
+  return h;
+}
+__device__ __forceinline__ void head_numerators_rec(const HeadRec& h, bool fix, int l16, float (&P)[16]) {
+  constexpr float BW = 2.0f / S, EPS = 1e-6f;
+  const float sc = h.sc, A = h.A, B = h.B, kap = h.kap, c = h.c;
   float off[5];
 #pragma unroll
-  for (int k = 0; k < 5; ++k) off[k] = fmaf((float)k * BW, sc, -c * L2E);
+  for (int k = 0; k < 5; ++k) off[k] = fmaf((float)k * BW, sc, h.off0);
   // select of the 1e-6 term:  no fix / c > 0 -> u,  fix and c == 0 -> min(u, v),  fix and c < 0 -> v
   const float bu = (fix && c < 0.f) ? 3.0e38f : 0.f;
   const float bv = (!fix || c > 0.f) ? 3.0e38f : 0.f;
 #pragma unroll
   for (int cc = 0; cc < 4; ++cc) {
-    const float t = (fmaf((float)(64 * cc + 4 * l16), BW, -1.0f)) - mu;       // edge - mu (the edge is exact in fp32)
+    const float t = (fmaf((float)(64 * cc + 4 * l16), BW, -1.0f)) - h.mu;       // edge - mu (the edge is exact in fp32)
     float u[5], vv[5];
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
@@ -388,6 +401,9 @@ __device__ __forceinline__ void head_numerators(float mu, float ls, bool fix, in
       }
     }
   }
+}
+__device__ __forceinline__ void head_numerators(float mu, float ls, bool fix, int l16, float (&P)[16]) {
+  head_numerators_rec(head_row_record(mu, ls, fix), fix, l16, P);
 }
 
 }  // namespace tc
