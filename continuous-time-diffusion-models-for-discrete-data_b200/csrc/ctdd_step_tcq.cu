@@ -247,7 +247,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     // (two independent rows per warp keep the pipes busy).  The raw logits rows arrive through a small smem ring that
     // cp.async.bulk fills two passes ahead, so no global-memory latency sits on the warp's critical path.
     const float* tabA = reinterpret_cast<const float*>(a.tab + TAB_A_OFF) + 4 * l16;
-    const float hb = (KM == KM_RATES) ? 1.0f : a.h * a.beta;   // rates-only ignores the step length
     uint64_t* const full_bar = rank == 0 ? &sm.full[0] : &sm.full_local[0];
     // passes of this CTA: pass P = 32 * tl + ps builds rows 2 ps, 2 ps + 1 of the CTA's 64 rows of its tl-th tile; warp pw
     // takes P = pw, pw + NPW, ..  The states are fetched two passes of the warp ahead;
@@ -257,7 +256,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     const uint32_t row00 = (uint32_t)pair * NT + rank * NH;      // first row of this CTA's half of its first tile
     const uint32_t rows32 = (uint32_t)a.rows;
     auto row_of = [&](int Pq) -> uint32_t { return row00 + (uint32_t)(Pq >> 5) * tile_rows + 2u * (uint32_t)(Pq & 31); };
-    const uint32_t scal_c_p = smem_u32(&sm.scal_c[0][0]), scal_x_p = smem_u32(&sm.scal_x[0][0]), band_p = smem_u32(&sm.band[0]);
+    const uint32_t scal_c_p = smem_u32(&sm.scal_c[0][0]), scal_x_p = smem_u32(&sm.scal_x[0][0]);
 
     // States: two passes of this warp ahead, into registers.
     auto fetch = [&](int Pq) -> int {
@@ -288,25 +287,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
     bool p_ok = false, p_have = false, p_last = false;
     auto finish_prev = [&]() {          // p_sum / p_dot hold the reduced values
       if (!p_have) return;
-      const float rs = __frcp_rn(p_sum);
-      float c1, c0;
-      if (TAULDR) {
-        c1 = hb * rs;                                            // lam_s = D_s * c1 * Rb[s,x]
-        c0 = 0.f;
-      } else {
-        const float inv = __frcp_rn(fmaf(p_dot, rs, 1e-35f));    // 1 / (pQ[x] + 1e-35)
-        c1 = hb * rs * inv;                                      // lam_s = (D_s * c1 + c0) * Rb[x,s]
-        c0 = hb * 1e-35f * inv;
-      }
-      if (l16 == 0) {   // one lane per half-warp: the row's scalars (the loader forwards the tile's 64 records to the partner CTA)
-        uint32_t bandx;
-        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(bandx) : "r"(band_p + (uint32_t)p_x));
-        const uint32_t sx = bandx | (p_ok ? (1u << 8) : 0u) | ((uint32_t)p_x << 10);
-        sts64(scal_c_p + (uint32_t)p_idx * 8u, __float_as_uint(c1), __float_as_uint(c0));
+      if (l16 == 0) {   // one lane per half-warp: the row's RAW sums and state; the loader warp turns the tile's 64 records
+                        // into the row scalars (reciprocals, rate scale, band mask) and forwards them to the partner CTA
+        const uint32_t sx = (p_ok ? (1u << 8) : 0u) | ((uint32_t)p_x << 10);
+        sts64(scal_c_p + (uint32_t)p_idx * 8u, __float_as_uint(p_sum), __float_as_uint(p_dot));
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(scal_x_p + (uint32_t)p_idx * 4u), "r"(sx) : "memory");
       }
       if (p_last) {
-        fence_proxy_async();     // the records are read by a bulk copy (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.scal_local[p_slot]);
       }
@@ -523,7 +510,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
         const bool more_f = lane == 31 && fwd < my_tiles;
         const bool more_g = group_lane && grp * NPW + GSZ * lane < total;
         const bool more_h = head_lane && grp * NPW + GSZ * hg < total;
-        if (!__any_sync(0xffffffffu, more_f || more_g || more_h)) break;
+        if (!__any_sync(0xffffffffu, more_f || more_g || more_h) && fwd >= my_tiles) break;
         bool did = false;
         if (HEAD) {
           // every group's slot of this round must be free (the three groups advance in lockstep here: one test each)
@@ -574,18 +561,47 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
           ++grp;
           did = true;
         }
+        // (fwd is kept by every lane; lane 31 tests and issues, all lanes turn the raw records into the row scalars)
+        const int fslot = fwd % RING;
+        const bool f_ready = fwd < my_tiles &&
+                             __shfl_sync(0xffffffffu, (lane == 31 && mbar_test(&sm.scal_local[fslot], (uint32_t)((fwd / RING) & 1))) ? 1 : 0, 31) != 0;
+        if (f_ready) {
+          const float hb = (KM == KM_RATES) ? 1.0f : a.h * a.beta;   // rates-only ignores the step length
+#pragma unroll
+          for (int rr = 0; rr < NH / 32; ++rr) {
+            const uint32_t idx = (uint32_t)fslot * NT + (uint32_t)(32 * rr + lane);       // (scal_*_p already point at this CTA's half)
+            float p_sum, p_dot;
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(p_sum), "=f"(p_dot) : "r"(scal_c_p + idx * 8u));
+            uint32_t sx;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sx) : "r"(scal_x_p + idx * 4u));
+            const float rs = __frcp_rn(p_sum);
+            float c1, c0;
+            if (TAULDR) {
+              c1 = hb * rs;                                            // lam_s = D_s * c1 * Rb[s,x]
+              c0 = 0.f;
+            } else {
+              const float inv = __frcp_rn(fmaf(p_dot, rs, 1e-35f));    // 1 / (pQ[x] + 1e-35)
+              c1 = hb * rs * inv;                                      // lam_s = (D_s * c1 + c0) * Rb[x,s]
+              c0 = hb * 1e-35f * inv;
+            }
+            sx |= (uint32_t)sm.band[(sx >> 10) & 255u];
+            sts64(scal_c_p + idx * 8u, __float_as_uint(c1), __float_as_uint(c0));
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(scal_x_p + idx * 4u), "r"(sx) : "memory");
+          }
+          fence_proxy_async();     // the records are read by a bulk copy (async proxy)
+          __syncwarp();
+        }
         if (more_f) {
-          const int slot = fwd % RING;
-          if (mbar_test(&sm.scal_local[slot], (uint32_t)((fwd / RING) & 1))) {
+          const int slot = fslot;
+          if (f_ready) {
             // local consumers: this arrival + the partner's 768 bytes complete the phase
             mbar_arrive_expect_tx(&sm.scal_full[slot], SCAL_TX_BYTES);
             const uint32_t bar = scal_full_remote + (uint32_t)slot * 8u;
             bulk_s2cluster(scal_c_remote + (uint32_t)slot * (NT * 8u), scal_c_p + (uint32_t)slot * (NT * 8u), NH * 8u, bar);
             bulk_s2cluster(scal_x_remote + (uint32_t)slot * (NT * 4u), scal_x_p + (uint32_t)slot * (NT * 4u), NH * 4u, bar);
-            ++fwd;
-            did = true;
           }
         }
+        if (f_ready) { ++fwd; did = true; }
         if (!__any_sync(0xffffffffu, did)) asm volatile("nanosleep.u32 32;");
       }
     }
