@@ -561,10 +561,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) step
           ++grp;
           did = true;
         }
-        // (fwd is kept by every lane; lane 31 tests and issues, all lanes turn the raw records into the row scalars)
+        // (fwd is kept by every lane; every lane tests the barrier itself - its own acquire of the producers' records - and all
+        // lanes turn the raw records into the row scalars; lane 31 issues the copies)
         const int fslot = fwd % RING;
-        const bool f_ready = fwd < my_tiles &&
-                             __shfl_sync(0xffffffffu, (lane == 31 && mbar_test(&sm.scal_local[fslot], (uint32_t)((fwd / RING) & 1))) ? 1 : 0, 31) != 0;
+        const bool f_ready = fwd < my_tiles && __all_sync(0xffffffffu, mbar_test(&sm.scal_local[fslot], (uint32_t)((fwd / RING) & 1)));
         if (f_ready) {
           const float hb = (KM == KM_RATES) ? 1.0f : a.h * a.beta;   // rates-only ignores the step length
 #pragma unroll
