@@ -37,7 +37,7 @@ enum : uint32_t {
 struct Philox4 { uint32_t w[4]; };
 
 __host__ __device__ __forceinline__ void philox_mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && !defined(CTDD_PHILOX_WIDE)
   lo = a * b;
   hi = __umulhi(a, b);
 #else
@@ -84,11 +84,15 @@ __host__ __device__ __forceinline__ uint32_t philox_word(const Philox4& p, int i
 }
 
 // Per-row 32-bit draw: one Philox call serves 4 consecutive global rows: counter = (sub, grow >> 2, ...).
+__host__ __device__ __forceinline__ Philox4 philox_row_call(uint64_t grow, uint32_t sub, uint64_t offset,
+                                                           uint32_t stream, uint64_t seed) {
+  return philox4x32_10(sub, (uint32_t)(grow >> 2), (uint32_t)offset,
+                       stream | (((uint32_t)(offset >> 32) & 0xFFFFu) << 8) | (((uint32_t)(grow >> 34) & 0xFFu) << 24),
+                       (uint32_t)seed, (uint32_t)(seed >> 32));
+}
 __host__ __device__ __forceinline__ uint32_t philox_row_word(uint64_t grow, uint32_t sub, uint64_t offset,
                                                             uint32_t stream, uint64_t seed) {
-  Philox4 p = philox4x32_10(sub, (uint32_t)(grow >> 2), (uint32_t)offset,
-                            stream | (((uint32_t)(offset >> 32) & 0xFFFFu) << 8) | (((uint32_t)(grow >> 34) & 0xFFu) << 24),
-                            (uint32_t)seed, (uint32_t)(seed >> 32));
+  const Philox4 p = philox_row_call(grow, sub, offset, stream, seed);
   return p.w[grow & 3];
 }
 

@@ -7,9 +7,17 @@
 // path (superposition map, ctdd_common.cuh), so the three are interchangeable up to fp32 rounding of the rates.
 // Reference arithmetic: lib/sampling/sampling.py:31-78 (rates), :127-160 (tau-leap), :278-293 (Euler),
 // :423-453 / :459-503 (midpoint), :170-221 (corrector); lib/models/model_utils.py:30-60.
+#define CTDD_PHILOX_WIDE 1   // this file is issue-bound on the Philox rounds: one 32x32->64 multiply per round half
 #include "ctdd_common.cuh"
 
 namespace ctdd {
+
+// softmax pieces of the small-S kernel: ex2.approx / rcp.approx (<= 2 ulp; the parity bar on the rates is 1e-4 relative)
+__device__ __forceinline__ float fast_rcp(float v) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
 
 struct StepArgs {
   int mode, branch, D, S, reject_multi;
@@ -57,8 +65,11 @@ __global__ void __launch_bounds__(128) step_small_kernel(StepArgs a_in) {
   StepArgs a = a_in;
   if (MODE >= 0) a.mode = MODE;
   if (BRANCH >= 0) a.branch = BRANCH;
-  __shared__ float sQ[S * S], sRb[S * S];
-  for (int i = threadIdx.x; i < S * S; i += blockDim.x) { sQ[i] = a.Q[i]; sRb[i] = a.Rb[i]; }
+  __shared__ float sQ[S * S], sRb[S * S], sQi[S * S];   // sQi = 1 / (q_t|0 + eps): the tauLDR denominator, once per CTA
+  for (int i = threadIdx.x; i < S * S; i += blockDim.x) {
+    const float q = a.Q[i];
+    sQ[i] = q; sRb[i] = a.Rb[i]; sQi[i] = 1.0f / (q + a.eps);
+  }
   __syncthreads();
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // local row group
   const long long r0 = g * 8;
@@ -86,12 +97,41 @@ __global__ void __launch_bounds__(128) step_small_kernel(StepArgs a_in) {
       }
     }
     int xe[8], xb[8];
+    const bool vec_x = nr == 8 && ((reinterpret_cast<uintptr_t>(a.x_eval) | reinterpret_cast<uintptr_t>(a.x_base) |
+                                    reinterpret_cast<uintptr_t>(a.x_out)) & 15) == 0;   // r0 is a multiple of 8
+    if (vec_x) {
+      const int4 e0 = __ldg(reinterpret_cast<const int4*>(a.x_eval + r0)), e1 = __ldg(reinterpret_cast<const int4*>(a.x_eval + r0) + 1);
+      xe[0] = e0.x; xe[1] = e0.y; xe[2] = e0.z; xe[3] = e0.w; xe[4] = e1.x; xe[5] = e1.y; xe[6] = e1.z; xe[7] = e1.w;
+      if (a.x_base) {
+        const int4 b0 = __ldg(reinterpret_cast<const int4*>(a.x_base + r0)), b1 = __ldg(reinterpret_cast<const int4*>(a.x_base + r0) + 1);
+        xb[0] = b0.x; xb[1] = b0.y; xb[2] = b0.z; xb[3] = b0.w; xb[4] = b1.x; xb[5] = b1.y; xb[6] = b1.z; xb[7] = b1.w;
+      } else {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const long long rr_ = r0 + (r < nr ? r : 0);
-      xe[r] = a.x_eval[rr_];
-      xb[r] = a.x_base ? a.x_base[rr_] : xe[r];
+        for (int r = 0; r < 8; ++r) xb[r] = xe[r];
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const long long rr_ = r0 + (r < nr ? r : 0);
+        xe[r] = a.x_eval[rr_];
+        xb[r] = a.x_base ? a.x_base[rr_] : xe[r];
+      }
     }
+    // per-row 32-bit uniforms (Euler / exact posterior): one Philox call serves 4 consecutive global rows, and the 8 rows
+    // of a thread start at a multiple of 8 (row_offset is one too), so 2 calls serve the thread
+    uint32_t rw[8];
+    if (a.mode == CTDD_MODE_EXACT || a.mode == CTDD_MODE_EULER || a.mode == CTDD_MODE_EULER_CORR) {
+      const uint64_t g0 = (uint64_t)(a.row_offset + r0);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const Philox4 pq = philox_row_call(g0 + 4 * q, 0, a.offset, STREAM_ROW, a.seed);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rw[4 * q + i] = pq.w[i];
+      }
+    }
+    int xn_out[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) xn_out[r] = 0;
     // rates: rate[r][s] holds rr with the s==x entry zeroed (the quantity every mode consumes)
     float rate[8][S];
 #pragma unroll
@@ -102,7 +142,8 @@ __global__ void __launch_bounds__(128) step_small_kernel(StepArgs a_in) {
       for (int s = 1; s < S; ++s) m = fmaxf(m, lg[r][s]);
       float e[S], sum = 0.f;
 #pragma unroll
-      for (int s = 0; s < S; ++s) { e[s] = expf(lg[r][s] - m); sum += e[s]; }
+      for (int s = 0; s < S; ++s) { e[s] = __expf(lg[r][s] - m); sum += e[s]; }
+      const float inv_sum = fast_rcp(sum);     // sum in [1, S]
       if (a.mode == CTDD_MODE_EXACT) {
         // sampling.py:1008-1052: weight[s'] = (sum_k p_k q_{t-h|0}[k,s']) * q_{t|t-h}[s', x]  (second factor: a.RbT[x][s'])
         float wgt[S];
@@ -110,18 +151,18 @@ __global__ void __launch_bounds__(128) step_small_kernel(StepArgs a_in) {
         for (int s = 0; s < S; ++s) {
           float acc = 0.f;
 #pragma unroll
-          for (int k = 0; k < S; ++k) acc = fmaf(e[k] / sum, sQ[k * S + s], acc);
+          for (int k = 0; k < S; ++k) acc = fmaf(e[k] * inv_sum, sQ[k * S + s], acc);
           wgt[s] = acc * __ldg(a.RbT + (size_t)x * S + s);
         }
-        const float v = u32_to_unit(philox_row_word((uint64_t)(a.row_offset + r0 + r), 0, a.offset, STREAM_ROW, a.seed));
+        const float v = u32_to_unit(rw[r]);
         const int xn = inv_cdf(S, v, [&](int s) {
           float w = 0.f;
 #pragma unroll
           for (int q = 0; q < S; ++q) w = (q == s) ? wgt[q] : w;
           return w;
         });
+        xn_out[r] = xn;
         if (r < nr) {
-          a.x_out[r0 + r] = xn;
           st.changed_base += (xn != xb[r]);
           st.changed_eval += (xn != x);
         }
@@ -133,7 +174,7 @@ __global__ void __launch_bounds__(128) step_small_kernel(StepArgs a_in) {
       if (a.branch == CTDD_BRANCH_TAULDR) {
         float w[S];
 #pragma unroll
-        for (int k = 0; k < S; ++k) w[k] = (e[k] / sum) / (sQ[k * S + x] + a.eps);
+        for (int k = 0; k < S; ++k) w[k] = (e[k] * inv_sum) * sQi[k * S + x];
 #pragma unroll
         for (int s = 0; s < S; ++s) {
           float acc = 0.f;
@@ -152,7 +193,7 @@ __global__ void __launch_bounds__(128) step_small_kernel(StepArgs a_in) {
           } else if (a.branch == CTDD_BRANCH_SDDM_REVERSE_PROB) {
             float acc = 0.f;
 #pragma unroll
-            for (int k = 0; k < S; ++k) acc = fmaf(e[k] / sum, sQ[k * S + s], acc);
+            for (int k = 0; k < S; ++k) acc = fmaf(e[k] * inv_sum, sQ[k * S + s], acc);
             ll[s] = logf(acc + 1e-35f);
           } else {
             float t[S], tm = -INFINITY;
@@ -206,7 +247,7 @@ __global__ void __launch_bounds__(128) step_small_kernel(StepArgs a_in) {
           for (int q = 0; q < S; ++q) w = (q == s) ? rate[r][q] : w;
           return __fmul_rn(w, h);
         });
-        a.x_out[r0 + r] = finalize_jump(xb[r], xe[r], jc.x, jc.y, a.reject_multi, S, st);
+        xn_out[r] = finalize_jump(xb[r], xe[r], jc.x, jc.y, a.reject_multi, S, st);
       }
     } else if (a.mode == CTDD_MODE_MIDPOINT_DRIFT) {
 #pragma unroll
@@ -217,8 +258,8 @@ __global__ void __launch_bounds__(128) step_small_kernel(StepArgs a_in) {
         const int ch = (int)rintf(0.5f * a.h * acc);
         int xn = xe[r] + ch;
         xn = xn < 0 ? 0 : (xn > S - 1 ? S - 1 : xn);
+        xn_out[r] = xn;
         if (r < nr) {
-          a.x_out[r0 + r] = xn;
           st.changed_base += (xn != xe[r]);
           st.changed_eval += (xn != xe[r]);
           st.nonzero += (ch != 0);
@@ -232,7 +273,7 @@ __global__ void __launch_bounds__(128) step_small_kernel(StepArgs a_in) {
         for (int s = 0; s < S; ++s) tot += rate[r][s];
         const float diag = fmaxf(0.f, 1.f - a.h * tot);
         const int x = xe[r];
-        const float v = u32_to_unit(philox_row_word((uint64_t)(a.row_offset + r0 + r), 0, a.offset, STREAM_ROW, a.seed));
+        const float v = u32_to_unit(rw[r]);
         float P[S];
 #pragma unroll
         for (int s = 0; s < S; ++s) P[s] = (s == x) ? diag : rate[r][s] * a.h;
@@ -242,12 +283,23 @@ __global__ void __launch_bounds__(128) step_small_kernel(StepArgs a_in) {
           for (int q = 0; q < S; ++q) w = (q == s) ? P[q] : w;
           return w;
         });
+        xn_out[r] = xn;
         if (r < nr) {
-          a.x_out[r0 + r] = xn;
           st.changed_base += (xn != xb[r]);
           st.changed_eval += (xn != x);
         }
       }
+    }
+    if (a.mode == CTDD_MODE_RATES_ONLY) {
+      // no state update
+    } else if (vec_x) {
+      int4* o = reinterpret_cast<int4*>(a.x_out + r0);
+      o[0] = make_int4(xn_out[0], xn_out[1], xn_out[2], xn_out[3]);
+      o[1] = make_int4(xn_out[4], xn_out[5], xn_out[6], xn_out[7]);
+    } else {
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r < nr) a.x_out[r0 + r] = xn_out[r];
     }
   }
   flush_stats(st, a.stats);
