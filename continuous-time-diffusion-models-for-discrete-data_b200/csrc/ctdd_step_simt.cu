@@ -37,7 +37,64 @@ struct StepArgs {
   float* rr_out;
   float* ratio_out;
   unsigned long long* stats;
+  uint32_t pk[20];       // Philox key schedule of `seed` (key of round r: pk[2r], pk[2r+1]), made once on the host
 };
+
+// Philox4x32-10 with the round keys read from the kernel arguments (constant bank operands): the same function as
+// philox4x32_10(c0, c1, c2, c3, seed_lo, seed_hi), 4 instructions per round instead of 6.
+__device__ __forceinline__ Philox4 philox_keyed(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t (&pk)[20]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ pk[2 * r];
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ pk[2 * r + 1];
+    c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
+  }
+  Philox4 o; o.w[0] = c0; o.w[1] = c1; o.w[2] = c2; o.w[3] = c3;
+  return o;
+}
+
+// Tau-leap of one row with S <= 8 states (one chunk of the superposition map): the draws, thresholds and sums of
+// tau_leap_row_seq (ctdd_common.cuh) with the row's Philox counter words prepared by the caller.
+//   c1 = low word of the global row, c2 = low word of the offset, c3 = stream word (philox_rowjump)
+template <int S>
+__device__ __forceinline__ int2 tau_leap_small(const float (&lam)[S], int x, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               const uint32_t (&pk)[20]) {
+  float tot = 0.f;
+#pragma unroll
+  for (int s = 0; s < S; ++s) tot = __fadd_rn(tot, lam[s]);
+  const Philox4 p0 = philox_keyed(0u, c1, c2, c3, pk);
+  const float v0 = u32_to_unit(p0.w[0]);
+  if (v0 >= tot) return make_int2(0, 0);          // P(K >= 1) <= tot: no jump (also tot <= 0 and NaN-free rows)
+  int K = poisson_from_unit(tot, v0);
+  if (K <= 0) return make_int2(0, 0);
+  if (K > JUMP_PICK_CAP) K = JUMP_PICK_CAP;
+  int jump = 0;
+  Philox4 pc = p0;
+  for (int j = 0; j < K; ++j) {
+    uint32_t w;
+    if (j < 3) {
+      w = philox_word(p0, 1 + j);
+    } else {
+      const int i = j - 3;
+      if ((i & 3) == 0) pc = philox_keyed(1u + (uint32_t)(i >> 2), c1, c2, c3, pk);
+      w = philox_word(pc, i & 3);
+    }
+    const float target = __fmul_rn(fminf(u32_to_unit(w), 0.99999994f), tot);
+    float cum = 0.f;
+    int last = 0, pick = -1;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      cum = __fadd_rn(cum, lam[s]);
+      if (lam[s] > 0.f) last = s;
+      if (pick < 0 && cum > target) pick = s;
+    }
+    if (pick < 0) pick = last;
+    jump += pick - x;
+  }
+  return make_int2(jump, K);
+}
 
 __device__ __forceinline__ const float* logits_row(const StepArgs& a, long long r) {
   const long long n = r / a.D, d = r - n * a.D;
@@ -124,7 +181,9 @@ __global__ void __launch_bounds__(128) step_small_kernel(StepArgs a_in) {
       const uint64_t g0 = (uint64_t)(a.row_offset + r0);
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
-        const Philox4 pq = philox_row_call(g0 + 4 * q, 0, a.offset, STREAM_ROW, a.seed);
+        const uint64_t gq = g0 + 4 * q;
+        const Philox4 pq = philox_keyed(0u, (uint32_t)(gq >> 2), (uint32_t)a.offset,
+                                        STREAM_ROW | (((uint32_t)(a.offset >> 32) & 0xFFFFu) << 8) | (((uint32_t)(gq >> 34) & 0xFFu) << 24), a.pk);
 #pragma unroll
         for (int i = 0; i < 4; ++i) rw[4 * q + i] = pq.w[i];
       }
@@ -237,16 +296,16 @@ __global__ void __launch_bounds__(128) step_small_kernel(StepArgs a_in) {
       }
     }
     if (a.mode == CTDD_MODE_TAU_LEAP || a.mode == CTDD_MODE_TAU_LEAP_CORR || a.mode == CTDD_MODE_MIDPOINT_JUMP) {
+      // the thread's 8 global rows share everything of the Philox counter but the low 3 bits of the row
+      const uint64_t g0 = (uint64_t)(a.row_offset + r0);
+      const uint32_t c3 = STREAM_JUMP | (((uint32_t)(a.offset >> 32) & 0xFFFFu) << 8) | (((uint32_t)(g0 >> 32) & 0xFFu) << 24);
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         if (r >= nr) continue;
-        const float h = a.h;
-        const int2 jc = tau_leap_row_seq(S, xe[r], (uint64_t)(a.row_offset + r0 + r), a.offset, a.seed, [&](int s) {
-          float w = 0.f;
+        float lam[S];
 #pragma unroll
-          for (int q = 0; q < S; ++q) w = (q == s) ? rate[r][q] : w;
-          return __fmul_rn(w, h);
-        });
+        for (int s = 0; s < S; ++s) lam[s] = __fmul_rn(rate[r][s], a.h);
+        const int2 jc = tau_leap_small<S>(lam, xe[r], (uint32_t)g0 | (uint32_t)r, (uint32_t)a.offset, c3, a.pk);
         xn_out[r] = finalize_jump(xb[r], xe[r], jc.x, jc.y, a.reject_multi, S, st);
       }
     } else if (a.mode == CTDD_MODE_MIDPOINT_DRIFT) {
@@ -485,6 +544,10 @@ int launch_step_simt(const ctdd_step_params* p, cudaStream_t st) {
   a.beta = p->beta; a.h = p->h; a.eps = p->eps; a.seed = p->seed; a.offset = p->offset;
   a.x_out = p->x_out; a.rr_out = p->rr_out; a.ratio_out = p->ratio_out;
   a.stats = reinterpret_cast<unsigned long long*>(p->stats_out);
+  for (int r = 0; r < 10; ++r) {
+    a.pk[2 * r] = (uint32_t)p->seed + (uint32_t)r * 0x9E3779B9u;
+    a.pk[2 * r + 1] = (uint32_t)(p->seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+  }
   const int S = p->S;
   if (S <= 8 && S >= 2) {
     const long long groups = (a.rows + 7) / 8;
