@@ -13,6 +13,11 @@
 namespace ctdd {
 
 // softmax pieces of the small-S kernel: ex2.approx / rcp.approx (<= 2 ulp; the parity bar on the rates is 1e-4 relative)
+__device__ __forceinline__ float fast_exp(float v) {       // v <= 0; flushes results below 2^-126 to zero
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v * 1.4426950408889634f));
+  return r;
+}
 __device__ __forceinline__ float fast_rcp(float v) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
@@ -56,18 +61,16 @@ __device__ __forceinline__ Philox4 philox_keyed(uint32_t c0, uint32_t c1, uint32
 }
 
 // Tau-leap of one row with S <= 8 states (one chunk of the superposition map): the draws, thresholds and sums of
-// tau_leap_row_seq (ctdd_common.cuh) with the row's Philox counter words prepared by the caller.
+// tau_leap_row_seq (ctdd_common.cuh) with the row's Philox counter words prepared by the caller.  Out of line: one
+// copy serves the 8 unrolled rows of a thread (the kernel was stalling on instruction fetch).
 //   c1 = low word of the global row, c2 = low word of the offset, c3 = stream word (philox_rowjump)
+//   tot = sequential fp32 sum of lam from 0, p0 = call 0 of the row (made by the caller, who has already handled the
+//   common case u(p0.w[0]) >= tot, i.e. no jump)
+template <int S> struct LamVec { float v[S]; };
 template <int S>
-__device__ __forceinline__ int2 tau_leap_small(const float (&lam)[S], int x, uint32_t c1, uint32_t c2, uint32_t c3,
-                                               const uint32_t (&pk)[20]) {
-  float tot = 0.f;
-#pragma unroll
-  for (int s = 0; s < S; ++s) tot = __fadd_rn(tot, lam[s]);
-  const Philox4 p0 = philox_keyed(0u, c1, c2, c3, pk);
-  const float v0 = u32_to_unit(p0.w[0]);
-  if (v0 >= tot) return make_int2(0, 0);          // P(K >= 1) <= tot: no jump (also tot <= 0 and NaN-free rows)
-  int K = poisson_from_unit(tot, v0);
+__device__ __noinline__ int2 tau_leap_small(LamVec<S> lam, float tot, Philox4 p0, int x, uint32_t c1, uint32_t c2,
+                                            uint32_t c3, uint32_t k0, uint32_t k1) {
+  int K = poisson_from_unit(tot, u32_to_unit(p0.w[0]));
   if (K <= 0) return make_int2(0, 0);
   if (K > JUMP_PICK_CAP) K = JUMP_PICK_CAP;
   int jump = 0;
@@ -78,7 +81,7 @@ __device__ __forceinline__ int2 tau_leap_small(const float (&lam)[S], int x, uin
       w = philox_word(p0, 1 + j);
     } else {
       const int i = j - 3;
-      if ((i & 3) == 0) pc = philox_keyed(1u + (uint32_t)(i >> 2), c1, c2, c3, pk);
+      if ((i & 3) == 0) pc = philox4x32_10(1u + (uint32_t)(i >> 2), c1, c2, c3, k0, k1);
       w = philox_word(pc, i & 3);
     }
     const float target = __fmul_rn(fminf(u32_to_unit(w), 0.99999994f), tot);
@@ -86,8 +89,8 @@ __device__ __forceinline__ int2 tau_leap_small(const float (&lam)[S], int x, uin
     int last = 0, pick = -1;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-      cum = __fadd_rn(cum, lam[s]);
-      if (lam[s] > 0.f) last = s;
+      cum = __fadd_rn(cum, lam.v[s]);
+      if (lam.v[s] > 0.f) last = s;
       if (pick < 0 && cum > target) pick = s;
     }
     if (pick < 0) pick = last;
@@ -117,11 +120,14 @@ __device__ __forceinline__ void flush_stats(const RowStats& st, unsigned long lo
 // small S: thread per 8 rows
 // MODE / BRANCH >= 0: the launch's mode and branch as compile-time constants (the two BASELINE configurations: every other
 // mode's code drops out of the instruction stream); -1: read from the arguments at run time.
-template <int S, int MODE = -1, int BRANCH = -1>
+// LEAN: the launch has dense logits and no rr_out / ratio_out (the samplers' call): the strided-row loads and the
+// (predicated, but issued) rate stores drop out as well.
+template <int S, int MODE = -1, int BRANCH = -1, bool LEAN = false>
 __global__ void __launch_bounds__(128) step_small_kernel(StepArgs a_in) {
   StepArgs a = a_in;
   if (MODE >= 0) a.mode = MODE;
   if (BRANCH >= 0) a.branch = BRANCH;
+  if (LEAN) { a.rr_out = nullptr; a.ratio_out = nullptr; a.ld = S; a.batch_stride = (long long)a.D * S; }
   __shared__ float sQ[S * S], sRb[S * S], sQi[S * S];   // sQi = 1 / (q_t|0 + eps): the tauLDR denominator, once per CTA
   for (int i = threadIdx.x; i < S * S; i += blockDim.x) {
     const float q = a.Q[i];
@@ -148,7 +154,7 @@ __global__ void __launch_bounds__(128) step_small_kernel(StepArgs a_in) {
     } else {
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        const float* p = logits_row(a, r0 + (r < nr ? r : 0));
+        const float* p = LEAN ? a.logits + (r0 + (r < nr ? r : 0)) * S : logits_row(a, r0 + (r < nr ? r : 0));
 #pragma unroll
         for (int s = 0; s < S; ++s) lg[r][s] = __ldg(p + s);
       }
@@ -200,8 +206,16 @@ __global__ void __launch_bounds__(128) step_small_kernel(StepArgs a_in) {
 #pragma unroll
       for (int s = 1; s < S; ++s) m = fmaxf(m, lg[r][s]);
       float e[S], sum = 0.f;
+      if (S == 2) {      // the larger logit's term is exp(0) = 1 exactly
+        const float d = lg[r][1] - lg[r][0];
+        const float es = fast_exp(-fabsf(d));
+        e[0] = d > 0.f ? es : 1.0f;
+        e[S - 1] = d > 0.f ? 1.0f : es;
+        sum = 1.0f + es;
+      } else {
 #pragma unroll
-      for (int s = 0; s < S; ++s) { e[s] = __expf(lg[r][s] - m); sum += e[s]; }
+        for (int s = 0; s < S; ++s) { e[s] = fast_exp(lg[r][s] - m); sum += e[s]; }
+      }
       const float inv_sum = fast_rcp(sum);     // sum in [1, S]
       if (a.mode == CTDD_MODE_EXACT) {
         // sampling.py:1008-1052: weight[s'] = (sum_k p_k q_{t-h|0}[k,s']) * q_{t|t-h}[s', x]  (second factor: a.RbT[x][s'])
@@ -302,11 +316,24 @@ __global__ void __launch_bounds__(128) step_small_kernel(StepArgs a_in) {
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         if (r >= nr) continue;
-        float lam[S];
+        LamVec<S> lam;
 #pragma unroll
-        for (int s = 0; s < S; ++s) lam[s] = __fmul_rn(rate[r][s], a.h);
-        const int2 jc = tau_leap_small<S>(lam, xe[r], (uint32_t)g0 | (uint32_t)r, (uint32_t)a.offset, c3, a.pk);
-        xn_out[r] = finalize_jump(xb[r], xe[r], jc.x, jc.y, a.reject_multi, S, st);
+        for (int s = 0; s < S; ++s) lam.v[s] = __fmul_rn(rate[r][s], a.h);
+        float tot = 0.f;
+#pragma unroll
+        for (int s = 0; s < S; ++s) tot = __fadd_rn(tot, lam.v[s]);
+        const Philox4 p0 = philox_keyed(0u, (uint32_t)g0 | (uint32_t)r, (uint32_t)a.offset, c3, a.pk);
+        const float v0 = u32_to_unit(p0.w[0]);
+        if (v0 >= tot) {       // P(K >= 1) <= tot: no jump (the common case) - finalize_jump(xb, xe, 0, 0, ...)
+          const int xn = xb[r] < 0 ? 0 : (xb[r] > S - 1 ? S - 1 : xb[r]);
+          st.changed_base += (xn != xb[r]);
+          st.changed_eval += (xn != xe[r]);
+          xn_out[r] = xn;
+        } else {
+          const int2 jc = tau_leap_small<S>(lam, tot, p0, xe[r], (uint32_t)g0 | (uint32_t)r, (uint32_t)a.offset, c3,
+                                            (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+          xn_out[r] = finalize_jump(xb[r], xe[r], jc.x, jc.y, a.reject_multi, S, st);
+        }
       }
     } else if (a.mode == CTDD_MODE_MIDPOINT_DRIFT) {
 #pragma unroll
@@ -553,16 +580,17 @@ int launch_step_simt(const ctdd_step_params* p, cudaStream_t st) {
     const long long groups = (a.rows + 7) / 8;
     const int threads = 128;
     const unsigned blocks = (unsigned)((groups + threads - 1) / threads);
+    const bool lean = !a.rr_out && !a.ratio_out && a.ld == S && a.batch_stride == (long long)a.D * S;
     switch (S) {
       case 2:   // C1: S = 2, tau-leaping on the tauLDR branch
-        if (a.mode == CTDD_MODE_TAU_LEAP && a.branch == CTDD_BRANCH_TAULDR)
-          step_small_kernel<2, CTDD_MODE_TAU_LEAP, CTDD_BRANCH_TAULDR><<<blocks, threads, 0, st>>>(a);
+        if (a.mode == CTDD_MODE_TAU_LEAP && a.branch == CTDD_BRANCH_TAULDR && lean)
+          step_small_kernel<2, CTDD_MODE_TAU_LEAP, CTDD_BRANCH_TAULDR, true><<<blocks, threads, 0, st>>>(a);
         else
           step_small_kernel<2><<<blocks, threads, 0, st>>>(a);
         break;
       case 3:   // C2: S = 3, Euler (LBJF) on the tauLDR branch
-        if (a.mode == CTDD_MODE_EULER && a.branch == CTDD_BRANCH_TAULDR)
-          step_small_kernel<3, CTDD_MODE_EULER, CTDD_BRANCH_TAULDR><<<blocks, threads, 0, st>>>(a);
+        if (a.mode == CTDD_MODE_EULER && a.branch == CTDD_BRANCH_TAULDR && lean)
+          step_small_kernel<3, CTDD_MODE_EULER, CTDD_BRANCH_TAULDR, true><<<blocks, threads, 0, st>>>(a);
         else
           step_small_kernel<3><<<blocks, threads, 0, st>>>(a);
         break;
