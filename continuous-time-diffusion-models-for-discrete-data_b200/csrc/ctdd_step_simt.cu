@@ -128,12 +128,27 @@ __global__ void __launch_bounds__(128) step_small_kernel(StepArgs a_in) {
   if (MODE >= 0) a.mode = MODE;
   if (BRANCH >= 0) a.branch = BRANCH;
   if (LEAN) { a.rr_out = nullptr; a.ratio_out = nullptr; a.ld = S; a.batch_stride = (long long)a.D * S; }
+  // TABLE (lean tauLDR launches without corrector): everything of h * rate[s] that does not depend on the logits is
+  // folded, once per CTA, into sT[x][k][s] = h * beta * Rb[s][x] * q[k][s] / (q[k][x] + eps), zero at s == x, so that
+  // h * rate[s] = (sum_k e_k sT[x][k][s]) / sum_k e_k: S*S FMAs and S multiplies per row
+  constexpr bool TABLE = LEAN && S == 2 && BRANCH == CTDD_BRANCH_TAULDR && (MODE == CTDD_MODE_TAU_LEAP || MODE == CTDD_MODE_EULER);
+  constexpr int TQ = (S * S + 3) / 4;                    // float4 per x
   __shared__ float sQ[S * S], sRb[S * S], sQi[S * S];   // sQi = 1 / (q_t|0 + eps): the tauLDR denominator, once per CTA
+  __shared__ float4 sT4[TABLE ? S * TQ : 1];
   for (int i = threadIdx.x; i < S * S; i += blockDim.x) {
     const float q = a.Q[i];
     sQ[i] = q; sRb[i] = a.Rb[i]; sQi[i] = 1.0f / (q + a.eps);
   }
   __syncthreads();
+  if (TABLE) {
+    float* sT = reinterpret_cast<float*>(sT4);
+    for (int i = threadIdx.x; i < S * TQ * 4; i += blockDim.x) {
+      const int x = i / (TQ * 4), ks = i - x * (TQ * 4), k = ks / S, t = ks - k * S;
+      sT[i] = (ks < S * S && t != x) ? ((a.beta * sRb[t * S + x]) * (sQ[k * S + t] * sQi[k * S + x])) * a.h : 0.f;
+    }
+    __syncthreads();
+  }
+  const float hh = TABLE ? 1.0f : a.h;      // TABLE: rate[][] already holds h * rate
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // local row group
   const long long r0 = g * 8;
   RowStats st = {0, 0, 0, 0, 0};
@@ -243,6 +258,22 @@ __global__ void __launch_bounds__(128) step_small_kernel(StepArgs a_in) {
         for (int s = 0; s < S; ++s) rate[r][s] = 0.f;
         continue;
       }
+      if (TABLE) {
+        float T[TQ * 4];
+#pragma unroll
+        for (int i = 0; i < TQ; ++i) {
+          const float4 t4 = sT4[x * TQ + i];
+          T[4 * i] = t4.x; T[4 * i + 1] = t4.y; T[4 * i + 2] = t4.z; T[4 * i + 3] = t4.w;
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          float acc = 0.f;
+#pragma unroll
+          for (int k = 0; k < S; ++k) acc = fmaf(e[k], T[k * S + s], acc);
+          rate[r][s] = acc * inv_sum;
+        }
+        continue;
+      }
       float ratio[S], rfull[S];
       if (a.branch == CTDD_BRANCH_TAULDR) {
         float w[S];
@@ -318,7 +349,7 @@ __global__ void __launch_bounds__(128) step_small_kernel(StepArgs a_in) {
         if (r >= nr) continue;
         LamVec<S> lam;
 #pragma unroll
-        for (int s = 0; s < S; ++s) lam.v[s] = __fmul_rn(rate[r][s], a.h);
+        for (int s = 0; s < S; ++s) lam.v[s] = TABLE ? rate[r][s] : __fmul_rn(rate[r][s], a.h);
         float tot = 0.f;
 #pragma unroll
         for (int s = 0; s < S; ++s) tot = __fadd_rn(tot, lam.v[s]);
@@ -357,12 +388,12 @@ __global__ void __launch_bounds__(128) step_small_kernel(StepArgs a_in) {
         float tot = 0.f;
 #pragma unroll
         for (int s = 0; s < S; ++s) tot += rate[r][s];
-        const float diag = fmaxf(0.f, 1.f - a.h * tot);
+        const float diag = fmaxf(0.f, 1.f - hh * tot);
         const int x = xe[r];
         const float v = u32_to_unit(rw[r]);
         float P[S];
 #pragma unroll
-        for (int s = 0; s < S; ++s) P[s] = (s == x) ? diag : rate[r][s] * a.h;
+        for (int s = 0; s < S; ++s) P[s] = (s == x) ? diag : rate[r][s] * hh;
         const int xn = inv_cdf(S, v, [&](int s) {
           float w = 0.f;
 #pragma unroll
