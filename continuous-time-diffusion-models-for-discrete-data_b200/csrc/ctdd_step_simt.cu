@@ -64,12 +64,13 @@ __device__ __forceinline__ Philox4 philox_keyed(uint32_t c0, uint32_t c1, uint32
 // tau_leap_row_seq (ctdd_common.cuh) with the row's Philox counter words prepared by the caller.  Out of line: one
 // copy serves the 8 unrolled rows of a thread (the kernel was stalling on instruction fetch).
 //   c1 = low word of the global row, c2 = low word of the offset, c3 = stream word (philox_rowjump)
-//   tot = sequential fp32 sum of lam from 0, p0 = call 0 of the row (made by the caller, who has already handled the
-//   common case u(p0.w[0]) >= tot, i.e. no jump)
+//   tot = sequential fp32 sum of lam from 0; the caller has already handled the common case u(call 0 word 0) >= tot,
+//   i.e. no jump
 template <int S> struct LamVec { float v[S]; };
 template <int S>
-__device__ __noinline__ int2 tau_leap_small(LamVec<S> lam, float tot, Philox4 p0, int x, uint32_t c1, uint32_t c2,
-                                            uint32_t c3, uint32_t k0, uint32_t k1) {
+__device__ __noinline__ int2 tau_leap_small(LamVec<S> lam, float tot, int x, uint32_t c1, uint32_t c2, uint32_t c3,
+                                            uint32_t k0, uint32_t k1) {
+  const Philox4 p0 = philox4x32_10(0u, c1, c2, c3, k0, k1);
   int K = poisson_from_unit(tot, u32_to_unit(p0.w[0]));
   if (K <= 0) return make_int2(0, 0);
   if (K > JUMP_PICK_CAP) K = JUMP_PICK_CAP;
@@ -120,10 +121,19 @@ __device__ __forceinline__ void flush_stats(const RowStats& st, unsigned long lo
 // small S: thread per 8 rows
 // MODE / BRANCH >= 0: the launch's mode and branch as compile-time constants (the two BASELINE configurations: every other
 // mode's code drops out of the instruction stream); -1: read from the arguments at run time.
+// The S = 2 lean instantiation is compiled for 8 CTAs of 128 threads per SM (64 registers) and runs as a grid-stride
+// kernel on a capped grid (a CTA pays its table prologue once for several groups of rows): 3.0 -> 3.2 TB/s at 33 M rows.
+// The S = 3 one measured 7 % slower that way (4.4 vs 4.8 TB/s) and keeps one group per thread.
+#ifndef CTDD_SMALL_MINB
+#define CTDD_SMALL_MINB 8
+#endif
+#ifndef CTDD_SMALL_GRIDCAP
+#define CTDD_SMALL_GRIDCAP 64u   // CTAs per SM of the capped grid
+#endif
 // LEAN: the launch has dense logits and no rr_out / ratio_out (the samplers' call): the strided-row loads and the
 // (predicated, but issued) rate stores drop out as well.
 template <int S, int MODE = -1, int BRANCH = -1, bool LEAN = false>
-__global__ void __launch_bounds__(128) step_small_kernel(StepArgs a_in) {
+__global__ void __launch_bounds__(128, (LEAN && S == 2) ? CTDD_SMALL_MINB : 0) step_small_kernel(StepArgs a_in) {
   StepArgs a = a_in;
   if (MODE >= 0) a.mode = MODE;
   if (BRANCH >= 0) a.branch = BRANCH;
@@ -149,10 +159,14 @@ __global__ void __launch_bounds__(128) step_small_kernel(StepArgs a_in) {
     __syncthreads();
   }
   const float hh = TABLE ? 1.0f : a.h;      // TABLE: rate[][] already holds h * rate
-  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // local row group
-  const long long r0 = g * 8;
   RowStats st = {0, 0, 0, 0, 0};
-  if (r0 < a.rows) {
+  // STRIDE: grid-stride over groups of 8 rows on a capped grid; otherwise one group per thread
+  constexpr bool STRIDE = LEAN && S == 2;
+  long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  do {
+    const long long r0 = g * 8;
+    if (r0 >= a.rows) break;
+    g += (long long)gridDim.x * blockDim.x;
     const int nr = (a.rows - r0) < 8 ? (int)(a.rows - r0) : 8;
     float lg[8][S];
     const bool contiguous = (a.ld == S) && (a.batch_stride == (long long)a.D * S) && nr == 8;
@@ -344,6 +358,11 @@ __global__ void __launch_bounds__(128) step_small_kernel(StepArgs a_in) {
       // the thread's 8 global rows share everything of the Philox counter but the low 3 bits of the row
       const uint64_t g0 = (uint64_t)(a.row_offset + r0);
       const uint32_t c3 = STREAM_JUMP | (((uint32_t)(a.offset >> 32) & 0xFFFFu) << 8) | (((uint32_t)(g0 >> 32) & 0xFFu) << 24);
+      // word 0 of call 0 of all 8 rows first: 8 independent Philox chains for the scheduler to interleave (the pick
+      // path, rare, makes its row's call again)
+      uint32_t w0[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) w0[r] = philox_keyed(0u, (uint32_t)g0 | (uint32_t)r, (uint32_t)a.offset, c3, a.pk).w[0];
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         if (r >= nr) continue;
@@ -353,15 +372,14 @@ __global__ void __launch_bounds__(128) step_small_kernel(StepArgs a_in) {
         float tot = 0.f;
 #pragma unroll
         for (int s = 0; s < S; ++s) tot = __fadd_rn(tot, lam.v[s]);
-        const Philox4 p0 = philox_keyed(0u, (uint32_t)g0 | (uint32_t)r, (uint32_t)a.offset, c3, a.pk);
-        const float v0 = u32_to_unit(p0.w[0]);
+        const float v0 = u32_to_unit(w0[r]);
         if (v0 >= tot) {       // P(K >= 1) <= tot: no jump (the common case) - finalize_jump(xb, xe, 0, 0, ...)
           const int xn = xb[r] < 0 ? 0 : (xb[r] > S - 1 ? S - 1 : xb[r]);
           st.changed_base += (xn != xb[r]);
           st.changed_eval += (xn != xe[r]);
           xn_out[r] = xn;
         } else {
-          const int2 jc = tau_leap_small<S>(lam, tot, p0, xe[r], (uint32_t)g0 | (uint32_t)r, (uint32_t)a.offset, c3,
+          const int2 jc = tau_leap_small<S>(lam, tot, xe[r], (uint32_t)g0 | (uint32_t)r, (uint32_t)a.offset, c3,
                                             (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
           xn_out[r] = finalize_jump(xb[r], xe[r], jc.x, jc.y, a.reject_multi, S, st);
         }
@@ -418,7 +436,7 @@ __global__ void __launch_bounds__(128) step_small_kernel(StepArgs a_in) {
       for (int r = 0; r < 8; ++r)
         if (r < nr) a.x_out[r0 + r] = xn_out[r];
     }
-  }
+  } while (STRIDE);
   flush_stats(st, a.stats);
 }
 
@@ -610,12 +628,13 @@ int launch_step_simt(const ctdd_step_params* p, cudaStream_t st) {
   if (S <= 8 && S >= 2) {
     const long long groups = (a.rows + 7) / 8;
     const int threads = 128;
-    const unsigned blocks = (unsigned)((groups + threads - 1) / threads);
+    unsigned blocks = (unsigned)((groups + threads - 1) / threads);
     const bool lean = !a.rr_out && !a.ratio_out && a.ld == S && a.batch_stride == (long long)a.D * S;
     switch (S) {
       case 2:   // C1: S = 2, tau-leaping on the tauLDR branch
-        if (a.mode == CTDD_MODE_TAU_LEAP && a.branch == CTDD_BRANCH_TAULDR && lean)
-          step_small_kernel<2, CTDD_MODE_TAU_LEAP, CTDD_BRANCH_TAULDR, true><<<blocks, threads, 0, st>>>(a);
+        if (a.mode == CTDD_MODE_TAU_LEAP && a.branch == CTDD_BRANCH_TAULDR && lean)    // grid-stride instantiation
+          step_small_kernel<2, CTDD_MODE_TAU_LEAP, CTDD_BRANCH_TAULDR, true>
+              <<<blocks > 148u * CTDD_SMALL_GRIDCAP ? 148u * CTDD_SMALL_GRIDCAP : blocks, threads, 0, st>>>(a);
         else
           step_small_kernel<2><<<blocks, threads, 0, st>>>(a);
         break;
