@@ -301,7 +301,9 @@ def run_ours(args, w, rank, world, local_rank):
     x = torch.clamp(x0 + torch.randint(-3, 4, x0.shape, device=dev), 0, S - 1).to(torch.int32)
     row_offset = rank * B * D          # B is a multiple of 8, so every rank's first global row is 8-aligned
     stats = torch.zeros((nsteps, 8), dtype=torch.int64, device=dev)
-    flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev) if B * D * S * 4 < (512 << 20) else None
+    # L2 flush for inputs smaller than L2; 1 GB so that the fill also outlasts the host's launch path (else the event
+    # pair around a 10-microsecond kernel times the Python call, not the kernel)
+    flush = torch.empty((1 << 30,), dtype=torch.uint8, device=dev) if B * D * S * 4 < (512 << 20) else None
 
     def step(i, xin, logits):
         return ops.reverse_step(mode, branch, logits, xin, Q[i], QT[i], Rb, RbT, beta[i], h, 1e-9, N=B, D=D, S=S,
