@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(128, (LEAN && S == 2) ? CTDD_SMALL_MINB : 0) s
   // folded, once per CTA, into sT[x][k][s] = h * beta * Rb[s][x] * q[k][s] / (q[k][x] + eps), zero at s == x, so that
   // h * rate[s] = (sum_k e_k sT[x][k][s]) / sum_k e_k: S*S FMAs and S multiplies per row
   constexpr bool TABLE = LEAN && S == 2 && BRANCH == CTDD_BRANCH_TAULDR && (MODE == CTDD_MODE_TAU_LEAP || MODE == CTDD_MODE_EULER);
+  constexpr bool ONE = TABLE && S == 2 && MODE == CTDD_MODE_TAU_LEAP;   // one jump target per row: only its rate is made
   constexpr int TQ = (S * S + 3) / 4;                    // float4 per x
   __shared__ float sQ[S * S], sRb[S * S], sQi[S * S];   // sQi = 1 / (q_t|0 + eps): the tauLDR denominator, once per CTA
   __shared__ float4 sT4[TABLE ? S * TQ : 1];
@@ -157,6 +158,14 @@ __global__ void __launch_bounds__(128, (LEAN && S == 2) ? CTDD_SMALL_MINB : 0) s
       sT[i] = (ks < S * S && t != x) ? ((a.beta * sRb[t * S + x]) * (sQ[k * S + t] * sQi[k * S + x])) * a.h : 0.f;
     }
     __syncthreads();
+    if (ONE) {       // S = 2: the only target of x is 1 - x; sT[x] = {T[x][0][1-x], T[x][1][1-x], -, -}
+      float v = 0.f;
+      const int x = threadIdx.x >> 2, k = threadIdx.x & 3;
+      if (threadIdx.x < 8 && k < 2) v = sT[x * 4 + k * 2 + (1 - x)];
+      __syncthreads();
+      if (threadIdx.x < 8) sT[threadIdx.x] = v;
+      __syncthreads();
+    }
   }
   const float hh = TABLE ? 1.0f : a.h;      // TABLE: rate[][] already holds h * rate
   RowStats st = {0, 0, 0, 0, 0};
@@ -272,6 +281,12 @@ __global__ void __launch_bounds__(128, (LEAN && S == 2) ? CTDD_SMALL_MINB : 0) s
         for (int s = 0; s < S; ++s) rate[r][s] = 0.f;
         continue;
       }
+      if (ONE) {
+        const float4 t4 = sT4[x];
+        rate[r][0] = fmaf(e[S - 1], t4.y, fmaf(e[0], t4.x, 0.f)) * inv_sum;      // h * rate of the state 1 - x
+        rate[r][S - 1] = 0.f;
+        continue;
+      }
       if (TABLE) {
         float T[TQ * 4];
 #pragma unroll
@@ -367,11 +382,17 @@ __global__ void __launch_bounds__(128, (LEAN && S == 2) ? CTDD_SMALL_MINB : 0) s
       for (int r = 0; r < 8; ++r) {
         if (r >= nr) continue;
         LamVec<S> lam;
-#pragma unroll
-        for (int s = 0; s < S; ++s) lam.v[s] = TABLE ? rate[r][s] : __fmul_rn(rate[r][s], a.h);
         float tot = 0.f;
+        if (ONE) {       // 0 + lam_0 + lam_1 with one of them zero
+          tot = rate[r][0];
+          lam.v[0] = xe[r] == 0 ? 0.f : tot;
+          lam.v[S - 1] = xe[r] == 0 ? tot : 0.f;
+        } else {
 #pragma unroll
-        for (int s = 0; s < S; ++s) tot = __fadd_rn(tot, lam.v[s]);
+          for (int s = 0; s < S; ++s) lam.v[s] = TABLE ? rate[r][s] : __fmul_rn(rate[r][s], a.h);
+#pragma unroll
+          for (int s = 0; s < S; ++s) tot = __fadd_rn(tot, lam.v[s]);
+        }
         const float v0 = u32_to_unit(w0[r]);
         if (v0 >= tot) {       // P(K >= 1) <= tot: no jump (the common case) - finalize_jump(xb, xe, 0, 0, ...)
           const int xn = xb[r] < 0 ? 0 : (xb[r] > S - 1 ? S - 1 : xb[r]);
