@@ -65,6 +65,31 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
   return o;
 }
 
+// Round keys of Philox4x32-10 for `seed` (key of round r: pk[2r], pk[2r+1]); the launchers make them once on the host
+// and pass them in the kernel arguments.
+inline void philox_key_schedule(unsigned long long seed, uint32_t (&pk)[20]) {
+  for (int r = 0; r < 10; ++r) {
+    pk[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
+    pk[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+  }
+}
+#ifdef __CUDACC__
+// Philox4x32-10 with the round keys read from the kernel arguments (constant bank operands): the same function as
+// philox4x32_10(c0, c1, c2, c3, seed_lo, seed_hi), 4 instructions per round instead of 6.
+__device__ __forceinline__ Philox4 philox_keyed(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t (&pk)[20]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ pk[2 * r];
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ pk[2 * r + 1];
+    c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
+  }
+  Philox4 o; o.w[0] = c0; o.w[1] = c1; o.w[2] = c2; o.w[3] = c3;
+  return o;
+}
+#endif
+
 // Tau-leap draws of one GLOBAL row: the states are cut into chunks of JUMP_CHUNK consecutive states; chunk q draws its
 // own total and picks from Philox calls (q << 16) + c of the row's stream, counter = (call, grow, offset_lo, stream | ...).
 //   call 0 word 0     -> uniform of the chunk's TOTAL jump count K ~ Poisson(sum of the chunk's lam_s)

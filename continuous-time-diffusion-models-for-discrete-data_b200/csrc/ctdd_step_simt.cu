@@ -45,21 +45,6 @@ struct StepArgs {
   uint32_t pk[20];       // Philox key schedule of `seed` (key of round r: pk[2r], pk[2r+1]), made once on the host
 };
 
-// Philox4x32-10 with the round keys read from the kernel arguments (constant bank operands): the same function as
-// philox4x32_10(c0, c1, c2, c3, seed_lo, seed_hi), 4 instructions per round instead of 6.
-__device__ __forceinline__ Philox4 philox_keyed(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t (&pk)[20]) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
-    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ pk[2 * r];
-    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ pk[2 * r + 1];
-    c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
-  }
-  Philox4 o; o.w[0] = c0; o.w[1] = c1; o.w[2] = c2; o.w[3] = c3;
-  return o;
-}
-
 // Tau-leap of one row with S <= 8 states (one chunk of the superposition map): the draws, thresholds and sums of
 // tau_leap_row_seq (ctdd_common.cuh) with the row's Philox counter words prepared by the caller.  Out of line: one
 // copy serves the 8 unrolled rows of a thread (the kernel was stalling on instruction fetch).
@@ -641,10 +626,7 @@ int launch_step_simt(const ctdd_step_params* p, cudaStream_t st) {
   a.beta = p->beta; a.h = p->h; a.eps = p->eps; a.seed = p->seed; a.offset = p->offset;
   a.x_out = p->x_out; a.rr_out = p->rr_out; a.ratio_out = p->ratio_out;
   a.stats = reinterpret_cast<unsigned long long*>(p->stats_out);
-  for (int r = 0; r < 10; ++r) {
-    a.pk[2 * r] = (uint32_t)p->seed + (uint32_t)r * 0x9E3779B9u;
-    a.pk[2 * r + 1] = (uint32_t)(p->seed >> 32) + (uint32_t)r * 0xBB67AE85u;
-  }
+  philox_key_schedule(p->seed, a.pk);
   const int S = p->S;
   if (S <= 8 && S >= 2) {
     const long long groups = (a.rows + 7) / 8;
