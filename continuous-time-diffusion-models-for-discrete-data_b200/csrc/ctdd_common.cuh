@@ -26,7 +26,7 @@ void count_launch(int n = 1);
 // RNG streams (Philox counter word c3)
 enum : uint32_t {
   STREAM_JUMP = 0,      // per-row tau-leap draws, per chunk of 32 states: call 0 word 0 = total count, further words = picks
-  STREAM_RESERVED = 1,
+  STREAM_JUMP_COUNT = 1, // S <= JUMP_SHARED_MAX_S: uniform of a row's total jump count, one call per 4 consecutive rows
   STREAM_ROW = 2,       // one 32-bit uniform per row (Euler categorical draw)
   STREAM_INIT = 3,      // initial samples
   STREAM_NOISE_XT = 4,  // forward noising x_t
@@ -97,8 +97,12 @@ __device__ __forceinline__ Philox4 philox_keyed(uint32_t c0, uint32_t c1, uint32
 // Each pick chooses its target state ~ Categorical(lam_s / sum) by inverse CDF: S independent Poisson counts through
 // the superposition identity, chunks independent of one another (oracle/rng.py poisson_rows is the op-for-op
 // restatement).  One warp of the tensor-path epilogue owns one chunk of a row, so no warp waits for another's total.
+// State spaces of at most JUMP_SHARED_MAX_S states (one chunk; a row is 4*S + 8 bytes, a Philox call per row would be the
+// whole cost of the step): the TOTAL's uniform of row g is word g & 3 of the call (0, g >> 2, offset, STREAM_JUMP_COUNT)
+// shared by 4 consecutive rows (philox_row_word); the picks still come from the row's own calls, words 1..3 of call 0 first.
 constexpr int JUMP_PICK_CAP = 4096;
 constexpr int JUMP_CHUNK = 32;
+constexpr int JUMP_SHARED_MAX_S = 8;
 __host__ __device__ __forceinline__ Philox4 philox_rowjump(uint64_t grow, uint32_t call, uint64_t offset, uint64_t seed) {
   return philox4x32_10(call, (uint32_t)grow, (uint32_t)offset,
                        STREAM_JUMP | (((uint32_t)(offset >> 32) & 0xFFFFu) << 8) | (((uint32_t)(grow >> 32) & 0xFFu) << 24),
@@ -209,7 +213,8 @@ __device__ __forceinline__ int2 tau_leap_row_seq(int S, int x, uint64_t grow, ui
     float tot = 0.f;
     for (int s = c0; s < c1; ++s) tot = __fadd_rn(tot, lam(s));
     const Philox4 p0 = philox_rowjump(grow, cbase, offset, seed);
-    int K = poisson_from_unit(tot, u32_to_unit(p0.w[0]));
+    const uint32_t w0 = S <= JUMP_SHARED_MAX_S ? philox_row_word(grow, 0, offset, STREAM_JUMP_COUNT, seed) : p0.w[0];
+    int K = poisson_from_unit(tot, u32_to_unit(w0));
     if (K <= 0) continue;
     if (K > JUMP_PICK_CAP) K = JUMP_PICK_CAP;
     Ksum += K;

@@ -49,14 +49,26 @@ struct StepArgs {
 // tau_leap_row_seq (ctdd_common.cuh) with the row's Philox counter words prepared by the caller.  Out of line: one
 // copy serves the 8 unrolled rows of a thread (the kernel was stalling on instruction fetch).
 //   c1 = low word of the global row, c2 = low word of the offset, c3 = stream word (philox_rowjump)
-//   tot = sequential fp32 sum of lam from 0; the caller has already handled the common case u(call 0 word 0) >= tot,
-//   i.e. no jump
+//   tot = sequential fp32 sum of lam from 0, v0 = the uniform of the total count (shared call, JUMP_SHARED_MAX_S);
+//   the caller has already handled the common case v0 >= tot, i.e. no jump
+// words of the per-row uniforms of 8 consecutive global rows starting at g0 (a multiple of 8): 2 calls
+__device__ __forceinline__ void row_words8(uint64_t g0, uint32_t stream, uint64_t offset, const uint32_t (&pk)[20], uint32_t (&rw)[8]) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const uint64_t gq = g0 + 4 * q;
+    const Philox4 pq = philox_keyed(0u, (uint32_t)(gq >> 2), (uint32_t)offset,
+                                    stream | (((uint32_t)(offset >> 32) & 0xFFFFu) << 8) | (((uint32_t)(gq >> 34) & 0xFFu) << 24), pk);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rw[4 * q + i] = pq.w[i];
+  }
+}
+
 template <int S> struct LamVec { float v[S]; };
 template <int S>
-__device__ __noinline__ int2 tau_leap_small(LamVec<S> lam, float tot, int x, uint32_t c1, uint32_t c2, uint32_t c3,
-                                            uint32_t k0, uint32_t k1) {
-  const Philox4 p0 = philox4x32_10(0u, c1, c2, c3, k0, k1);
-  int K = poisson_from_unit(tot, u32_to_unit(p0.w[0]));
+__device__ __noinline__ int2 tau_leap_small(LamVec<S> lam, float tot, float v0, int x, uint32_t c1, uint32_t c2,
+                                            uint32_t c3, uint32_t k0, uint32_t k1) {
+  const Philox4 p0 = philox4x32_10(0u, c1, c2, c3, k0, k1);      // words 1..3: picks 0..2
+  int K = poisson_from_unit(tot, v0);
   if (K <= 0) return make_int2(0, 0);
   if (K > JUMP_PICK_CAP) K = JUMP_PICK_CAP;
   int jump = 0;
@@ -203,20 +215,13 @@ __global__ void __launch_bounds__(128, (LEAN && S == 2) ? CTDD_SMALL_MINB : 0) s
         xb[r] = a.x_base ? a.x_base[rr_] : xe[r];
       }
     }
-    // per-row 32-bit uniforms (Euler / exact posterior): one Philox call serves 4 consecutive global rows, and the 8 rows
-    // of a thread start at a multiple of 8 (row_offset is one too), so 2 calls serve the thread
+    // per-row 32-bit uniforms (Euler / exact posterior: the row's draw; tau-leaping with S <= 8: the uniform of the
+    // row's total jump count): one Philox call serves 4 consecutive global rows, and the 8 rows of a thread start at a
+    // multiple of 8 (row_offset is one too), so 2 calls serve the thread
     uint32_t rw[8];
-    if (a.mode == CTDD_MODE_EXACT || a.mode == CTDD_MODE_EULER || a.mode == CTDD_MODE_EULER_CORR) {
-      const uint64_t g0 = (uint64_t)(a.row_offset + r0);
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const uint64_t gq = g0 + 4 * q;
-        const Philox4 pq = philox_keyed(0u, (uint32_t)(gq >> 2), (uint32_t)a.offset,
-                                        STREAM_ROW | (((uint32_t)(a.offset >> 32) & 0xFFFFu) << 8) | (((uint32_t)(gq >> 34) & 0xFFu) << 24), a.pk);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) rw[4 * q + i] = pq.w[i];
-      }
-    }
+    static_assert(S <= JUMP_SHARED_MAX_S, "the small-S kernel takes the jump count's uniform from the shared call");
+    if (a.mode == CTDD_MODE_EXACT || a.mode == CTDD_MODE_EULER || a.mode == CTDD_MODE_EULER_CORR)
+      row_words8((uint64_t)(a.row_offset + r0), STREAM_ROW, a.offset, a.pk, rw);
     int xn_out[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) xn_out[r] = 0;
@@ -358,11 +363,7 @@ __global__ void __launch_bounds__(128, (LEAN && S == 2) ? CTDD_SMALL_MINB : 0) s
       // the thread's 8 global rows share everything of the Philox counter but the low 3 bits of the row
       const uint64_t g0 = (uint64_t)(a.row_offset + r0);
       const uint32_t c3 = STREAM_JUMP | (((uint32_t)(a.offset >> 32) & 0xFFFFu) << 8) | (((uint32_t)(g0 >> 32) & 0xFFu) << 24);
-      // word 0 of call 0 of all 8 rows first: 8 independent Philox chains for the scheduler to interleave (the pick
-      // path, rare, makes its row's call again)
-      uint32_t w0[8];
-#pragma unroll
-      for (int r = 0; r < 8; ++r) w0[r] = philox_keyed(0u, (uint32_t)g0 | (uint32_t)r, (uint32_t)a.offset, c3, a.pk).w[0];
+      row_words8(g0, STREAM_JUMP_COUNT, a.offset, a.pk, rw);       // uniforms of the 8 rows' total jump counts
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         if (r >= nr) continue;
@@ -378,14 +379,14 @@ __global__ void __launch_bounds__(128, (LEAN && S == 2) ? CTDD_SMALL_MINB : 0) s
 #pragma unroll
           for (int s = 0; s < S; ++s) tot = __fadd_rn(tot, lam.v[s]);
         }
-        const float v0 = u32_to_unit(w0[r]);
+        const float v0 = u32_to_unit(rw[r]);
         if (v0 >= tot) {       // P(K >= 1) <= tot: no jump (the common case) - finalize_jump(xb, xe, 0, 0, ...)
           const int xn = xb[r] < 0 ? 0 : (xb[r] > S - 1 ? S - 1 : xb[r]);
           st.changed_base += (xn != xb[r]);
           st.changed_eval += (xn != xe[r]);
           xn_out[r] = xn;
         } else {
-          const int2 jc = tau_leap_small<S>(lam, tot, xe[r], (uint32_t)g0 | (uint32_t)r, (uint32_t)a.offset, c3,
+          const int2 jc = tau_leap_small<S>(lam, tot, v0, xe[r], (uint32_t)g0 | (uint32_t)r, (uint32_t)a.offset, c3,
                                             (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
           xn_out[r] = finalize_jump(xb[r], xe[r], jc.x, jc.y, a.reject_multi, S, st);
         }

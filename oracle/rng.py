@@ -17,6 +17,10 @@ This module defines that map bit-for-bit the way the CUDA kernels evaluate it:
     and independence); chunks are independent of one another, so no warp waits for another warp's total;
     Philox call c of chunk q of row g: counter ((q << 16) + c, g, offset, STREAM_JUMP); word 0 of call 0 is the
     total's uniform, words 1..3 picks 0..2, call 1 + (j-3)//4 word (j-3)%4 pick j >= 3;
+    state spaces of at most 8 states (one chunk; a row is only 4*S + 8 bytes, so a Philox call per row would be the
+    whole cost of the step): the total's uniform of row g is instead word g & 3 of the call
+    (0, g >> 2, offset, STREAM_JUMP_COUNT) shared by 4 consecutive rows, like the per-row uniforms below; the picks
+    (rare) still come from the row's own STREAM_JUMP calls, words 1..3 of call 0 first;
   * per-row uniforms (Euler, initial state, noising): one call serves 4 consecutive rows (word row & 3);
   * v = (word + 0.5) * 2^-32 in fp32; Poisson by upper-tail inverse CDF; categorical by sequential fp32 cumsum.
 """
@@ -25,7 +29,8 @@ from __future__ import annotations
 import numpy as np
 
 STREAM_JUMP = 0       # per-row tau-leap draws (total count + picks)
-STREAM_RESERVED = 1
+STREAM_JUMP_COUNT = 1  # S <= JUMP_SHARED_MAX_S: the total count's uniform, one call per 4 consecutive rows
+JUMP_SHARED_MAX_S = 8
 JUMP_PICK_CAP = 4096  # picks evaluated per chunk of a row (rows whose total exceeds it are clamp-saturated anyway)
 JUMP_CHUNK = 32       # consecutive states that share one superposition draw (one warp of the tensor-path epilogue)
 STREAM_ROW = 2
@@ -82,7 +87,7 @@ def rowjump_words(grow: np.ndarray, offset: int, seed: int, call) -> np.ndarray:
 
 
 def rowjump_total_unit(rows: int, row_offset: int, offset: int, seed: int) -> np.ndarray:
-    """fp32 (rows,): the uniform that decides the row's total jump count."""
+    """fp32 (rows,): the uniform that decides the total jump count of chunk 0 of a row with more than 8 states."""
     grow = np.arange(rows, dtype=np.uint64) + np.uint64(row_offset)
     return u32_to_unit(rowjump_words(grow, offset, seed, 0)[:, 0])
 
@@ -105,7 +110,13 @@ def rowjump_pick_units(grow: np.ndarray, offset: int, seed: int, npicks: int, ca
 
 def row_units(rows: int, row_offset: int, offset: int, stream: int, seed: int, sub: int = 0) -> np.ndarray:
     """fp32 (rows,) per-row uniforms v in (0, 1]."""
-    grow = np.arange(rows, dtype=np.uint64) + np.uint64(row_offset)
+    return row_units_at(np.arange(rows, dtype=np.uint64) + np.uint64(row_offset), offset, stream, seed, sub)
+
+
+def row_units_at(grow: np.ndarray, offset: int, stream: int, seed: int, sub: int = 0) -> np.ndarray:
+    """fp32 (len(grow),) per-row uniforms of the given global rows: word grow & 3 of the call of row group grow >> 2."""
+    grow = np.asarray(grow, dtype=np.uint64)
+    rows = grow.shape[0]
     w = philox4x32_10(np.uint64(sub), (grow >> np.uint64(2)) & _MASK, np.uint64(offset & 0xFFFFFFFF),
                       _c3(stream, offset, grow >> np.uint64(34)), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     words = np.stack(w, axis=-1)
@@ -194,12 +205,19 @@ def inv_cdf(weights: np.ndarray, v: np.ndarray) -> np.ndarray:
     return first.astype(np.int64)
 
 
-def _poisson_chunk(lam: np.ndarray, grow: np.ndarray, call_base: int, offset: int, seed: int):
+def count_units(grow: np.ndarray, offset: int, seed: int, call_base: int, shared: bool) -> np.ndarray:
+    """fp32 (len(grow),): the uniform that decides a chunk's total jump count (module docstring)."""
+    if shared:
+        return row_units_at(grow, offset, STREAM_JUMP_COUNT, seed)
+    return u32_to_unit(rowjump_words(grow, offset, seed, call_base)[:, 0])
+
+
+def _poisson_chunk(lam: np.ndarray, grow: np.ndarray, call_base: int, offset: int, seed: int, shared: bool = False):
     """One chunk of states of poisson_rows: (counts (rows, n) int64, K (rows,) int64); Philox calls call_base + c."""
     rows, n = lam.shape
     cum = np.cumsum(lam, axis=1, dtype=np.float32)
     tot = cum[:, -1]
-    v0 = u32_to_unit(rowjump_words(grow, offset, seed, call_base)[:, 0])
+    v0 = count_units(grow, offset, seed, call_base, shared)
     K = poisson_from_unit(tot, v0)
     counts = np.zeros((rows, n), dtype=np.int64)
     idx = np.flatnonzero(K > 0)
@@ -241,7 +259,7 @@ def poisson_rows(lam: np.ndarray, row_offset: int, offset: int, seed: int):
     K = np.zeros(rows, dtype=np.int64)
     for ci, c0 in enumerate(range(0, S, JUMP_CHUNK)):
         c1 = min(c0 + JUMP_CHUNK, S)
-        kc, Kc = _poisson_chunk(lam[:, c0:c1], grow, ci << 16, offset, seed)
+        kc, Kc = _poisson_chunk(lam[:, c0:c1], grow, ci << 16, offset, seed, shared=S <= JUMP_SHARED_MAX_S)
         counts[:, c0:c1] = kc
         K += Kc
     return counts, K
@@ -272,7 +290,7 @@ def poisson_rows_margin(lam: np.ndarray, row_offset: int, offset: int, seed: int
         cum = np.cumsum(w, axis=1, dtype=np.float32).astype(np.float64)
         tot = cum[:, -1]
         pos = tot > 0
-        v0 = u32_to_unit(rowjump_words(grow, offset, seed, ci << 16)[:, 0]).astype(np.float64)
+        v0 = count_units(grow, offset, seed, ci << 16, S <= JUMP_SHARED_MAX_S).astype(np.float64)
         K = poisson_from_unit(tot.astype(np.float32), v0.astype(np.float32))
         t = np.where(pos, tot, 1.0)
         with np.errstate(divide="ignore", invalid="ignore", over="ignore", under="ignore"):

@@ -2,13 +2,18 @@
 poisson_rows) draws S INDEPENDENT Poisson(lam_s) counts per row (superposition: total ~ Poisson(sum lam), picks ~
 Categorical(lam / sum)).  Checked here: marginal pmfs, means, pairwise independence, determinism, sharding."""
 import numpy as np
+import pytest
 from scipy.stats import poisson
 
 from oracle import rng
 
 
-def test_poisson_rows_marginals_and_independence():
-    lam_row = np.array([0.0, 0.02, 0.7, 0.0, 1.9, 0.3, 0.004, 2.5], dtype=np.float32)
+@pytest.mark.parametrize("extra_states", [0, 4], ids=["S8_shared_count_call", "S12_per_row_call"])
+def test_poisson_rows_marginals_and_independence(extra_states):
+    """Both maps of the total count's uniform: S <= 8 (word row & 3 of a call shared by 4 consecutive rows) and S > 8
+    (word 0 of the row's own call)."""
+    lam_row = np.array([0.0, 0.02, 0.7, 0.0, 1.9, 0.3, 0.004, 2.5] + [0.0] * extra_states, dtype=np.float32)
+    assert (len(lam_row) <= rng.JUMP_SHARED_MAX_S) == (extra_states == 0)
     n = 400_000
     lam = np.tile(lam_row, (n, 1))
     k, K = rng.poisson_rows(lam, 0, 7, 0xC7DD)
@@ -30,6 +35,27 @@ def test_poisson_rows_marginals_and_independence():
     # joint check on one pair: P(k_2 = 0, k_4 = 0) = exp(-(lam_2 + lam_4))
     both0 = ((k[:, 2] == 0) & (k[:, 4] == 0)).mean()
     assert abs(both0 - np.exp(-(0.7 + 1.9))) < 3e-3
+
+
+def test_small_state_spaces_share_the_count_call_between_four_rows():
+    """S <= 8: the count uniform of row g is word g & 3 of the STREAM_JUMP_COUNT call of row group g >> 2 (the same
+    per-row map as the Euler draw), the picks stay on the row's own call; rows that share a call draw independently."""
+    n, off, seed = 200_000, 5, 77
+    lam = np.tile(np.array([0.3, 0.0, 0.5], dtype=np.float32), (n, 1))
+    k, K = rng.poisson_rows(lam, 8, off, seed)
+    v0 = rng.row_units(n, 8, off, rng.STREAM_JUMP_COUNT, seed)
+    assert np.array_equal(K, rng.poisson_from_unit(lam.sum(1, dtype=np.float32), v0))
+    assert not np.array_equal(v0, rng.rowjump_total_unit(n, 8, off, seed))
+    one = np.flatnonzero(K == 1)                                   # rows with one jump: pick 0 = word 1 of the row's own call 0
+    pick = rng.rowjump_pick_units(np.arange(n, dtype=np.uint64)[one] + np.uint64(8), off, seed, 1)[:, 0]
+    want = np.where(np.minimum(pick, np.float32(0.99999994)) * np.float32(0.8) < np.float32(0.3), 0, 2)
+    assert np.array_equal(k[one].argmax(1), want)
+    Kf = K.astype(np.float64)
+    for d in (1, 2, 3):                                            # neighbours inside / across a call: uncorrelated counts
+        assert abs(np.corrcoef(Kf[:-d], Kf[d:])[0, 1]) < 0.01
+    quad = K[: n // 4 * 4].reshape(-1, 4)
+    p0 = np.exp(-0.8)
+    assert abs((quad == 0).all(1).mean() - p0 ** 4) < 4e-3         # P(all four rows of a call draw no jump)
 
 
 def test_poisson_rows_is_a_function_of_global_row_and_offset():
