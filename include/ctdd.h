@@ -18,7 +18,8 @@
  *     All randomness is counter-based Philox4x32-10 keyed on (seed, call offset, GLOBAL row), so results do
  *     not depend on the launch geometry or on the number of GPUs.  Tau-leap jump counts of a row are drawn
  *     through the Poisson superposition identity: total K ~ Poisson(sum_s lam_s), then K inverse-CDF picks
- *     over lam_s / sum (the same joint law as S independent Poisson draws; DESIGN.md §4.2, oracle/rng.py).
+ *     over lam_s / sum (the same joint law as S independent Poisson draws; DESIGN.md §4.2, oracle/rng.py);
+ *     with S <= 8 the uniform of K comes from a Philox call shared by 4 consecutive global rows.
  */
 #ifndef CTDD_H_
 #define CTDD_H_
