@@ -16,6 +16,11 @@ ncu --set full --clock-control none --import-source on -k regex:step_q -s 5 -c 1
     python bench.py --steps 4 --warmup 3 --no-cpu > $O/${TAG}_ncu_c4.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:bgemm -s 2 -c 1 -f -o $O/${TAG}_c5_bgemm \
     python bench.py --workload C5 --total-batch 512 --steps 2 --warmup 1 --no-cpu > $O/${TAG}_ncu_c5.log 2>&1
+python tools/small_probe.py > $O/${TAG}_small_probe.log 2>&1
+python tools/kernel_zoo.py > $O/${TAG}_zoo_timings.jsonl 2> $O/${TAG}_zoo.err
+ncu --set full --clock-control none --import-source on -k regex:step_small -s 30 -c 1 -f -o $O/${TAG}_c1_small \
+    python tools/small_probe.py > $O/${TAG}_ncu_c1.log 2>&1
+cat $O/${TAG}_small_probe.log
 cat $O/${TAG}_gputests.log
 tail -c 400 $O/${TAG}_bench_c4.json
 ls -la $O/${TAG}_*
