@@ -202,6 +202,38 @@ def test_row_offset_sharding_is_invariant():
                          row_offset=3, **kw)
 
 
+@pytest.mark.parametrize("fwd,mode_name", [("univar2_sqrtcos", "tau_leap"), ("univar3_logsqr", "euler"),
+                                           ("univar3_logsqr", "tau_leap"), ("univar5_log", "tau_leap")])
+def test_small_state_kernels_ragged_tail_and_row_offset(fwd, mode_name):
+    """The S <= 8 kernels (the lean S = 2 tau-leap / S = 3 Euler instantiations and the general one): a row count that is
+    not a multiple of the 8 rows a thread owns, a non-zero row offset, and the shared count call of 4 consecutive rows
+    across the shard boundary - against the oracle on the same uniforms, and full batch == two shards."""
+    from ctdd_b200 import ops
+    nat = _nat()
+    N, D, t, h, seed, off = 13, 21, 0.5, 0.08, 31, 6          # 273 rows = 34 groups of 8 + 1 row
+    fp, logits, x, S = _random_problem(fwd, N, D, t, 23, None)
+    tb = _tables(fp, t)
+    tt = torch.tensor([t], dtype=torch.float64).to(torch.float32)
+    rr, _ = oc.reverse_rates(logits, x, fp.transition(tt), fp.rate(tt), "CTElbo", "reverse_prob", 1e-9)
+    rz = oc._zero_at(rr, x)
+    mode = nat.MODE_EULER if mode_name == "euler" else nat.MODE_TAU_LEAP
+    kw = dict(Q=tb["Q"], QT=tb["QT"], Rb=tb["Rb"], RbT=tb["RbT"], beta=tb["beta"], h=h, eps=1e-9, S=S, D=D, seed=seed, offset=off)
+    row0 = 8 * D                                               # this batch sits behind 8 samples of another rank
+    got = ops.reverse_step(mode, nat.BRANCH_TAULDR, logits.cuda(), x.to(torch.int32).cuda(), N=N, row_offset=row0, **kw)["x"]
+    if mode_name == "euler":
+        want, _ = oc.euler_update(rz, x, h, S, off, seed, row_offset=row0)
+        margin = oc.euler_margin(rz, x, h, S, off, seed, row_offset=row0)
+    else:
+        want, _ = oc.tau_leap_update(rz, x, x, h, S, False, off, seed, row_offset=row0)
+        margin = oc.tau_leap_margin(rz, h, off, seed, row_offset=row0)
+    assert_only_ties(got.cpu().numpy().astype(np.int64), want.numpy(), margin, 1e-3, what=f"{fwd} {mode_name} ragged")
+    assert (got.cpu().numpy().astype(np.int64) != x.numpy()).mean() > 0.02          # the step does move states
+    lo = ops.reverse_step(mode, nat.BRANCH_TAULDR, logits[:8].cuda(), x[:8].to(torch.int32).cuda(), N=8, row_offset=row0, **kw)["x"]
+    hi = ops.reverse_step(mode, nat.BRANCH_TAULDR, logits[8:].cuda(), x[8:].to(torch.int32).cuda(), N=N - 8,
+                          row_offset=row0 + 8 * D, **kw)["x"]
+    assert torch.equal(got, torch.cat([lo, hi]))
+
+
 def test_initial_samples_and_noising_match_oracle():
     from ctdd_b200 import ops
     from ctdd_b200.lib.sampling import sampling
