@@ -114,6 +114,30 @@ __device__ __forceinline__ void flush_stats(const RowStats& st, unsigned long lo
   }
 }
 
+// The same counters summed per CTA in shared memory first: one global atomic per counter and CTA instead of one per warp
+// (the small-S kernels run tens of thousands of warps per launch onto the same 5 addresses).  Every thread of the CTA
+// must call it.
+__device__ __forceinline__ void flush_stats_cta(const RowStats& st, unsigned long long* stats) {
+#ifdef CTDD_WARP_STATS
+  flush_stats(st, stats);
+#else
+  if (!stats) return;            // uniform: a kernel argument
+  __shared__ int s_cnt[5];
+  if (threadIdx.x < 5) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  int v[5] = {st.changed_base, st.nonzero, st.changed_eval, st.jumped, st.multi};
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    int s = v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(&s_cnt[i], s);
+  }
+  __syncthreads();
+  if (threadIdx.x < 5 && s_cnt[threadIdx.x]) atomicAdd(stats + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------
 // small S: thread per 8 rows
 // MODE / BRANCH >= 0: the launch's mode and branch as compile-time constants (the two BASELINE configurations: every other
@@ -444,7 +468,7 @@ __global__ void __launch_bounds__(128, (LEAN && S == 2) ? CTDD_SMALL_MINB : 0) s
         if (r < nr) a.x_out[r0 + r] = xn_out[r];
     }
   } while (STRIDE);
-  flush_stats(st, a.stats);
+  flush_stats_cta(st, a.stats);
 }
 
 // ------------------------------------------------------------------------------------------------

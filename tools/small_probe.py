@@ -28,14 +28,15 @@ for wname, t in (("C1", 0.5), ("C2", 0.1)):
             return ops.reverse_step(mode, branch, lg, x, Q[0], QT[0], Rb, RbT, beta[0], h, 1e-9, N=B, D=D, S=S,
                                     reject_multi=not w["ordinal"], seed=1, offset=0, stats=stats)
         out = run(st)
+        with_stats = bool(os.environ.get("STATS"))       # STATS=1: the counters are accumulated in every timed call (the samplers' call)
         for _ in range(3):
-            run()
+            run(st if with_stats else None)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 20
         e0.record()
         for _ in range(reps):
-            run()
+            run(st if with_stats else None)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         by = (4.0 * S + 8.0) * B * D
