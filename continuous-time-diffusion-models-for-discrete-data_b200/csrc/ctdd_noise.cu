@@ -92,6 +92,62 @@ __global__ void __launch_bounds__(128) noise_xt_kernel(const float* __restrict__
   }
 }
 
+// Forward noising, CTA per SAMPLE b (used when D >= S: the D rows of a sample share S distinct rows of Q[b]): the 128
+// threads stage 128 rows Q[b, k0 .. k0 + 128, :] with coalesced loads, thread i turns row k0 + i into its sequential fp32
+// cumulative sums ONCE (instead of once per (b, d) row that starts there - D / S times less scanning and Q traffic), and
+// every (b, d) row whose x0 falls into the staged range does its binary search there.  Same sums, same crossing.
+constexpr int NOISE_PASS = 128;
+__global__ void __launch_bounds__(NOISE_PASS) noise_xt_sample_kernel(const float* __restrict__ Q, const int* __restrict__ x0,
+                                                                   int B, int D, int S, long long batch_offset,
+                                                                   unsigned long long seed, unsigned long long offset,
+                                                                   int* __restrict__ xt) {
+  extern __shared__ float srow[];      // [NOISE_PASS][S + 1]
+  __shared__ int s_last[NOISE_PASS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ld = S + 1;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const float* Qb = Q + (size_t)b * S * S;
+    const int* xb = x0 + (size_t)b * D;
+    for (int k0 = 0; k0 < S; k0 += NOISE_PASS) {
+      const int nk = (S - k0) < NOISE_PASS ? (S - k0) : NOISE_PASS;
+      const int jn = (nk - 32 * warp) < 32 ? (nk - 32 * warp) : 32;          // rows this warp stages (<= 0: none)
+#pragma unroll 4
+      for (int j = 0; j < jn; ++j) {
+        const float* q = Qb + (size_t)(k0 + 32 * warp + j) * S;
+        float* dst = srow + (size_t)(32 * warp + j) * ld;
+        for (int s = lane; s < S; s += 32) dst[s] = __ldg(q + s);
+      }
+      __syncwarp();
+      if ((int)threadIdx.x < nk) {          // the thread's own row was staged by its own warp
+        float* row = srow + (size_t)threadIdx.x * ld;
+        float acc = 0.f;
+        int last = 0;
+#pragma unroll 8
+        for (int s = 0; s < S; ++s) {
+          const float w = row[s];
+          acc += w;
+          if (w > 0.f) last = s;
+          row[s] = acc;
+        }
+        s_last[threadIdx.x] = last;
+      }
+      __syncthreads();
+      for (int d = threadIdx.x; d < D; d += NOISE_PASS) {
+        const unsigned rel = (unsigned)(xb[d] - k0);
+        if (rel < (unsigned)nk) {
+          const float* row = srow + (size_t)rel * ld;
+          const long long grow = (batch_offset + b) * D + d;
+          const float v = u32_to_unit(philox_row_word((uint64_t)grow, 0, offset, STREAM_NOISE_XT, seed));
+          const float target = fminf(v, 0.99999994f) * row[S - 1];
+          const int f = first_above(row, S, target);
+          xt[(size_t)b * D + d] = f < S ? f : s_last[rel];
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // one CTA per sample b: w[d] = beta_b * sum_{s != xt[d]} Rb[xt[d], s]; d* by inverse CDF over d;
 // new value by inverse CDF over Rb[xt[d*], .] with the diagonal removed.  The cumulative sums are sequential fp32 sums
 // (the oracle's order) made by ONE thread over shared-memory arrays with 128-bit accesses; the crossing is a binary search.
@@ -194,15 +250,25 @@ extern "C" int ctdd_noise_xt(const float* Q, const float* Rb, const float* beta,
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (dev < 0 || dev >= 64 || !((attr_done >> dev) & 1ull)) {
     cudaFuncSetAttribute(noise_xt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(noise_xt_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(xtilde_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (dev >= 0 && dev < 64) attr_done |= 1ull << dev;
   }
+  const size_t smem_s = (size_t)(S < NOISE_PASS ? S : NOISE_PASS) * (S + 1) * sizeof(float);
+  if (D >= S && smem_s <= 200 * 1024) {        // CTA per sample: every row of Q[b] is scanned once
+    const int per_sm = smem_s > 100 * 1024 ? 1 : (smem_s > 50 * 1024 ? 2 : 4);
+    long long blocks_s = (long long)sms * per_sm * 2;
+    if (blocks_s > B) blocks_s = B;
+    noise_xt_sample_kernel<<<(unsigned)blocks_s, NOISE_PASS, smem_s, st>>>(Q, x0, B, D, S, batch_offset, seed, offset, xt_out);
+    CTDD_CHECK_LAUNCH("noise_xt_sample_kernel");
+  } else {
   const long long rows = (long long)B * D;
   long long blocks = (rows + warps * 32 - 1) / (warps * 32);
   const long long cap = (long long)sms * (smem1 > 100 * 1024 ? 1 : 2) * 4;   // a few waves; the kernel strides over row batches
   if (blocks > cap) blocks = cap;
   noise_xt_kernel<<<(unsigned)blocks, warps * 32, smem1, st>>>(Q, x0, B, D, S, batch_offset, seed, offset, xt_out);
   CTDD_CHECK_LAUNCH("noise_xt_kernel");
+  }
   if (x_tilde_out) {
     const size_t smem2 = (size_t)(((S + 3) & ~3) + ((D + 3) & ~3)) * sizeof(float);
     if (smem2 > 200 * 1024) { set_error("ctdd_noise_xt: S + D too large for x_tilde"); return 2; }

@@ -241,18 +241,21 @@ def test_initial_samples_and_noising_match_oracle():
         x = sampling.get_initial_samples(50, 37, "cuda", S, dist, std, seed=77).cpu().numpy()
         want = oc.initial_samples(50, 37, S, dist, std, 77).numpy()
         assert mismatch_fraction(x, want) <= 1e-3
-    fp = oracle_forward("gauss32")
-    B, D, S = 12, 50, 32
-    g = np.random.Generator(np.random.PCG64(1))
-    x0 = torch.from_numpy(g.integers(0, S, (B, D)))
-    ts = torch.from_numpy(g.uniform(0.01, 1.0, B).astype(np.float32))
-    Q = fp.transition(ts)
-    beta = fp.beta(ts)
-    xt, xtil = ops.noise_xt(Q.cuda(), fp.base_rate.cuda(), beta.cuda(), x0.to(torch.int32).cuda(), seed=5, offset=3)
     from oracle import loss_oracle as lo
-    wxt, wtil = lo.noise_xt(Q, fp.rate(ts), x0, seed=5, offset=3)
-    assert mismatch_fraction(xt.cpu().numpy(), wxt.numpy()) <= 1e-3
-    assert mismatch_fraction(xtil.cpu().numpy(), wtil.numpy()) <= 5e-3
+    # D >= S: the CTA-per-sample kernel (each row of Q[b] scanned once); D < S: the lane-per-row kernel; gauss256 with
+    # D = 300: two passes of 128 staged rows
+    for fwd, B, D in (("gauss32", 12, 50), ("gauss32", 12, 20), ("gauss256", 5, 300)):
+        fp = oracle_forward(fwd)
+        S = fp.S
+        g = np.random.Generator(np.random.PCG64(1))
+        x0 = torch.from_numpy(g.integers(0, S, (B, D)))
+        ts = torch.from_numpy(g.uniform(0.01, 1.0, B).astype(np.float32))
+        Q = fp.transition(ts)
+        beta = fp.beta(ts)
+        xt, xtil = ops.noise_xt(Q.cuda(), fp.base_rate.cuda(), beta.cuda(), x0.to(torch.int32).cuda(), seed=5, offset=3)
+        wxt, wtil = lo.noise_xt(Q, fp.rate(ts), x0, seed=5, offset=3)
+        assert mismatch_fraction(xt.cpu().numpy(), wxt.numpy()) <= 1e-3, (fwd, D)
+        assert mismatch_fraction(xtil.cpu().numpy(), wtil.numpy()) <= 5e-3, (fwd, D)
 
 
 # ---------------------------------------------------------------------------------------------------------------
