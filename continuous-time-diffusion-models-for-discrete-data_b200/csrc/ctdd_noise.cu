@@ -92,49 +92,81 @@ __global__ void __launch_bounds__(128) noise_xt_kernel(const float* __restrict__
   }
 }
 
-// Forward noising, CTA per SAMPLE b (used when D >= S: the D rows of a sample share S distinct rows of Q[b]): the 128
-// threads stage 128 rows Q[b, k0 .. k0 + 128, :] with coalesced loads, thread i turns row k0 + i into its sequential fp32
-// cumulative sums ONCE (instead of once per (b, d) row that starts there - D / S times less scanning and Q traffic), and
-// every (b, d) row whose x0 falls into the staged range does its binary search there.  Same sums, same crossing.
-constexpr int NOISE_PASS = 128;
-__global__ void __launch_bounds__(NOISE_PASS) noise_xt_sample_kernel(const float* __restrict__ Q, const int* __restrict__ x0,
-                                                                   int B, int D, int S, long long batch_offset,
-                                                                   unsigned long long seed, unsigned long long offset,
-                                                                   int* __restrict__ xt) {
+// Forward noising, CTA per (SAMPLE b, block of NOISE_PASS rows of Q[b]) - used when D >= S: the D rows of a sample
+// share S distinct rows of Q[b].  The CTA stages rows Q[b, k0 .. k0 + NOISE_PASS, :] with coalesced loads, one thread per
+// staged row turns it into its sequential fp32 cumulative sums ONCE (instead of once per (b, d) row that starts there:
+// D / S times less scanning and Q traffic), and every (b, d) row whose x0 falls into the staged range does its binary
+// search there.  Same sums, same crossing as noise_xt_kernel.
+constexpr int NOISE_PASS = 64, NOISE_THREADS = 256;
+static_assert((NOISE_PASS / (NOISE_THREADS / 32)) % 4 == 0, "rows per warp are staged four at a time");
+__global__ void __launch_bounds__(NOISE_THREADS) noise_xt_sample_kernel(const float* __restrict__ Q, const int* __restrict__ x0,
+                                                                      int B, int D, int S, long long batch_offset,
+                                                                      unsigned long long seed, unsigned long long offset,
+                                                                      int* __restrict__ xt) {
   extern __shared__ float srow[];      // [NOISE_PASS][S + 1]
   __shared__ int s_last[NOISE_PASS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int RPW = NOISE_PASS / (NOISE_THREADS / 32);      // rows staged per warp
   const int ld = S + 1;
-  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+  const int npass = (S + NOISE_PASS - 1) / NOISE_PASS;
+  for (long long item = blockIdx.x; item < (long long)B * npass; item += gridDim.x) {
+    const int b = (int)(item / npass), k0 = (int)(item - (long long)b * npass) * NOISE_PASS;
     const float* Qb = Q + (size_t)b * S * S;
     const int* xb = x0 + (size_t)b * D;
-    for (int k0 = 0; k0 < S; k0 += NOISE_PASS) {
-      const int nk = (S - k0) < NOISE_PASS ? (S - k0) : NOISE_PASS;
-      const int jn = (nk - 32 * warp) < 32 ? (nk - 32 * warp) : 32;          // rows this warp stages (<= 0: none)
-#pragma unroll 4
-      for (int j = 0; j < jn; ++j) {
-        const float* q = Qb + (size_t)(k0 + 32 * warp + j) * S;
-        float* dst = srow + (size_t)(32 * warp + j) * ld;
-        for (int s = lane; s < S; s += 32) dst[s] = __ldg(q + s);
-      }
-      __syncwarp();
-      if ((int)threadIdx.x < nk) {          // the thread's own row was staged by its own warp
-        float* row = srow + (size_t)threadIdx.x * ld;
-        float acc = 0.f;
-        int last = 0;
-#pragma unroll 8
-        for (int s = 0; s < S; ++s) {
-          const float w = row[s];
-          acc += w;
-          if (w > 0.f) last = s;
-          row[s] = acc;
+    const int nk = (S - k0) < NOISE_PASS ? (S - k0) : NOISE_PASS;
+    // 4 rows x 8 columns-of-32 per lane in flight (the copy is latency-bound otherwise)
+    for (int j0 = 0; j0 < RPW; j0 += 4) {
+      for (int s0 = 0; s0 < S; s0 += 256) {
+        float v[4][8];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int i = RPW * warp + j0 + jj;
+          const float* q = Qb + (size_t)(k0 + (i < nk ? i : 0)) * S;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int sidx = s0 + 32 * u + lane;
+            v[jj][u] = (i < nk && sidx < S) ? __ldg(q + sidx) : 0.f;
+          }
         }
-        s_last[threadIdx.x] = last;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int i = RPW * warp + j0 + jj;
+          float* dst = srow + (size_t)i * ld;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int sidx = s0 + 32 * u + lane;
+            if (i < nk && sidx < S) dst[sidx] = v[jj][u];
+          }
+        }
       }
-      __syncthreads();
-      for (int d = threadIdx.x; d < D; d += NOISE_PASS) {
-        const unsigned rel = (unsigned)(xb[d] - k0);
-        if (rel < (unsigned)nk) {
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nk) {
+      float* row = srow + (size_t)threadIdx.x * ld;
+      float acc = 0.f;
+      int last = 0;
+#pragma unroll 8
+      for (int s = 0; s < S; ++s) {
+        const float w = row[s];
+        acc += w;
+        if (w > 0.f) last = s;
+        row[s] = acc;
+      }
+      s_last[threadIdx.x] = last;
+    }
+    __syncthreads();
+    for (int d0 = threadIdx.x; d0 < D; d0 += 8 * NOISE_THREADS) {
+      int xs[8];                         // 8 independent loads in flight (one load per trip left the loop latency-bound)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int d = d0 + u * NOISE_THREADS;
+        xs[u] = d < D ? __ldg(xb + d) : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int d = d0 + u * NOISE_THREADS;
+        const unsigned rel = (unsigned)(xs[u] - k0);
+        if (xs[u] >= 0 && rel < (unsigned)nk) {
           const float* row = srow + (size_t)rel * ld;
           const long long grow = (batch_offset + b) * D + d;
           const float v = u32_to_unit(philox_row_word((uint64_t)grow, 0, offset, STREAM_NOISE_XT, seed));
@@ -143,8 +175,8 @@ __global__ void __launch_bounds__(NOISE_PASS) noise_xt_sample_kernel(const float
           xt[(size_t)b * D + d] = f < S ? f : s_last[rel];
         }
       }
-      __syncthreads();
     }
+    __syncthreads();
   }
 }
 
@@ -184,10 +216,28 @@ __global__ void __launch_bounds__(256) xtilde_kernel(const float* __restrict__ R
   __shared__ int s_dstar;
   const int b = blockIdx.x;
   const float bt = beta[b];
-  for (int x = threadIdx.x; x < S; x += blockDim.x) {
-    float acc = 0.f;
-    for (int s = 0; s < S; ++s) acc += (s == x) ? 0.f : (Rb[(size_t)x * S + s] * bt);
-    soff[x] = acc;
+  // soff[x] = sum_{s != x} Rb[x][s] * beta_b, s ascending (the oracle's order); the rows are read through a 32 x 33
+  // tile per warp so that the global loads are coalesced (thread-per-row loads touched 32 lines each)
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    float* tile = sw + S4 + D4 + (size_t)warp * 32 * 33;
+    for (int xb0 = 32 * warp; xb0 < S; xb0 += 32 * nwarp) {
+      const int x = xb0 + lane;
+      float acc = 0.f;
+      for (int s0 = 0; s0 < S; s0 += 32) {
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j)
+          tile[j * 33 + lane] = (xb0 + j < S && s0 + lane < S) ? __ldg(Rb + (size_t)(xb0 + j) * S + s0 + lane) : 0.f;
+        __syncwarp();
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) {
+          const int sidx = s0 + l;
+          if (sidx < S) acc += (sidx == x) ? 0.f : (tile[lane * 33 + l] * bt);
+        }
+        __syncwarp();
+      }
+      if (x < S) soff[x] = acc;
+    }
   }
   __syncthreads();
   const int* xrow = xt + (size_t)b * D;
@@ -255,11 +305,12 @@ extern "C" int ctdd_noise_xt(const float* Q, const float* Rb, const float* beta,
     if (dev >= 0 && dev < 64) attr_done |= 1ull << dev;
   }
   const size_t smem_s = (size_t)(S < NOISE_PASS ? S : NOISE_PASS) * (S + 1) * sizeof(float);
-  if (D >= S && smem_s <= 200 * 1024) {        // CTA per sample: every row of Q[b] is scanned once
-    const int per_sm = smem_s > 100 * 1024 ? 1 : (smem_s > 50 * 1024 ? 2 : 4);
-    long long blocks_s = (long long)sms * per_sm * 2;
-    if (blocks_s > B) blocks_s = B;
-    noise_xt_sample_kernel<<<(unsigned)blocks_s, NOISE_PASS, smem_s, st>>>(Q, x0, B, D, S, batch_offset, seed, offset, xt_out);
+  if (D >= S && smem_s <= 200 * 1024) {        // every row of Q[b] is scanned once
+    const int per_sm = smem_s > 100 * 1024 ? 1 : (smem_s > 70 * 1024 ? 2 : (smem_s > 50 * 1024 ? 3 : 4));
+    const long long items = (long long)B * ((S + NOISE_PASS - 1) / NOISE_PASS);
+    long long blocks_s = (long long)sms * per_sm * 4;
+    if (blocks_s > items) blocks_s = items;
+    noise_xt_sample_kernel<<<(unsigned)blocks_s, NOISE_THREADS, smem_s, st>>>(Q, x0, B, D, S, batch_offset, seed, offset, xt_out);
     CTDD_CHECK_LAUNCH("noise_xt_sample_kernel");
   } else {
   const long long rows = (long long)B * D;
@@ -270,7 +321,7 @@ extern "C" int ctdd_noise_xt(const float* Q, const float* Rb, const float* beta,
   CTDD_CHECK_LAUNCH("noise_xt_kernel");
   }
   if (x_tilde_out) {
-    const size_t smem2 = (size_t)(((S + 3) & ~3) + ((D + 3) & ~3)) * sizeof(float);
+    const size_t smem2 = (size_t)(((S + 3) & ~3) + ((D + 3) & ~3) + 8 * 32 * 33) * sizeof(float);   // + one tile per warp
     if (smem2 > 200 * 1024) { set_error("ctdd_noise_xt: S + D too large for x_tilde"); return 2; }
     xtilde_kernel<<<B, 256, smem2, st>>>(Rb, beta, xt_out, D, S, batch_offset, seed, offset, x_tilde_out);
     CTDD_CHECK_LAUNCH("xtilde_kernel");
