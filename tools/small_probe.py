@@ -17,6 +17,8 @@ for wname, t in (("C1", 0.5), ("C2", 0.1)):
     Rb, RbT = model.base_rate_tables(dev)
     branch = nat.branch_for(w["loss"], None)
     mode = nat.MODE_EULER if w["mode"] == "euler" else nat.MODE_TAU_LEAP
+    if os.environ.get("MODE") == "corr":          # the corrector variants (general instantiation of the kernel)
+        mode = nat.MODE_EULER_CORR if w["mode"] == "euler" else nat.MODE_TAU_LEAP_CORR
     h = (w["max_t"] - w["min_t"]) / w["num_steps"]
     for mult in (1, 16):
         B = w["B"] * mult
