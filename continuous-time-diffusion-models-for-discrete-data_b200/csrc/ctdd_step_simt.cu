@@ -165,18 +165,18 @@ __global__ void __launch_bounds__(128, (LEAN && S == 2) ? CTDD_SMALL_MINB : 0) s
   constexpr bool TABLE = LEAN && S == 2 && BRANCH == CTDD_BRANCH_TAULDR && (MODE == CTDD_MODE_TAU_LEAP || MODE == CTDD_MODE_EULER);
   constexpr bool ONE = TABLE && S == 2 && MODE == CTDD_MODE_TAU_LEAP;   // one jump target per row: only its rate is made
   constexpr int TQ = (S * S + 3) / 4;                    // float4 per x
-  __shared__ float sQ[S * S], sRb[S * S], sQi[S * S];   // sQi = 1 / (q_t|0 + eps): the tauLDR denominator, once per CTA
+  __shared__ float sQ[S * S], sRb[S * S], sQi[S * S];   // sRb = beta * R_b (every use is that product); sQi = 1 / (q_t|0 + eps)
   __shared__ float4 sT4[TABLE ? S * TQ : 1];
   for (int i = threadIdx.x; i < S * S; i += blockDim.x) {
     const float q = a.Q[i];
-    sQ[i] = q; sRb[i] = a.Rb[i]; sQi[i] = 1.0f / (q + a.eps);
+    sQ[i] = q; sRb[i] = a.beta * a.Rb[i]; sQi[i] = 1.0f / (q + a.eps);
   }
   __syncthreads();
   if (TABLE) {
     float* sT = reinterpret_cast<float*>(sT4);
     for (int i = threadIdx.x; i < S * TQ * 4; i += blockDim.x) {
       const int x = i / (TQ * 4), ks = i - x * (TQ * 4), k = ks / S, t = ks - k * S;
-      sT[i] = (ks < S * S && t != x) ? ((a.beta * sRb[t * S + x]) * (sQ[k * S + t] * sQi[k * S + x])) * a.h : 0.f;
+      sT[i] = (ks < S * S && t != x) ? (sRb[t * S + x] * (sQ[k * S + t] * sQi[k * S + x])) * a.h : 0.f;
     }
     __syncthreads();
     if (ONE) {       // S = 2: the only target of x is 1 - x; sT[x] = {T[x][0][1-x], T[x][1][1-x], -, -}
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(128, (LEAN && S == 2) ? CTDD_SMALL_MINB : 0) s
 #pragma unroll
           for (int k = 0; k < S; ++k) acc = fmaf(w[k], sQ[k * S + s], acc);
           ratio[s] = acc;
-          rfull[s] = a.beta * sRb[s * S + x] * acc;
+          rfull[s] = sRb[s * S + x] * acc;
         }
       } else {
         float ll[S];
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(128, (LEAN && S == 2) ? CTDD_SMALL_MINB : 0) s
 #pragma unroll
         for (int s = 0; s < S; ++s) {
           ratio[s] = expf(ll[s] - llx);
-          rfull[s] = ratio[s] * (a.beta * sRb[x * S + s]);
+          rfull[s] = ratio[s] * sRb[x * S + s];
         }
       }
       if (r < nr) {
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(128, (LEAN && S == 2) ? CTDD_SMALL_MINB : 0) s
 #pragma unroll
       for (int s = 0; s < S; ++s) {
         float v = rfull[s];
-        if (corr) v = v + a.beta * sRb[x * S + s];
+        if (corr) v = v + sRb[x * S + s];
         rate[r][s] = (s == x) ? 0.f : v;
       }
     }
