@@ -154,7 +154,7 @@ __device__ __forceinline__ void flush_stats_cta(const RowStats& st, unsigned lon
 // LEAN: the launch has dense logits and no rr_out / ratio_out (the samplers' call): the strided-row loads and the
 // (predicated, but issued) rate stores drop out as well.
 template <int S, int MODE = -1, int BRANCH = -1, bool LEAN = false>
-__global__ void __launch_bounds__(128, (LEAN && S == 2) ? CTDD_SMALL_MINB : 0) step_small_kernel(StepArgs a_in) {
+__global__ void __launch_bounds__(128, (LEAN && S == 2 && MODE == CTDD_MODE_TAU_LEAP) ? CTDD_SMALL_MINB : 0) step_small_kernel(StepArgs a_in) {
   StepArgs a = a_in;
   if (MODE >= 0) a.mode = MODE;
   if (BRANCH >= 0) a.branch = BRANCH;
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(128, (LEAN && S == 2) ? CTDD_SMALL_MINB : 0) s
   const float hh = TABLE ? 1.0f : a.h;      // TABLE: rate[][] already holds h * rate
   RowStats st = {0, 0, 0, 0, 0};
   // STRIDE: grid-stride over groups of 8 rows on a capped grid; otherwise one group per thread
-  constexpr bool STRIDE = LEAN && S == 2;
+  constexpr bool STRIDE = LEAN && S == 2 && MODE == CTDD_MODE_TAU_LEAP;
   long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   do {
     const long long r0 = g * 8;
@@ -663,12 +663,24 @@ int launch_step_simt(const ctdd_step_params* p, cudaStream_t st) {
         if (a.mode == CTDD_MODE_TAU_LEAP && a.branch == CTDD_BRANCH_TAULDR && lean)    // grid-stride instantiation
           step_small_kernel<2, CTDD_MODE_TAU_LEAP, CTDD_BRANCH_TAULDR, true>
               <<<blocks > 148u * CTDD_SMALL_GRIDCAP ? 148u * CTDD_SMALL_GRIDCAP : blocks, threads, 0, st>>>(a);
+        else if (lean && a.branch == CTDD_BRANCH_TAULDR && a.mode == CTDD_MODE_TAU_LEAP_CORR)   // PCTauL's corrector step
+          step_small_kernel<2, CTDD_MODE_TAU_LEAP_CORR, CTDD_BRANCH_TAULDR, true><<<blocks, threads, 0, st>>>(a);
+        else if (lean && a.branch == CTDD_BRANCH_TAULDR && a.mode == CTDD_MODE_EULER)
+          step_small_kernel<2, CTDD_MODE_EULER, CTDD_BRANCH_TAULDR, true><<<blocks, threads, 0, st>>>(a);
+        else if (lean && a.branch == CTDD_BRANCH_TAULDR && a.mode == CTDD_MODE_EULER_CORR)
+          step_small_kernel<2, CTDD_MODE_EULER_CORR, CTDD_BRANCH_TAULDR, true><<<blocks, threads, 0, st>>>(a);
         else
           step_small_kernel<2><<<blocks, threads, 0, st>>>(a);
         break;
       case 3:   // C2: S = 3, Euler (LBJF) on the tauLDR branch
         if (a.mode == CTDD_MODE_EULER && a.branch == CTDD_BRANCH_TAULDR && lean)
           step_small_kernel<3, CTDD_MODE_EULER, CTDD_BRANCH_TAULDR, true><<<blocks, threads, 0, st>>>(a);
+        else if (lean && a.branch == CTDD_BRANCH_TAULDR && a.mode == CTDD_MODE_EULER_CORR)      // LBJF's corrector step
+          step_small_kernel<3, CTDD_MODE_EULER_CORR, CTDD_BRANCH_TAULDR, true><<<blocks, threads, 0, st>>>(a);
+        else if (lean && a.branch == CTDD_BRANCH_TAULDR && a.mode == CTDD_MODE_TAU_LEAP)
+          step_small_kernel<3, CTDD_MODE_TAU_LEAP, CTDD_BRANCH_TAULDR, true><<<blocks, threads, 0, st>>>(a);
+        else if (lean && a.branch == CTDD_BRANCH_TAULDR && a.mode == CTDD_MODE_TAU_LEAP_CORR)
+          step_small_kernel<3, CTDD_MODE_TAU_LEAP_CORR, CTDD_BRANCH_TAULDR, true><<<blocks, threads, 0, st>>>(a);
         else
           step_small_kernel<3><<<blocks, threads, 0, st>>>(a);
         break;
